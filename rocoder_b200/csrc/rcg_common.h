@@ -1,0 +1,104 @@
+// rcg_common.h -- types and the compile-time FFT plan shared by the sm_100a kernels,
+// the host table builder and the host-side emulator used by the CPU tests.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define RCG_HD __host__ __device__ __forceinline__
+#define RCG_D __device__ __forceinline__
+#include <cuda_runtime.h>
+typedef float2 cf;
+#else
+#define RCG_HD inline
+#define RCG_D inline
+struct alignas(8) cf { float x, y; };
+#endif
+
+RCG_HD cf make_cf(float x, float y) { cf r; r.x = x; r.y = y; return r; }
+
+namespace rcg {
+
+// ---- FFT plan ------------------------------------------------------------------------
+// A frame of W real samples is transformed as an H = W/2 point complex FFT of the
+// even/odd-packed samples (real-FFT split in the spectral step).  The H-point transform
+// is an in-place Cooley-Tukey over mixed power-of-two digits: forward = DIF passes
+// 0..NP-1 (natural order in, digit-reversed order out), inverse = DIT passes NP-1..0
+// (digit-reversed in, natural out), so no reordering pass ever runs.
+// Radices: log2(H) = 4*n16 + r -> one leading pass of radix 2^r (if r != 0) followed by
+// n16 radix-16 passes.
+constexpr int kMaxPasses = 5;
+
+struct PlanDesc {
+    int log2h;
+    int npasses;
+    int rlog2[kMaxPasses];  // log2 radix of pass p
+    int mlog2[kMaxPasses];  // log2 of M_p = stride between butterfly inputs in pass p
+    int klo[kMaxPasses];    // bit offset of digit p inside the bin index k
+};
+
+RCG_HD constexpr PlanDesc make_plan(int log2h) {
+    PlanDesc d{};
+    d.log2h = log2h;
+    int r = log2h % 4, n16 = log2h / 4, np = 0, used = 0;
+    if (r != 0) { d.rlog2[np] = r; d.klo[np] = used; used += r; d.mlog2[np] = log2h - used; np++; }
+    for (int i = 0; i < n16; i++) { d.rlog2[np] = 4; d.klo[np] = used; used += 4; d.mlog2[np] = log2h - used; np++; }
+    d.npasses = np;
+    return d;
+}
+
+// position (in natural cf units, before padding) of bin k after the forward passes, and
+// its inverse.  Fully unrolled: every shift is a compile-time constant.
+template <int LOG2H, int PASS = 0>
+RCG_HD constexpr int bin_to_pos(int k) {
+    constexpr PlanDesc d = make_plan(LOG2H);
+    if constexpr (PASS >= d.npasses) {
+        return 0;
+    } else {
+        return (((k >> d.klo[PASS]) & ((1 << d.rlog2[PASS]) - 1)) << d.mlog2[PASS]) | bin_to_pos<LOG2H, PASS + 1>(k);
+    }
+}
+template <int LOG2H, int PASS = 0>
+RCG_HD constexpr int pos_to_bin(int pos) {
+    constexpr PlanDesc d = make_plan(LOG2H);
+    if constexpr (PASS >= d.npasses) {
+        return 0;
+    } else {
+        return (((pos >> d.mlog2[PASS]) & ((1 << d.rlog2[PASS]) - 1)) << d.klo[PASS]) | pos_to_bin<LOG2H, PASS + 1>(pos);
+    }
+}
+
+// shared-memory padding: one cf of padding every 16 keeps stride-16 and stride-1 access
+// patterns of all passes on distinct 8-byte bank pairs.
+RCG_HD constexpr int phys(int i) { return i + (i >> 4); }
+RCG_HD constexpr int padded_len(int n) { return n + (n >> 4); }
+
+// threads cooperating on one frame, frames side by side in one CTA
+RCG_HD constexpr int threads_per_frame(int log2h) {
+    int h = 1 << log2h;
+    int nt = h / 16;
+    if (nt > 256) nt = 256;
+    if (log2h >= 14) nt = 512;
+    if (nt < 1) nt = 1;
+    return nt;
+}
+RCG_HD constexpr int frames_per_cta(int log2h) {
+    int nt = threads_per_frame(log2h);
+    int f = 256 / nt;
+    return f < 1 ? 1 : f;
+}
+
+// offsets (in cf) of the per-pass twiddle tables inside the packed table
+// table p holds (R_p - 1) * M_p entries: tw[(j-1)*M + m] = exp(-2 pi i * m*j / (R*M)); empty if M == 1
+RCG_HD constexpr int tw_offset(int log2h, int pass) {
+    const PlanDesc d = make_plan(log2h);
+    int off = 0;
+    for (int p = 0; p < pass; p++) {
+        int M = 1 << d.mlog2[p], R = 1 << d.rlog2[p];
+        if (M > 1) off += (R - 1) * M;
+    }
+    return off;
+}
+RCG_HD constexpr int tw_total(int log2h) { return tw_offset(log2h, make_plan(log2h).npasses); }
+
+}  // namespace rcg

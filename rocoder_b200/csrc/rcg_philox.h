@@ -1,0 +1,48 @@
+// rcg_philox.h -- Philox4x32-10 phase source (stands in for rand::thread_rng at
+// reference fft.rs:64, which is OS-seeded and irreproducible).  One block per bin
+// quadruple {k, W-k, H-k, H+k}; counter = (k, frame_lo, frame_hi, channel), key = seed.
+#pragma once
+#include "rcg_common.h"
+
+namespace rcg {
+
+struct PhiloxKeys { uint32_t k0[10], k1[10]; };  // round keys, precomputed on the host
+
+inline PhiloxKeys make_philox_keys(uint64_t seed) {
+    PhiloxKeys k;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; r++) { k.k0[r] = a; k.k1[r] = b; a += 0x9E3779B9u; b += 0xBB67AE85u; }
+    return k;
+}
+
+RCG_HD void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = (uint64_t)a * b;
+    lo = (uint32_t)p;
+    hi = (uint32_t)(p >> 32);
+#endif
+}
+
+RCG_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                          const PhiloxKeys& key, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t h0, l0, h1, l1;
+        mulhilo(0xD2511F53u, c0, h0, l0);
+        mulhilo(0xCD9E8D57u, c2, h1, l1);
+        uint32_t n0 = h1 ^ c1 ^ key.k0[r], n2 = h0 ^ c3 ^ key.k1[r];
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// rand 0.8.5 gen_range(0.0..PI) on f32 (fft.rs:13: the constant named TWO_PI is PI):
+// ((u >> 9) * 2^-23) * PI + 0.0
+RCG_HD float phase_from_u32(uint32_t u) {
+    return (float)(u >> 9) * 1.1920928955078125e-07f * 3.14159274101257324f;
+}
+
+}  // namespace rcg

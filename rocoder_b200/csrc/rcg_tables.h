@@ -1,0 +1,73 @@
+// rcg_tables.h -- host-side builders for the constant tables the kernels read:
+// Hann window (windows.rs:4-9), crossfade envelope (crossfade.rs:4-10), FFT twiddles.
+// Window and envelope use the reference's f32 expressions evaluated with the host libm, so
+// the values match what rocoder computes on the same machine; twiddles are rounded from
+// double.
+#pragma once
+#include <cmath>
+#include <vector>
+
+#include "rcg_common.h"
+
+namespace rcg {
+
+inline void host_hanning(float* out, size_t len) {
+    const float two_pi = 3.14159274101257324f * 2.0f;  // f32::consts::PI * 2.0
+    for (size_t i = 0; i < len; i++)
+        out[i] = 0.5f - (cosf(((float)i * two_pi) / (float)(len - 1)) * 0.5f);
+}
+
+inline void host_crossfade_compensation(float* out, size_t len) {
+    const float two_pi = 3.14159274101257324f * 2.0f;
+    const float hinv_sqrt2 = (1.0f + sqrtf(sqrtf(0.5f))) * 0.5f;
+    for (size_t i = 0; i < len; i++)
+        out[i] = 0.5f - ((1.0f - hinv_sqrt2) * cosf(((float)i * two_pi) / (float)(len - 1)));
+}
+
+inline int rt_pos_to_bin(const PlanDesc& d, int pos) {
+    int k = 0;
+    for (int p = 0; p < d.npasses; p++)
+        k |= ((pos >> d.mlog2[p]) & ((1 << d.rlog2[p]) - 1)) << d.klo[p];
+    return k;
+}
+inline int rt_bin_to_pos(const PlanDesc& d, int k) {
+    int pos = 0;
+    for (int p = 0; p < d.npasses; p++)
+        pos |= ((k >> d.klo[p]) & ((1 << d.rlog2[p]) - 1)) << d.mlog2[p];
+    return pos;
+}
+
+// packed per-pass twiddles: table p = [(R-1)][M], entry exp(-2 pi i m j / (R M))
+inline std::vector<cf> host_pass_twiddles(int log2h) {
+    const PlanDesc d = make_plan(log2h);
+    std::vector<cf> tw((size_t)tw_total(log2h));
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int p = 0; p < d.npasses; p++) {
+        const int M = 1 << d.mlog2[p], R = 1 << d.rlog2[p];
+        if (M == 1) continue;
+        cf* t = tw.data() + tw_offset(log2h, p);
+        for (int j = 1; j < R; j++)
+            for (int m = 0; m < M; m++) {
+                double a = -two_pi * (double)m * (double)j / ((double)R * (double)M);
+                t[(j - 1) * M + m] = make_cf((float)cos(a), (float)sin(a));
+            }
+    }
+    return tw;
+}
+
+// exp(-2 pi i k / W) for the bin k the spectral step's pair slot c owns
+inline std::vector<cf> host_spectral_twiddles(int log2h) {
+    const PlanDesc d = make_plan(log2h);
+    const int H = 1 << log2h, RL = 1 << d.rlog2[d.npasses - 1], HALF = RL / 2;
+    std::vector<cf> tw((size_t)H / 2);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int c = 0; c < H / 2; c++) {
+        int rho = c / HALF, kl = c - rho * HALF;
+        int k = rt_pos_to_bin(d, rho * RL + kl);
+        double a = -two_pi * (double)k / (double)(2 * H);
+        tw[c] = make_cf((float)cos(a), (float)sin(a));
+    }
+    return tw;
+}
+
+}  // namespace rcg

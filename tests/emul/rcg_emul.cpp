@@ -1,0 +1,96 @@
+// rcg_emul.cpp -- TEST INFRASTRUCTURE.  Executes the kernel's per-frame phases
+// (rocoder_b200/csrc/rcg_frame.h) on the host, one emulated thread at a time with a
+// barrier between phases, so that the CPU test suite can check the kernel's indexing,
+// digit-reversed spectral pairing, Philox slotting, overlap-add and resampling against the
+// oracle without a GPU.  Never loaded by the product.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../rocoder_b200/csrc/rcg_frame.h"
+#include "../../rocoder_b200/csrc/rcg_tables.h"
+
+using namespace rcg;
+
+struct HostExec {
+    int nt;
+    template <class F>
+    void par(F f) { for (int t = 0; t < nt; t++) f(t); }
+};
+
+template <int LOG2H>
+static int emul_run(StretchParams prm) {
+    using C = FrameCfg<LOG2H>;
+    const int W = C::W, H = C::H;
+    std::vector<float> window(W), env(H);
+    host_hanning(window.data(), W);
+    host_crossfade_compensation(env.data(), H);
+    std::vector<cf> tw = host_pass_twiddles(LOG2H), stw = host_spectral_twiddles(LOG2H);
+    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.spec_tw = stw.data();
+    std::vector<cf> S(C::SMEM_CF);
+    std::vector<float> tail(H);
+    HostExec ex{C::NT};
+    const int items = prm.channels * prm.n_runs;
+    for (int item = 0; item < items; item++)
+        run_work_item<LOG2H>(ex, S.data(), prm, item, tail.data(), true);
+    return 0;
+}
+
+template <int LOG2H>
+static int emul_boundary(StretchParams prm, const float* head, const float* tail_prev) {
+    using C = FrameCfg<LOG2H>;
+    std::vector<float> env(C::H);
+    host_crossfade_compensation(env.data(), C::H);
+    prm.env = env.data();
+    std::vector<cf> S(C::SMEM_CF);
+    HostExec ex{C::NT};
+    for (int c = 0; c < prm.channels; c++) run_boundary<LOG2H>(ex, S.data(), prm, c, head, tail_prev);
+    return 0;
+}
+
+extern "C" {
+
+// Processes frames [frame_begin, frame_end) of every channel.  See StretchParams.
+int rcg_emul_stretch(int log2w, const float* in, long long in_stride, long long in_origin,
+                     long long in_valid, float* out, long long out_stride, long long out_origin,
+                     long long frame_begin, long long frame_end, int run_len, int channels, int step,
+                     int pitch, int samples_needed, float amp, unsigned long long seed, unsigned flags,
+                     const float* tail_in, float* tail_out, float* head_out) {
+    StretchParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = in; p.in_stride = in_stride; p.in_origin = in_origin; p.in_valid = in_valid;
+    p.out = out; p.out_stride = out_stride; p.out_origin = out_origin;
+    p.frame_begin = frame_begin; p.frame_end = frame_end; p.run_len = run_len;
+    long long nf = frame_end - frame_begin;
+    p.n_runs = nf > 0 ? (int)((nf + run_len - 1) / run_len) : 0;
+    p.channels = channels; p.step = step; p.pitch = pitch; p.samples_needed = samples_needed;
+    p.amp = amp; p.inv_w = 1.0f / (float)(1 << log2w); p.flags = flags;
+    p.keys = make_philox_keys(seed);
+    p.tail_in = tail_in; p.tail_out = tail_out; p.head_out = head_out;
+    switch (log2w - 1) {
+#define CASE(L) case L: return emul_run<L>(p);
+        CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+#undef CASE
+    }
+    return -1;
+}
+
+int rcg_emul_boundary(int log2w, float* out, long long out_stride, long long out_origin,
+                      long long frame_begin, int channels, int pitch, int samples_needed, float amp,
+                      const float* head, const float* tail_prev) {
+    StretchParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = out; p.out_stride = out_stride; p.out_origin = out_origin;
+    p.frame_begin = frame_begin; p.channels = channels; p.pitch = pitch;
+    p.samples_needed = samples_needed; p.amp = amp;
+    switch (log2w - 1) {
+#define CASE(L) case L: return emul_boundary<L>(p, head, tail_prev);
+        CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+#undef CASE
+    }
+    return -1;
+}
+
+// bank-conflict audit: for every warp-wide shared-memory access pattern of one frame,
+// report how many 128-byte wavefronts the 64-bit accesses need (ideal: 2 per warp).
+}
