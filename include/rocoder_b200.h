@@ -1,0 +1,185 @@
+/*
+ * rocoder_b200.h -- C ABI of the B200-native rocoder stretch engine.
+ *
+ * Drop-in boundary for ONE path of ajyoon/rocoder: Stretcher::next_window ->
+ * ReFFT::resynth -> overlap-add -> integer resample (reference src/stretcher.rs,
+ * fft.rs, windows.rs, crossfade.rs, resampler.rs).  Plain pointers and sizes only; no
+ * exceptions or aborts cross this boundary; every entry point returns an rcg_status
+ * (0 = ok) and rcg_last_error() describes the last failure on the calling thread.
+ * An engine is single-threaded like the reference's Stretcher (it is moved into the one
+ * DSP thread, stretcher_processor.rs:55-71); distinct engines are independent.
+ *
+ * The shared library (librocoder_b200.so) is CUDA-only: there is no CPU fallback.
+ * Entry points marked [host] are pure host arithmetic and work without a GPU; everything
+ * else fails with RCG_ERR_CUDA / RCG_ERR_NO_DEVICE when no sm_100 device is present.
+ *
+ * Each declaration cites the reference interface it replaces as file:line relative to
+ * the reference's src/ directory.  INTEGRATION.md shows the Rust FFI binding.
+ */
+#ifndef ROCODER_B200_H
+#define ROCODER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCG_ABI_VERSION 1
+
+typedef enum rcg_status {
+    RCG_OK = 0,
+    RCG_ERR_INVALID_ARG = 1,
+    RCG_ERR_PITCH = 2,       /* pitch_multiple 0 (assert, stretcher.rs:40), -1 (panic, resampler.rs:11), or outside i8 */
+    RCG_ERR_WINDOW = 3,      /* window_len not a power of two in [64, 32768] */
+    RCG_ERR_STEP = 4,        /* sample_step_len outside 1..=W: the reference underflows usize at stretcher.rs:105-106 */
+    RCG_ERR_CUDA = 5,
+    RCG_ERR_NO_DEVICE = 6,
+    RCG_ERR_WOULD_BLOCK = 7, /* next_window needs input that has not been sent and the sender is not closed (recv() at stretcher.rs:125 would block) */
+    RCG_ERR_CAPACITY = 8,    /* caller buffer too small */
+    RCG_ERR_PLUGIN = 9,
+    RCG_ERR_STATE = 10
+} rcg_status;
+
+/* flags for rcg_config.flags */
+#define RCG_FLAG_RANDOM_SEED 1u   /* ignore `seed`, draw one from the OS like rand::thread_rng (fft.rs:64) */
+#define RCG_FLAG_BYPASS_RESYNTH 2u /* test hook: resynth(s)[n] = (s[n]*w[n])*w[n]; checks all indexing bit-exactly */
+
+/* Arguments of Stretcher::new (stretcher.rs:30-39) plus the phase seed and the device.
+ * The Hann window of main.rs:131 is built internally from window_len. */
+typedef struct rcg_config {
+    uint32_t struct_size;     /* sizeof(rcg_config) */
+    uint32_t channels;        /* AudioSpec.channels  (audio.rs:32-37); one Stretcher per channel (main.rs:133-153) */
+    uint32_t sample_rate;     /* AudioSpec.sample_rate */
+    uint32_t window_len;      /* -w, window.len() */
+    float factor;             /* -f */
+    float amplitude;          /* -a */
+    int32_t pitch_multiple;   /* -p (i8 in the reference) */
+    float buffer_dur_s;       /* -b, Duration::as_secs_f32 */
+    uint64_t seed;            /* Philox key; (seed, channel, frame, bin) fixes every phase */
+    int32_t device;           /* CUDA device ordinal */
+    uint32_t flags;
+    uint32_t max_lookahead_calls; /* streaming: calls computed per launch when input allows (0 = default 64) */
+    uint32_t first_channel;   /* channel index of row 0: Stretcher c of main.rs:133-153 is an engine with channels=1, first_channel=c */
+} rcg_config;
+
+/* The constants Stretcher::new derives (stretcher.rs:40-59), f32 arithmetic, truncating casts. */
+typedef struct rcg_plan_info {
+    float pitch_shifted_factor;       /* stretcher.rs:42-46 */
+    float corrected_amp_factor;       /* stretcher.rs:53 */
+    uint64_t window_len;
+    uint64_t half_window_len;         /* stretcher.rs:54 */
+    uint64_t samples_needed_per_window; /* stretcher.rs:47-51 */
+    uint64_t sample_step_len;         /* stretcher.rs:55 */
+    uint64_t frames_per_call;         /* trips of the while loop at stretcher.rs:91 */
+    uint64_t out_len_per_call;        /* resample() output length, resampler.rs:3-35 */
+} rcg_plan_info;
+
+/* ---- [host] arithmetic that must be bit-exact with the reference ----------------------- */
+/* stretcher.rs:40-59.  Validates pitch, window and step. */
+int rcg_plan(const rcg_config *cfg, rcg_plan_info *out);
+/* Calls / frames / output samples per channel for n_in input samples: the stop rule of
+ * stretcher.rs:123-135 + stretcher_processor.rs:64-68. */
+int rcg_expected_counts(const rcg_config *cfg, uint64_t n_in, uint64_t *calls, uint64_t *frames,
+                        uint64_t *out_len);
+/* windows::hanning, windows.rs:4-9 */
+int rcg_hanning(float *out, size_t len);
+/* crossfade::hanning_crossfade_compensation, crossfade.rs:4-10 */
+int rcg_hanning_crossfade_compensation(float *out, size_t len);
+/* Stretcher::channel_bound, stretcher.rs:82-85 */
+int rcg_channel_bound(const rcg_config *cfg, uint64_t *bound);
+/* phase the engine assigns to `bin` of `frame` of `channel` (replaces fft.rs:64) */
+float rcg_phase(uint64_t seed, uint32_t channel, uint64_t frame, uint32_t bin, uint32_t window_len);
+
+const char *rcg_last_error(void);
+const char *rcg_status_string(int status);
+int rcg_abi_version(void);
+
+/* ---- engine ---------------------------------------------------------------------------- */
+typedef struct rcg_engine rcg_engine;
+
+/* Stretcher::new for every channel + ReFFT::new (stretcher.rs:30-76, fft.rs:25-40). */
+int rcg_create(const rcg_config *cfg, rcg_engine **out);
+void rcg_destroy(rcg_engine *e);
+int rcg_get_plan(const rcg_engine *e, rcg_plan_info *out);
+
+/* -- batched, host buffers: what main.rs:133-160 + AudioBus::into_audio (audio.rs:152-172)
+ * do for a whole file.  in[c] holds n_in samples of channel c (the one chunk main.rs:148
+ * sends, sender then dropped); out[c] receives the concatenated windows.  Host<->device
+ * copies happen inside; pinned buffers (rcg_host_alloc) make them asynchronous. */
+int rcg_process_all(rcg_engine *e, const float *const *in, uint64_t n_in, float *const *out,
+                    uint64_t out_cap, uint64_t *n_out);
+
+/* -- batched, device-resident: calls [first_call, first_call + n_calls) of every channel.
+ * d_in[c * in_stride + i] is input sample in_origin + i of channel c; samples at or past
+ * in_origin + in_valid read as the zero padding of stretcher.rs:130.  d_out[c * out_stride]
+ * receives the windows of these calls back to back.
+ * How the half window carried into the first call is obtained (stretcher.rs:58-59, 112):
+ *   first_call == 0           zeros;
+ *   d_tail_in != NULL         [channels][W/2] second half of the preceding frame;
+ *   RCG_SEG_DEFER_FIRST       the first half-window block is NOT emitted; its raw first half
+ *                             goes to d_head_out [channels][W/2] and rcg_finish_boundary()
+ *                             completes it once the neighbour's tail has arrived;
+ *   otherwise                 the preceding frame is recomputed (needs in_origin <=
+ *                             (first_call*frames_per_call - 1) * sample_step_len).
+ * d_tail_out (optional) receives the second half of the last frame.  `stream` is a
+ * cudaStream_t (NULL = the engine's own stream); the call is asynchronous on it. */
+#define RCG_SEG_DEFER_FIRST 1u
+typedef struct rcg_segment {
+    const float *d_in;
+    int64_t in_stride;
+    int64_t in_origin;
+    int64_t in_valid;
+    float *d_out;
+    int64_t out_stride;
+    uint64_t first_call;
+    uint64_t n_calls;
+    const float *d_tail_in;
+    float *d_tail_out;
+    float *d_head_out;
+    uint32_t flags;
+    uint32_t reserved;
+    void *stream;
+} rcg_segment;
+int rcg_process_segment(rcg_engine *e, const rcg_segment *seg);
+/* Finish the deferred first block of a segment: ((head + tail_prev) * env) * amp, resampled,
+ * written where rcg_process_segment left the gap. */
+int rcg_finish_boundary(rcg_engine *e, float *d_out, int64_t out_stride, uint64_t first_call,
+                        const float *d_head, const float *d_tail_prev, void *stream);
+int rcg_synchronize(rcg_engine *e);
+
+/* -- streaming, one window at a time: the Stretcher API itself ----------------------------- */
+/* Sender<Vec<f32>>::send on the channel's input (main.rs:148, stretcher.rs:125-128) */
+int rcg_send(rcg_engine *e, uint32_t channel, const float *chunk, uint64_t n);
+/* dropping the Sender (main.rs:148-152): recv() then fails and the tail is zero padded */
+int rcg_close_input(rcg_engine *e, uint32_t channel);
+/* Stretcher::next_window, stretcher.rs:87-121 */
+int rcg_next_window(rcg_engine *e, uint32_t channel, float *out, uint64_t cap, uint64_t *n_out);
+/* Stretcher::is_done, stretcher.rs:78 */
+int rcg_is_done(rcg_engine *e, uint32_t channel, int *done);
+
+/* -- frequency-kernel plugin (fft.rs:76-108) -------------------------------------------------
+ * C form of the reference's Rust-ABI `apply(elapsed_ms, Vec<(f32,f32)>) -> Vec<(f32,f32)>`
+ * (fft.rs:93, README.md:108-113): in/out are n_bins interleaved (re, im) pairs, the full
+ * W-bin unnormalised spectrum in natural order.  Return 0; non-zero stands for a panic:
+ * the newest kernel is popped and the frame retried with the previous one, else passed
+ * through (fft.rs:101-106).  Called once per frame per channel, frames in order. */
+typedef int (*rcg_apply_fn)(size_t elapsed_ms, const float *in_re_im, size_t n_bins,
+                            float *out_re_im);
+/* what receiving a Library on kernel_recv does (fft.rs:78-81) */
+int rcg_push_frequency_kernel(rcg_engine *e, rcg_apply_fn fn);
+/* dlopen(path) and push its `apply` symbol (hotswapper.rs:85-86 + fft.rs:93-94) */
+int rcg_load_frequency_kernel(rcg_engine *e, const char *so_path);
+int rcg_frequency_kernel_count(const rcg_engine *e, uint32_t *n);
+
+/* -- helpers ------------------------------------------------------------------------------ */
+int rcg_host_alloc(void **ptr, size_t bytes); /* pinned host memory */
+int rcg_host_free(void *ptr);
+/* kernels launched by this engine so far */
+int rcg_launch_count(const rcg_engine *e, uint64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,19 @@
+"""rocoder_b200 -- B200-native engine for ajyoon/rocoder's stretch path.
+
+Only what the path needs lives here: csrc/ (sm_100a kernels + the C ABI behind
+include/rocoder_b200.h) and the host-side mirror of the reference's Stretcher /
+StretcherProcessor interface.  There is no CPU fallback: without librocoder_b200.so or
+without an sm_100 GPU the engine raises.
+"""
+from ._abi import (RCG_FLAG_BYPASS_RESYNTH, RCG_FLAG_RANDOM_SEED, RcgError, WouldBlock, LIB_PATH)
+from .engine import (Engine, PinnedBuffer, channel_bound, expected_counts, hanning,
+                     hanning_crossfade_compensation, phase, plan)
+from .stretcher import (AudioBus, AudioSpec, Disconnected, Receiver, Sender, Stretcher, StretcherProcessor,
+                        bounded, stretch, unbounded)
+
+__all__ = [
+    "Engine", "PinnedBuffer", "RcgError", "WouldBlock", "LIB_PATH", "RCG_FLAG_BYPASS_RESYNTH",
+    "RCG_FLAG_RANDOM_SEED", "channel_bound", "expected_counts", "hanning", "hanning_crossfade_compensation",
+    "phase", "plan", "AudioBus", "AudioSpec", "Disconnected", "Receiver", "Sender", "Stretcher",
+    "StretcherProcessor", "bounded", "stretch", "unbounded",
+]

@@ -1,0 +1,619 @@
+// rcg_engine.cu -- host side of librocoder_b200.so: the C ABI declared in
+// include/rocoder_b200.h.  Mirrors Stretcher / StretcherProcessor (reference
+// stretcher.rs, stretcher_processor.rs) on top of the fused sm_100a kernels.  CUDA only:
+// no CPU fallback exists; without a device every engine entry point fails loudly.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/rocoder_b200.h"
+#include "rcg_kernels.h"
+#include "rcg_tables.h"
+
+using namespace rcg;
+
+// ---------------------------------------------------------------------------- errors ------
+static thread_local char g_err[512] = "";
+
+static int fail(int status, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return fail(_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver           \
+                            ? RCG_ERR_NO_DEVICE : RCG_ERR_CUDA,                                \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* rcg_last_error(void) { return g_err; }
+extern "C" int rcg_abi_version(void) { return RCG_ABI_VERSION; }
+extern "C" const char* rcg_status_string(int s) {
+    switch (s) {
+        case RCG_OK: return "ok";
+        case RCG_ERR_INVALID_ARG: return "invalid argument";
+        case RCG_ERR_PITCH: return "invalid pitch multiple";
+        case RCG_ERR_WINDOW: return "unsupported window length";
+        case RCG_ERR_STEP: return "sample step outside 1..=window";
+        case RCG_ERR_CUDA: return "CUDA error";
+        case RCG_ERR_NO_DEVICE: return "no CUDA device";
+        case RCG_ERR_WOULD_BLOCK: return "input not available";
+        case RCG_ERR_CAPACITY: return "output buffer too small";
+        case RCG_ERR_PLUGIN: return "frequency kernel error";
+        case RCG_ERR_STATE: return "invalid engine state";
+    }
+    return "unknown status";
+}
+
+// ---------------------------------------------------------------------------- plan --------
+// Rust `as usize` on an f32: saturating, NaN -> 0
+static uint64_t f32_to_usize(float v) {
+    if (!(v == v) || v <= 0.0f) return 0;
+    if (v >= 18446744073709551615.0f) return UINT64_MAX;
+    return (uint64_t)v;
+}
+
+static uint64_t resample_len(uint64_t n, int p) {
+    if (p == 1) return n;
+    if (p > 1) return (n + (uint64_t)p - 1) / (uint64_t)p;
+    return n ? (n - 1) * (uint64_t)(-p) : 0;
+}
+
+static int log2_exact(uint32_t w) {
+    int l = 0;
+    while ((1u << l) < w) l++;
+    return (1u << l) == w ? l : -1;
+}
+
+extern "C" int rcg_plan(const rcg_config* cfg, rcg_plan_info* out) {
+    if (!cfg || !out) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    const int p = cfg->pitch_multiple;
+    if (p == 0) return fail(RCG_ERR_PITCH, "pitch_multiple must be non-zero (stretcher.rs:40)");
+    if (p == -1) return fail(RCG_ERR_PITCH, "invalid resample factor -1 (resampler.rs:11)");
+    if (p < -127 || p > 127) return fail(RCG_ERR_PITCH, "pitch_multiple outside the reference's i8 range");
+    const uint32_t W = cfg->window_len;
+    const int l2 = log2_exact(W);
+    if (l2 < 6 || l2 > 15)
+        return fail(RCG_ERR_WINDOW, "window_len %u: need a power of two in [64, 32768]", W);
+    if (cfg->channels == 0) return fail(RCG_ERR_INVALID_ARG, "channels must be >= 1");
+    const float abs_p = (float)(p < 0 ? -p : p);
+    // stretcher.rs:42-46
+    const float psf = p < 0 ? cfg->factor / abs_p : cfg->factor * abs_p;
+    // stretcher.rs:47-51
+    const uint64_t S = p < 0 ? f32_to_usize(ceilf((float)W / abs_p)) : (uint64_t)W * (uint64_t)(p < 0 ? -p : p);
+    const uint64_t H = W / 2;
+    // stretcher.rs:55
+    const uint64_t step = f32_to_usize((float)W / (psf * 2.0f));
+    if (step < 1 || step > W)
+        return fail(RCG_ERR_STEP, "sample_step_len %llu outside 1..=%u (factor %g, pitch %d)",
+                    (unsigned long long)step, W, (double)cfg->factor, p);
+    out->pitch_shifted_factor = psf;
+    out->corrected_amp_factor = fmaxf(4.0f, psf / 4.0f) * cfg->amplitude;  // stretcher.rs:53
+    out->window_len = W;
+    out->half_window_len = H;
+    out->samples_needed_per_window = S;
+    out->sample_step_len = step;
+    out->frames_per_call = (S + H - 1) / H;
+    out->out_len_per_call = resample_len(S, p);
+    return RCG_OK;
+}
+
+static void counts_for(const rcg_plan_info& pl, uint64_t n_in, uint64_t* calls, uint64_t* frames, uint64_t* out_len) {
+    // first frame j with j*step + W > n_in sets `done` (stretcher.rs:124-131); the call that
+    // contains it is still completed and emitted; the processor stops before the next one.
+    const uint64_t j1 = n_in < pl.window_len ? 0 : (n_in - pl.window_len) / pl.sample_step_len + 1;
+    const uint64_t c = j1 / pl.frames_per_call + 1;
+    if (calls) *calls = c;
+    if (frames) *frames = c * pl.frames_per_call;
+    if (out_len) *out_len = c * pl.out_len_per_call;
+}
+
+extern "C" int rcg_expected_counts(const rcg_config* cfg, uint64_t n_in, uint64_t* calls, uint64_t* frames,
+                                   uint64_t* out_len) {
+    rcg_plan_info pl;
+    int rc = rcg_plan(cfg, &pl);
+    if (rc) return rc;
+    counts_for(pl, n_in, calls, frames, out_len);
+    return RCG_OK;
+}
+
+extern "C" int rcg_hanning(float* out, size_t len) {
+    if (!out) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    host_hanning(out, len);
+    return RCG_OK;
+}
+extern "C" int rcg_hanning_crossfade_compensation(float* out, size_t len) {
+    if (!out) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    host_crossfade_compensation(out, len);
+    return RCG_OK;
+}
+extern "C" int rcg_channel_bound(const rcg_config* cfg, uint64_t* bound) {
+    if (!cfg || !bound) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    // stretcher.rs:82-85
+    *bound = f32_to_usize(ceilf(((float)cfg->window_len / (float)cfg->sample_rate) / cfg->buffer_dur_s));
+    return RCG_OK;
+}
+extern "C" float rcg_phase(uint64_t seed, uint32_t channel, uint64_t frame, uint32_t bin, uint32_t W) {
+    const uint32_t H = W / 2, Q = H / 2;
+    uint32_t pair, word;
+    if (bin <= Q) { pair = bin; word = 0; }
+    else if (bin <= H) { pair = H - bin; word = 2; }
+    else if (bin < H + Q) { pair = bin - H; word = 3; }
+    else { pair = W - bin; word = 1; }
+    uint32_t u[4];
+    philox4x32_10(pair, (uint32_t)frame, (uint32_t)(frame >> 32), channel, make_philox_keys(seed), u);
+    return phase_from_u32(u[word]);
+}
+
+// ---------------------------------------------------------------------------- engine ------
+struct ChannelState {
+    std::vector<float> input;      // samples [input_base, input_base + input.size())
+    uint64_t input_base = 0;
+    uint64_t received = 0;         // total samples sent
+    bool closed = false;
+    bool done = false;
+    uint64_t next_call = 0;        // next call to compute
+    std::deque<std::pair<std::vector<float>, bool>> ready;  // (window, used zero padding)
+    float* d_tail[2] = {nullptr, nullptr};
+    int tail_cur = 0;
+};
+
+struct rcg_engine {
+    rcg_config cfg{};
+    rcg_plan_info plan{};
+    int log2w = 0;
+    int device = 0;
+    int sm_count = 0;
+    LaunchGeometry geo{};
+    int max_grid = 0;
+    PhiloxKeys keys{};
+    uint64_t seed = 0;
+    float *d_window = nullptr, *d_env = nullptr, *d_scratch = nullptr;
+    cf *d_tw = nullptr, *d_spec_tw = nullptr;
+    cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+    uint64_t launches = 0;
+    // process_all buffers (grow only)
+    float *d_in = nullptr, *d_out = nullptr, *d_tail_pp[2] = {nullptr, nullptr};
+    size_t d_in_cap = 0, d_out_cap = 0;
+    std::vector<cudaEvent_t> events;
+    // streaming
+    std::vector<ChannelState> ch;
+    float *d_sin = nullptr, *d_sout = nullptr, *h_sout = nullptr;
+    size_t d_sin_cap = 0, d_sout_cap = 0, h_sout_cap = 0;
+    // plugins (fft.rs:22: kernels: Vec<Library>)
+    std::vector<rcg_apply_fn> kernels;
+    std::vector<void*> libs;
+};
+
+static int pick_run_len(uint64_t frames_per_channel, uint32_t channels, int slots) {
+    // minimise waves * (frames per item + 1 halo frame)
+    if (frames_per_channel == 0) return 1;
+    uint64_t best_cost = UINT64_MAX;
+    int best = 1;
+    const int rmax = (int)std::min<uint64_t>(frames_per_channel, 512);
+    for (int r = 1; r <= rmax; r++) {
+        uint64_t items = (uint64_t)channels * ((frames_per_channel + r - 1) / r);
+        uint64_t waves = (items + slots - 1) / slots;
+        uint64_t cost = waves * (uint64_t)(r + 1);
+        if (cost < best_cost) { best_cost = cost; best = r; }
+    }
+    return best;
+}
+
+extern "C" int rcg_create(const rcg_config* cfg, rcg_engine** out) {
+    if (!cfg || !out) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(rcg_config))
+        return fail(RCG_ERR_INVALID_ARG, "rcg_config.struct_size %u != %zu", cfg->struct_size, sizeof(rcg_config));
+    rcg_plan_info pl;
+    int rc = rcg_plan(cfg, &pl);
+    if (rc) return rc;
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) return fail(RCG_ERR_NO_DEVICE, "no CUDA device");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(RCG_ERR_INVALID_ARG, "device %d of %d", cfg->device, ndev);
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(RCG_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", cfg->device,
+                    prop.major, prop.minor);
+    rcg_engine* e = new rcg_engine();
+    e->cfg = *cfg;
+    e->plan = pl;
+    e->log2w = log2_exact(cfg->window_len);
+    e->device = cfg->device;
+    e->sm_count = prop.multiProcessorCount;
+    e->seed = cfg->seed;
+    if (cfg->flags & RCG_FLAG_RANDOM_SEED) {
+        std::random_device rd;
+        e->seed = ((uint64_t)rd() << 32) ^ rd();
+    }
+    e->keys = make_philox_keys(e->seed);
+    auto bail = [&](int status) { rcg_destroy(e); return status; };
+#define TRY_E(expr)                                                                                  \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return bail(fail(RCG_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)));        \
+    } while (0)
+    TRY_E(stretch_geometry(e->log2w, &e->geo));
+    if (e->geo.max_ctas_per_sm < 1) return bail(fail(RCG_ERR_CUDA, "stretch kernel does not fit on an SM"));
+    e->max_grid = e->sm_count * e->geo.max_ctas_per_sm;
+    const size_t W = cfg->window_len, H = W / 2;
+    std::vector<float> window(W), env(H);
+    host_hanning(window.data(), W);           // main.rs:131
+    host_crossfade_compensation(env.data(), H);  // stretcher.rs:56
+    std::vector<cf> tw = host_pass_twiddles(e->log2w - 1), stw = host_spectral_twiddles(e->log2w - 1);
+    TRY_E(cudaMalloc(&e->d_window, W * sizeof(float)));
+    TRY_E(cudaMalloc(&e->d_env, H * sizeof(float)));
+    TRY_E(cudaMalloc(&e->d_tw, std::max<size_t>(tw.size(), 1) * sizeof(cf)));
+    TRY_E(cudaMalloc(&e->d_spec_tw, stw.size() * sizeof(cf)));
+    TRY_E(cudaMalloc(&e->d_scratch, (size_t)e->max_grid * e->geo.frames_per_cta * H * sizeof(float)));
+    TRY_E(cudaMemcpy(e->d_window, window.data(), W * sizeof(float), cudaMemcpyHostToDevice));
+    TRY_E(cudaMemcpy(e->d_env, env.data(), H * sizeof(float), cudaMemcpyHostToDevice));
+    TRY_E(cudaMemcpy(e->d_tw, tw.data(), tw.size() * sizeof(cf), cudaMemcpyHostToDevice));
+    TRY_E(cudaMemcpy(e->d_spec_tw, stw.data(), stw.size() * sizeof(cf), cudaMemcpyHostToDevice));
+    TRY_E(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    TRY_E(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
+    TRY_E(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) TRY_E(cudaMalloc(&e->d_tail_pp[i], (size_t)cfg->channels * H * sizeof(float)));
+    e->ch.resize(cfg->channels);
+    for (auto& c : e->ch)
+        for (int i = 0; i < 2; i++) {
+            TRY_E(cudaMalloc(&c.d_tail[i], H * sizeof(float)));
+            TRY_E(cudaMemset(c.d_tail[i], 0, H * sizeof(float)));
+        }
+#undef TRY_E
+    *out = e;
+    return RCG_OK;
+}
+
+extern "C" void rcg_destroy(rcg_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->d2h) cudaStreamSynchronize(e->d2h);
+    if (e->h2d) cudaStreamSynchronize(e->h2d);
+    cudaFree(e->d_window); cudaFree(e->d_env); cudaFree(e->d_tw); cudaFree(e->d_spec_tw); cudaFree(e->d_scratch);
+    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_tail_pp[0]); cudaFree(e->d_tail_pp[1]);
+    cudaFree(e->d_sin); cudaFree(e->d_sout);
+    if (e->h_sout) cudaFreeHost(e->h_sout);
+    for (auto& c : e->ch) { cudaFree(c.d_tail[0]); cudaFree(c.d_tail[1]); }
+    for (auto ev : e->events) cudaEventDestroy(ev);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->h2d) cudaStreamDestroy(e->h2d);
+    if (e->d2h) cudaStreamDestroy(e->d2h);
+    for (void* l : e->libs) dlclose(l);
+    delete e;
+}
+
+extern "C" int rcg_get_plan(const rcg_engine* e, rcg_plan_info* out) {
+    if (!e || !out) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    *out = e->plan;
+    return RCG_OK;
+}
+extern "C" int rcg_launch_count(const rcg_engine* e, uint64_t* n) {
+    if (!e || !n) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    *n = e->launches;
+    return RCG_OK;
+}
+extern "C" int rcg_synchronize(rcg_engine* e) {
+    if (!e) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->h2d));
+    CUDA_TRY(cudaStreamSynchronize(e->d2h));
+    return RCG_OK;
+}
+
+static void fill_params(const rcg_engine* e, StretchParams& p) {
+    memset(&p, 0, sizeof(p));
+    p.window = e->d_window; p.env = e->d_env; p.tw = e->d_tw; p.spec_tw = e->d_spec_tw;
+    p.tail_scratch = e->d_scratch;
+    p.channels = (int)e->cfg.channels;
+    p.step = (int)e->plan.sample_step_len;
+    p.pitch = e->cfg.pitch_multiple;
+    p.samples_needed = (int)e->plan.samples_needed_per_window;
+    p.amp = e->plan.corrected_amp_factor;
+    p.inv_w = 1.0f / (float)e->cfg.window_len;
+    p.flags = (e->cfg.flags & RCG_FLAG_BYPASS_RESYNTH) ? kFlagBypass : 0u;
+    p.keys = e->keys;
+}
+
+// launch calls [first_call, first_call + n_calls) for `channels` rows
+static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream,
+                          int channel_offset = 0) {
+    if (!e->kernels.empty())
+        return fail(RCG_ERR_PLUGIN, "frequency kernels are not supported on this path yet");
+    if (s.n_calls == 0) return RCG_OK;
+    StretchParams p;
+    fill_params(e, p);
+    const uint64_t k = e->plan.frames_per_call;
+    p.in = s.d_in; p.in_stride = s.in_stride; p.in_origin = s.in_origin; p.in_valid = s.in_valid;
+    p.out = s.d_out; p.out_stride = s.out_stride;
+    p.out_origin = (long long)(s.first_call * e->plan.out_len_per_call);
+    p.frame_begin = (long long)(s.first_call * k);
+    p.frame_end = (long long)((s.first_call + s.n_calls) * k);
+    p.channels = channels;
+    p.channel_offset = (int)e->cfg.first_channel + channel_offset;
+    p.tail_in = s.d_tail_in; p.tail_out = s.d_tail_out; p.head_out = s.d_head_out;
+    if (s.flags & RCG_SEG_DEFER_FIRST) {
+        if (!s.d_head_out) return fail(RCG_ERR_INVALID_ARG, "RCG_SEG_DEFER_FIRST needs d_head_out");
+        p.flags |= kFlagDeferFirst;
+    }
+    const bool needs_halo = p.frame_begin > 0 && !s.d_tail_in && !(s.flags & RCG_SEG_DEFER_FIRST);
+    if (needs_halo && s.in_origin > (p.frame_begin - 1) * (long long)p.step)
+        return fail(RCG_ERR_INVALID_ARG, "segment starts at frame %lld but its input starts past the halo frame",
+                    p.frame_begin);
+    const uint64_t nframes = (uint64_t)(p.frame_end - p.frame_begin);
+    const int slots = e->max_grid * e->geo.frames_per_cta;
+    p.run_len = pick_run_len(nframes, (uint32_t)channels, slots);
+    p.n_runs = (int)((nframes + p.run_len - 1) / p.run_len);
+    const long long items = (long long)p.n_runs * channels;
+    const int groups = (int)((items + e->geo.frames_per_cta - 1) / e->geo.frames_per_cta);
+    const int grid = std::min(groups, e->max_grid);
+    cudaError_t ce = launch_stretch(e->log2w, p, grid, stream);
+    if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "stretch kernel launch failed: %s", cudaGetErrorString(ce));
+    e->launches++;
+    return RCG_OK;
+}
+
+extern "C" int rcg_process_segment(rcg_engine* e, const rcg_segment* seg) {
+    if (!e || !seg || !seg->d_in || !seg->d_out) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    cudaStream_t st = seg->stream ? (cudaStream_t)seg->stream : e->stream;
+    return launch_segment(e, *seg, (int)e->cfg.channels, st);
+}
+
+extern "C" int rcg_finish_boundary(rcg_engine* e, float* d_out, int64_t out_stride, uint64_t first_call,
+                                   const float* d_head, const float* d_tail_prev, void* stream) {
+    if (!e || !d_out || !d_head || !d_tail_prev) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    StretchParams p;
+    fill_params(e, p);
+    p.out = d_out; p.out_stride = out_stride;
+    p.out_origin = (long long)(first_call * e->plan.out_len_per_call);
+    p.frame_begin = (long long)(first_call * e->plan.frames_per_call);
+    cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+    cudaError_t ce = launch_boundary(e->log2w, p, d_head, d_tail_prev, st);
+    if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "boundary kernel launch failed: %s", cudaGetErrorString(ce));
+    e->launches++;
+    return RCG_OK;
+}
+
+static cudaEvent_t get_event(rcg_engine* e, size_t i) {
+    while (e->events.size() <= i) {
+        cudaEvent_t ev;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        e->events.push_back(ev);
+    }
+    return e->events[i];
+}
+
+// -- batched, host buffers -----------------------------------------------------------------------
+extern "C" int rcg_process_all(rcg_engine* e, const float* const* in, uint64_t n_in, float* const* out,
+                               uint64_t out_cap, uint64_t* n_out) {
+    if (!e || !out || (!in && n_in)) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(e->device));
+    const uint32_t C = e->cfg.channels;
+    uint64_t calls, frames, out_len;
+    counts_for(e->plan, n_in, &calls, &frames, &out_len);
+    if (out_len > out_cap)
+        return fail(RCG_ERR_CAPACITY, "output needs %llu samples per channel, capacity %llu",
+                    (unsigned long long)out_len, (unsigned long long)out_cap);
+    const size_t in_stride = ((size_t)n_in + 3) & ~(size_t)3;
+    const size_t out_stride = ((size_t)out_len + 3) & ~(size_t)3;
+    if (e->d_in_cap < in_stride * C) {
+        cudaFree(e->d_in); e->d_in = nullptr; e->d_in_cap = 0;
+        CUDA_TRY(cudaMalloc(&e->d_in, std::max<size_t>(in_stride * C, 4) * sizeof(float)));
+        e->d_in_cap = in_stride * C;
+    }
+    if (e->d_out_cap < out_stride * C) {
+        cudaFree(e->d_out); e->d_out = nullptr; e->d_out_cap = 0;
+        CUDA_TRY(cudaMalloc(&e->d_out, std::max<size_t>(out_stride * C, 4) * sizeof(float)));
+        e->d_out_cap = out_stride * C;
+    }
+    // chunks: enough frames per chunk to keep every work lane busy for >= 16 frames,
+    // at most 16 chunks, so that device->host copies of finished chunks overlap compute
+    const uint64_t k = e->plan.frames_per_call, step = e->plan.sample_step_len, W = e->plan.window_len;
+    const uint64_t slots = (uint64_t)e->max_grid * e->geo.frames_per_cta;
+    uint64_t min_calls = (slots * 16 + k * C - 1) / (k * C);
+    uint64_t chunk_calls = std::max<uint64_t>(min_calls, (calls + 15) / 16);
+    chunk_calls = std::max<uint64_t>(1, std::min(chunk_calls, calls));
+    uint64_t uploaded = 0;  // samples of every channel already on the device
+    size_t ev_i = 0;
+    int pp = 0;
+    for (uint64_t c0 = 0; c0 < calls; c0 += chunk_calls) {
+        const uint64_t nc = std::min(chunk_calls, calls - c0);
+        // input this chunk reads: up to the end of its last frame
+        const uint64_t need = std::min<uint64_t>(n_in, ((c0 + nc) * k - 1) * step + W);
+        if (need > uploaded) {
+            for (uint32_t c = 0; c < C; c++)
+                CUDA_TRY(cudaMemcpyAsync(e->d_in + c * in_stride + uploaded, in[c] + uploaded,
+                                         (need - uploaded) * sizeof(float), cudaMemcpyHostToDevice, e->h2d));
+            uploaded = need;
+            cudaEvent_t up = get_event(e, ev_i++);
+            CUDA_TRY(cudaEventRecord(up, e->h2d));
+            CUDA_TRY(cudaStreamWaitEvent(e->stream, up, 0));
+        }
+        rcg_segment s{};
+        s.d_in = e->d_in; s.in_stride = (int64_t)in_stride; s.in_origin = 0; s.in_valid = (int64_t)n_in;
+        s.d_out = e->d_out + c0 * e->plan.out_len_per_call; s.out_stride = (int64_t)out_stride;
+        s.first_call = c0; s.n_calls = nc;
+        s.d_tail_in = c0 ? e->d_tail_pp[pp] : nullptr;
+        s.d_tail_out = e->d_tail_pp[pp ^ 1];
+        pp ^= 1;
+        int rc = launch_segment(e, s, (int)C, e->stream);
+        if (rc) return rc;
+        cudaEvent_t done = get_event(e, ev_i++);
+        CUDA_TRY(cudaEventRecord(done, e->stream));
+        CUDA_TRY(cudaStreamWaitEvent(e->d2h, done, 0));
+        const uint64_t o0 = c0 * e->plan.out_len_per_call, on = nc * e->plan.out_len_per_call;
+        for (uint32_t c = 0; c < C; c++)
+            CUDA_TRY(cudaMemcpyAsync(out[c] + o0, e->d_out + c * out_stride + o0, on * sizeof(float),
+                                     cudaMemcpyDeviceToHost, e->d2h));
+    }
+    CUDA_TRY(cudaStreamSynchronize(e->d2h));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    if (n_out)
+        for (uint32_t c = 0; c < C; c++) n_out[c] = out_len;
+    return RCG_OK;
+}
+
+// -- streaming: Stretcher::next_window ---------------------------------------------------------
+extern "C" int rcg_send(rcg_engine* e, uint32_t channel, const float* chunk, uint64_t n) {
+    if (!e || channel >= e->cfg.channels || (!chunk && n)) return fail(RCG_ERR_INVALID_ARG, "bad channel or chunk");
+    ChannelState& c = e->ch[channel];
+    if (c.closed) return fail(RCG_ERR_STATE, "channel %u input is closed", channel);
+    c.input.insert(c.input.end(), chunk, chunk + n);
+    c.received += n;
+    return RCG_OK;
+}
+extern "C" int rcg_close_input(rcg_engine* e, uint32_t channel) {
+    if (!e || channel >= e->cfg.channels) return fail(RCG_ERR_INVALID_ARG, "bad channel");
+    e->ch[channel].closed = true;
+    return RCG_OK;
+}
+extern "C" int rcg_is_done(rcg_engine* e, uint32_t channel, int* done) {
+    if (!e || channel >= e->cfg.channels || !done) return fail(RCG_ERR_INVALID_ARG, "bad channel");
+    *done = e->ch[channel].done ? 1 : 0;
+    return RCG_OK;
+}
+
+static int stream_compute(rcg_engine* e, uint32_t channel) {
+    ChannelState& c = e->ch[channel];
+    const uint64_t k = e->plan.frames_per_call, step = e->plan.sample_step_len, W = e->plan.window_len;
+    const uint64_t H = W / 2, olen = e->plan.out_len_per_call;
+    const uint64_t N = c.received;
+    uint64_t lookahead = e->cfg.max_lookahead_calls ? e->cfg.max_lookahead_calls : 64;
+    // calls whose every frame is fully covered by received input
+    auto call_end_sample = [&](uint64_t call) { return ((call + 1) * k - 1) * step + W; };
+    uint64_t n = 0;
+    if (c.closed) {
+        // recv() fails: frames are zero padded (stretcher.rs:129-131); run to the last call the
+        // reference would make, or one call at a time beyond it
+        uint64_t total;
+        counts_for(e->plan, N, &total, nullptr, nullptr);
+        n = c.next_call < total ? std::min(lookahead, total - c.next_call) : 1;
+    } else {
+        while (n < lookahead && call_end_sample(c.next_call + n) <= N) n++;
+        if (n == 0) return fail(RCG_ERR_WOULD_BLOCK, "channel %u: call %llu needs %llu samples, %llu sent", channel,
+                                (unsigned long long)c.next_call, (unsigned long long)call_end_sample(c.next_call),
+                                (unsigned long long)N);
+    }
+    const uint64_t f_first = c.next_call * k;
+    const uint64_t s_first = f_first * step;
+    const uint64_t s_last = std::min<uint64_t>(N, call_end_sample(c.next_call + n - 1));
+    const uint64_t n_samp = s_last > s_first ? s_last - s_first : 0;
+    if (e->d_sin_cap < n_samp + 4) {
+        cudaFree(e->d_sin); e->d_sin = nullptr;
+        CUDA_TRY(cudaMalloc(&e->d_sin, (n_samp + 4) * 2 * sizeof(float)));
+        e->d_sin_cap = (n_samp + 4) * 2;
+    }
+    if (e->d_sout_cap < n * olen) {
+        cudaFree(e->d_sout); e->d_sout = nullptr;
+        if (e->h_sout) cudaFreeHost(e->h_sout);
+        e->h_sout = nullptr;
+        CUDA_TRY(cudaMalloc(&e->d_sout, std::max<uint64_t>(n * olen, 4) * sizeof(float)));
+        CUDA_TRY(cudaMallocHost(&e->h_sout, std::max<uint64_t>(n * olen, 4) * sizeof(float)));
+        e->d_sout_cap = n * olen;
+    }
+    if (n_samp)
+        CUDA_TRY(cudaMemcpyAsync(e->d_sin, c.input.data() + (s_first - c.input_base), n_samp * sizeof(float),
+                                 cudaMemcpyHostToDevice, e->stream));
+    rcg_segment s{};
+    s.d_in = e->d_sin; s.in_stride = (int64_t)e->d_sin_cap; s.in_origin = (int64_t)s_first; s.in_valid = (int64_t)n_samp;
+    s.d_out = e->d_sout; s.out_stride = (int64_t)e->d_sout_cap;
+    s.first_call = c.next_call; s.n_calls = n;
+    s.d_tail_in = c.next_call ? c.d_tail[c.tail_cur] : nullptr;
+    s.d_tail_out = c.d_tail[c.tail_cur ^ 1];
+    int rc = launch_segment(e, s, 1, e->stream, (int)channel);
+    if (rc) return rc;
+    c.tail_cur ^= 1;
+    CUDA_TRY(cudaMemcpyAsync(e->h_sout, e->d_sout, n * olen * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (uint64_t i = 0; i < n; i++) {
+        const bool padded = c.closed && call_end_sample(c.next_call + i) > N;
+        c.ready.emplace_back(std::vector<float>(e->h_sout + i * olen, e->h_sout + (i + 1) * olen), padded);
+    }
+    c.next_call += n;
+    // drop consumed input (truncate_front at stretcher.rs:105-106)
+    const uint64_t keep_from = std::min<uint64_t>(N, c.next_call * k * step);
+    if (keep_from > c.input_base + (1u << 20) || (c.closed && keep_from >= N)) {
+        c.input.erase(c.input.begin(), c.input.begin() + (keep_from - c.input_base));
+        c.input_base = keep_from;
+    }
+    (void)H;
+    return RCG_OK;
+}
+
+extern "C" int rcg_next_window(rcg_engine* e, uint32_t channel, float* out, uint64_t cap, uint64_t* n_out) {
+    if (!e || channel >= e->cfg.channels || !out) return fail(RCG_ERR_INVALID_ARG, "bad channel or buffer");
+    if (cap < e->plan.out_len_per_call)
+        return fail(RCG_ERR_CAPACITY, "window needs %llu samples", (unsigned long long)e->plan.out_len_per_call);
+    CUDA_TRY(cudaSetDevice(e->device));
+    ChannelState& c = e->ch[channel];
+    if (c.ready.empty()) {
+        int rc = stream_compute(e, channel);
+        if (rc) return rc;
+    }
+    auto& w = c.ready.front();
+    memcpy(out, w.first.data(), w.first.size() * sizeof(float));
+    if (n_out) *n_out = w.first.size();
+    if (w.second) c.done = true;  // stretcher.rs:131
+    c.ready.pop_front();
+    return RCG_OK;
+}
+
+// -- plugins -------------------------------------------------------------------------------------
+extern "C" int rcg_push_frequency_kernel(rcg_engine* e, rcg_apply_fn fn) {
+    if (!e || !fn) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    e->kernels.push_back(fn);
+    return RCG_OK;
+}
+extern "C" int rcg_load_frequency_kernel(rcg_engine* e, const char* so_path) {
+    if (!e || !so_path) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    void* lib = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) return fail(RCG_ERR_PLUGIN, "dlopen(%s): %s", so_path, dlerror());
+    void* sym = dlsym(lib, "apply");
+    if (!sym) {
+        dlclose(lib);
+        return fail(RCG_ERR_PLUGIN, "%s has no `apply` symbol", so_path);
+    }
+    e->libs.push_back(lib);
+    e->kernels.push_back((rcg_apply_fn)sym);
+    return RCG_OK;
+}
+extern "C" int rcg_frequency_kernel_count(const rcg_engine* e, uint32_t* n) {
+    if (!e || !n) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    *n = (uint32_t)e->kernels.size();
+    return RCG_OK;
+}
+
+// -- helpers -------------------------------------------------------------------------------------
+extern "C" int rcg_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    CUDA_TRY(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return RCG_OK;
+}
+extern "C" int rcg_host_free(void* ptr) {
+    CUDA_TRY(cudaFreeHost(ptr));
+    return RCG_OK;
+}

@@ -54,6 +54,7 @@ struct StretchParams {
     int run_len;            // frames per work item
     int n_runs;             // work items per channel
     int channels;
+    int channel_offset;     // channel index of row 0 (phase counter)
     int step;               // sample_step_len (stretcher.rs:55)
     int pitch;              // pitch_multiple
     int samples_needed;     // S (stretcher.rs:47-51)
@@ -167,7 +168,7 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
         if (c == 0) {
             // k = 0: bins 0 and H are real: X[0] = a + b, X[H] = a - b
             cf z0 = S[0];
-            philox4x32_10(0u, f_lo, f_hi, (uint32_t)channel, prm.keys, u);
+            philox4x32_10(0u, f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
             float m0 = fabsf(z0.x + z0.y), mh = fabsf(z0.x - z0.y);
             float s, c0, ch;
             sincos_phase(phase_from_u32(u[0]), s, c0);
@@ -177,7 +178,7 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
             // k = H/2 pairs with itself: X[H/2] = conj(Z[H/2]); Z'[H/2] = 2 conj(Y[H/2])
             const int pq = phys(bin_to_pos<LOG2H>(C::H / 2));
             cf zq = S[pq];
-            philox4x32_10((uint32_t)(C::H / 2), f_lo, f_hi, (uint32_t)channel, prm.keys, u);
+            philox4x32_10((uint32_t)(C::H / 2), f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
             float mq = sqrtf(zq.x * zq.x + zq.y * zq.y);
             float sa, ca, sb, cb;
             sincos_phase(phase_from_u32(u[0]), sa, ca);
@@ -188,7 +189,7 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
         const int pa = phys(pos), pb = phys(bin_to_pos<LOG2H>(C::H - k));
         const cf za = S[pa], zb = S[pb];
         const cf tw = ld_cf(prm.spec_tw + c);  // exp(-2 pi i k / W)
-        philox4x32_10((uint32_t)k, f_lo, f_hi, (uint32_t)channel, prm.keys, u);
+        philox4x32_10((uint32_t)k, f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
         // P = za + conj(zb), Q = za - conj(zb), U = -i t Q
         float pr = za.x + zb.x, pi = za.y - zb.y, qr = za.x - zb.x, qi = za.y + zb.y;
         float tqr = tw.x * qr - tw.y * qi, tqi = tw.x * qi + tw.y * qr;

@@ -1,0 +1,114 @@
+// rcg_kernels.cu -- sm_100a kernels of the stretch path.
+//
+// stretch_kernel: one frame lane (NT threads) owns a run of consecutive frames of one channel
+// and, per frame, does everything ReFFT::resynth + the body of Stretcher::next_window do
+// (reference fft.rs:42-74, stretcher.rs:94-112, resampler.rs:3-35) without leaving the SM:
+//   window * samples -> packed real FFT (in-place radix-16 passes in shared memory)
+//   -> |X| -> Philox random phases for all W bins -> Hermitian fold -> inverse real FFT
+//   -> /W * window -> overlap-add with the carried half window -> envelope * amp -> resample.
+// HBM sees each input sample once per overlapping frame (L2 absorbs the overlap) and each
+// output sample exactly once.  No tensor cores: nothing here is a dense contraction.
+#include "rcg_kernels.h"
+
+namespace rcg {
+
+struct DeviceExec {
+    int t;
+    template <class F>
+    __device__ __forceinline__ void par(F f) {
+        f(t);
+        __syncthreads();
+    }
+};
+
+template <int LOG2H>
+constexpr int min_ctas() { return LOG2H >= 14 ? 1 : 3; }
+
+template <int LOG2H>
+__global__ void __launch_bounds__(FrameCfg<LOG2H>::NT * FrameCfg<LOG2H>::FPC, min_ctas<LOG2H>())
+stretch_kernel(const __grid_constant__ StretchParams prm, int n_items) {
+    using C = FrameCfg<LOG2H>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x / C::NT;
+    DeviceExec ex{(int)(threadIdx.x % C::NT)};
+    cf* S = reinterpret_cast<cf*>(smem_raw) + lane * C::SMEM_CF;
+    float* tail = prm.tail_scratch + ((long long)blockIdx.x * C::FPC + lane) * C::H;
+    const int n_groups = (n_items + C::FPC - 1) / C::FPC;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int item = g * C::FPC + lane;
+        run_work_item<LOG2H>(ex, S, prm, item, tail, item < n_items);
+    }
+}
+
+template <int LOG2H>
+__global__ void __launch_bounds__(FrameCfg<LOG2H>::NT)
+boundary_kernel(const __grid_constant__ StretchParams prm, const float* head, const float* tail_prev) {
+    using C = FrameCfg<LOG2H>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DeviceExec ex{(int)threadIdx.x};
+    run_boundary<LOG2H>(ex, reinterpret_cast<cf*>(smem_raw), prm, (int)blockIdx.x, head, tail_prev);
+}
+
+template <int LOG2H>
+static cudaError_t geometry_t(LaunchGeometry* g) {
+    using C = FrameCfg<LOG2H>;
+    g->threads = C::NT * C::FPC;
+    g->frames_per_cta = C::FPC;
+    g->smem_bytes = (size_t)C::FPC * C::SMEM_CF * sizeof(cf);
+    cudaError_t e = cudaFuncSetAttribute(stretch_kernel<LOG2H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)g->smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(boundary_kernel<LOG2H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(C::SMEM_CF * sizeof(cf)));
+    if (e != cudaSuccess) return e;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stretch_kernel<LOG2H>, g->threads, g->smem_bytes);
+    g->max_ctas_per_sm = n;
+    return e;
+}
+
+template <int LOG2H>
+static cudaError_t launch_t(const StretchParams& prm, int grid, cudaStream_t stream) {
+    using C = FrameCfg<LOG2H>;
+    const int n_items = prm.channels * prm.n_runs;
+    if (n_items <= 0) return cudaSuccess;
+    stretch_kernel<LOG2H><<<grid, C::NT * C::FPC, (size_t)C::FPC * C::SMEM_CF * sizeof(cf), stream>>>(prm, n_items);
+    return cudaGetLastError();
+}
+
+template <int LOG2H>
+static cudaError_t boundary_t(const StretchParams& prm, const float* head, const float* tail_prev,
+                              cudaStream_t stream) {
+    using C = FrameCfg<LOG2H>;
+    boundary_kernel<LOG2H><<<prm.channels, C::NT, C::SMEM_CF * sizeof(cf), stream>>>(prm, head, tail_prev);
+    return cudaGetLastError();
+}
+
+#define RCG_DISPATCH(log2w, CALL)                                    \
+    switch ((log2w) - 1) {                                           \
+        case 5: return CALL(5);   case 6: return CALL(6);            \
+        case 7: return CALL(7);   case 8: return CALL(8);            \
+        case 9: return CALL(9);   case 10: return CALL(10);          \
+        case 11: return CALL(11); case 12: return CALL(12);          \
+        case 13: return CALL(13); case 14: return CALL(14);          \
+        default: return cudaErrorInvalidValue;                       \
+    }
+
+cudaError_t stretch_geometry(int log2w, LaunchGeometry* g) {
+#define CALL(L) geometry_t<L>(g)
+    RCG_DISPATCH(log2w, CALL)
+#undef CALL
+}
+cudaError_t launch_stretch(int log2w, const StretchParams& prm, int grid, cudaStream_t stream) {
+#define CALL(L) launch_t<L>(prm, grid, stream)
+    RCG_DISPATCH(log2w, CALL)
+#undef CALL
+}
+cudaError_t launch_boundary(int log2w, const StretchParams& prm, const float* head, const float* tail_prev,
+                            cudaStream_t stream) {
+#define CALL(L) boundary_t<L>(prm, head, tail_prev, stream)
+    RCG_DISPATCH(log2w, CALL)
+#undef CALL
+}
+
+}  // namespace rcg

@@ -1,0 +1,24 @@
+// rcg_kernels.h -- host-callable launchers of the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rcg_frame.h"
+
+namespace rcg {
+
+struct LaunchGeometry {
+    int threads;          // per CTA
+    int frames_per_cta;   // work lanes per CTA
+    size_t smem_bytes;
+    int max_ctas_per_sm;  // occupancy of the stretch kernel
+};
+
+// log2w in [6, 15].  Returns cudaErrorInvalidValue for unsupported sizes.
+cudaError_t stretch_geometry(int log2w, LaunchGeometry* g);
+// Launch the fused stretch kernel over prm.channels * prm.n_runs work items with `grid`
+// persistent CTAs.  prm.tail_scratch must hold grid * frames_per_cta * H floats.
+cudaError_t launch_stretch(int log2w, const StretchParams& prm, int grid, cudaStream_t stream);
+cudaError_t launch_boundary(int log2w, const StretchParams& prm, const float* head, const float* tail_prev,
+                            cudaStream_t stream);
+
+}  // namespace rcg

@@ -1,0 +1,230 @@
+"""Engine: thin object wrapper over the C ABI (include/rocoder_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _abi
+from ._abi import RcgError, WouldBlock, check, lib, make_config, rcg_plan_info, rcg_segment
+
+
+def _ptr(x) -> Optional[int]:
+    """device/host pointer of a torch tensor, numpy array, int or None"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    raise TypeError(f"cannot take a pointer of {type(x)}")
+
+
+def hanning(n: int) -> np.ndarray:
+    """windows::hanning (reference windows.rs:4-9)"""
+    out = np.empty(n, np.float32)
+    check(lib().rcg_hanning(out.ctypes.data, n))
+    return out
+
+
+def hanning_crossfade_compensation(n: int) -> np.ndarray:
+    """crossfade::hanning_crossfade_compensation (reference crossfade.rs:4-10)"""
+    out = np.empty(n, np.float32)
+    check(lib().rcg_hanning_crossfade_compensation(out.ctypes.data, n))
+    return out
+
+
+def phase(seed: int, channel: int, frame: int, bin_: int, window_len: int) -> float:
+    return float(lib().rcg_phase(seed, channel, frame, bin_, window_len))
+
+
+def _plan_dict(p: rcg_plan_info) -> dict:
+    return {name: getattr(p, name) for name, _ in rcg_plan_info._fields_}
+
+
+def plan(factor: float = 1.0, pitch_multiple: int = 1, window_len: int = 16384, amplitude: float = 1.0,
+         channels: int = 1, sample_rate: int = 44100) -> dict:
+    """Constants of Stretcher::new (reference stretcher.rs:40-59). Pure host arithmetic."""
+    cfg = make_config(channels, sample_rate, window_len, factor, amplitude, pitch_multiple)
+    p = rcg_plan_info()
+    check(lib().rcg_plan(C.byref(cfg), C.byref(p)))
+    return _plan_dict(p)
+
+
+def expected_counts(n_in: int, factor: float = 1.0, pitch_multiple: int = 1, window_len: int = 16384):
+    """(calls, frames, output samples) per channel (stop rule of stretcher.rs:123-135)."""
+    cfg = make_config(1, 44100, window_len, factor, 1.0, pitch_multiple)
+    a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    check(lib().rcg_expected_counts(C.byref(cfg), n_in, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
+def channel_bound(window_len: int, sample_rate: int, buffer_dur_s: float) -> int:
+    cfg = make_config(1, sample_rate, window_len, buffer_dur_s=buffer_dur_s)
+    b = C.c_uint64()
+    check(lib().rcg_channel_bound(C.byref(cfg), C.byref(b)))
+    return b.value
+
+
+class PinnedBuffer:
+    """float32 host buffer in page-locked memory (rcg_host_alloc)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        n = int(np.prod(self.shape)) if self.shape else 1
+        self._ptr = C.c_void_p()
+        check(lib().rcg_host_alloc(C.byref(self._ptr), max(n, 1) * 4))
+        buf = (C.c_float * max(n, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=np.float32, count=n).reshape(self.shape)
+
+    def free(self):
+        if self._ptr is not None and self._ptr.value:
+            self.array = None
+            lib().rcg_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """All channels of one stretch job on one GPU."""
+
+    def __init__(self, channels: int, sample_rate: int, window_len: int = 16384, factor: float = 1.0,
+                 amplitude: float = 1.0, pitch_multiple: int = 1, buffer_dur_s: float = 1.0, seed: int = 0,
+                 device: int = 0, flags: int = 0, max_lookahead_calls: int = 0, first_channel: int = 0):
+        self._h = C.c_void_p()
+        self.cfg = make_config(channels, sample_rate, window_len, factor, amplitude, pitch_multiple, buffer_dur_s,
+                               seed, device, flags, max_lookahead_calls, first_channel)
+        check(lib().rcg_create(C.byref(self.cfg), C.byref(self._h)))
+        p = rcg_plan_info()
+        check(lib().rcg_get_plan(self._h, C.byref(p)))
+        self.plan = _plan_dict(p)
+        self.channels = channels
+        self._keep = []  # plugin callbacks must outlive the engine
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            lib().rcg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- batched ---------------------------------------------------------------------------
+    def expected_counts(self, n_in: int):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(lib().rcg_expected_counts(C.byref(self.cfg), n_in, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def process_all_into(self, inp: np.ndarray, out: np.ndarray) -> int:
+        """inp [C, N] float32 -> out [C, >= out_len] float32 (host buffers). Returns out_len."""
+        assert inp.dtype == np.float32 and out.dtype == np.float32
+        assert inp.ndim == 2 and out.ndim == 2 and inp.shape[0] == self.channels == out.shape[0]
+        assert inp.strides[1] == 4 and out.strides[1] == 4
+        ins = (C.c_void_p * self.channels)(*[inp[c].ctypes.data for c in range(self.channels)])
+        outs = (C.c_void_p * self.channels)(*[out[c].ctypes.data for c in range(self.channels)])
+        n_out = (C.c_uint64 * self.channels)()
+        check(lib().rcg_process_all(self._h, ins, inp.shape[1], outs, out.shape[1], n_out))
+        return int(n_out[0])
+
+    def process_all(self, inp: np.ndarray) -> np.ndarray:
+        inp = np.ascontiguousarray(inp, dtype=np.float32)
+        if inp.ndim == 1:
+            inp = inp[None, :]
+        _, _, out_len = self.expected_counts(inp.shape[1])
+        out = np.empty((self.channels, out_len), np.float32)
+        self.process_all_into(inp, out)
+        return out
+
+    def process_segment(self, d_in, in_stride: int, in_origin: int, in_valid: int, d_out, out_stride: int,
+                        first_call: int, n_calls: int, tail_in=None, tail_out=None, head_out=None,
+                        defer_first: bool = False, stream: Optional[int] = None) -> None:
+        s = rcg_segment()
+        s.d_in = _ptr(d_in); s.in_stride = in_stride; s.in_origin = in_origin; s.in_valid = in_valid
+        s.d_out = _ptr(d_out); s.out_stride = out_stride
+        s.first_call = first_call; s.n_calls = n_calls
+        s.d_tail_in = _ptr(tail_in); s.d_tail_out = _ptr(tail_out); s.d_head_out = _ptr(head_out)
+        s.flags = _abi.RCG_SEG_DEFER_FIRST if defer_first else 0
+        s.stream = stream
+        check(lib().rcg_process_segment(self._h, C.byref(s)))
+
+    def finish_boundary(self, d_out, out_stride: int, first_call: int, head, tail_prev,
+                        stream: Optional[int] = None) -> None:
+        check(lib().rcg_finish_boundary(self._h, _ptr(d_out), out_stride, first_call, _ptr(head), _ptr(tail_prev),
+                                        stream))
+
+    def synchronize(self) -> None:
+        check(lib().rcg_synchronize(self._h))
+
+    # -- streaming -------------------------------------------------------------------------
+    def send(self, channel: int, chunk) -> None:
+        chunk = np.ascontiguousarray(chunk, dtype=np.float32)
+        check(lib().rcg_send(self._h, channel, chunk.ctypes.data, chunk.size))
+
+    def close_input(self, channel: int) -> None:
+        check(lib().rcg_close_input(self._h, channel))
+
+    def next_window(self, channel: int) -> np.ndarray:
+        out = np.empty(self.plan["out_len_per_call"], np.float32)
+        n = C.c_uint64()
+        check(lib().rcg_next_window(self._h, channel, out.ctypes.data, out.size, C.byref(n)))
+        return out[: n.value]
+
+    def is_done(self, channel: int) -> bool:
+        d = C.c_int()
+        check(lib().rcg_is_done(self._h, channel, C.byref(d)))
+        return bool(d.value)
+
+    # -- plugins ---------------------------------------------------------------------------
+    def push_frequency_kernel(self, fn) -> None:
+        """fn(elapsed_ms, spectrum: complex64[W]) -> complex64[W]; raising stands for a panic."""
+        W = self.cfg.window_len
+
+        def tramp(elapsed_ms, pin, n_bins, pout):
+            try:
+                a = np.ctypeslib.as_array(pin, shape=(2 * n_bins,)).view(np.complex64)
+                r = np.asarray(fn(int(elapsed_ms), a), dtype=np.complex64)
+                if r.shape[0] != n_bins:
+                    return 2
+                np.ctypeslib.as_array(pout, shape=(2 * n_bins,))[:] = r.view(np.float32)
+                return 0
+            except Exception:
+                return 1
+
+        cb = _abi.APPLY_FN(tramp)
+        self._keep.append(cb)
+        check(lib().rcg_push_frequency_kernel(self._h, cb))
+        del W
+
+    def load_frequency_kernel(self, so_path: str) -> None:
+        check(lib().rcg_load_frequency_kernel(self._h, so_path.encode()))
+
+    def frequency_kernel_count(self) -> int:
+        n = C.c_uint32()
+        check(lib().rcg_frequency_kernel_count(self._h, C.byref(n)))
+        return n.value
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        check(lib().rcg_launch_count(self._h, C.byref(n)))
+        return n.value
+
+
+__all__ = ["Engine", "PinnedBuffer", "RcgError", "WouldBlock", "hanning", "hanning_crossfade_compensation",
+           "plan", "expected_counts", "channel_bound", "phase"]

@@ -1,0 +1,26 @@
+"""Shared parity cases: (n_in, factor, pitch, window_len).  Sized so the oracle finishes in
+seconds.  They cover every resample branch (p=1, p>1 incl. odd, p<-1 incl. the dropped
+samples quirk at p<=-3), ragged / short / empty input, and every FFT plan shape."""
+
+SMALL_CASES = [
+    (5000, 1.0, 1, 256),
+    (5000, 2.0, 2, 256),
+    (7001, 3.0, -2, 512),
+    (9000, 20.0, -3, 1024),     # BASELINE config 4's flags at a small window
+    (3000, 1.5, 3, 128),
+    (100, 1.0, 1, 64),          # input shorter than one window
+    (0, 1.0, 1, 64),            # empty input: one all-zero call
+    (4097, 0.5, 1, 2048),       # speed-up: step == W
+    (30000, 4.0, 1, 2048),
+    (40000, 8.0, 2, 4096),
+    (50000, 2.0, -4, 8192),
+    (6000, 2.5, 5, 512),
+    (2048, 1.0, 1, 1024),       # exactly two windows
+]
+LARGE_CASES = [
+    (70000, 8.0, 2, 16384),     # BASELINE config 2's flags
+    (100000, 1.0, 1, 16384),    # config 1
+    (60000, 20.0, -3, 16384),   # config 4
+    (90000, 3.0, 1, 32768),
+    (50000, 2.0, 1, 16384),     # config 5
+]

@@ -55,7 +55,7 @@ int rcg_emul_stretch(int log2w, const float* in, long long in_stride, long long 
                      long long in_valid, float* out, long long out_stride, long long out_origin,
                      long long frame_begin, long long frame_end, int run_len, int channels, int step,
                      int pitch, int samples_needed, float amp, unsigned long long seed, unsigned flags,
-                     const float* tail_in, float* tail_out, float* head_out) {
+                     int first_channel, const float* tail_in, float* tail_out, float* head_out) {
     StretchParams p;
     memset(&p, 0, sizeof(p));
     p.in = in; p.in_stride = in_stride; p.in_origin = in_origin; p.in_valid = in_valid;
@@ -63,7 +63,7 @@ int rcg_emul_stretch(int log2w, const float* in, long long in_stride, long long 
     p.frame_begin = frame_begin; p.frame_end = frame_end; p.run_len = run_len;
     long long nf = frame_end - frame_begin;
     p.n_runs = nf > 0 ? (int)((nf + run_len - 1) / run_len) : 0;
-    p.channels = channels; p.step = step; p.pitch = pitch; p.samples_needed = samples_needed;
+    p.channels = channels; p.channel_offset = first_channel; p.step = step; p.pitch = pitch; p.samples_needed = samples_needed;
     p.amp = amp; p.inv_w = 1.0f / (float)(1 << log2w); p.flags = flags;
     p.keys = make_philox_keys(seed);
     p.tail_in = tail_in; p.tail_out = tail_out; p.head_out = head_out;
