@@ -88,15 +88,36 @@ RCG_HD constexpr int frames_per_cta(int log2h) {
     return f < 1 ? 1 : f;
 }
 
-// offsets (in cf) of the per-pass twiddle tables inside the packed table
-// table p holds (R_p - 1) * M_p entries: tw[(j-1)*M + m] = exp(-2 pi i * m*j / (R*M)); empty if M == 1
-RCG_HD constexpr int tw_offset(int log2h, int pass) {
+// ---- twiddle tables --------------------------------------------------------------------
+// Pass p needs w^(m*j), w = exp(-2 pi i / (R*M)), m < M, 0 < j < R.  How they are stored:
+//   none      M == 1
+//   full      M <= 16 (or a radix-2 pass with M < 64): [(R-1)][M], L1-resident
+//   pow       R >= 4, M > 16: only the power-of-two exponents j = 1, 2, 4, 8 are stored
+//             ([log2 R][M]); the others are products of two stored/kept values
+//   twolevel  R == 2, M >= 64: w^m = A[m >> 6] * B[m & 63]  (A: M/64 entries, B: 64)
+enum TwScheme : int { kTwNone = 0, kTwFull = 1, kTwPow = 2, kTwTwoLevel = 3 };
+
+RCG_HD constexpr int tw_scheme(int log2h, int pass) {
     const PlanDesc d = make_plan(log2h);
-    int off = 0;
-    for (int p = 0; p < pass; p++) {
-        int M = 1 << d.mlog2[p], R = 1 << d.rlog2[p];
-        if (M > 1) off += (R - 1) * M;
+    const int M = 1 << d.mlog2[pass], R = 1 << d.rlog2[pass];
+    if (M == 1) return kTwNone;
+    if (R == 2) return M >= 64 ? kTwTwoLevel : kTwFull;
+    if (M <= 16) return kTwFull;
+    return kTwPow;
+}
+RCG_HD constexpr int tw_size(int log2h, int pass) {
+    const PlanDesc d = make_plan(log2h);
+    const int M = 1 << d.mlog2[pass], R = 1 << d.rlog2[pass];
+    switch (tw_scheme(log2h, pass)) {
+        case kTwFull: return (R - 1) * M;
+        case kTwPow: return d.rlog2[pass] * M;
+        case kTwTwoLevel: return M / 64 + 64;
+        default: return 0;
     }
+}
+RCG_HD constexpr int tw_offset(int log2h, int pass) {
+    int off = 0;
+    for (int p = 0; p < pass; p++) off += tw_size(log2h, p);
     return off;
 }
 RCG_HD constexpr int tw_total(int log2h) { return tw_offset(log2h, make_plan(log2h).npasses); }

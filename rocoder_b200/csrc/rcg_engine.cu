@@ -196,6 +196,11 @@ struct rcg_engine {
     std::vector<ChannelState> ch;
     float *d_sin = nullptr, *d_sout = nullptr, *h_sout = nullptr;
     size_t d_sin_cap = 0, d_sout_cap = 0, h_sout_cap = 0;
+    // plugin path buffers: spectra of one batch of frames, device + pinned host
+    cf *d_spec = nullptr, *h_spec = nullptr;
+    size_t spec_cap = 0;  // in cf
+    float* d_plug_tail[2] = {nullptr, nullptr};
+    std::vector<float> plug_tmp;
     // plugins (fft.rs:22: kernels: Vec<Library>)
     std::vector<rcg_apply_fn> kernels;
     std::vector<void*> libs;
@@ -293,7 +298,9 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     if (e->h2d) cudaStreamSynchronize(e->h2d);
     cudaFree(e->d_window); cudaFree(e->d_env); cudaFree(e->d_tw); cudaFree(e->d_spec_tw); cudaFree(e->d_scratch);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_tail_pp[0]); cudaFree(e->d_tail_pp[1]);
-    cudaFree(e->d_sin); cudaFree(e->d_sout);
+    cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_spec);
+    cudaFree(e->d_plug_tail[0]); cudaFree(e->d_plug_tail[1]);
+    if (e->h_spec) cudaFreeHost(e->h_spec);
     if (e->h_sout) cudaFreeHost(e->h_sout);
     for (auto& c : e->ch) { cudaFree(c.d_tail[0]); cudaFree(c.d_tail[1]); }
     for (auto ev : e->events) cudaEventDestroy(ev);
@@ -338,13 +345,21 @@ static void fill_params(const rcg_engine* e, StretchParams& p) {
 }
 
 // launch calls [first_call, first_call + n_calls) for `channels` rows
+struct SpectrumRef { cf* spectrum; long long frame0, frames; };
+
 static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream,
-                          int channel_offset = 0) {
-    if (!e->kernels.empty())
-        return fail(RCG_ERR_PLUGIN, "frequency kernels are not supported on this path yet");
+                          int channel_offset = 0, const SpectrumRef* spec = nullptr) {
     if (s.n_calls == 0) return RCG_OK;
+    auto misaligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) != 0; };
+    if (misaligned(s.d_out) || (s.out_stride & 1) || misaligned(s.d_tail_in) || misaligned(s.d_tail_out) ||
+        misaligned(s.d_head_out))
+        return fail(RCG_ERR_INVALID_ARG, "d_out / tail / head buffers must be 8-byte aligned and out_stride even");
     StretchParams p;
     fill_params(e, p);
+    if (spec) {
+        p.flags |= kFlagSpectrumIn;
+        p.spectrum = spec->spectrum; p.spec_frame0 = spec->frame0; p.spec_frames = spec->frames;
+    }
     const uint64_t k = e->plan.frames_per_call;
     p.in = s.d_in; p.in_stride = s.in_stride; p.in_origin = s.in_origin; p.in_valid = s.in_valid;
     p.out = s.d_out; p.out_stride = s.out_stride;
@@ -359,7 +374,7 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
         p.flags |= kFlagDeferFirst;
     }
     const bool needs_halo = p.frame_begin > 0 && !s.d_tail_in && !(s.flags & RCG_SEG_DEFER_FIRST);
-    if (needs_halo && s.in_origin > (p.frame_begin - 1) * (long long)p.step)
+    if (needs_halo && !spec && s.in_origin > (p.frame_begin - 1) * (long long)p.step)
         return fail(RCG_ERR_INVALID_ARG, "segment starts at frame %lld but its input starts past the halo frame",
                     p.frame_begin);
     const uint64_t nframes = (uint64_t)(p.frame_end - p.frame_begin);
@@ -375,11 +390,111 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
     return RCG_OK;
 }
 
+
+// ---- frequency-kernel path (fft.rs:76-108) ---------------------------------------------------
+// apply the kernel stack to one frame's spectrum in place; mirrors the pop-and-retry of
+// fft.rs:101-106: a failing kernel is dropped for good, the previous one is tried, and with none
+// left the spectrum passes through unchanged.
+static void apply_kernels(rcg_engine* e, float* spectrum, size_t n_bins) {
+    while (!e->kernels.empty()) {
+        const size_t ms = (size_t)std::chrono::duration_cast<std::chrono::milliseconds>(
+                              std::chrono::system_clock::now().time_since_epoch()).count();  // fft.rs:89-92
+        e->plug_tmp.resize(2 * n_bins);
+        if (e->kernels.back()(ms, spectrum, n_bins, e->plug_tmp.data()) == 0) {
+            memcpy(spectrum, e->plug_tmp.data(), 2 * n_bins * sizeof(float));
+            return;
+        }
+        e->kernels.pop_back();  // "kernel panicked, retrying with last or noop."
+    }
+}
+
+// calls [first_call, first_call + n_calls) with host frequency kernels: analysis kernel ->
+// spectra to the host -> apply() per frame in the reference's order -> back -> synthesis kernel
+static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream,
+                               int channel_offset) {
+    const uint64_t k = e->plan.frames_per_call, W = e->plan.window_len, H = W / 2;
+    const uint64_t budget_cf = (uint64_t)256 << 17;  // 256 MiB of spectra per batch
+    uint64_t fpb = std::max<uint64_t>(k + 1, budget_cf / ((uint64_t)channels * W));  // frames/channel/batch
+    uint64_t cpb = std::max<uint64_t>(1, (fpb - 1) / k);
+    fpb = cpb * k + 1;
+    const size_t need = (size_t)channels * fpb * W;
+    if (e->spec_cap < need) {
+        cudaFree(e->d_spec); e->d_spec = nullptr;
+        if (e->h_spec) cudaFreeHost(e->h_spec);
+        e->h_spec = nullptr; e->spec_cap = 0;
+        CUDA_TRY(cudaMalloc(&e->d_spec, need * sizeof(cf)));
+        CUDA_TRY(cudaMallocHost(&e->h_spec, need * sizeof(cf)));
+        e->spec_cap = need;
+    }
+    for (int i = 0; i < 2; i++)
+        if (!e->d_plug_tail[i]) CUDA_TRY(cudaMalloc(&e->d_plug_tail[i], (size_t)e->cfg.channels * H * sizeof(float)));
+    const uint64_t end = s.first_call + s.n_calls;
+    int pp = 0;
+    for (uint64_t c0 = s.first_call; c0 < end; c0 += cpb) {
+        const uint64_t nb = std::min(cpb, end - c0);
+        const bool first = (c0 == s.first_call), last = (c0 + nb == end);
+        long long f0 = (long long)(c0 * k), f1 = (long long)((c0 + nb) * k);
+        // the first batch recomputes the halo frame unless the carried half window is provided
+        const bool halo = first && f0 > 0 && !s.d_tail_in && !(s.flags & RCG_SEG_DEFER_FIRST);
+        const long long a0 = halo ? f0 - 1 : f0;
+        if (halo && s.in_origin > a0 * (long long)e->plan.sample_step_len)
+            return fail(RCG_ERR_INVALID_ARG, "segment input starts past its halo frame");
+        StretchParams p;
+        fill_params(e, p);
+        p.in = s.d_in; p.in_stride = s.in_stride; p.in_origin = s.in_origin; p.in_valid = s.in_valid;
+        p.channels = channels;
+        p.channel_offset = (int)e->cfg.first_channel + channel_offset;
+        p.frame_begin = a0; p.frame_end = f1;
+        p.spectrum = e->d_spec; p.spec_frame0 = a0; p.spec_frames = f1 - a0;
+        const int slots = e->max_grid * e->geo.frames_per_cta;
+        const uint64_t nframes = (uint64_t)(f1 - a0);
+        p.run_len = (int)std::max<uint64_t>(1, (nframes * channels + slots - 1) / slots);
+        p.n_runs = (int)((nframes + p.run_len - 1) / p.run_len);
+        const long long items = (long long)p.n_runs * channels;
+        const int grid = (int)std::min<long long>((items + e->geo.frames_per_cta - 1) / e->geo.frames_per_cta, e->max_grid);
+        cudaError_t ce = launch_analysis(e->log2w, p, grid, stream);
+        if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "analysis kernel launch failed: %s", cudaGetErrorString(ce));
+        e->launches++;
+        const size_t bytes = (size_t)channels * nframes * W * sizeof(cf);
+        CUDA_TRY(cudaMemcpyAsync(e->h_spec, e->d_spec, bytes, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        // reference order (stretcher_processor.rs:62-70): call by call, channel by channel, frame by frame
+        if (halo)
+            for (int c = 0; c < channels; c++) apply_kernels(e, reinterpret_cast<float*>(e->h_spec + (size_t)c * nframes * W), W);
+        for (uint64_t call = c0; call < c0 + nb; call++)
+            for (int c = 0; c < channels; c++)
+                for (uint64_t r = 0; r < k; r++) {
+                    const size_t fi = (size_t)((long long)(call * k + r) - a0);
+                    apply_kernels(e, reinterpret_cast<float*>(e->h_spec + ((size_t)c * nframes + fi) * W), W);
+                }
+        CUDA_TRY(cudaMemcpyAsync(e->d_spec, e->h_spec, bytes, cudaMemcpyHostToDevice, stream));
+        rcg_segment b = s;
+        b.first_call = c0; b.n_calls = nb;
+        b.d_out = s.d_out + (c0 - s.first_call) * e->plan.out_len_per_call;
+        b.d_tail_in = first ? s.d_tail_in : e->d_plug_tail[pp];
+        b.d_tail_out = (last && s.d_tail_out) ? s.d_tail_out : e->d_plug_tail[pp ^ 1];
+        b.d_head_out = first ? s.d_head_out : nullptr;
+        b.flags = first ? s.flags : 0u;
+        pp ^= 1;
+        SpectrumRef ref{e->d_spec, a0, f1 - a0};
+        int rc = launch_segment(e, b, channels, stream, channel_offset, &ref);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(stream));  // the spectrum buffer is reused by the next batch
+    }
+    return RCG_OK;
+}
+
+static int run_segment(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream, int channel_offset) {
+    if (!e->kernels.empty() && !(e->cfg.flags & RCG_FLAG_BYPASS_RESYNTH))
+        return run_segment_plugins(e, s, channels, stream, channel_offset);
+    return launch_segment(e, s, channels, stream, channel_offset);
+}
+
 extern "C" int rcg_process_segment(rcg_engine* e, const rcg_segment* seg) {
     if (!e || !seg || !seg->d_in || !seg->d_out) return fail(RCG_ERR_INVALID_ARG, "null argument");
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = seg->stream ? (cudaStream_t)seg->stream : e->stream;
-    return launch_segment(e, *seg, (int)e->cfg.channels, st);
+    return run_segment(e, *seg, (int)e->cfg.channels, st, 0);
 }
 
 extern "C" int rcg_finish_boundary(rcg_engine* e, float* d_out, int64_t out_stride, uint64_t first_call,
@@ -460,7 +575,7 @@ extern "C" int rcg_process_all(rcg_engine* e, const float* const* in, uint64_t n
         s.d_tail_in = c0 ? e->d_tail_pp[pp] : nullptr;
         s.d_tail_out = e->d_tail_pp[pp ^ 1];
         pp ^= 1;
-        int rc = launch_segment(e, s, (int)C, e->stream);
+        int rc = run_segment(e, s, (int)C, e->stream, 0);
         if (rc) return rc;
         cudaEvent_t done = get_event(e, ev_i++);
         CUDA_TRY(cudaEventRecord(done, e->stream));
@@ -544,7 +659,7 @@ static int stream_compute(rcg_engine* e, uint32_t channel) {
     s.first_call = c.next_call; s.n_calls = n;
     s.d_tail_in = c.next_call ? c.d_tail[c.tail_cur] : nullptr;
     s.d_tail_out = c.d_tail[c.tail_cur ^ 1];
-    int rc = launch_segment(e, s, 1, e->stream, (int)channel);
+    int rc = run_segment(e, s, 1, e->stream, (int)channel);
     if (rc) return rc;
     c.tail_cur ^= 1;
     CUDA_TRY(cudaMemcpyAsync(e->h_sout, e->d_sout, n * olen * sizeof(float), cudaMemcpyDeviceToHost, e->stream));

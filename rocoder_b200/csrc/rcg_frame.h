@@ -28,6 +28,7 @@ namespace rcg {
 enum : uint32_t {
     kFlagBypass = 1u,      // test hook: resynth(s)[n] = (s[n]*w[n])*w[n]  (no FFT, no phases)
     kFlagDeferFirst = 2u,  // do not emit block frame_begin; write its raw first half to head_out
+    kFlagSpectrumIn = 4u,  // plugin path: magnitudes come from prm.spectrum (plugin output), not the FFT
 };
 
 // Everything one launch needs.  Global indices (samples, frames, output positions) are
@@ -61,6 +62,11 @@ struct StretchParams {
     float amp;              // corrected_amp_factor (stretcher.rs:53)
     float inv_w;            // 1 / W (exact: W is a power of two)
     uint32_t flags;
+    // plugin path (fft.rs:76-108): full W-bin complex spectra, natural order,
+    // [channel][frame - spec_frame0][W]
+    cf* spectrum;
+    long long spec_frame0;
+    long long spec_frames;  // frames per channel in the buffer
     PhiloxKeys keys;
 };
 
@@ -75,11 +81,25 @@ struct FrameCfg {
     static constexpr int RLAST = 1 << make_plan(LOG2H).rlog2[NP - 1];
 };
 
+// ---- global loads ---------------------------------------------------------------------
+// Streaming data (input samples, window, envelope) bypasses L1 allocation so that the small
+// twiddle tables stay L1-resident; tables go through the normal read-only path.
 RCG_HD float ld_stream(const float* p) {
 #if defined(__CUDA_ARCH__)
-    return __ldg(p);
+    float r;
+    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
 #else
     return *p;
+#endif
+}
+RCG_HD cf ld_stream2(const float* p) {  // p must be 8-byte aligned
+#if defined(__CUDA_ARCH__)
+    cf r;
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+#else
+    return make_cf(p[0], p[1]);
 #endif
 }
 RCG_HD cf ld_cf(const cf* p) {
@@ -89,66 +109,167 @@ RCG_HD cf ld_cf(const cf* p) {
     return *p;
 #endif
 }
+RCG_HD cf ld_pair(const float* p) { return *reinterpret_cast<const cf*>(p); }
+RCG_HD void st_pair(float* p, float a, float b) { *reinterpret_cast<cf*>(p) = make_cf(a, b); }
 
-// ---- LOAD: samples * window -> even/odd packed complex, natural order (fft.rs:51-58) ----
-template <int LOG2H>
-RCG_HD void phase_load(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
-    using C = FrameCfg<LOG2H>;
-    const float* in = prm.in + (long long)channel * prm.in_stride;
-    const long long base = frame * (long long)prm.step - prm.in_origin;
-    for (int m = t; m < C::H; m += C::NT) {
-        long long i0 = base + 2 * m;
-        float x0 = (i0 >= 0 && i0 < prm.in_valid) ? ld_stream(in + i0) : 0.0f;
-        float x1 = (i0 + 1 >= 0 && i0 + 1 < prm.in_valid) ? ld_stream(in + i0 + 1) : 0.0f;
-        float w0 = ld_stream(prm.window + 2 * m), w1 = ld_stream(prm.window + 2 * m + 1);
-        S[phys(m)] = make_cf(RCG_MUL(x0, w0), RCG_MUL(x1, w1));
+// ---- twiddles -------------------------------------------------------------------------
+RCG_HD void cmul(float ar, float ai, float br, float bi, float& cr, float& ci) {
+    cr = ar * br - ai * bi;
+    ci = ar * bi + ai * br;
+}
+// x[j] *= w (CONJ: x[j] *= conj(w))
+template <bool CONJ>
+RCG_HD void tw_apply(float& xr, float& xi, float wr, float wi) {
+    float nr, ni;
+    if constexpr (CONJ) { nr = xr * wr + xi * wi; ni = xi * wr - xr * wi; }
+    else { nr = xr * wr - xi * wi; ni = xi * wr + xr * wi; }
+    xr = nr; xi = ni;
+}
+
+// Multiply element j (1 <= j < R) of a butterfly by w^(m*j) (or its conjugate), w = the pass's
+// principal root, using the table layout tw_scheme() selected.
+template <int LOG2H, int PASS, bool CONJ, int R>
+RCG_HD void twiddle_butterfly(float (&xr)[R], float (&xi)[R], const cf* tw, int m) {
+    constexpr int SCHEME = tw_scheme(LOG2H, PASS);
+    constexpr int M = 1 << make_plan(LOG2H).mlog2[PASS];
+    if constexpr (SCHEME == kTwFull) {
+#pragma unroll
+        for (int j = 1; j < R; j++) {
+            const cf w = ld_cf(tw + (j - 1) * M + m);
+            tw_apply<CONJ>(xr[j], xi[j], w.x, w.y);
+        }
+    } else if constexpr (SCHEME == kTwTwoLevel) {
+        static_assert(SCHEME != kTwTwoLevel || R == 2, "two-level tables serve radix-2 passes");
+        const cf a = ld_cf(tw + (m >> 6)), b = ld_cf(tw + M / 64 + (m & 63));
+        float wr, wi;
+        cmul(a.x, a.y, b.x, b.y, wr, wi);
+        tw_apply<CONJ>(xr[1], xi[1], wr, wi);
+    } else if constexpr (SCHEME == kTwPow) {
+        // stored: w1, w2, w4, w8; kept products: w3 = w1 w2, w12 = w8 w4; every other exponent is
+        // one product of two of those (depth <= 2 multiplications from correctly rounded tables)
+        const cf w1 = ld_cf(tw + m), w2 = ld_cf(tw + M + m);
+        tw_apply<CONJ>(xr[1], xi[1], w1.x, w1.y);
+        tw_apply<CONJ>(xr[2], xi[2], w2.x, w2.y);
+        float w3r, w3i;
+        cmul(w1.x, w1.y, w2.x, w2.y, w3r, w3i);
+        tw_apply<CONJ>(xr[3], xi[3], w3r, w3i);
+        if constexpr (R >= 8) {
+            const cf w4 = ld_cf(tw + 2 * M + m);
+            float tr, ti;
+            tw_apply<CONJ>(xr[4], xi[4], w4.x, w4.y);
+            cmul(w4.x, w4.y, w1.x, w1.y, tr, ti); tw_apply<CONJ>(xr[5], xi[5], tr, ti);
+            cmul(w4.x, w4.y, w2.x, w2.y, tr, ti); tw_apply<CONJ>(xr[6], xi[6], tr, ti);
+            cmul(w4.x, w4.y, w3r, w3i, tr, ti);   tw_apply<CONJ>(xr[7], xi[7], tr, ti);
+            if constexpr (R >= 16) {
+                const cf w8 = ld_cf(tw + 3 * M + m);
+                tw_apply<CONJ>(xr[8], xi[8], w8.x, w8.y);
+                cmul(w8.x, w8.y, w1.x, w1.y, tr, ti); tw_apply<CONJ>(xr[9], xi[9], tr, ti);
+                cmul(w8.x, w8.y, w2.x, w2.y, tr, ti); tw_apply<CONJ>(xr[10], xi[10], tr, ti);
+                cmul(w8.x, w8.y, w3r, w3i, tr, ti);   tw_apply<CONJ>(xr[11], xi[11], tr, ti);
+                float w12r, w12i;
+                cmul(w8.x, w8.y, w4.x, w4.y, w12r, w12i);
+                tw_apply<CONJ>(xr[12], xi[12], w12r, w12i);
+                cmul(w12r, w12i, w1.x, w1.y, tr, ti); tw_apply<CONJ>(xr[13], xi[13], tr, ti);
+                cmul(w12r, w12i, w2.x, w2.y, tr, ti); tw_apply<CONJ>(xr[14], xi[14], tr, ti);
+                cmul(w12r, w12i, w3r, w3i, tr, ti);   tw_apply<CONJ>(xr[15], xi[15], tr, ti);
+            }
+        }
     }
 }
 
-// ---- one in-place FFT pass ------------------------------------------------------------
+// shared-memory offset of butterfly input a relative to input 0: phys(base + a*M) - phys(base)
+// is a compile-time constant because M is 1 or a multiple of 16
+template <int M>
+RCG_HD constexpr int slot_off(int a) {
+    static_assert(M == 1 || (M % 16) == 0, "pass strides are 1 or multiples of 16");
+    return M == 1 ? a : a * (M + (M >> 4));
+}
+
+// ---- LOAD fused with forward pass 0 ---------------------------------------------------------
+// samples * window (fft.rs:51-58) -> even/odd packed complex z[n] = (x[2n], x[2n+1]) -> first
+// DIF pass straight from global memory -> shared memory.
+template <int LOG2H>
+RCG_HD void phase_load(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
+    using C = FrameCfg<LOG2H>;
+    constexpr int RL = make_plan(LOG2H).rlog2[0], R = 1 << RL, ML = make_plan(LOG2H).mlog2[0], M = 1 << ML;
+    const float* in = prm.in + (long long)channel * prm.in_stride;
+    const long long base = frame * (long long)prm.step - prm.in_origin;
+    const bool bypass = prm.flags & kFlagBypass;
+    const bool interior = base >= 0 && base + C::W <= prm.in_valid;
+    const bool aligned = interior && ((reinterpret_cast<unsigned long long>(in + base) & 7ull) == 0);
+    const cf* tw = prm.tw + tw_offset(LOG2H, 0);
+#pragma unroll 2
+    for (int m = t; m < M; m += C::NT) {
+        float xr[R], xi[R];
+#pragma unroll
+        for (int a = 0; a < R; a++) {
+            const int n = m + a * M;  // packed index: samples 2n, 2n+1
+            float x0, x1;
+            if (aligned) {
+                const cf x = ld_stream2(in + base + 2 * n);
+                x0 = x.x; x1 = x.y;
+            } else {
+                const long long i0 = base + 2 * n;
+                x0 = (i0 >= 0 && i0 < prm.in_valid) ? ld_stream(in + i0) : 0.0f;
+                x1 = (i0 + 1 >= 0 && i0 + 1 < prm.in_valid) ? ld_stream(in + i0 + 1) : 0.0f;
+            }
+            const cf w = ld_stream2(prm.window + 2 * n);
+            xr[a] = RCG_MUL(x0, w.x); xi[a] = RCG_MUL(x1, w.y);
+        }
+        if (!bypass) {
+            Dft<R>::run(xr, xi);
+            twiddle_butterfly<LOG2H, 0, false, R>(xr, xi, tw, m);
+        }
+        cf* p = S + phys(m);
+#pragma unroll
+        for (int j = 0; j < R; j++) p[slot_off<M>(j)] = make_cf(xr[j], xi[j]);
+    }
+}
+
+// ---- one in-place FFT pass (passes 1..NP-1; pass 0 is fused into load / overlap-add) ---------
 template <int LOG2H, int PASS, bool INV>
 RCG_HD void phase_fft_pass(cf* S, int t, const cf* tw_all) {
     using C = FrameCfg<LOG2H>;
     constexpr int RL = make_plan(LOG2H).rlog2[PASS], R = 1 << RL, ML = make_plan(LOG2H).mlog2[PASS], M = 1 << ML;
     constexpr int NB = C::H / R;
-    constexpr int TWOFF = tw_offset(LOG2H, PASS);
-    const cf* tw = tw_all + TWOFF;
+    const cf* tw = tw_all + tw_offset(LOG2H, PASS);
     for (int b = t; b < NB; b += C::NT) {
         const int m = b & (M - 1), blk = b >> ML;
-        const int base = (blk << (ML + RL)) + m;
+        cf* p = S + phys((blk << (ML + RL)) + m);
         float xr[R], xi[R];
 #pragma unroll
         for (int a = 0; a < R; a++) {
-            cf v = S[phys(base + (a << ML))];
+            const cf v = p[slot_off<M>(a)];
             xr[a] = v.x; xi[a] = v.y;
         }
-        if constexpr (INV && M > 1) {
-#pragma unroll
-            for (int a = 1; a < R; a++) {  // conj twiddle on the inputs (DIT)
-                cf w = ld_cf(tw + (a - 1) * M + m);
-                float nr = xr[a] * w.x + xi[a] * w.y, ni = xi[a] * w.x - xr[a] * w.y;
-                xr[a] = nr; xi[a] = ni;
-            }
-        }
-        if constexpr (INV) Dft<R>::run(xi, xr); else Dft<R>::run(xr, xi);
-        if constexpr (!INV && M > 1) {
-#pragma unroll
-            for (int j = 1; j < R; j++) {  // twiddle on the outputs (DIF)
-                cf w = ld_cf(tw + (j - 1) * M + m);
-                float nr = xr[j] * w.x - xi[j] * w.y, ni = xi[j] * w.x + xr[j] * w.y;
-                xr[j] = nr; xi[j] = ni;
-            }
+        if constexpr (INV) {
+            twiddle_butterfly<LOG2H, PASS, true, R>(xr, xi, tw, m);  // conj twiddle on the inputs (DIT)
+            Dft<R>::run(xi, xr);
+        } else {
+            Dft<R>::run(xr, xi);
+            twiddle_butterfly<LOG2H, PASS, false, R>(xr, xi, tw, m);  // twiddle on the outputs (DIF)
         }
 #pragma unroll
-        for (int j = 0; j < R; j++) S[phys(base + (j << ML))] = make_cf(xr[j], xi[j]);
+        for (int j = 0; j < R; j++) p[slot_off<M>(j)] = make_cf(xr[j], xi[j]);
     }
 }
 
+// phases are k * 2^-23 * PI with k < 2^23, i.e. in [0, PI): the SFU's sin/cos (abs. error
+// ~2^-21) is accurate far beyond the 1e-4 PCM tolerance and costs 3 instructions instead of ~90
 RCG_HD void sincos_phase(float phi, float& s, float& c) {
 #if defined(__CUDA_ARCH__)
-    sincosf(phi, &s, &c);
+    __sincosf(phi, &s, &c);
 #else
     s = sinf(phi); c = cosf(phi);
+#endif
+}
+RCG_HD float fast_sqrt(float v) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+#else
+    return sqrtf(v);
 #endif
 }
 
@@ -179,7 +300,7 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
             const int pq = phys(bin_to_pos<LOG2H>(C::H / 2));
             cf zq = S[pq];
             philox4x32_10((uint32_t)(C::H / 2), f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
-            float mq = sqrtf(zq.x * zq.x + zq.y * zq.y);
+            float mq = fast_sqrt(zq.x * zq.x + zq.y * zq.y);
             float sa, ca, sb, cb;
             sincos_phase(phase_from_u32(u[0]), sa, ca);
             sincos_phase(phase_from_u32(u[1]), sb, cb);
@@ -195,16 +316,17 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
         float tqr = tw.x * qr - tw.y * qi, tqi = tw.x * qi + tw.y * qr;
         float ur = tqi, ui = -tqr;
         // X[k] = (P + U)/2, conj(X[H-k]) = (P - U)/2
-        float xkr = 0.5f * (pr + ur), xki = 0.5f * (pi + ui);
-        float xbr = 0.5f * (pr - ur), xbi = 0.5f * (pi - ui);
-        float mk = sqrtf(xkr * xkr + xki * xki), mb = sqrtf(xbr * xbr + xbi * xbi);
+        // (halves folded into the magnitudes below: |X[k]| = |P + U| / 2)
+        float xkr = pr + ur, xki = pi + ui;
+        float xbr = pr - ur, xbi = pi - ui;
+        float mk = fast_sqrt(xkr * xkr + xki * xki), mb = fast_sqrt(xbr * xbr + xbi * xbi);
         float s0, c0, s1, c1, s2, c2, s3, c3;
         sincos_phase(phase_from_u32(u[0]), s0, c0);  // bin k
         sincos_phase(phase_from_u32(u[1]), s1, c1);  // bin W - k
         sincos_phase(phase_from_u32(u[2]), s2, c2);  // bin H - k
         sincos_phase(phase_from_u32(u[3]), s3, c3);  // bin H + k
         // Hermitian part of the W-bin random-phase spectrum: Y[k] = |X[k]| (e^{i phi_k} + e^{-i phi_{W-k}}) / 2
-        float hk = 0.5f * mk, hb = 0.5f * mb;
+        float hk = 0.25f * mk, hb = 0.25f * mb;
         float ykr = hk * (c0 + c1), yki = hk * (s0 - s1);
         float ybr = hb * (c2 + c3), ybi = hb * (s2 - s3);
         // A = Y[k] + conj(Y[H-k]), B = Y[k] - conj(Y[H-k]), Cc = i conj(t) B
@@ -215,48 +337,146 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
     }
 }
 
+// ---- plugin path, analysis side: real-FFT split -> the full W-bin spectrum the reference hands
+// to `apply` (fft.rs:87: every bin of the complex FFT of the real windowed frame)
+template <int LOG2H>
+RCG_HD void phase_spectrum_out(const cf* S, int t, const StretchParams& prm, int channel, long long frame) {
+    using C = FrameCfg<LOG2H>;
+    constexpr int HALF = C::RLAST / 2;
+    cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * C::W;
+    for (int c = t; c < C::H / 2; c += C::NT) {
+        const int rho = c / HALF, kl = c - rho * HALF;
+        const int pos = rho * C::RLAST + kl;
+        const int k = pos_to_bin<LOG2H>(pos);
+        if (c == 0) {
+            cf z0 = S[0];
+            X[0] = make_cf(z0.x + z0.y, 0.0f);
+            X[C::H] = make_cf(z0.x - z0.y, 0.0f);
+            cf zq = S[phys(bin_to_pos<LOG2H>(C::H / 2))];
+            X[C::H / 2] = make_cf(zq.x, -zq.y);
+            X[C::H + C::H / 2] = zq;
+            continue;
+        }
+        const cf za = S[phys(pos)], zb = S[phys(bin_to_pos<LOG2H>(C::H - k))];
+        const cf tw = ld_cf(prm.spec_tw + c);
+        float pr = za.x + zb.x, pi = za.y - zb.y, qr = za.x - zb.x, qi = za.y + zb.y;
+        float tqr = tw.x * qr - tw.y * qi, tqi = tw.x * qi + tw.y * qr;
+        float ur = tqi, ui = -tqr;
+        float xkr = 0.5f * (pr + ur), xki = 0.5f * (pi + ui);   // X[k]
+        float xbr = 0.5f * (pr - ur), xbi = 0.5f * (pi - ui);   // conj(X[H-k])
+        X[k] = make_cf(xkr, xki);
+        X[C::W - k] = make_cf(xkr, -xki);
+        X[C::H - k] = make_cf(xbr, -xbi);
+        X[C::H + k] = make_cf(xbr, xbi);
+    }
+}
+
+RCG_HD float cf_norm(cf v) { return sqrtf(v.x * v.x + v.y * v.y); }
+
+// ---- plugin path, synthesis side: |apply(X)[k]| for each of the W bins (only the norm of the
+// plugin's output survives, fft.rs:67) -> random phase -> Hermitian fold -> inverse pre-pass
+template <int LOG2H>
+RCG_HD void phase_spectral_in(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
+    using C = FrameCfg<LOG2H>;
+    constexpr int HALF = C::RLAST / 2;
+    const cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * C::W;
+    const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
+    const uint32_t chan = (uint32_t)(channel + prm.channel_offset);
+    for (int c = t; c < C::H / 2; c += C::NT) {
+        const int rho = c / HALF, kl = c - rho * HALF;
+        const int pos = rho * C::RLAST + kl;
+        const int k = pos_to_bin<LOG2H>(pos);
+        uint32_t u[4];
+        if (c == 0) {
+            philox4x32_10(0u, f_lo, f_hi, chan, prm.keys, u);
+            float s, c0, ch;
+            sincos_phase(phase_from_u32(u[0]), s, c0);
+            sincos_phase(phase_from_u32(u[2]), s, ch);
+            float y0 = cf_norm(X[0]) * c0, yh = cf_norm(X[C::H]) * ch;
+            S[0] = make_cf(y0 + yh, y0 - yh);
+            philox4x32_10((uint32_t)(C::H / 2), f_lo, f_hi, chan, prm.keys, u);
+            float sa, ca, sb, cb;
+            sincos_phase(phase_from_u32(u[0]), sa, ca);
+            sincos_phase(phase_from_u32(u[1]), sb, cb);
+            float ma = cf_norm(X[C::H / 2]), mb = cf_norm(X[C::H + C::H / 2]);
+            S[phys(bin_to_pos<LOG2H>(C::H / 2))] = make_cf(ma * ca + mb * cb, -(ma * sa - mb * sb));
+            continue;
+        }
+        const cf tw = ld_cf(prm.spec_tw + c);
+        philox4x32_10((uint32_t)k, f_lo, f_hi, chan, prm.keys, u);
+        const float m0 = cf_norm(X[k]), m1 = cf_norm(X[C::W - k]), m2 = cf_norm(X[C::H - k]), m3 = cf_norm(X[C::H + k]);
+        float s0, c0, s1, c1, s2, c2, s3, c3;
+        sincos_phase(phase_from_u32(u[0]), s0, c0);
+        sincos_phase(phase_from_u32(u[1]), s1, c1);
+        sincos_phase(phase_from_u32(u[2]), s2, c2);
+        sincos_phase(phase_from_u32(u[3]), s3, c3);
+        float ykr = 0.5f * (m0 * c0 + m1 * c1), yki = 0.5f * (m0 * s0 - m1 * s1);
+        float ybr = 0.5f * (m2 * c2 + m3 * c3), ybi = 0.5f * (m2 * s2 - m3 * s3);
+        float ar = ykr + ybr, ai = yki - ybi, br = ykr - ybr, bi = yki + ybi;
+        float cr = -(tw.x * bi - tw.y * br), ci = tw.x * br + tw.y * bi;
+        S[phys(pos)] = make_cf(ar + cr, ai + ci);
+        S[phys(bin_to_pos<LOG2H>(C::H - k))] = make_cf(ar - cr, -(ai - ci));
+    }
+}
+
 // value i (0..W) of the frame held as packed pairs
 RCG_HD float frame_value(const cf* S, int i) {
     cf v = S[phys(i >> 1)];
     return (i & 1) ? v.y : v.x;
 }
 
-// ---- EMIT part 1: scale + synthesis window (fft.rs:70-73), overlap-add with the carried
-// half window, envelope, amplitude (stretcher.rs:96-102).  Arithmetic order is the
-// reference's: ((re / W) * w), then ((y + tail) * env) * amp.
+// ---- inverse pass 0 fused with EMIT part 1: last DIT pass out of shared memory, then scale +
+// synthesis window (fft.rs:70-73), overlap-add with the carried half window, envelope,
+// amplitude (stretcher.rs:96-102).  Arithmetic order is the reference's: ((re / W) * w), then
+// ((y + tail) * env) * amp.  A thread owns packed outputs n = m + a*M, a < R: those with a < R/2
+// are the first half window (emitted), the others the second half (carried to the next frame);
+// both map onto the same slots of the carried buffer, so no other thread ever touches them.
 template <int LOG2H>
 RCG_HD void phase_ola(cf* S, int t, const StretchParams& prm, int channel, long long frame,
                       float* tail, bool emit, bool write_head) {
     using C = FrameCfg<LOG2H>;
+    constexpr int RL = make_plan(LOG2H).rlog2[0], R = 1 << RL, ML = make_plan(LOG2H).mlog2[0], M = 1 << ML;
+    constexpr int RH = R / 2;
     const bool bypass = prm.flags & kFlagBypass;
     float* out = prm.out + (long long)channel * prm.out_stride;
-    for (int m = t; m < C::H / 2; m += C::NT) {
-        const cf a = S[phys(m)], b = S[phys(m + C::H / 2)];
-        const float wa0 = ld_stream(prm.window + 2 * m), wa1 = ld_stream(prm.window + 2 * m + 1);
-        const float wb0 = ld_stream(prm.window + C::H + 2 * m), wb1 = ld_stream(prm.window + C::H + 2 * m + 1);
-        float y0, y1, t0, t1;
-        if (bypass) {
-            y0 = RCG_MUL(a.x, wa0); y1 = RCG_MUL(a.y, wa1);
-            t0 = RCG_MUL(b.x, wb0); t1 = RCG_MUL(b.y, wb1);
-        } else {
-            y0 = RCG_MUL(RCG_MUL(a.x, prm.inv_w), wa0); y1 = RCG_MUL(RCG_MUL(a.y, prm.inv_w), wa1);
-            t0 = RCG_MUL(RCG_MUL(b.x, prm.inv_w), wb0); t1 = RCG_MUL(RCG_MUL(b.y, prm.inv_w), wb1);
+    const cf* tw = prm.tw + tw_offset(LOG2H, 0);
+#pragma unroll 2
+    for (int m = t; m < M; m += C::NT) {
+        cf* p = S + phys(m);
+        float xr[R], xi[R];
+#pragma unroll
+        for (int a = 0; a < R; a++) {
+            const cf v = p[slot_off<M>(a)];
+            xr[a] = v.x; xi[a] = v.y;
         }
-        const float o0 = tail[2 * m], o1 = tail[2 * m + 1];
-        tail[2 * m] = t0; tail[2 * m + 1] = t1;
-        if (write_head) {
-            float* head = prm.head_out + (long long)channel * C::H;
-            head[2 * m] = y0; head[2 * m + 1] = y1;
+        if (!bypass) {
+            twiddle_butterfly<LOG2H, 0, true, R>(xr, xi, tw, m);
+            Dft<R>::run(xi, xr);
         }
-        if (emit) {
-            const float e0 = ld_stream(prm.env + 2 * m), e1 = ld_stream(prm.env + 2 * m + 1);
-            const float z0 = RCG_MUL(RCG_MUL(RCG_ADD(y0, o0), e0), prm.amp);
-            const float z1 = RCG_MUL(RCG_MUL(RCG_ADD(y1, o1), e1), prm.amp);
-            if (prm.pitch == 1) {
-                const long long o = frame * (long long)C::H + 2 * m - prm.out_origin;
-                out[o] = z0; out[o + 1] = z1;
+#pragma unroll
+        for (int a = 0; a < RH; a++) {
+            const int n = m + a * M;              // packed index inside the first half window
+            const cf wa = ld_stream2(prm.window + 2 * n), wb = ld_stream2(prm.window + C::H + 2 * n);
+            float y0, y1, t0, t1;
+            if (bypass) {
+                y0 = RCG_MUL(xr[a], wa.x); y1 = RCG_MUL(xi[a], wa.y);
+                t0 = RCG_MUL(xr[a + RH], wb.x); t1 = RCG_MUL(xi[a + RH], wb.y);
             } else {
-                S[phys(m)] = make_cf(z0, z1);  // staged for the resampling gather
+                y0 = RCG_MUL(RCG_MUL(xr[a], prm.inv_w), wa.x); y1 = RCG_MUL(RCG_MUL(xi[a], prm.inv_w), wa.y);
+                t0 = RCG_MUL(RCG_MUL(xr[a + RH], prm.inv_w), wb.x); t1 = RCG_MUL(RCG_MUL(xi[a + RH], prm.inv_w), wb.y);
+            }
+            const cf old = ld_pair(tail + 2 * n);
+            st_pair(tail + 2 * n, t0, t1);
+            if (write_head) st_pair(prm.head_out + (long long)channel * C::H + 2 * n, y0, y1);
+            if (emit) {
+                const cf e = ld_stream2(prm.env + 2 * n);
+                const float z0 = RCG_MUL(RCG_MUL(RCG_ADD(y0, old.x), e.x), prm.amp);
+                const float z1 = RCG_MUL(RCG_MUL(RCG_ADD(y1, old.y), e.y), prm.amp);
+                if (prm.pitch == 1) {
+                    st_pair(out + (frame * (long long)C::H + 2 * n - prm.out_origin), z0, z1);
+                } else {
+                    p[slot_off<M>(a)] = make_cf(z0, z1);  // staged at packed index n for the resampling gather
+                }
             }
         }
     }
@@ -294,7 +514,7 @@ RCG_HD void phase_resample(const cf* S, int t, const StretchParams& prm, int cha
 template <int LOG2H, bool INV, int PASS, class Exec>
 RCG_HD void fft_all(Exec& ex, cf* S, const StretchParams& prm, bool work) {
     using C = FrameCfg<LOG2H>;
-    if constexpr (PASS >= 0 && PASS < C::NP) {
+    if constexpr (PASS >= 1 && PASS < C::NP) {
         ex.par([&](int t) { if (work) phase_fft_pass<LOG2H, PASS, INV>(S, t, prm.tw); });
         fft_all<LOG2H, INV, INV ? PASS - 1 : PASS + 1>(ex, S, prm, work);
     }
@@ -329,11 +549,16 @@ RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, f
         const bool is_halo = (it == 0);
         const bool work = active && (is_halo ? halo : f < f1);
         const bool bypass = prm.flags & kFlagBypass;
-        ex.par([&](int t) { if (work) phase_load<LOG2H>(S, t, prm, channel, f); });
-        if (!bypass) {
-            fft_all<LOG2H, false, 0>(ex, S, prm, work);
-            ex.par([&](int t) { if (work) phase_spectral<LOG2H>(S, t, prm, channel, f); });
+        if (prm.flags & kFlagSpectrumIn) {
+            ex.par([&](int t) { if (work) phase_spectral_in<LOG2H>(S, t, prm, channel, f); });
             fft_all<LOG2H, true, C::NP - 1>(ex, S, prm, work);
+        } else {
+            ex.par([&](int t) { if (work) phase_load<LOG2H>(S, t, prm, channel, f); });
+            if (!bypass) {
+                fft_all<LOG2H, false, 1>(ex, S, prm, work);
+                ex.par([&](int t) { if (work) phase_spectral<LOG2H>(S, t, prm, channel, f); });
+                fft_all<LOG2H, true, C::NP - 1>(ex, S, prm, work);
+            }
         }
         const bool head = work && defer && f == f0;
         const bool emit = work && !is_halo && !head;
@@ -347,6 +572,21 @@ RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, f
             float* dst = prm.tail_out + (long long)channel * C::H;
             for (int i = t; i < C::H; i += C::NT) dst[i] = tail[i];
         });
+    }
+}
+
+// ---- plugin path: analysis of a run of frames (window, forward FFT, full spectrum to HBM) ----
+template <int LOG2H, class Exec>
+RCG_HD void run_analysis_item(Exec& ex, cf* S, const StretchParams& prm, int item, bool active) {
+    const int channel = active ? item / prm.n_runs : 0;
+    const int run = active ? item - channel * prm.n_runs : 0;
+    const long long f0 = prm.frame_begin + (long long)run * prm.run_len;
+    for (int it = 0; it < prm.run_len; it++) {
+        const long long f = f0 + it;
+        const bool work = active && f < prm.frame_end;
+        ex.par([&](int t) { if (work) phase_load<LOG2H>(S, t, prm, channel, f); });
+        fft_all<LOG2H, false, 1>(ex, S, prm, work);
+        ex.par([&](int t) { if (work) phase_spectrum_out<LOG2H>(S, t, prm, channel, f); });
     }
 }
 

@@ -40,6 +40,22 @@ stretch_kernel(const __grid_constant__ StretchParams prm, int n_items) {
     }
 }
 
+// plugin path, analysis half: frames -> full complex spectra in HBM for the host `apply` call
+template <int LOG2H>
+__global__ void __launch_bounds__(FrameCfg<LOG2H>::NT * FrameCfg<LOG2H>::FPC, min_ctas<LOG2H>())
+analysis_kernel(const __grid_constant__ StretchParams prm, int n_items) {
+    using C = FrameCfg<LOG2H>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x / C::NT;
+    DeviceExec ex{(int)(threadIdx.x % C::NT)};
+    cf* S = reinterpret_cast<cf*>(smem_raw) + lane * C::SMEM_CF;
+    const int n_groups = (n_items + C::FPC - 1) / C::FPC;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const int item = g * C::FPC + lane;
+        run_analysis_item<LOG2H>(ex, S, prm, item, item < n_items);
+    }
+}
+
 template <int LOG2H>
 __global__ void __launch_bounds__(FrameCfg<LOG2H>::NT)
 boundary_kernel(const __grid_constant__ StretchParams prm, const float* head, const float* tail_prev) {
@@ -58,6 +74,9 @@ static cudaError_t geometry_t(LaunchGeometry* g) {
     cudaError_t e = cudaFuncSetAttribute(stretch_kernel<LOG2H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)g->smem_bytes);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(analysis_kernel<LOG2H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)g->smem_bytes);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(boundary_kernel<LOG2H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(C::SMEM_CF * sizeof(cf)));
     if (e != cudaSuccess) return e;
@@ -73,6 +92,15 @@ static cudaError_t launch_t(const StretchParams& prm, int grid, cudaStream_t str
     const int n_items = prm.channels * prm.n_runs;
     if (n_items <= 0) return cudaSuccess;
     stretch_kernel<LOG2H><<<grid, C::NT * C::FPC, (size_t)C::FPC * C::SMEM_CF * sizeof(cf), stream>>>(prm, n_items);
+    return cudaGetLastError();
+}
+
+template <int LOG2H>
+static cudaError_t analysis_t(const StretchParams& prm, int grid, cudaStream_t stream) {
+    using C = FrameCfg<LOG2H>;
+    const int n_items = prm.channels * prm.n_runs;
+    if (n_items <= 0) return cudaSuccess;
+    analysis_kernel<LOG2H><<<grid, C::NT * C::FPC, (size_t)C::FPC * C::SMEM_CF * sizeof(cf), stream>>>(prm, n_items);
     return cudaGetLastError();
 }
 
@@ -101,6 +129,11 @@ cudaError_t stretch_geometry(int log2w, LaunchGeometry* g) {
 }
 cudaError_t launch_stretch(int log2w, const StretchParams& prm, int grid, cudaStream_t stream) {
 #define CALL(L) launch_t<L>(prm, grid, stream)
+    RCG_DISPATCH(log2w, CALL)
+#undef CALL
+}
+cudaError_t launch_analysis(int log2w, const StretchParams& prm, int grid, cudaStream_t stream) {
+#define CALL(L) analysis_t<L>(prm, grid, stream)
     RCG_DISPATCH(log2w, CALL)
 #undef CALL
 }

@@ -18,6 +18,8 @@ cudaError_t stretch_geometry(int log2w, LaunchGeometry* g);
 // Launch the fused stretch kernel over prm.channels * prm.n_runs work items with `grid`
 // persistent CTAs.  prm.tail_scratch must hold grid * frames_per_cta * H floats.
 cudaError_t launch_stretch(int log2w, const StretchParams& prm, int grid, cudaStream_t stream);
+// plugin path: spectra of frames [frame_begin, frame_end) into prm.spectrum
+cudaError_t launch_analysis(int log2w, const StretchParams& prm, int grid, cudaStream_t stream);
 cudaError_t launch_boundary(int log2w, const StretchParams& prm, const float* head, const float* tail_prev,
                             cudaStream_t stream);
 

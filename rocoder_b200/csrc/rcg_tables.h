@@ -4,6 +4,7 @@
 // the values match what rocoder computes on the same machine; twiddles are rounded from
 // double.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -37,20 +38,34 @@ inline int rt_bin_to_pos(const PlanDesc& d, int k) {
     return pos;
 }
 
-// packed per-pass twiddles: table p = [(R-1)][M], entry exp(-2 pi i m j / (R M))
+// packed per-pass twiddles in the layout rcg_common.h's tw_scheme() prescribes
 inline std::vector<cf> host_pass_twiddles(int log2h) {
     const PlanDesc d = make_plan(log2h);
-    std::vector<cf> tw((size_t)tw_total(log2h));
+    std::vector<cf> tw((size_t)std::max(tw_total(log2h), 1));
     const double two_pi = 6.283185307179586476925286766559;
+    auto w = [&](double num, double den) {
+        double a = -two_pi * num / den;
+        return make_cf((float)cos(a), (float)sin(a));
+    };
     for (int p = 0; p < d.npasses; p++) {
         const int M = 1 << d.mlog2[p], R = 1 << d.rlog2[p];
-        if (M == 1) continue;
+        const double N = (double)R * (double)M;
         cf* t = tw.data() + tw_offset(log2h, p);
-        for (int j = 1; j < R; j++)
-            for (int m = 0; m < M; m++) {
-                double a = -two_pi * (double)m * (double)j / ((double)R * (double)M);
-                t[(j - 1) * M + m] = make_cf((float)cos(a), (float)sin(a));
-            }
+        switch (tw_scheme(log2h, p)) {
+            case kTwFull:
+                for (int j = 1; j < R; j++)
+                    for (int m = 0; m < M; m++) t[(j - 1) * M + m] = w((double)m * j, N);
+                break;
+            case kTwPow:
+                for (int i = 0; i < d.rlog2[p]; i++)
+                    for (int m = 0; m < M; m++) t[i * M + m] = w((double)m * (1 << i), N);
+                break;
+            case kTwTwoLevel:
+                for (int hi = 0; hi < M / 64; hi++) t[hi] = w((double)hi * 64, N);
+                for (int lo = 0; lo < 64; lo++) t[M / 64 + lo] = w((double)lo, N);
+                break;
+            default: break;
+        }
     }
     return tw;
 }

@@ -10,6 +10,16 @@ from . import _abi
 from ._abi import RcgError, WouldBlock, check, lib, make_config, rcg_plan_info, rcg_segment
 
 
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the handle that explicitly names the default stream
+
+
+def _stream(stream: Optional[int]) -> Optional[int]:
+    """None -> the engine's own stream; 0 (torch's default stream handle) -> cudaStreamLegacy"""
+    if stream is None:
+        return None
+    return CUDA_STREAM_LEGACY if stream == 0 else stream
+
+
 def _ptr(x) -> Optional[int]:
     """device/host pointer of a torch tensor, numpy array, int or None"""
     if x is None:
@@ -136,7 +146,7 @@ class Engine:
         """inp [C, N] float32 -> out [C, >= out_len] float32 (host buffers). Returns out_len."""
         assert inp.dtype == np.float32 and out.dtype == np.float32
         assert inp.ndim == 2 and out.ndim == 2 and inp.shape[0] == self.channels == out.shape[0]
-        assert inp.strides[1] == 4 and out.strides[1] == 4
+        assert (inp.shape[1] == 0 or inp.strides[1] == 4) and out.strides[1] == 4
         ins = (C.c_void_p * self.channels)(*[inp[c].ctypes.data for c in range(self.channels)])
         outs = (C.c_void_p * self.channels)(*[out[c].ctypes.data for c in range(self.channels)])
         n_out = (C.c_uint64 * self.channels)()
@@ -161,13 +171,13 @@ class Engine:
         s.first_call = first_call; s.n_calls = n_calls
         s.d_tail_in = _ptr(tail_in); s.d_tail_out = _ptr(tail_out); s.d_head_out = _ptr(head_out)
         s.flags = _abi.RCG_SEG_DEFER_FIRST if defer_first else 0
-        s.stream = stream
+        s.stream = _stream(stream)
         check(lib().rcg_process_segment(self._h, C.byref(s)))
 
     def finish_boundary(self, d_out, out_stride: int, first_call: int, head, tail_prev,
                         stream: Optional[int] = None) -> None:
         check(lib().rcg_finish_boundary(self._h, _ptr(d_out), out_stride, first_call, _ptr(head), _ptr(tail_prev),
-                                        stream))
+                                        _stream(stream)))
 
     def synchronize(self) -> None:
         check(lib().rcg_synchronize(self._h))

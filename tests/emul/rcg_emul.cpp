@@ -91,6 +91,60 @@ int rcg_emul_boundary(int log2w, float* out, long long out_stride, long long out
     return -1;
 }
 
+}  // extern "C"
+
+// Plugin path (fft.rs:76-108) on the host: analysis phases -> full spectra -> `apply` per frame ->
+// synthesis phases with kFlagSpectrumIn.  Whole channels in one go (frames [0, frame_end)).
+typedef int (*apply_fn)(size_t, const float*, size_t, float*);
+
+template <int LOG2H>
+static int emul_plugin(StretchParams prm, apply_fn fn) {
+    using C = FrameCfg<LOG2H>;
+    const int W = C::W, H = C::H;
+    std::vector<float> window(W), env(H);
+    host_hanning(window.data(), W);
+    host_crossfade_compensation(env.data(), H);
+    std::vector<cf> tw = host_pass_twiddles(LOG2H), stw = host_spectral_twiddles(LOG2H);
+    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.spec_tw = stw.data();
+    const long long nf = prm.frame_end - prm.frame_begin;
+    std::vector<cf> spec((size_t)prm.channels * nf * W);
+    prm.spectrum = spec.data(); prm.spec_frame0 = prm.frame_begin; prm.spec_frames = nf;
+    std::vector<cf> S(C::SMEM_CF);
+    std::vector<float> tail(H), tmp(2 * W);
+    HostExec ex{C::NT};
+    const int items = prm.channels * prm.n_runs;
+    for (int item = 0; item < items; item++) run_analysis_item<LOG2H>(ex, S.data(), prm, item, true);
+    for (long long f = 0; f < nf; f++)
+        for (int c = 0; c < prm.channels; c++) {
+            float* x = reinterpret_cast<float*>(spec.data() + ((size_t)c * nf + f) * W);
+            if (fn && fn(1234, x, W, tmp.data()) == 0) memcpy(x, tmp.data(), sizeof(float) * 2 * W);
+        }
+    prm.flags |= kFlagSpectrumIn;
+    for (int item = 0; item < items; item++) run_work_item<LOG2H>(ex, S.data(), prm, item, tail.data(), true);
+    return 0;
+}
+
+extern "C" {
+int rcg_emul_stretch_plugin(int log2w, const float* in, long long in_stride, long long in_valid, float* out,
+                            long long out_stride, long long frame_end, int run_len, int channels, int step,
+                            int pitch, int samples_needed, float amp, unsigned long long seed, apply_fn fn) {
+    StretchParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = in; p.in_stride = in_stride; p.in_valid = in_valid;
+    p.out = out; p.out_stride = out_stride;
+    p.frame_begin = 0; p.frame_end = frame_end; p.run_len = run_len;
+    p.n_runs = frame_end > 0 ? (int)((frame_end + run_len - 1) / run_len) : 0;
+    p.channels = channels; p.step = step; p.pitch = pitch; p.samples_needed = samples_needed;
+    p.amp = amp; p.inv_w = 1.0f / (float)(1 << log2w);
+    p.keys = make_philox_keys(seed);
+    switch (log2w - 1) {
+#define CASE(L) case L: return emul_plugin<L>(p, fn);
+        CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+#undef CASE
+    }
+    return -1;
+}
+
 // bank-conflict audit: for every warp-wide shared-memory access pattern of one frame,
 // report how many 128-byte wavefronts the 64-bit accesses need (ideal: 2 per warp).
 }

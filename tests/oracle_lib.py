@@ -214,6 +214,9 @@ def emulator() -> C.CDLL:
                                        C.c_int, C.c_float, C.c_ulonglong, C.c_uint, C.c_int, PF, PF, PF]
         E.rcg_emul_boundary.argtypes = [C.c_int, PF, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                                         C.c_int, C.c_float, PF, PF]
+        E.rcg_emul_stretch_plugin.argtypes = [C.c_int, PF, C.c_longlong, C.c_longlong, PF, C.c_longlong,
+                                              C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                              C.c_ulonglong, APPLY_FN]
         _emul = E
     return _emul
 
@@ -255,6 +258,21 @@ def emul_process_all(x: np.ndarray, factor: float, pitch: int, W: int, seed: int
     calls, _, out_len = expected_counts(x.shape[1], factor, pitch, W)
     out = np.full((x.shape[0], out_len), np.nan, np.float32)
     emul_segment(x, 0, out, factor, pitch, W, 0, calls, seed, amplitude, run_len, bypass)
+    return out
+
+
+def emul_process_all_plugin(x: np.ndarray, factor: float, pitch: int, W: int, plugin, seed: int = 0,
+                            amplitude: float = 1.0, run_len: int = 5) -> np.ndarray:
+    """kernel phases of the frequency-kernel path on the host; plugin is a C-ABI `apply` callable"""
+    x = np.ascontiguousarray(x, np.float32)
+    c = constants(factor, pitch, W, amplitude)
+    calls, frames, out_len = expected_counts(x.shape[1], factor, pitch, W)
+    out = np.full((x.shape[0], out_len), np.nan, np.float32)
+    cb = APPLY_FN(plugin)
+    rc = emulator().rcg_emul_stretch_plugin(int(np.log2(W)), _pf(x), x.strides[0] // 4, x.shape[1], _pf(out),
+                                            out.strides[0] // 4, frames, run_len, x.shape[0], c["sample_step_len"],
+                                            pitch, c["samples_needed_per_window"], c["corrected_amp_factor"], seed, cb)
+    assert rc == 0
     return out
 
 

@@ -1,0 +1,116 @@
+"""Frequency-kernel path (reference fft.rs:76-108): the kernel's analysis / synthesis phases on the
+host (CPU) and through the C ABI (GPU) against the oracle's literal plugin call site."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+import plugins
+
+
+def _input(n, seed=1):
+    rng = np.random.default_rng(seed)
+    return ((rng.random((2, n), dtype=np.float32) * 2 - 1) * 0.5).astype(np.float32)
+
+
+CASES = [(6000, 2.0, 1, 256), (9000, 3.0, 2, 1024), (7000, 4.0, -2, 512), (40000, 2.0, 1, 16384)]
+PLUGS = [plugins.amplitude_x2, plugins.lowpass_asymmetric, plugins.tilt]
+
+
+@pytest.mark.parametrize("n,f,p,W", CASES[:3])
+@pytest.mark.parametrize("plug", PLUGS, ids=lambda f: f.__name__)
+def test_emulated_plugin_path_matches_oracle(n, f, p, W, plug):
+    x = _input(n)
+    ref = ol.process_all(x, f, p, W, seed=4, precision=64, plugin=plug)
+    got = ol.emul_process_all_plugin(x, f, p, W, plug, seed=4)
+    assert np.abs(got - ref).max() <= 1e-4 and ol.snr_db(ref, got) > 100.0
+
+
+def test_identity_plugin_equals_fused_path():
+    """pass-through spectra (no kernel loaded yet, fft.rs:82-85) reproduce the fused kernel up to
+    the rounding of the two different magnitude formulas"""
+    x = _input(8000)
+    def ident(ms, pin, n, pout):
+        a, b = plugins._views(pin, n, pout)
+        b[:] = a
+        return 0
+    a = ol.emul_process_all(x, 2.0, 2, 512, seed=3)
+    b = ol.emul_process_all_plugin(x, 2.0, 2, 512, ident, seed=3)
+    assert np.abs(a - b).max() < 1e-6
+
+
+def test_amplitude_plugin_doubles_output():
+    """only magnitudes survive (fft.rs:67) and everything downstream is linear in them"""
+    x = _input(8000)
+    a = ol.process_all(x, 2.0, 1, 512, seed=3)
+    b = ol.process_all(x, 2.0, 1, 512, seed=3, plugin=plugins.amplitude_x2)
+    assert np.array_equal(b, a * np.float32(2.0))
+
+
+def test_oracle_plugin_panic_falls_back():
+    """fft.rs:101-106: a panicking kernel is popped and the frame passes through"""
+    x = _input(5000)
+    a = ol.process_all(x, 2.0, 1, 256, seed=3)
+    b = ol.process_all(x, 2.0, 1, 256, seed=3, plugin=plugins.panics)
+    assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,f,p,W", CASES)
+@pytest.mark.parametrize("plug", PLUGS, ids=lambda f: f.__name__)
+def test_gpu_plugin_path_matches_oracle(n, f, p, W, plug):
+    import ctypes as C
+    import rocoder_b200 as rb
+    from rocoder_b200 import _abi
+    x = _input(n)
+    ref = ol.process_all(x, f, p, W, seed=4, precision=64, plugin=plug)
+    with rb.Engine(2, 48000, W, f, 1.0, p, seed=4) as e:
+        cb = _abi.APPLY_FN(plug)
+        _abi.check(_abi.lib().rcg_push_frequency_kernel(e._h, cb))
+        assert e.frequency_kernel_count() == 1
+        got = e.process_all(x)
+    assert np.abs(got - ref).max() <= 1e-4 and ol.snr_db(ref, got) > 100.0
+
+
+@pytest.mark.gpu
+def test_gpu_plugin_python_callable_and_fallback():
+    import rocoder_b200 as rb
+    x = _input(9000)
+    with rb.Engine(2, 48000, 1024, 2.0, 1.0, 1, seed=4) as e:
+        plain = e.process_all(x)
+    with rb.Engine(2, 48000, 1024, 2.0, 1.0, 1, seed=4) as e:
+        e.push_frequency_kernel(lambda ms, spec: spec * np.float32(2.0))
+        doubled = e.process_all(x)
+    assert np.array_equal(doubled, plain * np.float32(2.0))
+    with rb.Engine(2, 48000, 1024, 2.0, 1.0, 1, seed=4) as e:
+        e.push_frequency_kernel(lambda ms, spec: spec * np.float32(2.0))   # older kernel
+        def bad(ms, spec):
+            raise RuntimeError("panic")
+        e.push_frequency_kernel(bad)                                       # newest kernel panics
+        out = e.process_all(x)
+        assert e.frequency_kernel_count() == 1                             # popped (fft.rs:104)
+    assert np.array_equal(out, doubled)
+
+
+@pytest.mark.gpu
+def test_gpu_plugin_streaming_and_shared_object(tmp_path):
+    """hot-swap role: compile a C kernel to a shared object, load it (rcg_load_frequency_kernel)"""
+    import subprocess
+    import rocoder_b200 as rb
+    src = tmp_path / "kernel.c"
+    src.write_text("#include <stddef.h>\n"
+                   "int apply(size_t ms, const float* in, size_t n, float* out) {\n"
+                   "  for (size_t i = 0; i < 2 * n; i++) out[i] = in[i] * 2.0f; return 0; }\n")
+    so = tmp_path / "kernel.so"
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", str(so), str(src)])
+    x = _input(9000)[:1]
+    ref = ol.process_all(x, 2.0, 1, 1024, seed=4, precision=64, plugin=plugins.amplitude_x2)
+    with rb.Engine(1, 48000, 1024, 2.0, 1.0, 1, seed=4, max_lookahead_calls=2) as e:
+        e.load_frequency_kernel(str(so))
+        e.send(0, x[0])
+        e.close_input(0)
+        wins = []
+        while not e.is_done(0):
+            wins.append(e.next_window(0))
+    got = np.concatenate(wins)[None, :]
+    assert np.abs(got - ref).max() <= 1e-4 and ol.snr_db(ref, got) > 100.0
