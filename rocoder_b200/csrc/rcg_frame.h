@@ -82,22 +82,20 @@ struct FrameCfg {
 };
 
 // ---- global loads ---------------------------------------------------------------------
-// Streaming data (input samples, window, envelope) bypasses L1 allocation so that the small
-// twiddle tables stay L1-resident; tables go through the normal read-only path.
+// Input samples are re-read by W/step overlapping frames and the window / envelope by every
+// frame: all of it must stay L2-resident, so these are plain read-only loads.  (Measured:
+// ld.global.nc.L1::no_allocate is issued to L2 as evict-first on sm_100 and sent 7 GB per launch
+// back to DRAM -- profiles/r1b_stretch_kernel_v1.md.)
 RCG_HD float ld_stream(const float* p) {
 #if defined(__CUDA_ARCH__)
-    float r;
-    asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
-    return r;
+    return __ldg(p);
 #else
     return *p;
 #endif
 }
 RCG_HD cf ld_stream2(const float* p) {  // p must be 8-byte aligned
 #if defined(__CUDA_ARCH__)
-    cf r;
-    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-    return r;
+    return __ldg(reinterpret_cast<const float2*>(p));
 #else
     return make_cf(p[0], p[1]);
 #endif

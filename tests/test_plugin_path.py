@@ -81,7 +81,7 @@ def test_gpu_plugin_python_callable_and_fallback():
     with rb.Engine(2, 48000, 1024, 2.0, 1.0, 1, seed=4) as e:
         e.push_frequency_kernel(lambda ms, spec: spec * np.float32(2.0))
         doubled = e.process_all(x)
-    assert np.array_equal(doubled, plain * np.float32(2.0))
+    assert np.abs(doubled - plain * np.float32(2.0)).max() < 2e-6   # fused vs plugin path: different rounding
     with rb.Engine(2, 48000, 1024, 2.0, 1.0, 1, seed=4) as e:
         e.push_frequency_kernel(lambda ms, spec: spec * np.float32(2.0))   # older kernel
         def bad(ms, spec):
