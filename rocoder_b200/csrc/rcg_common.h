@@ -30,22 +30,37 @@ namespace rcg {
 constexpr int kMaxPasses = 5;
 
 struct PlanDesc {
-    int log2h;
+    int log2h;              // log2 of the transform size this plan describes
+    int hr;                 // half-rate synthesis plan (see make_plan)
     int npasses;
     int rlog2[kMaxPasses];  // log2 radix of pass p
     int mlog2[kMaxPasses];  // log2 of M_p = stride between butterfly inputs in pass p
     int klo[kMaxPasses];    // bit offset of digit p inside the bin index k
 };
 
-RCG_HD constexpr PlanDesc make_plan(int log2h) {
+// hr = true describes the half-rate synthesis transform used for even pitch multiples: a
+// 2^(log2h-1) point inverse with the same passes but the last radix halved (16 -> 8).  Its
+// data live in the slots of the full layout whose last digit is < 8, so its pass strides in
+// shared memory are those of the full plan (see expand_hr()), while mlog2/klo are the logical
+// ones that index the twiddle tables.
+RCG_HD constexpr PlanDesc make_plan(int log2h, bool hr = false) {
     PlanDesc d{};
-    d.log2h = log2h;
+    const int size_log2 = hr ? log2h - 1 : log2h;
+    d.log2h = size_log2;
+    d.hr = hr ? 1 : 0;
+    int rl[kMaxPasses] = {0, 0, 0, 0, 0};
     int r = log2h % 4, n16 = log2h / 4, np = 0, used = 0;
-    if (r != 0) { d.rlog2[np] = r; d.klo[np] = used; used += r; d.mlog2[np] = log2h - used; np++; }
-    for (int i = 0; i < n16; i++) { d.rlog2[np] = 4; d.klo[np] = used; used += 4; d.mlog2[np] = log2h - used; np++; }
+    if (r != 0) rl[np++] = r;
+    for (int i = 0; i < n16; i++) rl[np++] = 4;
+    if (hr) rl[np - 1] -= 1;
+    for (int p = 0; p < np; p++) { d.rlog2[p] = rl[p]; d.klo[p] = used; used += rl[p]; d.mlog2[p] = size_log2 - used; }
     d.npasses = np;
     return d;
 }
+
+// logical index of the half-rate transform -> slot index of the full layout (zero inserted at
+// bit 3: the last digit only takes values 0..7 of its 16 slots)
+RCG_HD constexpr int expand_hr(int x) { return ((x >> 3) << 4) | (x & 7); }
 
 // position (in natural cf units, before padding) of bin k after the forward passes, and
 // its inverse.  Fully unrolled: every shift is a compile-time constant.
@@ -97,29 +112,32 @@ RCG_HD constexpr int frames_per_cta(int log2h) {
 //   twolevel  R == 2, M >= 64: w^m = A[m >> 6] * B[m & 63]  (A: M/64 entries, B: 64)
 enum TwScheme : int { kTwNone = 0, kTwFull = 1, kTwPow = 2, kTwTwoLevel = 3 };
 
-RCG_HD constexpr int tw_scheme(int log2h, int pass) {
-    const PlanDesc d = make_plan(log2h);
+RCG_HD constexpr int tw_scheme(int log2h, int pass, bool hr = false) {
+    const PlanDesc d = make_plan(log2h, hr);
     const int M = 1 << d.mlog2[pass], R = 1 << d.rlog2[pass];
     if (M == 1) return kTwNone;
     if (R == 2) return M >= 64 ? kTwTwoLevel : kTwFull;
     if (M <= 16) return kTwFull;
     return kTwPow;
 }
-RCG_HD constexpr int tw_size(int log2h, int pass) {
-    const PlanDesc d = make_plan(log2h);
+RCG_HD constexpr int tw_size(int log2h, int pass, bool hr = false) {
+    const PlanDesc d = make_plan(log2h, hr);
     const int M = 1 << d.mlog2[pass], R = 1 << d.rlog2[pass];
-    switch (tw_scheme(log2h, pass)) {
+    switch (tw_scheme(log2h, pass, hr)) {
         case kTwFull: return (R - 1) * M;
         case kTwPow: return d.rlog2[pass] * M;
         case kTwTwoLevel: return M / 64 + 64;
         default: return 0;
     }
 }
-RCG_HD constexpr int tw_offset(int log2h, int pass) {
+// full-plan tables first, then the half-rate plan's
+RCG_HD constexpr int tw_offset(int log2h, int pass, bool hr = false) {
     int off = 0;
-    for (int p = 0; p < pass; p++) off += tw_size(log2h, p);
+    const int np = make_plan(log2h).npasses;
+    if (hr) for (int p = 0; p < np; p++) off += tw_size(log2h, p, false);
+    for (int p = 0; p < pass; p++) off += tw_size(log2h, p, hr);
     return off;
 }
-RCG_HD constexpr int tw_total(int log2h) { return tw_offset(log2h, make_plan(log2h).npasses); }
+RCG_HD constexpr int tw_total(int log2h) { return tw_offset(log2h, make_plan(log2h).npasses, true); }
 
 }  // namespace rcg

@@ -184,8 +184,8 @@ struct rcg_engine {
     int max_grid = 0;
     PhiloxKeys keys{};
     uint64_t seed = 0;
-    float *d_window = nullptr, *d_env = nullptr, *d_scratch = nullptr;
-    cf *d_tw = nullptr, *d_spec_tw = nullptr;
+    float *d_window = nullptr, *d_env = nullptr, *d_scratch = nullptr, *d_window_even = nullptr, *d_env_even = nullptr;
+    cf *d_tw = nullptr, *d_spec_tw = nullptr, *d_spec_tw_hr = nullptr;
     cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
     uint64_t launches = 0;
     // process_all buffers (grow only)
@@ -203,6 +203,7 @@ struct rcg_engine {
     std::vector<float> plug_tmp;
     // plugins (fft.rs:22: kernels: Vec<Library>)
     std::vector<rcg_apply_fn> kernels;
+    bool had_kernels = false;  // a kernel was pushed at some point (even if all have since failed)
     std::vector<void*> libs;
 };
 
@@ -266,6 +267,14 @@ extern "C" int rcg_create(const rcg_config* cfg, rcg_engine** out) {
     host_hanning(window.data(), W);           // main.rs:131
     host_crossfade_compensation(env.data(), H);  // stretcher.rs:56
     std::vector<cf> tw = host_pass_twiddles(e->log2w - 1), stw = host_spectral_twiddles(e->log2w - 1);
+    std::vector<cf> stw_hr = host_spectral_twiddles_hr(e->log2w - 1);
+    std::vector<float> we = host_decimate2(window), ee = host_decimate2(env);
+    TRY_E(cudaMalloc(&e->d_window_even, we.size() * sizeof(float)));
+    TRY_E(cudaMalloc(&e->d_env_even, ee.size() * sizeof(float)));
+    TRY_E(cudaMalloc(&e->d_spec_tw_hr, stw_hr.size() * sizeof(cf)));
+    TRY_E(cudaMemcpy(e->d_window_even, we.data(), we.size() * sizeof(float), cudaMemcpyHostToDevice));
+    TRY_E(cudaMemcpy(e->d_env_even, ee.data(), ee.size() * sizeof(float), cudaMemcpyHostToDevice));
+    TRY_E(cudaMemcpy(e->d_spec_tw_hr, stw_hr.data(), stw_hr.size() * sizeof(cf), cudaMemcpyHostToDevice));
     TRY_E(cudaMalloc(&e->d_window, W * sizeof(float)));
     TRY_E(cudaMalloc(&e->d_env, H * sizeof(float)));
     TRY_E(cudaMalloc(&e->d_tw, std::max<size_t>(tw.size(), 1) * sizeof(cf)));
@@ -297,6 +306,7 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     if (e->d2h) cudaStreamSynchronize(e->d2h);
     if (e->h2d) cudaStreamSynchronize(e->h2d);
     cudaFree(e->d_window); cudaFree(e->d_env); cudaFree(e->d_tw); cudaFree(e->d_spec_tw); cudaFree(e->d_scratch);
+    cudaFree(e->d_window_even); cudaFree(e->d_env_even); cudaFree(e->d_spec_tw_hr);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_tail_pp[0]); cudaFree(e->d_tail_pp[1]);
     cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_spec);
     cudaFree(e->d_plug_tail[0]); cudaFree(e->d_plug_tail[1]);
@@ -330,9 +340,17 @@ extern "C" int rcg_synchronize(rcg_engine* e) {
     return RCG_OK;
 }
 
+// Even pitch multiples keep only even output samples (resampler.rs:15-18): the synthesis side
+// then runs at half size.  Not with frequency kernels loaded (that path keeps the full layout), so
+// the carried half windows of fused and plugin launches are never mixed within one engine state.
+static bool engine_half_rate(const rcg_engine* e) {
+    return use_half_rate(e->cfg.pitch_multiple, 0u) && e->kernels.empty() && !e->had_kernels;
+}
+
 static void fill_params(const rcg_engine* e, StretchParams& p) {
     memset(&p, 0, sizeof(p));
     p.window = e->d_window; p.env = e->d_env; p.tw = e->d_tw; p.spec_tw = e->d_spec_tw;
+    p.spec_tw_hr = e->d_spec_tw_hr; p.window_even = e->d_window_even; p.env_even = e->d_env_even;
     p.tail_scratch = e->d_scratch;
     p.channels = (int)e->cfg.channels;
     p.step = (int)e->plan.sample_step_len;
@@ -360,6 +378,7 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
         p.flags |= kFlagSpectrumIn;
         p.spectrum = spec->spectrum; p.spec_frame0 = spec->frame0; p.spec_frames = spec->frames;
     }
+    if (engine_half_rate(e)) p.flags |= kFlagHalfRate;
     const uint64_t k = e->plan.frames_per_call;
     p.in = s.d_in; p.in_stride = s.in_stride; p.in_origin = s.in_origin; p.in_valid = s.in_valid;
     p.out = s.d_out; p.out_stride = s.out_stride;
@@ -506,6 +525,7 @@ extern "C" int rcg_finish_boundary(rcg_engine* e, float* d_out, int64_t out_stri
     p.out = d_out; p.out_stride = out_stride;
     p.out_origin = (long long)(first_call * e->plan.out_len_per_call);
     p.frame_begin = (long long)(first_call * e->plan.frames_per_call);
+    if (engine_half_rate(e)) p.flags |= kFlagHalfRate;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
     cudaError_t ce = launch_boundary(e->log2w, p, d_head, d_tail_prev, st);
     if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "boundary kernel launch failed: %s", cudaGetErrorString(ce));
@@ -698,13 +718,24 @@ extern "C" int rcg_next_window(rcg_engine* e, uint32_t channel, float* out, uint
 }
 
 // -- plugins -------------------------------------------------------------------------------------
+// With an even pitch multiple the fused path carries even samples only between launches; the
+// first kernel must therefore be pushed before any audio has been processed.
+static int check_kernel_push(rcg_engine* e) {
+    if (e->launches > 0 && !e->had_kernels && use_half_rate(e->cfg.pitch_multiple, 0u))
+        return fail(RCG_ERR_STATE, "with an even pitch multiple the first frequency kernel must be pushed before processing starts");
+    return RCG_OK;
+}
+
 extern "C" int rcg_push_frequency_kernel(rcg_engine* e, rcg_apply_fn fn) {
     if (!e || !fn) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (int rc = check_kernel_push(e)) return rc;
     e->kernels.push_back(fn);
+    e->had_kernels = true;
     return RCG_OK;
 }
 extern "C" int rcg_load_frequency_kernel(rcg_engine* e, const char* so_path) {
     if (!e || !so_path) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (int rc = check_kernel_push(e)) return rc;
     void* lib = dlopen(so_path, RTLD_NOW | RTLD_LOCAL);
     if (!lib) return fail(RCG_ERR_PLUGIN, "dlopen(%s): %s", so_path, dlerror());
     void* sym = dlsym(lib, "apply");
@@ -714,6 +745,7 @@ extern "C" int rcg_load_frequency_kernel(rcg_engine* e, const char* so_path) {
     }
     e->libs.push_back(lib);
     e->kernels.push_back((rcg_apply_fn)sym);
+    e->had_kernels = true;
     return RCG_OK;
 }
 extern "C" int rcg_frequency_kernel_count(const rcg_engine* e, uint32_t* n) {

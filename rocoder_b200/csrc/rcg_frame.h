@@ -29,7 +29,14 @@ enum : uint32_t {
     kFlagBypass = 1u,      // test hook: resynth(s)[n] = (s[n]*w[n])*w[n]  (no FFT, no phases)
     kFlagDeferFirst = 2u,  // do not emit block frame_begin; write its raw first half to head_out
     kFlagSpectrumIn = 4u,  // plugin path: magnitudes come from prm.spectrum (plugin output), not the FFT
+    kFlagHalfRate = 8u,    // even pitch multiple > 0: only even output samples survive the decimation
+                           // (resampler.rs:15-18), so the synthesis side runs at half size
 };
+
+// the one rule both the engine and the test emulator use to pick the half-rate path
+RCG_HD bool use_half_rate(int pitch, uint32_t flags) {
+    return pitch > 0 && (pitch & 1) == 0 && !(flags & kFlagSpectrumIn);
+}
 
 // Everything one launch needs.  Global indices (samples, frames, output positions) are
 // absolute within the channel so that segments of a long input computed by different
@@ -46,6 +53,9 @@ struct StretchParams {
     const float* env;       // [H]   crossfade::hanning_crossfade_compensation (crossfade.rs:4-10)
     const cf* tw;           // packed per-pass twiddles
     const cf* spec_tw;      // [H/2] exp(-2 pi i k/W) in the spectral step's pair order
+    const cf* spec_tw_hr;   // [H/4] the same in the half-rate quad order
+    const float* window_even;  // [H]   window[2i]   (half-rate synthesis)
+    const float* env_even;     // [H/2] env[2i]
     float* tail_scratch;    // [work lanes][H] carried second half window (stretcher.rs:101-102)
     const float* tail_in;   // optional [channels][H]: second half of frame frame_begin-1
     float* tail_out;        // optional [channels][H]: second half of frame frame_end-1
@@ -126,10 +136,10 @@ RCG_HD void tw_apply(float& xr, float& xi, float wr, float wi) {
 
 // Multiply element j (1 <= j < R) of a butterfly by w^(m*j) (or its conjugate), w = the pass's
 // principal root, using the table layout tw_scheme() selected.
-template <int LOG2H, int PASS, bool CONJ, int R>
+template <int LOG2H, int PASS, bool CONJ, int R, bool HR = false>
 RCG_HD void twiddle_butterfly(float (&xr)[R], float (&xi)[R], const cf* tw, int m) {
-    constexpr int SCHEME = tw_scheme(LOG2H, PASS);
-    constexpr int M = 1 << make_plan(LOG2H).mlog2[PASS];
+    constexpr int SCHEME = tw_scheme(LOG2H, PASS, HR);
+    constexpr int M = 1 << make_plan(LOG2H, HR).mlog2[PASS];
     if constexpr (SCHEME == kTwFull) {
 #pragma unroll
         for (int j = 1; j < R; j++) {
@@ -271,6 +281,93 @@ RCG_HD float fast_sqrt(float v) {
 #endif
 }
 
+// One bin pair (kk, H-kk) of the half-size forward transform: real-FFT split -> magnitudes of
+// bins kk and H-kk -> the four random phases of bins {kk, W-kk, H-kk, H+kk} (one Philox block)
+// -> Hermitian fold.  Returns A = Y[kk] + conj(Y[H-kk]) and B = Y[kk] - conj(Y[H-kk]) where
+// Y[k] = |X[k]| (e^{i phi_k} + e^{-i phi_{W-k}}) / 2 is the Hermitian part of the reference's
+// W-bin spectrum (fft.rs:65-68): the real part of its inverse FFT is the inverse of Y.
+RCG_HD void pair_fold(cf za, cf zb, cf tw, const uint32_t (&u)[4], float& ar, float& ai, float& br, float& bi) {
+    // P = za + conj(zb), Q = za - conj(zb), U = -i t Q;  X[kk] = (P + U)/2, conj(X[H-kk]) = (P - U)/2
+    float pr = za.x + zb.x, pi = za.y - zb.y, qr = za.x - zb.x, qi = za.y + zb.y;
+    float tqr = tw.x * qr - tw.y * qi, tqi = tw.x * qi + tw.y * qr;
+    float ur = tqi, ui = -tqr;
+    float xkr = pr + ur, xki = pi + ui;   // halves folded into the 0.25 below
+    float xbr = pr - ur, xbi = pi - ui;
+    float mk = fast_sqrt(xkr * xkr + xki * xki), mb = fast_sqrt(xbr * xbr + xbi * xbi);
+    float s0, c0, s1, c1, s2, c2, s3, c3;
+    sincos_phase(phase_from_u32(u[0]), s0, c0);  // bin kk
+    sincos_phase(phase_from_u32(u[1]), s1, c1);  // bin W - kk
+    sincos_phase(phase_from_u32(u[2]), s2, c2);  // bin H - kk
+    sincos_phase(phase_from_u32(u[3]), s3, c3);  // bin H + kk
+    float hk = 0.25f * mk, hb = 0.25f * mb;
+    float ykr = hk * (c0 + c1), yki = hk * (s0 - s1);
+    float ybr = hb * (c2 + c3), ybi = hb * (s2 - s3);
+    ar = ykr + ybr; ai = yki - ybi; br = ykr - ybr; bi = yki + ybi;
+}
+
+// ---- SPECTRAL, half-rate synthesis (even pitch multiples) --------------------------------------
+// Only y[2n] is ever emitted, and y[2n] = IFFT_H(E)[n] with E[k] = Y[k] + conj(Y[H-k]) (= the A
+// of pair_fold), itself Hermitian.  So the inverse is a real transform of length H done as a
+// complex one of length Q = H/2: Z''[k] = (E[k] + conj(E[Q-k])) + i e^{2 pi i k/H} (E[k] - conj(E[Q-k])).
+// One thread owns the quad {k, H-k, Q-k, Q+k} (two pairs, two Philox blocks) and leaves Z''[k],
+// Z''[Q-k] in the slots of bins k and Q-k: the slots of the full layout whose last digit is < 8,
+// which is exactly the layout the half-rate inverse passes walk (make_plan(.., hr)).
+template <int LOG2H>
+RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
+    using C = FrameCfg<LOG2H>;
+    constexpr int QUARTER = C::RLAST / 4;
+    constexpr int Q = C::H / 2;
+    const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
+    const uint32_t chan = (uint32_t)(channel + prm.channel_offset);
+    for (int c = t; c < C::H / 4; c += C::NT) {
+        const int rho = c / QUARTER, kl = c - rho * QUARTER;
+        const int pos = rho * C::RLAST + kl;
+        const int k = pos_to_bin<LOG2H>(pos);
+        uint32_t u[4];
+        if (c == 0) {
+            // E[0] = Y[0] + Y[H] (both real), E[Q] = 2 Re Y[Q]
+            cf z0 = S[0];
+            philox4x32_10(0u, f_lo, f_hi, chan, prm.keys, u);
+            float m0 = fabsf(z0.x + z0.y), mh = fabsf(z0.x - z0.y);
+            float s, c0, ch;
+            sincos_phase(phase_from_u32(u[0]), s, c0);
+            sincos_phase(phase_from_u32(u[2]), s, ch);
+            const float e0 = m0 * c0 + mh * ch;
+            cf zq = S[phys(bin_to_pos<LOG2H>(Q))];
+            philox4x32_10((uint32_t)Q, f_lo, f_hi, chan, prm.keys, u);
+            float mq = fast_sqrt(zq.x * zq.x + zq.y * zq.y);
+            float ca, cb;
+            sincos_phase(phase_from_u32(u[0]), s, ca);
+            sincos_phase(phase_from_u32(u[1]), s, cb);
+            const float eq = mq * (ca + cb);
+            S[0] = make_cf(e0 + eq, e0 - eq);
+            // k = Q/2 pairs with itself: Z''[Q/2] = 2 conj(E[Q/2]); its twiddle is exp(-i pi/4)
+            const int ph = phys(bin_to_pos<LOG2H>(Q / 2));
+            const cf za = S[ph], zb = S[phys(bin_to_pos<LOG2H>(C::H - Q / 2))];
+            philox4x32_10((uint32_t)(Q / 2), f_lo, f_hi, chan, prm.keys, u);
+            float ar, ai, br, bi;
+            pair_fold(za, zb, make_cf(0.70710678118654752f, -0.70710678118654752f), u, ar, ai, br, bi);
+            S[ph] = make_cf(2.0f * ar, -2.0f * ai);
+            continue;
+        }
+        const int pa = phys(pos), pc = phys(bin_to_pos<LOG2H>(Q - k));
+        const cf za = S[pa], zb = S[phys(bin_to_pos<LOG2H>(C::H - k))];
+        const cf zc = S[pc], zd = S[phys(bin_to_pos<LOG2H>(Q + k))];
+        const cf tw = ld_cf(prm.spec_tw_hr + c);  // exp(-2 pi i k / W)
+        float ar, ai, er, ei, br, bi;
+        philox4x32_10((uint32_t)k, f_lo, f_hi, chan, prm.keys, u);
+        pair_fold(za, zb, tw, u, ar, ai, br, bi);                              // E[k]
+        philox4x32_10((uint32_t)(Q - k), f_lo, f_hi, chan, prm.keys, u);
+        pair_fold(zc, zd, make_cf(-tw.y, -tw.x), u, er, ei, br, bi);          // E[Q-k]; exp(-2 pi i (Q-k)/W) = -i conj(tw)
+        // A2 = E[k] + conj(E[Q-k]), B2 = E[k] - conj(E[Q-k]), C2 = i conj(t2) B2, t2 = exp(-2 pi i k/H) = tw^2
+        const float a2r = ar + er, a2i = ai - ei, b2r = ar - er, b2i = ai + ei;
+        const float t2r = tw.x * tw.x - tw.y * tw.y, t2i = 2.0f * tw.x * tw.y;
+        const float cr = -(t2r * b2i - t2i * b2r), ci = t2r * b2r + t2i * b2i;
+        S[pa] = make_cf(a2r + cr, a2i + ci);       // Z''[k]
+        S[pc] = make_cf(a2r - cr, -(a2i - ci));    // Z''[Q-k] = conj(A2 - C2)
+    }
+}
+
 // ---- SPECTRAL: real-FFT split -> |X[k]| -> random phases for all W bins -> Hermitian
 // fold -> pre-pass of the real inverse (fft.rs:63-69).  One thread owns the bin pair
 // (k, H-k) of the half-size transform, i.e. bins {k, W-k, H-k, H+k} of the W-point one.
@@ -309,26 +406,9 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
         const cf za = S[pa], zb = S[pb];
         const cf tw = ld_cf(prm.spec_tw + c);  // exp(-2 pi i k / W)
         philox4x32_10((uint32_t)k, f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
-        // P = za + conj(zb), Q = za - conj(zb), U = -i t Q
-        float pr = za.x + zb.x, pi = za.y - zb.y, qr = za.x - zb.x, qi = za.y + zb.y;
-        float tqr = tw.x * qr - tw.y * qi, tqi = tw.x * qi + tw.y * qr;
-        float ur = tqi, ui = -tqr;
-        // X[k] = (P + U)/2, conj(X[H-k]) = (P - U)/2
-        // (halves folded into the magnitudes below: |X[k]| = |P + U| / 2)
-        float xkr = pr + ur, xki = pi + ui;
-        float xbr = pr - ur, xbi = pi - ui;
-        float mk = fast_sqrt(xkr * xkr + xki * xki), mb = fast_sqrt(xbr * xbr + xbi * xbi);
-        float s0, c0, s1, c1, s2, c2, s3, c3;
-        sincos_phase(phase_from_u32(u[0]), s0, c0);  // bin k
-        sincos_phase(phase_from_u32(u[1]), s1, c1);  // bin W - k
-        sincos_phase(phase_from_u32(u[2]), s2, c2);  // bin H - k
-        sincos_phase(phase_from_u32(u[3]), s3, c3);  // bin H + k
-        // Hermitian part of the W-bin random-phase spectrum: Y[k] = |X[k]| (e^{i phi_k} + e^{-i phi_{W-k}}) / 2
-        float hk = 0.25f * mk, hb = 0.25f * mb;
-        float ykr = hk * (c0 + c1), yki = hk * (s0 - s1);
-        float ybr = hb * (c2 + c3), ybi = hb * (s2 - s3);
         // A = Y[k] + conj(Y[H-k]), B = Y[k] - conj(Y[H-k]), Cc = i conj(t) B
-        float ar = ykr + ybr, ai = yki - ybi, br = ykr - ybr, bi = yki + ybi;
+        float ar, ai, br, bi;
+        pair_fold(za, zb, tw, u, ar, ai, br, bi);
         float cr = -(tw.x * bi - tw.y * br), ci = tw.x * br + tw.y * bi;
         S[pa] = make_cf(ar + cr, ai + ci);      // Z'[k]   = A + Cc
         S[pb] = make_cf(ar - cr, -(ai - ci));   // Z'[H-k] = conj(A - Cc)
@@ -480,16 +560,124 @@ RCG_HD void phase_ola(cf* S, int t, const StretchParams& prm, int channel, long 
     }
 }
 
+// ---- half-rate synthesis: inverse DIT pass PASS >= 1 of the Q-point transform ---------------------
+// Logical indices of the hr plan, physical slots of the full layout (expand_hr).
+template <int LOG2H, int PASS>
+RCG_HD void phase_fft_pass_hr(cf* S, int t, const cf* tw_all) {
+    using C = FrameCfg<LOG2H>;
+    constexpr PlanDesc P = make_plan(LOG2H, true);
+    constexpr int RL = P.rlog2[PASS], R = 1 << RL, ML = P.mlog2[PASS], M = 1 << ML;
+    constexpr int NB = (C::H / 2) / R;
+    constexpr int STRIDE = (M == 1) ? 1 : 2 * M;   // physical stride between butterfly inputs
+    static_assert(M == 1 || M >= 8, "hr pass strides are 1 or multiples of 8");
+    const cf* tw = tw_all + tw_offset(LOG2H, PASS, true);
+    for (int b = t; b < NB; b += C::NT) {
+        const int m = b & (M - 1), blk = b >> ML;
+        cf* p = S + phys(expand_hr((blk << (ML + RL)) + m));
+        float xr[R], xi[R];
+#pragma unroll
+        for (int a = 0; a < R; a++) {
+            const cf v = p[slot_off<STRIDE>(a)];
+            xr[a] = v.x; xi[a] = v.y;
+        }
+        twiddle_butterfly<LOG2H, PASS, true, R, true>(xr, xi, tw, m);
+        Dft<R>::run(xi, xr);
+#pragma unroll
+        for (int j = 0; j < R; j++) p[slot_off<STRIDE>(j)] = make_cf(xr[j], xi[j]);
+    }
+}
+
+// value i of the staged half-rate block (packed pairs at the hr slots)
+RCG_HD float frame_value_hr(const cf* S, int i) {
+    cf v = S[phys(expand_hr(i >> 1))];
+    return (i & 1) ? v.y : v.x;
+}
+
+// ---- half-rate synthesis: last DIT pass + /W * window + overlap-add + envelope * amp on the even
+// samples only.  ye[i] = y[2i], i < H: i < Q is the emitted half window, the rest is carried.
+// The carried buffer, head_out / tail_in / tail_out then hold even samples ([Q] per channel).
+template <int LOG2H>
+RCG_HD void phase_ola_hr(cf* S, int t, const StretchParams& prm, int channel, long long frame,
+                         float* tail, bool emit, bool write_head) {
+    using C = FrameCfg<LOG2H>;
+    constexpr PlanDesc P = make_plan(LOG2H, true);
+    constexpr int RL = P.rlog2[0], R = 1 << RL, ML = P.mlog2[0], M = 1 << ML;
+    constexpr int RH = R / 2, Q = C::H / 2;
+    constexpr int STRIDE = (M == 1) ? 1 : 2 * M;
+    float* out = prm.out + (long long)channel * prm.out_stride;
+    if (prm.flags & kFlagBypass) {
+        // test hook: y[n] = (s[n] w[n]) w[n]; the load phase left s[2n] w[2n] in S[phys(n)].x
+        for (int i = t; i < Q; i += C::NT) {
+            const float y = RCG_MUL(S[phys(i)].x, prm.window_even[i]);
+            const float tl = RCG_MUL(S[phys(i + Q)].x, prm.window_even[i + Q]);
+            const float old = tail[i];
+            tail[i] = tl;
+            if (write_head) prm.head_out[(long long)channel * C::H + i] = y;
+            if (emit) {
+                const float z = RCG_MUL(RCG_MUL(RCG_ADD(y, old), prm.env_even[i]), prm.amp);
+                if (prm.pitch == 2) out[frame * (long long)Q + i - prm.out_origin] = z;
+                else S[phys(i)].x = z;  // staged in the slot only this thread reads
+            }
+        }
+        return;
+    }
+    const cf* tw = prm.tw + tw_offset(LOG2H, 0, true);
+#pragma unroll 2
+    for (int m = t; m < M; m += C::NT) {
+        cf* p = S + phys(expand_hr(m));
+        float xr[R], xi[R];
+#pragma unroll
+        for (int a = 0; a < R; a++) {
+            const cf v = p[slot_off<STRIDE>(a)];
+            xr[a] = v.x; xi[a] = v.y;
+        }
+        twiddle_butterfly<LOG2H, 0, true, R, true>(xr, xi, tw, m);
+        Dft<R>::run(xi, xr);
+#pragma unroll
+        for (int a = 0; a < RH; a++) {
+            const int n = m + a * M;   // packed index: even samples 2n, 2n+1 of the emitted half
+            const cf wa = ld_stream2(prm.window_even + 2 * n), wb = ld_stream2(prm.window_even + Q + 2 * n);
+            const float y0 = RCG_MUL(RCG_MUL(xr[a], prm.inv_w), wa.x), y1 = RCG_MUL(RCG_MUL(xi[a], prm.inv_w), wa.y);
+            const float t0 = RCG_MUL(RCG_MUL(xr[a + RH], prm.inv_w), wb.x), t1 = RCG_MUL(RCG_MUL(xi[a + RH], prm.inv_w), wb.y);
+            const cf old = ld_pair(tail + 2 * n);
+            st_pair(tail + 2 * n, t0, t1);
+            if (write_head) st_pair(prm.head_out + (long long)channel * C::H + 2 * n, y0, y1);
+            if (emit) {
+                const cf e = ld_stream2(prm.env_even + 2 * n);
+                const float z0 = RCG_MUL(RCG_MUL(RCG_ADD(y0, old.x), e.x), prm.amp);
+                const float z1 = RCG_MUL(RCG_MUL(RCG_ADD(y1, old.y), e.y), prm.amp);
+                if (prm.pitch == 2) {
+                    st_pair(out + (frame * (long long)Q + 2 * n - prm.out_origin), z0, z1);
+                } else {
+                    p[slot_off<STRIDE>(a)] = make_cf(z0, z1);  // staged for the decimating gather
+                }
+            }
+        }
+    }
+}
+
 // ---- EMIT part 2: integer resample of the finished half window held in S[0..H/2)
 // (resampler.rs:3-35).  p > 1: out[g / p] = z[g] for g % p == 0 (g = absolute index into the
 // overlap-added stream; calls tile it exactly since S = W*p).  p < -1: one frame per call;
 // the first S samples are linearly interpolated |p| times, S-1 intervals (math.rs:28-30).
 template <int LOG2H>
-RCG_HD void phase_resample(const cf* S, int t, const StretchParams& prm, int channel, long long frame) {
+RCG_HD void phase_resample(const cf* S, int t, const StretchParams& prm, int channel, long long frame,
+                           bool plain_stage = false) {
     using C = FrameCfg<LOG2H>;
     float* out = prm.out + (long long)channel * prm.out_stride;
     const int p = prm.pitch;
-    if (p > 1) {
+    if (p > 1 && (prm.flags & kFlagHalfRate)) {
+        // staged block = even samples ze[i] = z[2i], i < Q; out[g/p] = z[g] <=> out[ge/(p/2)] = ze[ge]
+        constexpr int Q = C::H / 2;
+        const int pe = p / 2;
+        const bool bypass = plain_stage || (prm.flags & kFlagBypass);  // staged as S[phys(i)].x
+        const long long g0 = frame * (long long)Q;
+        const long long o_begin = (g0 + pe - 1) / pe, o_end = (g0 + Q + pe - 1) / pe;
+        for (long long o = o_begin + t; o < o_end; o += C::NT) {
+            const int i = (int)(o * pe - g0);
+            out[o - prm.out_origin] = bypass ? S[phys(i)].x : frame_value_hr(S, i);
+        }
+    } else if (p > 1) {
         const long long g0 = frame * (long long)C::H;
         const long long o_begin = (g0 + p - 1) / p, o_end = (g0 + C::H + p - 1) / p;
         for (long long o = o_begin + t; o < o_end; o += C::NT) {
@@ -506,6 +694,14 @@ RCG_HD void phase_resample(const cf* S, int t, const StretchParams& prm, int cha
             const float ratio = RCG_DIV((float)j, (float)q);
             dst[tt] = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), ratio));
         }
+    }
+}
+
+template <int LOG2H, int PASS, class Exec>
+RCG_HD void fft_inv_hr(Exec& ex, cf* S, const StretchParams& prm, bool work) {
+    if constexpr (PASS >= 1) {
+        ex.par([&](int t) { if (work) phase_fft_pass_hr<LOG2H, PASS>(S, t, prm.tw); });
+        fft_inv_hr<LOG2H, PASS - 1>(ex, S, prm, work);
     }
 }
 
@@ -541,6 +737,7 @@ RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, f
         const float* src = have_tail_in ? prm.tail_in + (long long)channel * C::H : nullptr;
         for (int i = t; i < C::H; i += C::NT) tail[i] = src ? src[i] : 0.0f;
     });
+    const bool half_rate = prm.flags & kFlagHalfRate;
     const int n_iter = prm.run_len + 1;  // uniform trip count for every lane of the CTA
     for (int it = 0; it < n_iter; it++) {
         const long long f = f0 - 1 + it;
@@ -554,15 +751,26 @@ RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, f
             ex.par([&](int t) { if (work) phase_load<LOG2H>(S, t, prm, channel, f); });
             if (!bypass) {
                 fft_all<LOG2H, false, 1>(ex, S, prm, work);
-                ex.par([&](int t) { if (work) phase_spectral<LOG2H>(S, t, prm, channel, f); });
-                fft_all<LOG2H, true, C::NP - 1>(ex, S, prm, work);
+                if (half_rate) {
+                    ex.par([&](int t) { if (work) phase_spectral_hr<LOG2H>(S, t, prm, channel, f); });
+                    fft_inv_hr<LOG2H, C::NP - 1>(ex, S, prm, work);
+                } else {
+                    ex.par([&](int t) { if (work) phase_spectral<LOG2H>(S, t, prm, channel, f); });
+                    fft_all<LOG2H, true, C::NP - 1>(ex, S, prm, work);
+                }
             }
         }
         const bool head = work && defer && f == f0;
         const bool emit = work && !is_halo && !head;
-        ex.par([&](int t) { if (work) phase_ola<LOG2H>(S, t, prm, channel, f, tail, emit, head); });
-        if (prm.pitch != 1)
-            ex.par([&](int t) { if (emit) phase_resample<LOG2H>(S, t, prm, channel, f); });
+        if (half_rate) {
+            ex.par([&](int t) { if (work) phase_ola_hr<LOG2H>(S, t, prm, channel, f, tail, emit, head); });
+            if (prm.pitch != 2)
+                ex.par([&](int t) { if (emit) phase_resample<LOG2H>(S, t, prm, channel, f); });
+        } else {
+            ex.par([&](int t) { if (work) phase_ola<LOG2H>(S, t, prm, channel, f, tail, emit, head); });
+            if (prm.pitch != 1)
+                ex.par([&](int t) { if (emit) phase_resample<LOG2H>(S, t, prm, channel, f); });
+        }
     }
     if (prm.tail_out != nullptr) {
         ex.par([&](int t) {
@@ -596,6 +804,20 @@ RCG_HD void run_boundary(Exec& ex, cf* S, const StretchParams& prm, int channel,
     using C = FrameCfg<LOG2H>;
     float* out = prm.out + (long long)channel * prm.out_stride;
     const long long frame = prm.frame_begin;
+    if (prm.flags & kFlagHalfRate) {  // head / tail hold even samples: ze[i] = ((head + tail) * env[2i]) * amp
+        constexpr int Q = C::H / 2;
+        ex.par([&](int t) {
+            const float* h = head + (long long)channel * C::H;
+            const float* tp = tail_prev + (long long)channel * C::H;
+            for (int i = t; i < Q; i += C::NT) {
+                const float z = RCG_MUL(RCG_MUL(RCG_ADD(h[i], tp[i]), prm.env_even[i]), prm.amp);
+                if (prm.pitch == 2) out[frame * (long long)Q + i - prm.out_origin] = z;
+                else S[phys(i)].x = z;
+            }
+        });
+        if (prm.pitch != 2) ex.par([&](int t) { phase_resample<LOG2H>(S, t, prm, channel, frame, true); });
+        return;
+    }
     ex.par([&](int t) {
         for (int m = t; m < C::H / 2; m += C::NT) {
             const float* h = head + (long long)channel * C::H;

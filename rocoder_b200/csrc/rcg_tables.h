@@ -38,33 +38,36 @@ inline int rt_bin_to_pos(const PlanDesc& d, int k) {
     return pos;
 }
 
-// packed per-pass twiddles in the layout rcg_common.h's tw_scheme() prescribes
+// packed per-pass twiddles in the layout rcg_common.h's tw_scheme() prescribes: the full plan's
+// tables followed by the half-rate synthesis plan's
 inline std::vector<cf> host_pass_twiddles(int log2h) {
-    const PlanDesc d = make_plan(log2h);
     std::vector<cf> tw((size_t)std::max(tw_total(log2h), 1));
     const double two_pi = 6.283185307179586476925286766559;
     auto w = [&](double num, double den) {
         double a = -two_pi * num / den;
         return make_cf((float)cos(a), (float)sin(a));
     };
-    for (int p = 0; p < d.npasses; p++) {
-        const int M = 1 << d.mlog2[p], R = 1 << d.rlog2[p];
-        const double N = (double)R * (double)M;
-        cf* t = tw.data() + tw_offset(log2h, p);
-        switch (tw_scheme(log2h, p)) {
-            case kTwFull:
-                for (int j = 1; j < R; j++)
-                    for (int m = 0; m < M; m++) t[(j - 1) * M + m] = w((double)m * j, N);
-                break;
-            case kTwPow:
-                for (int i = 0; i < d.rlog2[p]; i++)
-                    for (int m = 0; m < M; m++) t[i * M + m] = w((double)m * (1 << i), N);
-                break;
-            case kTwTwoLevel:
-                for (int hi = 0; hi < M / 64; hi++) t[hi] = w((double)hi * 64, N);
-                for (int lo = 0; lo < 64; lo++) t[M / 64 + lo] = w((double)lo, N);
-                break;
-            default: break;
+    for (int hr = 0; hr < 2; hr++) {
+        const PlanDesc d = make_plan(log2h, hr != 0);
+        for (int p = 0; p < d.npasses; p++) {
+            const int M = 1 << d.mlog2[p], R = 1 << d.rlog2[p];
+            const double N = (double)R * (double)M;
+            cf* t = tw.data() + tw_offset(log2h, p, hr != 0);
+            switch (tw_scheme(log2h, p, hr != 0)) {
+                case kTwFull:
+                    for (int j = 1; j < R; j++)
+                        for (int m = 0; m < M; m++) t[(j - 1) * M + m] = w((double)m * j, N);
+                    break;
+                case kTwPow:
+                    for (int i = 0; i < d.rlog2[p]; i++)
+                        for (int m = 0; m < M; m++) t[i * M + m] = w((double)m * (1 << i), N);
+                    break;
+                case kTwTwoLevel:
+                    for (int hi = 0; hi < M / 64; hi++) t[hi] = w((double)hi * 64, N);
+                    for (int lo = 0; lo < 64; lo++) t[M / 64 + lo] = w((double)lo, N);
+                    break;
+                default: break;
+            }
         }
     }
     return tw;
@@ -83,6 +86,29 @@ inline std::vector<cf> host_spectral_twiddles(int log2h) {
         tw[c] = make_cf((float)cos(a), (float)sin(a));
     }
     return tw;
+}
+
+// half-rate synthesis: exp(-2 pi i k / W) for the bin k the quad slot c owns (k < W/8 ... in the
+// spectral step's order: c -> (rho, kl), kl < 4, position rho*16 + kl)
+inline std::vector<cf> host_spectral_twiddles_hr(int log2h) {
+    const PlanDesc d = make_plan(log2h);
+    const int H = 1 << log2h, RL = 1 << d.rlog2[d.npasses - 1], QUARTER = RL / 4;
+    std::vector<cf> tw((size_t)std::max(H / 4, 1));
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int c = 0; c < H / 4; c++) {
+        int rho = c / QUARTER, kl = c - rho * QUARTER;
+        int k = rt_pos_to_bin(d, rho * RL + kl);
+        double a = -two_pi * (double)k / (double)(2 * H);
+        tw[c] = make_cf((float)cos(a), (float)sin(a));
+    }
+    return tw;
+}
+
+// even samples of a table (half-rate synthesis reads window[2i], env[2i])
+inline std::vector<float> host_decimate2(const std::vector<float>& v) {
+    std::vector<float> o((v.size() + 1) / 2);
+    for (size_t i = 0; i < o.size(); i++) o[i] = v[2 * i];
+    return o;
 }
 
 }  // namespace rcg

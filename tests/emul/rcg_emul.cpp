@@ -18,6 +18,8 @@ struct HostExec {
     void par(F f) { for (int t = 0; t < nt; t++) f(t); }
 };
 
+static int g_disable_half_rate = 0;
+
 template <int LOG2H>
 static int emul_run(StretchParams prm) {
     using C = FrameCfg<LOG2H>;
@@ -26,7 +28,11 @@ static int emul_run(StretchParams prm) {
     host_hanning(window.data(), W);
     host_crossfade_compensation(env.data(), H);
     std::vector<cf> tw = host_pass_twiddles(LOG2H), stw = host_spectral_twiddles(LOG2H);
+    std::vector<cf> stw_hr = host_spectral_twiddles_hr(LOG2H);
+    std::vector<float> we = host_decimate2(window), ee = host_decimate2(env);
     prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.spec_tw = stw.data();
+    prm.spec_tw_hr = stw_hr.data(); prm.window_even = we.data(); prm.env_even = ee.data();
+    if (use_half_rate(prm.pitch, prm.flags) && !g_disable_half_rate) prm.flags |= kFlagHalfRate;
     std::vector<cf> S(C::SMEM_CF);
     std::vector<float> tail(H);
     HostExec ex{C::NT};
@@ -41,7 +47,9 @@ static int emul_boundary(StretchParams prm, const float* head, const float* tail
     using C = FrameCfg<LOG2H>;
     std::vector<float> env(C::H);
     host_crossfade_compensation(env.data(), C::H);
-    prm.env = env.data();
+    std::vector<float> ee = host_decimate2(env);
+    prm.env = env.data(); prm.env_even = ee.data();
+    if (use_half_rate(prm.pitch, prm.flags) && !g_disable_half_rate) prm.flags |= kFlagHalfRate;
     std::vector<cf> S(C::SMEM_CF);
     HostExec ex{C::NT};
     for (int c = 0; c < prm.channels; c++) run_boundary<LOG2H>(ex, S.data(), prm, c, head, tail_prev);
@@ -49,6 +57,9 @@ static int emul_boundary(StretchParams prm, const float* head, const float* tail
 }
 
 extern "C" {
+
+// force the full-rate synthesis path even for even pitch multiples (A/B checks)
+void rcg_emul_disable_half_rate(int v) { g_disable_half_rate = v; }
 
 // Processes frames [frame_begin, frame_end) of every channel.  See StretchParams.
 int rcg_emul_stretch(int log2w, const float* in, long long in_stride, long long in_origin,

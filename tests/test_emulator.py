@@ -98,3 +98,25 @@ def test_channel_index_keys_the_phases():
     calls = ol.expected_counts(6000, 2.0, 1, 256)[0]
     ol.emul_segment(np.ascontiguousarray(x[1:2]), 0, solo, 2.0, 1, 256, 0, calls, seed=1, first_channel=1)
     assert np.array_equal(solo[0], out[1])
+
+
+@pytest.mark.parametrize("p", [2, 4, 6])
+@pytest.mark.parametrize("W", [64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768])
+def test_half_rate_synthesis_even_pitch(p, W):
+    """even pitch multiples run the synthesis side at half size (only y[2n] survives the
+    decimation, resampler.rs:15-18): same results as the full-rate path up to rounding, for every
+    FFT plan shape, bit-exact indexing, and within tolerance of the oracle"""
+    n = 12 * W + 37
+    f = 2.0
+    x = _input(n, seed=W + p)
+    byp = ol.process_all(x, f, p, W, mode=ol.RO_PHASE_BYPASS)
+    assert np.array_equal(ol.emul_process_all(x, f, p, W, bypass=True), byp)
+    hr = ol.emul_process_all(x, f, p, W, seed=5)
+    ol.emulator().rcg_emul_disable_half_rate(1)
+    try:
+        full = ol.emul_process_all(x, f, p, W, seed=5)
+    finally:
+        ol.emulator().rcg_emul_disable_half_rate(0)
+    assert np.abs(hr - full).max() < 2e-6
+    ref = ol.process_all(x, f, p, W, seed=5, precision=64)
+    assert np.abs(hr - ref).max() <= 1e-4 and ol.snr_db(ref, hr) > 100.0
