@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librocoder_b200.so")
+# RCG_LIB selects another build of the same library (scripts/variant_bench.sh); never a fallback
+LIB_PATH = os.environ.get("RCG_LIB") or os.path.join(_HERE, "librocoder_b200.so")
 
 RCG_OK = 0
 RCG_ERR_INVALID_ARG = 1

@@ -11,6 +11,19 @@
 #include "rcg_dft.h"
 #include "rcg_philox.h"
 
+// tuning knobs (scripts/variant_bench.sh builds variants with -D...)
+#ifndef RCG_LOAD_UNROLL
+#define RCG_LOAD_UNROLL 2
+#endif
+#ifndef RCG_OLA_UNROLL
+#define RCG_OLA_UNROLL 2
+#endif
+#ifndef RCG_FUSE_OLA_LOAD
+#define RCG_FUSE_OLA_LOAD 1
+#endif
+#define RCG_PRAGMA(x) _Pragma(#x)
+#define RCG_UNROLL(n) RCG_PRAGMA(unroll n)
+
 #if defined(__CUDA_ARCH__)
 #define RCG_MUL(a, b) __fmul_rn((a), (b))
 #define RCG_ADD(a, b) __fadd_rn((a), (b))
@@ -29,6 +42,7 @@ enum : uint32_t {
     kFlagBypass = 1u,      // test hook: resynth(s)[n] = (s[n]*w[n])*w[n]  (no FFT, no phases)
     kFlagDeferFirst = 2u,  // do not emit block frame_begin; write its raw first half to head_out
     kFlagSpectrumIn = 4u,  // plugin path: magnitudes come from prm.spectrum (plugin output), not the FFT
+    kFlagNoFuse = 16u,     // tuning / test hook: keep load and overlap-add as separate phases
     kFlagHalfRate = 8u,    // even pitch multiple > 0: only even output samples survive the decimation
                            // (resampler.rs:15-18), so the synthesis side runs at half size
 };
@@ -197,40 +211,67 @@ RCG_HD constexpr int slot_off(int a) {
 // samples * window (fft.rs:51-58) -> even/odd packed complex z[n] = (x[2n], x[2n+1]) -> first
 // DIF pass straight from global memory -> shared memory.
 template <int LOG2H>
+struct LoadCtx {
+    const float* in;   // channel row
+    long long base;    // local index of the frame's first sample
+    bool bypass, aligned;
+    const cf* tw;
+};
+template <int LOG2H>
+RCG_HD LoadCtx<LOG2H> make_load_ctx(const StretchParams& prm, int channel, long long frame) {
+    using C = FrameCfg<LOG2H>;
+    LoadCtx<LOG2H> c;
+    c.in = prm.in + (long long)channel * prm.in_stride;
+    c.base = frame * (long long)prm.step - prm.in_origin;
+    c.bypass = prm.flags & kFlagBypass;
+    const bool interior = c.base >= 0 && c.base + C::W <= prm.in_valid;
+    c.aligned = interior && ((reinterpret_cast<unsigned long long>(c.in + c.base) & 7ull) == 0);
+    c.tw = prm.tw + tw_offset(LOG2H, 0);
+    return c;
+}
+// global loads of butterfly m of pass 0 (packed samples n = m + a*M) times the window
+template <int LOG2H, int R>
+RCG_HD void load_fetch(const LoadCtx<LOG2H>& c, const StretchParams& prm, int m, float (&xr)[R], float (&xi)[R]) {
+    constexpr int M = 1 << make_plan(LOG2H).mlog2[0];
+#pragma unroll
+    for (int a = 0; a < R; a++) {
+        const int n = m + a * M;  // packed index: samples 2n, 2n+1
+        float x0, x1;
+        if (c.aligned) {
+            const cf x = ld_stream2(c.in + c.base + 2 * n);
+            x0 = x.x; x1 = x.y;
+        } else {
+            const long long i0 = c.base + 2 * n;
+            x0 = (i0 >= 0 && i0 < prm.in_valid) ? ld_stream(c.in + i0) : 0.0f;
+            x1 = (i0 + 1 >= 0 && i0 + 1 < prm.in_valid) ? ld_stream(c.in + i0 + 1) : 0.0f;
+        }
+        const cf w = ld_stream2(prm.window + 2 * n);
+        xr[a] = RCG_MUL(x0, w.x); xi[a] = RCG_MUL(x1, w.y);
+    }
+}
+// first DIF pass on the fetched values -> shared memory
+template <int LOG2H, int R>
+RCG_HD void load_finish(cf* S, const LoadCtx<LOG2H>& c, int m, float (&xr)[R], float (&xi)[R]) {
+    constexpr int M = 1 << make_plan(LOG2H).mlog2[0];
+    if (!c.bypass) {
+        Dft<R>::run(xr, xi);
+        twiddle_butterfly<LOG2H, 0, false, R>(xr, xi, c.tw, m);
+    }
+    cf* p = S + phys(m);
+#pragma unroll
+    for (int j = 0; j < R; j++) p[slot_off<M>(j)] = make_cf(xr[j], xi[j]);
+}
+
+template <int LOG2H>
 RCG_HD void phase_load(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
     using C = FrameCfg<LOG2H>;
-    constexpr int RL = make_plan(LOG2H).rlog2[0], R = 1 << RL, ML = make_plan(LOG2H).mlog2[0], M = 1 << ML;
-    const float* in = prm.in + (long long)channel * prm.in_stride;
-    const long long base = frame * (long long)prm.step - prm.in_origin;
-    const bool bypass = prm.flags & kFlagBypass;
-    const bool interior = base >= 0 && base + C::W <= prm.in_valid;
-    const bool aligned = interior && ((reinterpret_cast<unsigned long long>(in + base) & 7ull) == 0);
-    const cf* tw = prm.tw + tw_offset(LOG2H, 0);
-#pragma unroll 2
+    constexpr int R = 1 << make_plan(LOG2H).rlog2[0], M = 1 << make_plan(LOG2H).mlog2[0];
+    const LoadCtx<LOG2H> c = make_load_ctx<LOG2H>(prm, channel, frame);
+RCG_UNROLL(RCG_LOAD_UNROLL)
     for (int m = t; m < M; m += C::NT) {
         float xr[R], xi[R];
-#pragma unroll
-        for (int a = 0; a < R; a++) {
-            const int n = m + a * M;  // packed index: samples 2n, 2n+1
-            float x0, x1;
-            if (aligned) {
-                const cf x = ld_stream2(in + base + 2 * n);
-                x0 = x.x; x1 = x.y;
-            } else {
-                const long long i0 = base + 2 * n;
-                x0 = (i0 >= 0 && i0 < prm.in_valid) ? ld_stream(in + i0) : 0.0f;
-                x1 = (i0 + 1 >= 0 && i0 + 1 < prm.in_valid) ? ld_stream(in + i0 + 1) : 0.0f;
-            }
-            const cf w = ld_stream2(prm.window + 2 * n);
-            xr[a] = RCG_MUL(x0, w.x); xi[a] = RCG_MUL(x1, w.y);
-        }
-        if (!bypass) {
-            Dft<R>::run(xr, xi);
-            twiddle_butterfly<LOG2H, 0, false, R>(xr, xi, tw, m);
-        }
-        cf* p = S + phys(m);
-#pragma unroll
-        for (int j = 0; j < R; j++) p[slot_off<M>(j)] = make_cf(xr[j], xi[j]);
+        load_fetch<LOG2H, R>(c, prm, m, xr, xi);
+        load_finish<LOG2H, R>(S, c, m, xr, xi);
     }
 }
 
@@ -509,18 +550,24 @@ RCG_HD float frame_value(const cf* S, int i) {
 // ((y + tail) * env) * amp.  A thread owns packed outputs n = m + a*M, a < R: those with a < R/2
 // are the first half window (emitted), the others the second half (carried to the next frame);
 // both map onto the same slots of the carried buffer, so no other thread ever touches them.
+// With load_next (pitch 1 only: nothing is staged in the slots) the thread then refills its own
+// slots with the next frame: no barrier is needed in between, and the next frame's global loads
+// are in flight while this frame's half window is finished.
 template <int LOG2H>
 RCG_HD void phase_ola(cf* S, int t, const StretchParams& prm, int channel, long long frame,
-                      float* tail, bool emit, bool write_head) {
+                      float* tail, bool emit, bool write_head, bool load_next = false) {
     using C = FrameCfg<LOG2H>;
     constexpr int RL = make_plan(LOG2H).rlog2[0], R = 1 << RL, ML = make_plan(LOG2H).mlog2[0], M = 1 << ML;
     constexpr int RH = R / 2;
     const bool bypass = prm.flags & kFlagBypass;
     float* out = prm.out + (long long)channel * prm.out_stride;
     const cf* tw = prm.tw + tw_offset(LOG2H, 0);
-#pragma unroll 2
+    const LoadCtx<LOG2H> nx = make_load_ctx<LOG2H>(prm, channel, frame + 1);
+RCG_UNROLL(RCG_OLA_UNROLL)
     for (int m = t; m < M; m += C::NT) {
         cf* p = S + phys(m);
+        float nr[R], ni[R];
+        if (load_next) load_fetch<LOG2H, R>(nx, prm, m, nr, ni);
         float xr[R], xi[R];
 #pragma unroll
         for (int a = 0; a < R; a++) {
@@ -557,6 +604,7 @@ RCG_HD void phase_ola(cf* S, int t, const StretchParams& prm, int channel, long 
                 }
             }
         }
+        if (load_next) load_finish<LOG2H, R>(S, nx, m, nr, ni);
     }
 }
 
@@ -596,9 +644,12 @@ RCG_HD float frame_value_hr(const cf* S, int i) {
 // ---- half-rate synthesis: last DIT pass + /W * window + overlap-add + envelope * amp on the even
 // samples only.  ye[i] = y[2i], i < H: i < Q is the emitted half window, the rest is carried.
 // The carried buffer, head_out / tail_in / tail_out then hold even samples ([Q] per channel).
+// With load_next (pitch 2 only) the thread then loads the next frame into the two pass-0
+// butterflies whose slots it owns or nobody uses any more: m1 = its own hr slot, m2 = m1 | 8 (the
+// sibling slot the half-rate inverse never touched).
 template <int LOG2H>
 RCG_HD void phase_ola_hr(cf* S, int t, const StretchParams& prm, int channel, long long frame,
-                         float* tail, bool emit, bool write_head) {
+                         float* tail, bool emit, bool write_head, bool load_next = false) {
     using C = FrameCfg<LOG2H>;
     constexpr PlanDesc P = make_plan(LOG2H, true);
     constexpr int RL = P.rlog2[0], R = 1 << RL, ML = P.mlog2[0], M = 1 << ML;
@@ -622,9 +673,15 @@ RCG_HD void phase_ola_hr(cf* S, int t, const StretchParams& prm, int channel, lo
         return;
     }
     const cf* tw = prm.tw + tw_offset(LOG2H, 0, true);
-#pragma unroll 2
+    const LoadCtx<LOG2H> nx = make_load_ctx<LOG2H>(prm, channel, frame + 1);
+RCG_UNROLL(RCG_OLA_UNROLL)
     for (int m = t; m < M; m += C::NT) {
         cf* p = S + phys(expand_hr(m));
+        float n1r[R], n1i[R], n2r[R], n2i[R];
+        if (load_next) {
+            load_fetch<LOG2H, R>(nx, prm, expand_hr(m), n1r, n1i);
+            load_fetch<LOG2H, R>(nx, prm, expand_hr(m) | 8, n2r, n2i);
+        }
         float xr[R], xi[R];
 #pragma unroll
         for (int a = 0; a < R; a++) {
@@ -652,6 +709,10 @@ RCG_HD void phase_ola_hr(cf* S, int t, const StretchParams& prm, int channel, lo
                     p[slot_off<STRIDE>(a)] = make_cf(z0, z1);  // staged for the decimating gather
                 }
             }
+        }
+        if (load_next) {
+            load_finish<LOG2H, R>(S, nx, expand_hr(m), n1r, n1i);
+            load_finish<LOG2H, R>(S, nx, expand_hr(m) | 8, n2r, n2i);
         }
     }
 }
@@ -738,17 +799,28 @@ RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, f
         for (int i = t; i < C::H; i += C::NT) tail[i] = src ? src[i] : 0.0f;
     });
     const bool half_rate = prm.flags & kFlagHalfRate;
+    const bool bypass = prm.flags & kFlagBypass;
+    const bool spectrum_in = prm.flags & kFlagSpectrumIn;
+    // Load of frame f+1 fused into the overlap-add phase of frame f: possible when that phase leaves
+    // nothing staged in shared memory (pitch 1, or pitch 2 on the half-rate path).
+    const bool fuse = RCG_FUSE_OLA_LOAD && !(prm.flags & kFlagNoFuse) && !bypass && !spectrum_in &&
+                      (half_rate ? prm.pitch == 2 : prm.pitch == 1);
     const int n_iter = prm.run_len + 1;  // uniform trip count for every lane of the CTA
+    if (fuse) {
+        const bool pro = active && (halo || f0 < f1);
+        const long long first = halo ? f0 - 1 : f0;
+        ex.par([&](int t) { if (pro) phase_load<LOG2H>(S, t, prm, channel, first); });
+    }
     for (int it = 0; it < n_iter; it++) {
         const long long f = f0 - 1 + it;
         const bool is_halo = (it == 0);
         const bool work = active && (is_halo ? halo : f < f1);
-        const bool bypass = prm.flags & kFlagBypass;
-        if (prm.flags & kFlagSpectrumIn) {
+        const bool load_next = fuse && work && (it + 1 < n_iter) && (f + 1 < f1);
+        if (spectrum_in) {
             ex.par([&](int t) { if (work) phase_spectral_in<LOG2H>(S, t, prm, channel, f); });
             fft_all<LOG2H, true, C::NP - 1>(ex, S, prm, work);
         } else {
-            ex.par([&](int t) { if (work) phase_load<LOG2H>(S, t, prm, channel, f); });
+            if (!fuse) ex.par([&](int t) { if (work) phase_load<LOG2H>(S, t, prm, channel, f); });
             if (!bypass) {
                 fft_all<LOG2H, false, 1>(ex, S, prm, work);
                 if (half_rate) {
@@ -763,11 +835,11 @@ RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, f
         const bool head = work && defer && f == f0;
         const bool emit = work && !is_halo && !head;
         if (half_rate) {
-            ex.par([&](int t) { if (work) phase_ola_hr<LOG2H>(S, t, prm, channel, f, tail, emit, head); });
+            ex.par([&](int t) { if (work) phase_ola_hr<LOG2H>(S, t, prm, channel, f, tail, emit, head, load_next); });
             if (prm.pitch != 2)
                 ex.par([&](int t) { if (emit) phase_resample<LOG2H>(S, t, prm, channel, f); });
         } else {
-            ex.par([&](int t) { if (work) phase_ola<LOG2H>(S, t, prm, channel, f, tail, emit, head); });
+            ex.par([&](int t) { if (work) phase_ola<LOG2H>(S, t, prm, channel, f, tail, emit, head, load_next); });
             if (prm.pitch != 1)
                 ex.par([&](int t) { if (emit) phase_resample<LOG2H>(S, t, prm, channel, f); });
         }

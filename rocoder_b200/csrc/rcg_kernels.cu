@@ -21,8 +21,11 @@ struct DeviceExec {
     }
 };
 
+#ifndef RCG_MIN_CTAS
+#define RCG_MIN_CTAS 3
+#endif
 template <int LOG2H>
-constexpr int min_ctas() { return LOG2H >= 14 ? 1 : 3; }
+constexpr int min_ctas() { return LOG2H >= 14 ? 1 : RCG_MIN_CTAS; }
 
 template <int LOG2H>
 __global__ void __launch_bounds__(FrameCfg<LOG2H>::NT * FrameCfg<LOG2H>::FPC, min_ctas<LOG2H>())
@@ -112,6 +115,13 @@ static cudaError_t boundary_t(const StretchParams& prm, const float* head, const
     return cudaGetLastError();
 }
 
+#ifdef RCG_ONLY_LOG2H  /* experiment builds: one window size only, to compile in seconds */
+#define RCG_DISPATCH(log2w, CALL)                                    \
+    switch ((log2w) - 1) {                                           \
+        case RCG_ONLY_LOG2H: return CALL(RCG_ONLY_LOG2H);            \
+        default: return cudaErrorInvalidValue;                       \
+    }
+#else
 #define RCG_DISPATCH(log2w, CALL)                                    \
     switch ((log2w) - 1) {                                           \
         case 5: return CALL(5);   case 6: return CALL(6);            \
@@ -121,6 +131,7 @@ static cudaError_t boundary_t(const StretchParams& prm, const float* head, const
         case 13: return CALL(13); case 14: return CALL(14);          \
         default: return cudaErrorInvalidValue;                       \
     }
+#endif
 
 cudaError_t stretch_geometry(int log2w, LaunchGeometry* g) {
 #define CALL(L) geometry_t<L>(g)

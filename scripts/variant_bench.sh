@@ -1,0 +1,12 @@
+#!/bin/bash
+# Build variants of the kernels (only W=16384) with different -D flags on the GPU box and time them.
+# usage: bash scripts/variant_bench.sh "name1:-DFOO=1 -DBAR=2" "name2:..." ...
+mkdir -p gpurun_out/variants
+for spec in "$@"; do
+  name="${spec%%:*}"; flags="${spec#*:}"
+  out=gpurun_out/variants/lib_${name}.so
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC -shared \
+       -DRCG_ONLY_LOG2H=13 $flags -o $out rocoder_b200/csrc/rcg_kernels.cu rocoder_b200/csrc/rcg_engine.cu -ldl 2> gpurun_out/variants/${name}.build.log \
+    || { echo "{\"tag\": \"$name\", \"error\": \"build failed\"}"; continue; }
+  RCG_LIB=$out python scripts/kernel_time.py --tag "$name" $KT_ARGS 2>> gpurun_out/variants/${name}.build.log
+done

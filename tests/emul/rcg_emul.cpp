@@ -12,13 +12,21 @@
 
 using namespace rcg;
 
+// Threads of a phase run one after the other.  A phase must not depend on the order (no thread may
+// read what another wrote in the same phase): the tests run every case in ascending and descending
+// thread order and demand identical results, which exposes intra-phase races.
+static int g_reverse_threads = 0;
 struct HostExec {
     int nt;
     template <class F>
-    void par(F f) { for (int t = 0; t < nt; t++) f(t); }
+    void par(F f) {
+        if (g_reverse_threads) for (int t = nt - 1; t >= 0; t--) f(t);
+        else for (int t = 0; t < nt; t++) f(t);
+    }
 };
 
 static int g_disable_half_rate = 0;
+static int g_no_fuse = 0;
 
 template <int LOG2H>
 static int emul_run(StretchParams prm) {
@@ -33,6 +41,7 @@ static int emul_run(StretchParams prm) {
     prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.spec_tw = stw.data();
     prm.spec_tw_hr = stw_hr.data(); prm.window_even = we.data(); prm.env_even = ee.data();
     if (use_half_rate(prm.pitch, prm.flags) && !g_disable_half_rate) prm.flags |= kFlagHalfRate;
+    if (g_no_fuse) prm.flags |= kFlagNoFuse;
     std::vector<cf> S(C::SMEM_CF);
     std::vector<float> tail(H);
     HostExec ex{C::NT};
@@ -60,6 +69,9 @@ extern "C" {
 
 // force the full-rate synthesis path even for even pitch multiples (A/B checks)
 void rcg_emul_disable_half_rate(int v) { g_disable_half_rate = v; }
+// keep load and overlap-add as separate phases (A/B checks of the fused phase)
+void rcg_emul_no_fuse(int v) { g_no_fuse = v; }
+void rcg_emul_reverse_threads(int v) { g_reverse_threads = v; }
 
 // Processes frames [frame_begin, frame_end) of every channel.  See StretchParams.
 int rcg_emul_stretch(int log2w, const float* in, long long in_stride, long long in_origin,

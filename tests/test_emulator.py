@@ -120,3 +120,40 @@ def test_half_rate_synthesis_even_pitch(p, W):
     assert np.abs(hr - full).max() < 2e-6
     ref = ol.process_all(x, f, p, W, seed=5, precision=64)
     assert np.abs(hr - ref).max() <= 1e-4 and ol.snr_db(ref, hr) > 100.0
+
+
+@pytest.mark.parametrize("n,f,p,W", [(30000, 4.0, 1, 2048), (40000, 8.0, 2, 4096), (70000, 8.0, 2, 16384),
+                                     (100000, 1.0, 1, 16384), (3000, 2.0, 2, 64), (5000, 1.0, 1, 256),
+                                     (90000, 3.0, 1, 32768), (9000, 2.0, 2, 1024)])
+@pytest.mark.parametrize("run_len", [1, 4, 1000])
+def test_fused_ola_load_phase_is_bit_identical(n, f, p, W, run_len):
+    """pitch 1 / pitch 2 fuse the next frame's load into the overlap-add phase (no barrier between):
+    bit-identical to the separate phases, for every run length (halo frames, ragged last runs)"""
+    x = _input(n, seed=W)
+    fused = ol.emul_process_all(x, f, p, W, seed=5, run_len=run_len)
+    ol.emulator().rcg_emul_no_fuse(1)
+    try:
+        plain = ol.emul_process_all(x, f, p, W, seed=5, run_len=run_len)
+    finally:
+        ol.emulator().rcg_emul_no_fuse(0)
+    assert not np.isnan(fused).any()
+    assert np.array_equal(fused, plain)
+
+
+@pytest.mark.parametrize("n,f,p,W", [(30000, 4.0, 1, 2048), (40000, 8.0, 2, 4096), (70000, 8.0, 2, 16384),
+                                     (9000, 20.0, -3, 1024), (6000, 2.5, 5, 512), (9000, 2.0, 4, 1024),
+                                     (90000, 3.0, 1, 32768), (3000, 2.0, 2, 64)])
+def test_phases_are_race_free(n, f, p, W):
+    """no thread reads, within one phase, what another thread wrote in that phase: executing the
+    emulated threads in descending instead of ascending order changes nothing (full path, bypass path)"""
+    x = _input(n, seed=W + 1)
+    E = ol.emulator()
+    a = ol.emul_process_all(x, f, p, W, seed=5)
+    b0 = ol.emul_process_all(x, f, p, W, bypass=True)
+    E.rcg_emul_reverse_threads(1)
+    try:
+        b = ol.emul_process_all(x, f, p, W, seed=5)
+        b1 = ol.emul_process_all(x, f, p, W, bypass=True)
+    finally:
+        E.rcg_emul_reverse_threads(0)
+    assert np.array_equal(a, b) and np.array_equal(b0, b1)
