@@ -13,13 +13,13 @@
 
 // tuning knobs (scripts/variant_bench.sh builds variants with -D...)
 #ifndef RCG_LOAD_UNROLL
-#define RCG_LOAD_UNROLL 2
+#define RCG_LOAD_UNROLL 4
 #endif
 #ifndef RCG_OLA_UNROLL
 #define RCG_OLA_UNROLL 2
 #endif
 #ifndef RCG_FUSE_OLA_LOAD
-#define RCG_FUSE_OLA_LOAD 1
+#define RCG_FUSE_OLA_LOAD 0   // measured slower on B200 (9.1 vs 8.0 ms on config 2): off by default
 #endif
 #define RCG_PRAGMA(x) _Pragma(#x)
 #define RCG_UNROLL(n) RCG_PRAGMA(unroll n)
@@ -230,14 +230,16 @@ RCG_HD LoadCtx<LOG2H> make_load_ctx(const StretchParams& prm, int channel, long 
     return c;
 }
 // global loads of butterfly m of pass 0 (packed samples n = m + a*M) times the window
-template <int LOG2H, int R>
+// (ALIGNED: the whole frame lies inside the input and is 8-byte aligned -> branch-free float2 loads,
+// which lets the compiler batch the loads of several unrolled iterations)
+template <int LOG2H, int R, bool ALIGNED>
 RCG_HD void load_fetch(const LoadCtx<LOG2H>& c, const StretchParams& prm, int m, float (&xr)[R], float (&xi)[R]) {
     constexpr int M = 1 << make_plan(LOG2H).mlog2[0];
 #pragma unroll
     for (int a = 0; a < R; a++) {
         const int n = m + a * M;  // packed index: samples 2n, 2n+1
         float x0, x1;
-        if (c.aligned) {
+        if constexpr (ALIGNED) {
             const cf x = ld_stream2(c.in + c.base + 2 * n);
             x0 = x.x; x1 = x.y;
         } else {
@@ -250,10 +252,10 @@ RCG_HD void load_fetch(const LoadCtx<LOG2H>& c, const StretchParams& prm, int m,
     }
 }
 // first DIF pass on the fetched values -> shared memory
-template <int LOG2H, int R>
+template <int LOG2H, int R, bool BYPASS = false>
 RCG_HD void load_finish(cf* S, const LoadCtx<LOG2H>& c, int m, float (&xr)[R], float (&xi)[R]) {
     constexpr int M = 1 << make_plan(LOG2H).mlog2[0];
-    if (!c.bypass) {
+    if constexpr (!BYPASS) {
         Dft<R>::run(xr, xi);
         twiddle_butterfly<LOG2H, 0, false, R>(xr, xi, c.tw, m);
     }
@@ -267,11 +269,25 @@ RCG_HD void phase_load(cf* S, int t, const StretchParams& prm, int channel, long
     using C = FrameCfg<LOG2H>;
     constexpr int R = 1 << make_plan(LOG2H).rlog2[0], M = 1 << make_plan(LOG2H).mlog2[0];
     const LoadCtx<LOG2H> c = make_load_ctx<LOG2H>(prm, channel, frame);
+    if (c.bypass) {
+        for (int m = t; m < M; m += C::NT) {
+            float xr[R], xi[R];
+            load_fetch<LOG2H, R, false>(c, prm, m, xr, xi);
+            load_finish<LOG2H, R, true>(S, c, m, xr, xi);
+        }
+    } else if (c.aligned) {
 RCG_UNROLL(RCG_LOAD_UNROLL)
-    for (int m = t; m < M; m += C::NT) {
-        float xr[R], xi[R];
-        load_fetch<LOG2H, R>(c, prm, m, xr, xi);
-        load_finish<LOG2H, R>(S, c, m, xr, xi);
+        for (int m = t; m < M; m += C::NT) {
+            float xr[R], xi[R];
+            load_fetch<LOG2H, R, true>(c, prm, m, xr, xi);
+            load_finish<LOG2H, R>(S, c, m, xr, xi);
+        }
+    } else {
+        for (int m = t; m < M; m += C::NT) {
+            float xr[R], xi[R];
+            load_fetch<LOG2H, R, false>(c, prm, m, xr, xi);
+            load_finish<LOG2H, R>(S, c, m, xr, xi);
+        }
     }
 }
 
@@ -553,13 +569,13 @@ RCG_HD float frame_value(const cf* S, int i) {
 // With load_next (pitch 1 only: nothing is staged in the slots) the thread then refills its own
 // slots with the next frame: no barrier is needed in between, and the next frame's global loads
 // are in flight while this frame's half window is finished.
-template <int LOG2H>
-RCG_HD void phase_ola(cf* S, int t, const StretchParams& prm, int channel, long long frame,
-                      float* tail, bool emit, bool write_head, bool load_next = false) {
+template <int LOG2H, bool BYPASS>
+RCG_HD void phase_ola_impl(cf* S, int t, const StretchParams& prm, int channel, long long frame,
+                           float* tail, bool emit, bool write_head, bool load_next) {
     using C = FrameCfg<LOG2H>;
     constexpr int RL = make_plan(LOG2H).rlog2[0], R = 1 << RL, ML = make_plan(LOG2H).mlog2[0], M = 1 << ML;
     constexpr int RH = R / 2;
-    const bool bypass = prm.flags & kFlagBypass;
+    constexpr bool bypass = BYPASS;
     float* out = prm.out + (long long)channel * prm.out_stride;
     const cf* tw = prm.tw + tw_offset(LOG2H, 0);
     const LoadCtx<LOG2H> nx = make_load_ctx<LOG2H>(prm, channel, frame + 1);
@@ -567,14 +583,14 @@ RCG_UNROLL(RCG_OLA_UNROLL)
     for (int m = t; m < M; m += C::NT) {
         cf* p = S + phys(m);
         float nr[R], ni[R];
-        if (load_next) load_fetch<LOG2H, R>(nx, prm, m, nr, ni);
+        if (load_next) load_fetch<LOG2H, R, false>(nx, prm, m, nr, ni);
         float xr[R], xi[R];
 #pragma unroll
         for (int a = 0; a < R; a++) {
             const cf v = p[slot_off<M>(a)];
             xr[a] = v.x; xi[a] = v.y;
         }
-        if (!bypass) {
+        if constexpr (!bypass) {
             twiddle_butterfly<LOG2H, 0, true, R>(xr, xi, tw, m);
             Dft<R>::run(xi, xr);
         }
@@ -583,7 +599,7 @@ RCG_UNROLL(RCG_OLA_UNROLL)
             const int n = m + a * M;              // packed index inside the first half window
             const cf wa = ld_stream2(prm.window + 2 * n), wb = ld_stream2(prm.window + C::H + 2 * n);
             float y0, y1, t0, t1;
-            if (bypass) {
+            if constexpr (bypass) {
                 y0 = RCG_MUL(xr[a], wa.x); y1 = RCG_MUL(xi[a], wa.y);
                 t0 = RCG_MUL(xr[a + RH], wb.x); t1 = RCG_MUL(xi[a + RH], wb.y);
             } else {
@@ -592,9 +608,9 @@ RCG_UNROLL(RCG_OLA_UNROLL)
             }
             const cf old = ld_pair(tail + 2 * n);
             st_pair(tail + 2 * n, t0, t1);
+            const cf e = ld_stream2(prm.env + 2 * n);   // unconditional: keeps the loop body free of branches around loads
             if (write_head) st_pair(prm.head_out + (long long)channel * C::H + 2 * n, y0, y1);
             if (emit) {
-                const cf e = ld_stream2(prm.env + 2 * n);
                 const float z0 = RCG_MUL(RCG_MUL(RCG_ADD(y0, old.x), e.x), prm.amp);
                 const float z1 = RCG_MUL(RCG_MUL(RCG_ADD(y1, old.y), e.y), prm.amp);
                 if (prm.pitch == 1) {
@@ -606,6 +622,12 @@ RCG_UNROLL(RCG_OLA_UNROLL)
         }
         if (load_next) load_finish<LOG2H, R>(S, nx, m, nr, ni);
     }
+}
+template <int LOG2H>
+RCG_HD void phase_ola(cf* S, int t, const StretchParams& prm, int channel, long long frame,
+                      float* tail, bool emit, bool write_head, bool load_next = false) {
+    if (prm.flags & kFlagBypass) phase_ola_impl<LOG2H, true>(S, t, prm, channel, frame, tail, emit, write_head, false);
+    else phase_ola_impl<LOG2H, false>(S, t, prm, channel, frame, tail, emit, write_head, load_next);
 }
 
 // ---- half-rate synthesis: inverse DIT pass PASS >= 1 of the Q-point transform ---------------------
@@ -679,8 +701,8 @@ RCG_UNROLL(RCG_OLA_UNROLL)
         cf* p = S + phys(expand_hr(m));
         float n1r[R], n1i[R], n2r[R], n2i[R];
         if (load_next) {
-            load_fetch<LOG2H, R>(nx, prm, expand_hr(m), n1r, n1i);
-            load_fetch<LOG2H, R>(nx, prm, expand_hr(m) | 8, n2r, n2i);
+            load_fetch<LOG2H, R, false>(nx, prm, expand_hr(m), n1r, n1i);
+            load_fetch<LOG2H, R, false>(nx, prm, expand_hr(m) | 8, n2r, n2i);
         }
         float xr[R], xi[R];
 #pragma unroll
@@ -698,9 +720,9 @@ RCG_UNROLL(RCG_OLA_UNROLL)
             const float t0 = RCG_MUL(RCG_MUL(xr[a + RH], prm.inv_w), wb.x), t1 = RCG_MUL(RCG_MUL(xi[a + RH], prm.inv_w), wb.y);
             const cf old = ld_pair(tail + 2 * n);
             st_pair(tail + 2 * n, t0, t1);
+            const cf e = ld_stream2(prm.env_even + 2 * n);  // unconditional: no branches around loads
             if (write_head) st_pair(prm.head_out + (long long)channel * C::H + 2 * n, y0, y1);
             if (emit) {
-                const cf e = ld_stream2(prm.env_even + 2 * n);
                 const float z0 = RCG_MUL(RCG_MUL(RCG_ADD(y0, old.x), e.x), prm.amp);
                 const float z1 = RCG_MUL(RCG_MUL(RCG_ADD(y1, old.y), e.y), prm.amp);
                 if (prm.pitch == 2) {
