@@ -1,0 +1,64 @@
+"""Time sharding across real GPUs over NCCL (skipped on a single-GPU box): 2 ranks stretch one
+long input with the carried half window exchanged once; the concatenated result equals the
+single-GPU run bit for bit."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, f, p, W, n, tmp):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ol.ROOT)
+    import rocoder_b200 as rb
+    from rocoder_b200.sharding import TimeShardedStretch, input_span
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        rng = np.random.default_rng(9)
+        x = ((rng.random((2, n), dtype=np.float32) * 2 - 1) * 0.5).astype(np.float32)
+        eng = rb.Engine(2, 48000, W, f, 1.0, p, seed=5, device=rank)
+        calls = eng.expected_counts(n)[0]
+        job = TimeShardedStretch(eng, eng.plan, 2, calls, rank, world, torch.device("cuda", rank))
+        s0, s1 = input_span(eng.plan, job.c0, job.c1, n)
+        seg = torch.from_numpy(np.ascontiguousarray(x[:, s0:s1])).cuda()
+        out = torch.full((2, max(job.out_len(), 2)), float("nan"), device="cuda")
+        job.run(seg, s0, out, stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        np.save(os.path.join(tmp, f"out{rank}.npy"), out.cpu().numpy()[:, :job.out_len()])
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("f,p,W,n", [(8.0, 2, 16384, 400000), (3.0, -3, 4096, 200000), (2.0, 1, 1024, 90000)])
+def test_two_gpus_equal_one(tmp_path, f, p, W, n):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import rocoder_b200 as rb
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), f, p, W, n, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(9)
+    x = ((rng.random((2, n), dtype=np.float32) * 2 - 1) * 0.5).astype(np.float32)
+    with rb.Engine(2, 48000, W, f, 1.0, p, seed=5) as e:
+        whole = e.process_all(x)
+    got = np.concatenate([np.load(tmp_path / f"out{r}.npy") for r in range(world)], axis=1)
+    assert np.array_equal(got, whole)
