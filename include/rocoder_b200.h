@@ -126,8 +126,8 @@ int rcg_process_all(rcg_engine *e, const float *const *in, uint64_t n_in, float 
  * d_tail_out (optional) receives the second half of the last frame.  `stream` is a
  * cudaStream_t: NULL = the engine's own non-blocking stream; pass cudaStreamLegacy
  * ((cudaStream_t)0x1) to name the default stream explicitly.  The call is asynchronous on it
- * (with frequency kernels pushed it synchronises: the spectra visit the host).  d_out, the
- * tail / head buffers must be 8-byte aligned and out_stride even.  One launch at a time per
+ * (with frequency kernels pushed it synchronises: the spectra visit the host).  The tail / head
+ * buffers must be 8-byte aligned; for pitch multiples 1 and 2 so must d_out, with out_stride even.  One launch at a time per
  * engine: the carried-half-window scratch is shared by consecutive launches. */
 #define RCG_SEG_DEFER_FIRST 1u
 typedef struct rcg_segment {

@@ -369,9 +369,13 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
                           int channel_offset = 0, const SpectrumRef* spec = nullptr) {
     if (s.n_calls == 0) return RCG_OK;
     auto misaligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) != 0; };
-    if (misaligned(s.d_out) || (s.out_stride & 1) || misaligned(s.d_tail_in) || misaligned(s.d_tail_out) ||
-        misaligned(s.d_head_out))
-        return fail(RCG_ERR_INVALID_ARG, "d_out / tail / head buffers must be 8-byte aligned and out_stride even");
+    // float2 stores: the carried / head buffers always; the output only where it is written
+    // directly from the overlap-add phase (pitch 1, and pitch 2 on the half-rate path)
+    const bool direct_out = e->cfg.pitch_multiple == 1 || (e->cfg.pitch_multiple == 2 && engine_half_rate(e));
+    if (misaligned(s.d_tail_in) || misaligned(s.d_tail_out) || misaligned(s.d_head_out))
+        return fail(RCG_ERR_INVALID_ARG, "tail / head buffers must be 8-byte aligned");
+    if (direct_out && (misaligned(s.d_out) || (s.out_stride & 1)))
+        return fail(RCG_ERR_INVALID_ARG, "d_out must be 8-byte aligned and out_stride even for pitch multiples 1 and 2");
     StretchParams p;
     fill_params(e, p);
     if (spec) {

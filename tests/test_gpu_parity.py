@@ -229,3 +229,27 @@ def test_full_size_config2_properties():
     head = ol.process_all(x[:1, :16384 * 3], 8.0, 2, 16384, seed=1234, precision=64)
     m = 16384 * 8  # calls whose frames never touch the oracle's zero padding
     assert np.abs(out[0, :m] - head[0, :m]).max() <= TOL_MAX_ABS
+
+
+def test_odd_output_stride_with_negative_pitch():
+    """p <= -2 emits (S-1)*|p| samples per call (odd for W=4096, p=-3): segments then start at odd,
+    4-byte-aligned offsets; only the direct-store modes (pitch 1 / 2) need 8-byte alignment"""
+    import torch
+    n, f, p, W = 60000, 3.0, -3, 4096
+    x = _input(n, seed=2)
+    with rb.Engine(2, 48000, W, f, 1.0, p, seed=5) as e:
+        whole = e.process_all(x)
+        calls, _, out_len = e.expected_counts(n)
+        olen = e.plan["out_len_per_call"]
+        assert olen % 2 == 1
+        dx = torch.from_numpy(x).cuda()
+        out = torch.full((2, out_len), float("nan"), device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        e.process_segment(dx, dx.stride(0), 0, n, out, out.stride(0), 0, 1, stream=st)
+        e.process_segment(dx, dx.stride(0), 0, n, out[:, olen:], out.stride(0), 1, calls - 1, stream=st)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), whole)
+    with rb.Engine(2, 48000, W, 2.0, 1.0, 1, seed=5) as e:   # pitch 1 still insists on alignment
+        out = torch.zeros((2, 8 * W + 1), device="cuda")
+        with pytest.raises(rb.RcgError):
+            e.process_segment(dx, dx.stride(0), 0, n, out[:, 1:], out.stride(0), 0, 2, stream=st)

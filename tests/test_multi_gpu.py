@@ -59,8 +59,10 @@ def _worker(rank, world, port, f, p, W, n, tmp):
         np.save(os.path.join(tmp, f"out{rank}.npy"), out.cpu().numpy()[:, :job.out_len()])
         dist.barrier()
         _log(tmp, rank, "done")
-    finally:
         dist.destroy_process_group()
+    except BaseException as exc:  # never hang the peer in a collective: die loudly instead
+        _log(tmp, rank, f"FAILED: {exc!r}")
+        os._exit(1)
 
 
 @pytest.mark.timeout(150)
