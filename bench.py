@@ -43,6 +43,15 @@ N_IN = SAMPLE_RATE * SECONDS
 WORKLOAD = "config2: 10 min stereo 48 kHz noise+chirp, -f 8 -p 2 -w 16384"
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/)"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"]), d["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -246,6 +255,7 @@ def run_ours(args):
         kt.append(kev0.elapsed_time(kev1))
     k_ms = statistics.mean(kt)
     peak, peak_src = measured_peaks()
+    traffic, traffic_src = measured_traffic() if world == 1 else (None, None)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     flops = frames * CHANNELS * (2 * 5 * WINDOW * 14 + 20 * WINDOW)
 
@@ -283,7 +293,7 @@ def run_ours(args):
                        "frames_per_gpu": frames * CHANNELS, "l2": "inputs+outputs larger than L2 (0.23 GB in, 1.84 GB out per step)",
                        "exchange": "channels x W/2 fp32 carried half window, rank r -> r+1, NCCL p2p" if world > 1 else "none"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "stretch_kernel<13>",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "stretch_kernel<13>",
                          "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                          "fp32_tflops_algorithmic": flops / (k_ms * 1e-3) / 1e12,
                          "note": "compute(FP32/shared-memory)-bound path: see DESIGN.md for why frac is capped"},
