@@ -89,8 +89,8 @@ extern "C" int rcg_plan(const rcg_config* cfg, rcg_plan_info* out) {
     if (p < -127 || p > 127) return fail(RCG_ERR_PITCH, "pitch_multiple outside the reference's i8 range");
     const uint32_t W = cfg->window_len;
     const int l2 = log2_exact(W);
-    if (l2 < 6 || l2 > 15)
-        return fail(RCG_ERR_WINDOW, "window_len %u: need a power of two in [64, 32768]", W);
+    if (l2 < 6 || l2 > 16)
+        return fail(RCG_ERR_WINDOW, "window_len %u: need a power of two in [64, 65536]", W);
     if (cfg->channels == 0) return fail(RCG_ERR_INVALID_ARG, "channels must be >= 1");
     const float abs_p = (float)(p < 0 ? -p : p);
     // stretcher.rs:42-46
@@ -186,6 +186,9 @@ struct rcg_engine {
     uint64_t seed = 0;
     float *d_window = nullptr, *d_env = nullptr, *d_scratch = nullptr, *d_window_even = nullptr, *d_env_even = nullptr;
     cf *d_tw = nullptr, *d_spec_tw = nullptr, *d_spec_tw_hr = nullptr;
+    bool pair = false;        // W = 65536: a frame across a 2-CTA cluster
+    PairTables pt{};
+    cf *d_pair_cross = nullptr, *d_pair_even = nullptr, *d_pair_odd = nullptr;
     cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
     uint64_t launches = 0;
     // process_all buffers (grow only)
@@ -259,15 +262,32 @@ extern "C" int rcg_create(const rcg_config* cfg, rcg_engine** out) {
         if (_e != cudaSuccess)                                                                       \
             return bail(fail(RCG_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)));        \
     } while (0)
-    TRY_E(stretch_geometry(e->log2w, &e->geo));
-    if (e->geo.max_ctas_per_sm < 1) return bail(fail(RCG_ERR_CUDA, "stretch kernel does not fit on an SM"));
-    e->max_grid = e->sm_count * e->geo.max_ctas_per_sm;
+    e->pair = (e->log2w == 16);
+    if (e->pair) {
+        TRY_E(pair_geometry(&e->geo));
+        e->max_grid = e->sm_count / 2;   // clusters
+    } else {
+        TRY_E(stretch_geometry(e->log2w, &e->geo));
+        if (e->geo.max_ctas_per_sm < 1) return bail(fail(RCG_ERR_CUDA, "stretch kernel does not fit on an SM"));
+        e->max_grid = e->sm_count * e->geo.max_ctas_per_sm;
+    }
     const size_t W = cfg->window_len, H = W / 2;
     std::vector<float> window(W), env(H);
     host_hanning(window.data(), W);           // main.rs:131
     host_crossfade_compensation(env.data(), H);  // stretcher.rs:56
-    std::vector<cf> tw = host_pass_twiddles(e->log2w - 1), stw = host_spectral_twiddles(e->log2w - 1);
-    std::vector<cf> stw_hr = host_spectral_twiddles_hr(e->log2w - 1);
+    const int plan_log2h = e->pair ? kPairLog2HL : e->log2w - 1;   // the in-CTA transform
+    std::vector<cf> tw = host_pass_twiddles(plan_log2h), stw = host_spectral_twiddles(plan_log2h);
+    std::vector<cf> stw_hr = host_spectral_twiddles_hr(plan_log2h);
+    if (e->pair) {
+        std::vector<cf> cross = host_pair_cross_twiddles(e->log2w - 1);
+        std::vector<cf> se = host_pair_spectral_twiddles(e->log2w - 1, 0), so = host_pair_spectral_twiddles(e->log2w - 1, 1);
+        TRY_E(cudaMalloc(&e->d_pair_cross, cross.size() * sizeof(cf)));
+        TRY_E(cudaMalloc(&e->d_pair_even, se.size() * sizeof(cf)));
+        TRY_E(cudaMalloc(&e->d_pair_odd, so.size() * sizeof(cf)));
+        TRY_E(cudaMemcpy(e->d_pair_cross, cross.data(), cross.size() * sizeof(cf), cudaMemcpyHostToDevice));
+        TRY_E(cudaMemcpy(e->d_pair_even, se.data(), se.size() * sizeof(cf), cudaMemcpyHostToDevice));
+        TRY_E(cudaMemcpy(e->d_pair_odd, so.data(), so.size() * sizeof(cf), cudaMemcpyHostToDevice));
+    }
     std::vector<float> we = host_decimate2(window), ee = host_decimate2(env);
     TRY_E(cudaMalloc(&e->d_window_even, we.size() * sizeof(float)));
     TRY_E(cudaMalloc(&e->d_env_even, ee.size() * sizeof(float)));
@@ -279,7 +299,10 @@ extern "C" int rcg_create(const rcg_config* cfg, rcg_engine** out) {
     TRY_E(cudaMalloc(&e->d_env, H * sizeof(float)));
     TRY_E(cudaMalloc(&e->d_tw, std::max<size_t>(tw.size(), 1) * sizeof(cf)));
     TRY_E(cudaMalloc(&e->d_spec_tw, stw.size() * sizeof(cf)));
-    TRY_E(cudaMalloc(&e->d_scratch, (size_t)e->max_grid * e->geo.frames_per_cta * H * sizeof(float)));
+    const size_t scratch_floats = e->pair ? (size_t)std::max<int>(e->max_grid, (int)cfg->channels) * 3 * H
+                                          : (size_t)e->max_grid * e->geo.frames_per_cta * H;
+    TRY_E(cudaMalloc(&e->d_scratch, scratch_floats * sizeof(float)));
+    e->pt = PairTables{e->d_pair_cross, e->d_pair_even, e->d_pair_odd, e->d_scratch};
     TRY_E(cudaMemcpy(e->d_window, window.data(), W * sizeof(float), cudaMemcpyHostToDevice));
     TRY_E(cudaMemcpy(e->d_env, env.data(), H * sizeof(float), cudaMemcpyHostToDevice));
     TRY_E(cudaMemcpy(e->d_tw, tw.data(), tw.size() * sizeof(cf), cudaMemcpyHostToDevice));
@@ -307,6 +330,7 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     if (e->h2d) cudaStreamSynchronize(e->h2d);
     cudaFree(e->d_window); cudaFree(e->d_env); cudaFree(e->d_tw); cudaFree(e->d_spec_tw); cudaFree(e->d_scratch);
     cudaFree(e->d_window_even); cudaFree(e->d_env_even); cudaFree(e->d_spec_tw_hr);
+    cudaFree(e->d_pair_cross); cudaFree(e->d_pair_even); cudaFree(e->d_pair_odd);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_tail_pp[0]); cudaFree(e->d_tail_pp[1]);
     cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_spec);
     cudaFree(e->d_plug_tail[0]); cudaFree(e->d_plug_tail[1]);
@@ -344,7 +368,7 @@ extern "C" int rcg_synchronize(rcg_engine* e) {
 // then runs at half size.  Not with frequency kernels loaded (that path keeps the full layout), so
 // the carried half windows of fused and plugin launches are never mixed within one engine state.
 static bool engine_half_rate(const rcg_engine* e) {
-    return use_half_rate(e->cfg.pitch_multiple, 0u) && e->kernels.empty() && !e->had_kernels;
+    return use_half_rate(e->cfg.pitch_multiple, 0u) && e->kernels.empty() && !e->had_kernels && !e->pair;
 }
 
 static void fill_params(const rcg_engine* e, StretchParams& p) {
@@ -407,7 +431,7 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
     const long long items = (long long)p.n_runs * channels;
     const int groups = (int)((items + e->geo.frames_per_cta - 1) / e->geo.frames_per_cta);
     const int grid = std::min(groups, e->max_grid);
-    cudaError_t ce = launch_stretch(e->log2w, p, grid, stream);
+    cudaError_t ce = e->pair ? launch_stretch_pair(p, e->pt, grid, stream) : launch_stretch(e->log2w, p, grid, stream);
     if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "stretch kernel launch failed: %s", cudaGetErrorString(ce));
     e->launches++;
     return RCG_OK;
@@ -508,6 +532,8 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
 }
 
 static int run_segment(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream, int channel_offset) {
+    if (e->pair && !e->kernels.empty())
+        return fail(RCG_ERR_PLUGIN, "frequency kernels are not supported at window_len 65536 yet");
     if (!e->kernels.empty() && !(e->cfg.flags & RCG_FLAG_BYPASS_RESYNTH))
         return run_segment_plugins(e, s, channels, stream, channel_offset);
     return launch_segment(e, s, channels, stream, channel_offset);
@@ -531,7 +557,8 @@ extern "C" int rcg_finish_boundary(rcg_engine* e, float* d_out, int64_t out_stri
     p.frame_begin = (long long)(first_call * e->plan.frames_per_call);
     if (engine_half_rate(e)) p.flags |= kFlagHalfRate;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    cudaError_t ce = launch_boundary(e->log2w, p, d_head, d_tail_prev, st);
+    cudaError_t ce = e->pair ? launch_boundary_pair(p, e->pt, d_head, d_tail_prev, st)
+                             : launch_boundary(e->log2w, p, d_head, d_tail_prev, st);
     if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "boundary kernel launch failed: %s", cudaGetErrorString(ce));
     e->launches++;
     return RCG_OK;

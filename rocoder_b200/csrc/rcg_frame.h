@@ -428,7 +428,8 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
 // ---- SPECTRAL: real-FFT split -> |X[k]| -> random phases for all W bins -> Hermitian
 // fold -> pre-pass of the real inverse (fft.rs:63-69).  One thread owns the bin pair
 // (k, H-k) of the half-size transform, i.e. bins {k, W-k, H-k, H+k} of the W-point one.
-template <int LOG2H>
+// KMUL: the global bin index of local bin j is j*KMUL (2 for the even-bin half of a CTA pair).
+template <int LOG2H, int KMUL = 1>
 RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
     using C = FrameCfg<LOG2H>;
     constexpr int HALF = C::RLAST / 2;
@@ -451,7 +452,7 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
             // k = H/2 pairs with itself: X[H/2] = conj(Z[H/2]); Z'[H/2] = 2 conj(Y[H/2])
             const int pq = phys(bin_to_pos<LOG2H>(C::H / 2));
             cf zq = S[pq];
-            philox4x32_10((uint32_t)(C::H / 2), f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
+            philox4x32_10((uint32_t)(C::H / 2 * KMUL), f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
             float mq = fast_sqrt(zq.x * zq.x + zq.y * zq.y);
             float sa, ca, sb, cb;
             sincos_phase(phase_from_u32(u[0]), sa, ca);
@@ -462,7 +463,7 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
         const int pa = phys(pos), pb = phys(bin_to_pos<LOG2H>(C::H - k));
         const cf za = S[pa], zb = S[pb];
         const cf tw = ld_cf(prm.spec_tw + c);  // exp(-2 pi i k / W)
-        philox4x32_10((uint32_t)k, f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
+        philox4x32_10((uint32_t)(k * KMUL), f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
         // A = Y[k] + conj(Y[H-k]), B = Y[k] - conj(Y[H-k]), Cc = i conj(t) B
         float ar, ai, br, bi;
         pair_fold(za, zb, tw, u, ar, ai, br, bi);

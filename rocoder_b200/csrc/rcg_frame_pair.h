@@ -1,0 +1,244 @@
+// rcg_frame_pair.h -- W = 65536: one frame across a 2-CTA thread-block cluster.
+//
+// The packed H = 32768 point complex transform (256 KB) does not fit one SM's shared memory, so
+// the first DIF radix-2 stage is taken across the CTA pair: CTA 0 keeps u[n] = z[n] + z[n+H/2]
+// (-> even bins), CTA 1 keeps v[n] = (z[n] - z[n+H/2]) w_H^n (-> odd bins); each then runs the
+// ordinary 16384-point in-place transform of rcg_frame.h on its half.  The spectral step stays
+// local because bin k pairs with H-k of the same parity.  After the local inverses the last DIT
+// radix-2 stage reads the peer's half through distributed shared memory: CTA 0 produces the
+// first half window (emitted), CTA 1 the second half (carried to the next frame through a
+// double-buffered global scratch).  Same reference arithmetic as rcg_frame.h (fft.rs:42-74,
+// stretcher.rs:96-112, resampler.rs:3-35).
+#pragma once
+#include "rcg_frame.h"
+
+namespace rcg {
+
+constexpr int kPairLog2HL = 14;              // local transform: 16384 points
+constexpr int kPairHL = 1 << kPairLog2HL;    // H/2
+constexpr int kPairH = 2 * kPairHL;          // 32768
+constexpr int kPairW = 2 * kPairH;           // 65536
+constexpr int kPairTwLen = kPairHL / 64 + 64;  // two-level table for w_H^n, n < H/2
+
+struct PairTables {
+    const cf* cross_tw;      // [kPairTwLen]: A[n >> 6] (exp(-2 pi i 64 a / H)) then B[n & 63]
+    const cf* spec_tw_even;  // [HL/2]: exp(-2 pi i (2j) / W) in the local pair order
+    const cf* spec_tw_odd;   // [HL/2]: exp(-2 pi i (2j+1) / W)
+    float* scratch;          // per cluster: tail[2][H] then stage[H]
+};
+
+RCG_HD cf pair_cross_tw(const cf* tab, int n) {
+    const cf a = ld_cf(tab + (n >> 6)), b = ld_cf(tab + kPairHL / 64 + (n & 63));
+    cf w;
+    cmul(a.x, a.y, b.x, b.y, w.x, w.y);
+    return w;
+}
+
+// ---- LOAD + cross-CTA radix-2 DIF stage ---------------------------------------------------------
+RCG_HD void pair_phase_load(cf* S, int r, int t, const StretchParams& prm, const PairTables& pt, int channel,
+                            long long frame) {
+    using C = FrameCfg<kPairLog2HL>;
+    const float* in = prm.in + (long long)channel * prm.in_stride;
+    const long long base = frame * (long long)prm.step - prm.in_origin;
+    const bool bypass = prm.flags & kFlagBypass;
+    auto sample = [&](long long i) { return (i >= 0 && i < prm.in_valid) ? ld_stream(in + i) : 0.0f; };
+    for (int n = t; n < kPairHL; n += C::NT) {
+        const cf wa = ld_stream2(prm.window + 2 * n), wb = ld_stream2(prm.window + kPairH + 2 * n);
+        const float a0 = RCG_MUL(sample(base + 2 * n), wa.x), a1 = RCG_MUL(sample(base + 2 * n + 1), wa.y);
+        const float b0 = RCG_MUL(sample(base + kPairH + 2 * n), wb.x), b1 = RCG_MUL(sample(base + kPairH + 2 * n + 1), wb.y);
+        cf v;
+        if (bypass) {
+            v = r == 0 ? make_cf(a0, a1) : make_cf(b0, b1);
+        } else if (r == 0) {
+            v = make_cf(a0 + b0, a1 + b1);
+        } else {
+            const cf w = pair_cross_tw(pt.cross_tw, n);
+            const float dr = a0 - b0, di = a1 - b1;
+            v = make_cf(dr * w.x - di * w.y, di * w.x + dr * w.y);
+        }
+        S[phys(n)] = v;
+    }
+}
+
+// ---- SPECTRAL, odd bins (CTA 1): k = 2j+1 pairs with H-k = 2(HL-1-j)+1; no self-paired bins ----
+RCG_HD void pair_phase_spectral_odd(cf* S, int t, const StretchParams& prm, const PairTables& pt, int channel,
+                                    long long frame) {
+    using C = FrameCfg<kPairLog2HL>;
+    constexpr int HALF = C::RLAST / 2;
+    const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
+    const uint32_t chan = (uint32_t)(channel + prm.channel_offset);
+    for (int c = t; c < kPairHL / 2; c += C::NT) {
+        const int rho = c / HALF, kl = c - rho * HALF;
+        const int pos = rho * C::RLAST + kl;
+        const int j = pos_to_bin<kPairLog2HL>(pos);
+        const int k = 2 * j + 1;
+        const int pa = phys(pos), pb = phys(bin_to_pos<kPairLog2HL>(kPairHL - 1 - j));
+        const cf za = S[pa], zb = S[pb];
+        const cf tw = ld_cf(pt.spec_tw_odd + c);
+        uint32_t u[4];
+        philox4x32_10((uint32_t)k, f_lo, f_hi, chan, prm.keys, u);
+        float ar, ai, br, bi;
+        pair_fold(za, zb, tw, u, ar, ai, br, bi);
+        const float cr = -(tw.x * bi - tw.y * br), ci = tw.x * br + tw.y * bi;
+        S[pa] = make_cf(ar + cr, ai + ci);
+        S[pb] = make_cf(ar - cr, -(ai - ci));
+    }
+}
+
+// ---- cross-CTA radix-2 DIT stage + overlap-add -------------------------------------------------------
+// CTA 0: first half window: /W * window, + carried half, * envelope * amp, emit (pitch 1) or stage
+// in global memory for the resampling gather.  CTA 1: second half window -> carried buffer.
+RCG_HD void pair_phase_ola(const cf* S, const cf* peer, int r, int t, const StretchParams& prm, const PairTables& pt,
+                           int channel, long long frame, const float* tail_old, float* tail_new, float* stage,
+                           bool emit, bool write_head) {
+    using C = FrameCfg<kPairLog2HL>;
+    const bool bypass = prm.flags & kFlagBypass;
+    float* out = prm.out + (long long)channel * prm.out_stride;
+    const float scale = bypass ? 1.0f : prm.inv_w;
+    for (int n = t; n < kPairHL; n += C::NT) {
+        float zr, zi;
+        if (bypass) {
+            const cf own = S[phys(n)];
+            zr = own.x; zi = own.y;
+        } else {
+            const cf u = r == 0 ? S[phys(n)] : peer[phys(n)];
+            const cf v = r == 0 ? peer[phys(n)] : S[phys(n)];
+            const cf w = pair_cross_tw(pt.cross_tw, n);  // conj(w) v
+            const float pr = v.x * w.x + v.y * w.y, pi = v.y * w.x - v.x * w.y;
+            zr = r == 0 ? u.x + pr : u.x - pr;
+            zi = r == 0 ? u.y + pi : u.y - pi;
+        }
+        if (r == 0) {
+            const cf wa = ld_stream2(prm.window + 2 * n);
+            const float y0 = RCG_MUL(RCG_MUL(zr, scale), wa.x), y1 = RCG_MUL(RCG_MUL(zi, scale), wa.y);
+            if (write_head) st_pair(prm.head_out + (long long)channel * kPairH + 2 * n, y0, y1);
+            if (emit) {
+                const cf old = ld_pair(tail_old + 2 * n);
+                const cf e = ld_stream2(prm.env + 2 * n);
+                const float z0 = RCG_MUL(RCG_MUL(RCG_ADD(y0, old.x), e.x), prm.amp);
+                const float z1 = RCG_MUL(RCG_MUL(RCG_ADD(y1, old.y), e.y), prm.amp);
+                if (prm.pitch == 1) st_pair(out + (frame * (long long)kPairH + 2 * n - prm.out_origin), z0, z1);
+                else st_pair(stage + 2 * n, z0, z1);
+            }
+        } else {
+            const cf wb = ld_stream2(prm.window + kPairH + 2 * n);
+            st_pair(tail_new + 2 * n, RCG_MUL(RCG_MUL(zr, scale), wb.x), RCG_MUL(RCG_MUL(zi, scale), wb.y));
+        }
+    }
+}
+
+// resample from the staged half window in global memory (CTA 0 only)
+RCG_HD void pair_phase_resample(const float* stage, int t, const StretchParams& prm, int channel, long long frame) {
+    using C = FrameCfg<kPairLog2HL>;
+    float* out = prm.out + (long long)channel * prm.out_stride;
+    const int p = prm.pitch;
+    if (p > 1) {
+        const long long g0 = frame * (long long)kPairH;
+        const long long o_begin = (g0 + p - 1) / p, o_end = (g0 + kPairH + p - 1) / p;
+        for (long long o = o_begin + t; o < o_end; o += C::NT) out[o - prm.out_origin] = stage[(int)(o * p - g0)];
+    } else if (p < -1) {
+        const int q = -p;
+        const int n = (prm.samples_needed - 1) * q;
+        float* dst = out + (frame * (long long)n - prm.out_origin);
+        for (int tt = t; tt < n; tt += C::NT) {
+            const int i = tt / q, j = tt - i * q;
+            const float cur = stage[i], nxt = stage[i + 1];
+            dst[tt] = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), RCG_DIV((float)j, (float)q)));
+        }
+    }
+}
+
+// Exec for the pair: par(f) runs f(r, t) for every thread of both CTAs, then a CTA barrier;
+// par_cluster(f) ends in a cluster barrier (release/acquire) instead.  bufs[r] is CTA r's buffer.
+template <int PASS, bool INV, class Exec>
+RCG_HD void pair_fft_all(Exec& ex, cf* const (&bufs)[2], const StretchParams& prm, bool work) {
+    if constexpr (PASS >= 0 && PASS < FrameCfg<kPairLog2HL>::NP) {
+        ex.par([&](int r, int t) { if (work) phase_fft_pass<kPairLog2HL, PASS, INV>(bufs[r], t, prm.tw); });
+        pair_fft_all<INV ? PASS - 1 : PASS + 1, INV>(ex, bufs, prm, work);
+    }
+}
+
+template <class Exec>
+RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], const StretchParams& prm, const PairTables& pt,
+                               int item, float* scratch, bool active) {
+    using C = FrameCfg<kPairLog2HL>;
+    const int channel = active ? item / prm.n_runs : 0;
+    const int run = active ? item - channel * prm.n_runs : 0;
+    const long long f0 = prm.frame_begin + (long long)run * prm.run_len;
+    long long f1 = f0 + prm.run_len;
+    if (f1 > prm.frame_end) f1 = prm.frame_end;
+    const bool first_run = (run == 0);
+    const bool defer = first_run && (prm.flags & kFlagDeferFirst) && f0 > 0;
+    const bool have_tail_in = first_run && prm.tail_in != nullptr && f0 > 0;
+    const bool halo = active && f0 > 0 && !defer && !have_tail_in;
+    const bool bypass = prm.flags & kFlagBypass;
+    float* tails[2] = {scratch, scratch + kPairH};
+    float* stage = scratch + 2 * kPairH;
+    // carried half window for the first iteration lives in tails[0]
+    ex.par_cluster([&](int r, int t) {
+        if (!active || r != 1) return;
+        const float* src = have_tail_in ? prm.tail_in + (long long)channel * kPairH : nullptr;
+        for (int i = t; i < kPairH; i += C::NT) tails[0][i] = src ? src[i] : 0.0f;
+    });
+    const int n_iter = prm.run_len + 1;
+    int cnt = 0;  // frames done so far: the carried half window is in tails[cnt & 1]
+    for (int it = 0; it < n_iter; it++) {
+        const long long f = f0 - 1 + it;
+        const bool is_halo = (it == 0);
+        const bool work = active && (is_halo ? halo : f < f1);
+        const bool head = work && defer && f == f0;
+        const bool emit = work && !is_halo && !head;
+        ex.par([&](int r, int t) { if (work) pair_phase_load(bufs[r], r, t, prm, pt, channel, f); });
+        if (!bypass) {
+            pair_fft_all<0, false>(ex, bufs, prm, work);
+            ex.par([&](int r, int t) {
+                if (!work) return;
+                if (r == 0) {
+                    StretchParams pe = prm;
+                    pe.spec_tw = pt.spec_tw_even;
+                    phase_spectral<kPairLog2HL, 2>(bufs[0], t, pe, channel, f);
+                } else {
+                    pair_phase_spectral_odd(bufs[1], t, prm, pt, channel, f);
+                }
+            });
+            pair_fft_all<C::NP - 1, true>(ex, bufs, prm, work);
+        }
+        ex.cluster_sync();   // both halves of the inverse are complete
+        ex.par_cluster([&](int r, int t) {   // ends in a cluster barrier: peers are done reading, tails are visible
+            if (work) pair_phase_ola(bufs[r], bufs[r ^ 1], r, t, prm, pt, channel, f, tails[cnt & 1], tails[(cnt & 1) ^ 1],
+                                     stage, emit, head);
+        });
+        if (work) cnt++;
+        if (prm.pitch != 1)
+            ex.par([&](int r, int t) { if (emit && r == 0) pair_phase_resample(stage, t, prm, channel, f); });
+    }
+    if (prm.tail_out != nullptr) {
+        ex.par([&](int r, int t) {
+            if (!active || f1 != prm.frame_end || r != 1) return;
+            const float* last = tails[cnt & 1];
+            float* dst = prm.tail_out + (long long)channel * kPairH;
+            for (int i = t; i < kPairH; i += C::NT) dst[i] = last[i];
+        });
+    }
+}
+
+// boundary block at W = 65536 (one CTA per channel, staging in the cluster scratch of slot `channel`)
+template <class ExecCta>
+RCG_HD void run_boundary_pair(ExecCta& ex, const StretchParams& prm, int channel, const float* head,
+                              const float* tail_prev, float* stage) {
+    using C = FrameCfg<kPairLog2HL>;
+    float* out = prm.out + (long long)channel * prm.out_stride;
+    const long long frame = prm.frame_begin;
+    ex.par([&](int t) {
+        const float* h = head + (long long)channel * kPairH;
+        const float* tp = tail_prev + (long long)channel * kPairH;
+        for (int i = t; i < kPairH; i += C::NT) {
+            const float z = RCG_MUL(RCG_MUL(RCG_ADD(h[i], tp[i]), prm.env[i]), prm.amp);
+            if (prm.pitch == 1) out[frame * (long long)kPairH + i - prm.out_origin] = z;
+            else stage[i] = z;
+        }
+    });
+    if (prm.pitch != 1) ex.par([&](int t) { pair_phase_resample(stage, t, prm, channel, frame); });
+}
+
+}  // namespace rcg

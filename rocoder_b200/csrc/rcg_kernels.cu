@@ -10,6 +10,12 @@
 // output sample exactly once.  No tensor cores: nothing here is a dense contraction.
 #include "rcg_kernels.h"
 
+#include <cooperative_groups.h>
+
+#include "rcg_frame_pair.h"
+
+namespace cg = cooperative_groups;
+
 namespace rcg {
 
 struct DeviceExec {
@@ -66,6 +72,68 @@ boundary_kernel(const __grid_constant__ StretchParams prm, const float* head, co
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeviceExec ex{(int)threadIdx.x};
     run_boundary<LOG2H>(ex, reinterpret_cast<cf*>(smem_raw), prm, (int)blockIdx.x, head, tail_prev);
+}
+
+// ---- W = 65536: a frame across a 2-CTA cluster (rcg_frame_pair.h) -------------------------------
+struct PairDeviceExec {
+    int r, t;
+    template <class F>
+    __device__ __forceinline__ void par(F f) {
+        f(r, t);
+        __syncthreads();
+    }
+    template <class F>
+    __device__ __forceinline__ void par_cluster(F f) {
+        f(r, t);
+        __threadfence();            // carried half windows travel through global memory
+        cg::this_cluster().sync();  // barrier.cluster arrive.release / wait.acquire
+    }
+    __device__ __forceinline__ void cluster_sync() { cg::this_cluster().sync(); }
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FrameCfg<kPairLog2HL>::NT, 1)
+stretch_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, int n_items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank();
+    cf* S = reinterpret_cast<cf*>(smem_raw);
+    cf* bufs[2];
+    bufs[r] = S;
+    bufs[r ^ 1] = cluster.map_shared_rank(S, r ^ 1);   // the peer's half, read through DSMEM
+    PairDeviceExec ex{r, (int)threadIdx.x};
+    const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
+    float* scratch = pt.scratch + (long long)cid * 3 * kPairH;
+    for (int item = cid; item < n_items; item += ncl) run_work_item_pair(ex, bufs, prm, pt, item, scratch, true);
+    cluster.sync();  // no CTA may exit while its peer can still read its shared memory
+}
+
+__global__ void __launch_bounds__(FrameCfg<kPairLog2HL>::NT)
+boundary_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, const float* head,
+                     const float* tail_prev) {
+    DeviceExec ex{(int)threadIdx.x};
+    float* stage = pt.scratch + (long long)blockIdx.x * 3 * kPairH + 2 * kPairH;
+    run_boundary_pair(ex, prm, (int)blockIdx.x, head, tail_prev, stage);
+}
+
+cudaError_t pair_geometry(LaunchGeometry* g) {
+    using C = FrameCfg<kPairLog2HL>;
+    g->threads = C::NT;
+    g->frames_per_cta = 1;
+    g->smem_bytes = (size_t)C::SMEM_CF * sizeof(cf);
+    g->max_ctas_per_sm = 1;
+    return cudaFuncSetAttribute(stretch_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
+}
+cudaError_t launch_stretch_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream) {
+    using C = FrameCfg<kPairLog2HL>;
+    const int n_items = prm.channels * prm.n_runs;
+    if (n_items <= 0) return cudaSuccess;
+    stretch_pair_kernel<<<2 * n_clusters, C::NT, (size_t)C::SMEM_CF * sizeof(cf), stream>>>(prm, pt, n_items);
+    return cudaGetLastError();
+}
+cudaError_t launch_boundary_pair(const StretchParams& prm, const PairTables& pt, const float* head, const float* tail_prev,
+                                 cudaStream_t stream) {
+    boundary_pair_kernel<<<prm.channels, FrameCfg<kPairLog2HL>::NT, 0, stream>>>(prm, pt, head, tail_prev);
+    return cudaGetLastError();
 }
 
 template <int LOG2H>

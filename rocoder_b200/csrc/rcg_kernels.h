@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "rcg_frame.h"
+#include "rcg_frame_pair.h"
 
 namespace rcg {
 
@@ -22,5 +23,12 @@ cudaError_t launch_stretch(int log2w, const StretchParams& prm, int grid, cudaSt
 cudaError_t launch_analysis(int log2w, const StretchParams& prm, int grid, cudaStream_t stream);
 cudaError_t launch_boundary(int log2w, const StretchParams& prm, const float* head, const float* tail_prev,
                             cudaStream_t stream);
+
+// W = 65536 (log2w == 16): a frame across a 2-CTA cluster; pt.scratch holds 3*H floats per cluster
+// (and per channel for the boundary kernel)
+cudaError_t pair_geometry(LaunchGeometry* g);
+cudaError_t launch_stretch_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream);
+cudaError_t launch_boundary_pair(const StretchParams& prm, const PairTables& pt, const float* head, const float* tail_prev,
+                                 cudaStream_t stream);
 
 }  // namespace rcg

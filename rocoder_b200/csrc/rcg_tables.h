@@ -104,6 +104,32 @@ inline std::vector<cf> host_spectral_twiddles_hr(int log2h) {
     return tw;
 }
 
+// ---- W = 65536 (CTA pair, rcg_frame_pair.h) ---------------------------------------------------
+// two-level table for w_H^n = exp(-2 pi i n / H), n < H/2: A[n >> 6] then B[n & 63]
+inline std::vector<cf> host_pair_cross_twiddles(int log2h) {
+    const int H = 1 << log2h, HL = H / 2;
+    std::vector<cf> tw((size_t)HL / 64 + 64);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int a = 0; a < HL / 64; a++) { double x = -two_pi * (double)(a * 64) / H; tw[a] = make_cf((float)cos(x), (float)sin(x)); }
+    for (int b = 0; b < 64; b++) { double x = -two_pi * (double)b / H; tw[HL / 64 + b] = make_cf((float)cos(x), (float)sin(x)); }
+    return tw;
+}
+// exp(-2 pi i (2j + odd) / W) for the local bin j the pair slot c of the half-size plan owns
+inline std::vector<cf> host_pair_spectral_twiddles(int log2h, int odd) {
+    const int log2hl = log2h - 1;
+    const PlanDesc d = make_plan(log2hl);
+    const int HL = 1 << log2hl, RL = 1 << d.rlog2[d.npasses - 1], HALF = RL / 2;
+    std::vector<cf> tw((size_t)HL / 2);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int c = 0; c < HL / 2; c++) {
+        int rho = c / HALF, kl = c - rho * HALF;
+        int j = rt_pos_to_bin(d, rho * RL + kl);
+        double a = -two_pi * (double)(2 * j + odd) / (double)(4 * HL);
+        tw[c] = make_cf((float)cos(a), (float)sin(a));
+    }
+    return tw;
+}
+
 // even samples of a table (half-rate synthesis reads window[2i], env[2i])
 inline std::vector<float> host_decimate2(const std::vector<float>& v) {
     std::vector<float> o((v.size() + 1) / 2);

@@ -23,4 +23,7 @@ LARGE_CASES = [
     (60000, 20.0, -3, 16384),   # config 4
     (90000, 3.0, 1, 32768),
     (50000, 2.0, 1, 16384),     # config 5
+    (300000, 4.0, 1, 65536),    # config 3's largest window: a frame across a 2-CTA cluster
+    (200000, 4.0, 2, 65536),
+    (200000, 3.0, -3, 65536),
 ]

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../rocoder_b200/csrc/rcg_frame.h"
+#include "../../rocoder_b200/csrc/rcg_frame_pair.h"
 #include "../../rocoder_b200/csrc/rcg_tables.h"
 
 using namespace rcg;
@@ -51,6 +52,51 @@ static int emul_run(StretchParams prm) {
     return 0;
 }
 
+// W = 65536: both CTAs of the pair, phase by phase
+struct PairHostExec {
+    int nt;
+    template <class F>
+    void par(F f) {
+        for (int r = 0; r < 2; r++) {
+            const int rr = g_reverse_threads ? 1 - r : r;
+            if (g_reverse_threads) for (int t = nt - 1; t >= 0; t--) f(rr, t);
+            else for (int t = 0; t < nt; t++) f(rr, t);
+        }
+    }
+    template <class F>
+    void par_cluster(F f) { par(f); }
+    void cluster_sync() {}
+};
+
+static int emul_run_pair(StretchParams prm) {
+    using C = FrameCfg<kPairLog2HL>;
+    std::vector<float> window(kPairW), env(kPairH);
+    host_hanning(window.data(), kPairW);
+    host_crossfade_compensation(env.data(), kPairH);
+    std::vector<cf> tw = host_pass_twiddles(kPairLog2HL);
+    std::vector<cf> cross = host_pair_cross_twiddles(kPairLog2HL + 1);
+    std::vector<cf> se = host_pair_spectral_twiddles(kPairLog2HL + 1, 0), so = host_pair_spectral_twiddles(kPairLog2HL + 1, 1);
+    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data();
+    std::vector<float> scratch(3 * (size_t)kPairH);
+    PairTables pt{cross.data(), se.data(), so.data(), scratch.data()};
+    std::vector<cf> S0(C::SMEM_CF), S1(C::SMEM_CF);
+    cf* bufs[2] = {S0.data(), S1.data()};
+    PairHostExec ex{C::NT};
+    const int items = prm.channels * prm.n_runs;
+    for (int item = 0; item < items; item++) run_work_item_pair(ex, bufs, prm, pt, item, scratch.data(), true);
+    return 0;
+}
+
+static int emul_boundary_pair(StretchParams prm, const float* head, const float* tail_prev) {
+    using C = FrameCfg<kPairLog2HL>;
+    std::vector<float> env(kPairH), stage(kPairH);
+    host_crossfade_compensation(env.data(), kPairH);
+    prm.env = env.data();
+    HostExec ex{C::NT};
+    for (int c = 0; c < prm.channels; c++) run_boundary_pair(ex, prm, c, head, tail_prev, stage.data());
+    return 0;
+}
+
 template <int LOG2H>
 static int emul_boundary(StretchParams prm, const float* head, const float* tail_prev) {
     using C = FrameCfg<LOG2H>;
@@ -90,6 +136,7 @@ int rcg_emul_stretch(int log2w, const float* in, long long in_stride, long long 
     p.amp = amp; p.inv_w = 1.0f / (float)(1 << log2w); p.flags = flags;
     p.keys = make_philox_keys(seed);
     p.tail_in = tail_in; p.tail_out = tail_out; p.head_out = head_out;
+    if (log2w == 16) return emul_run_pair(p);
     switch (log2w - 1) {
 #define CASE(L) case L: return emul_run<L>(p);
         CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
@@ -106,6 +153,7 @@ int rcg_emul_boundary(int log2w, float* out, long long out_stride, long long out
     p.out = out; p.out_stride = out_stride; p.out_origin = out_origin;
     p.frame_begin = frame_begin; p.channels = channels; p.pitch = pitch;
     p.samples_needed = samples_needed; p.amp = amp;
+    if (log2w == 16) return emul_boundary_pair(p, head, tail_prev);
     switch (log2w - 1) {
 #define CASE(L) case L: return emul_boundary<L>(p, head, tail_prev);
         CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)

@@ -35,7 +35,7 @@ def test_binding_covers_the_header():
 
 @pytest.mark.parametrize("f", [0.5, 0.75, 1.0, 1.3, 1.7, 2.0, 3.0, 4.0, 8.0, 13.37, 20.0, 100.0])
 @pytest.mark.parametrize("p", [1, 2, 3, 5, 7, -2, -3, -4, -7])
-@pytest.mark.parametrize("W", [64, 1024, 16384, 32768])
+@pytest.mark.parametrize("W", [64, 1024, 16384, 65536])
 def test_plan_bit_exact_with_oracle(f, p, W):
     want = ol.constants(f, p, W, amplitude=0.7)
     ok = 1 <= want["sample_step_len"] <= W

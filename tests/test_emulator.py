@@ -13,7 +13,7 @@ def _input(n, seed=1):
     return ((rng.random((2, n), dtype=np.float32) * 2 - 1) * 0.5).astype(np.float32)
 
 
-@pytest.mark.parametrize("n,f,p,W", SMALL_CASES + LARGE_CASES[:3])
+@pytest.mark.parametrize("n,f,p,W", SMALL_CASES + LARGE_CASES[:3] + LARGE_CASES[-3:])
 def test_bypass_bit_exact(n, f, p, W):
     """all integer indexing (frame cursor, OLA blocks, decimation / lerp positions) is bit-exact"""
     x = _input(n)
@@ -157,3 +157,42 @@ def test_phases_are_race_free(n, f, p, W):
     finally:
         E.rcg_emul_reverse_threads(0)
     assert np.array_equal(a, b) and np.array_equal(b0, b1)
+
+
+@pytest.mark.parametrize("f,p,n", [(2.0, 1, 300000), (4.0, 2, 200000), (3.0, -3, 200000), (1.0, 3, 150000)])
+def test_window_65536_cta_pair(f, p, n):
+    """W = 65536 splits a frame across a 2-CTA cluster (even / odd bins, DSMEM exchange of the last
+    radix-2 stage): bit-exact indexing, PCM within tolerance, order-independent phases"""
+    W = 65536
+    x = _input(n, seed=p + 7)
+    assert np.array_equal(ol.emul_process_all(x, f, p, W, bypass=True), ol.process_all(x, f, p, W, mode=ol.RO_PHASE_BYPASS))
+    ref = ol.process_all(x, f, p, W, seed=5, precision=64)
+    got = ol.emul_process_all(x, f, p, W, seed=5, run_len=2)
+    assert np.abs(got - ref).max() <= 1e-4 and ol.snr_db(ref, got) > 100.0
+    ol.emulator().rcg_emul_reverse_threads(1)
+    try:
+        again = ol.emul_process_all(x, f, p, W, seed=5, run_len=3)
+    finally:
+        ol.emulator().rcg_emul_reverse_threads(0)
+    assert np.array_equal(got, again)
+
+
+def test_window_65536_segments():
+    f, p, W, n = 2.0, 1, 65536, 500000
+    x = _input(n, seed=3)
+    calls, _, out_len = ol.expected_counts(n, f, p, W)
+    whole = ol.emul_process_all(x, f, p, W, seed=5)
+    c = ol.constants(f, p, W)
+    k, step, olen, H = c["frames_per_call"], c["sample_step_len"], c["out_len_per_call"], W // 2
+    cuts = [0, calls // 2, calls]
+    out = np.full_like(whole, np.nan)
+    heads, tails = [], []
+    for c0, c1 in zip(cuts[:-1], cuts[1:]):
+        s0 = c0 * k * step
+        head, tail_out = np.zeros((2, H), np.float32), np.zeros((2, H), np.float32)
+        ol.emul_segment(np.ascontiguousarray(x[:, s0:]), s0, out[:, c0 * olen:], f, p, W, c0, c1 - c0, seed=5,
+                        tail_out=tail_out, head_out=head, defer_first=c0 > 0)
+        heads.append(head)
+        tails.append(tail_out)
+    ol.emul_boundary(out[:, cuts[1] * olen:], f, p, W, cuts[1], heads[1], tails[0])
+    assert np.array_equal(out, whole)

@@ -253,3 +253,34 @@ def test_odd_output_stride_with_negative_pitch():
         out = torch.zeros((2, 8 * W + 1), device="cuda")
         with pytest.raises(rb.RcgError):
             e.process_segment(dx, dx.stride(0), 0, n, out[:, 1:], out.stride(0), 0, 2, stream=st)
+
+
+def test_window_65536_streaming_and_segments():
+    """W = 65536 (2-CTA cluster per frame): streaming next_window and deferred-boundary segments equal
+    the batched run bit for bit"""
+    import torch
+    n, f, p, W = 600000, 2.0, 2, 65536
+    x = _input(n, seed=12)
+    with rb.Engine(2, 48000, W, f, 1.0, p, seed=5) as e:
+        whole = e.process_all(x)
+        calls, _, out_len = e.expected_counts(n)
+        olen, H = e.plan["out_len_per_call"], W // 2
+        dx = torch.from_numpy(x).cuda()
+        st = torch.cuda.current_stream().cuda_stream
+        out = torch.full((2, out_len), float("nan"), device="cuda")
+        cuts = [0, calls // 2, calls]
+        heads = [torch.zeros(2, H, device="cuda") for _ in cuts]
+        tails = [torch.zeros(2, H, device="cuda") for _ in cuts]
+        for i, (c0, c1) in enumerate(zip(cuts[:-1], cuts[1:])):
+            e.process_segment(dx, dx.stride(0), 0, n, out[:, c0 * olen:], out.stride(0), c0, c1 - c0,
+                              tail_out=tails[i], head_out=heads[i], defer_first=c0 > 0, stream=st)
+        e.finish_boundary(out[:, cuts[1] * olen:], out.stride(0), cuts[1], heads[1], tails[0], stream=st)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), whole)
+    with rb.Engine(1, 48000, W, f, 1.0, p, seed=5, max_lookahead_calls=2) as e:
+        e.send(0, x[0])
+        e.close_input(0)
+        wins = []
+        while not e.is_done(0):
+            wins.append(e.next_window(0))
+    assert np.array_equal(np.concatenate(wins), whole[0])
