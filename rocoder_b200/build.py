@@ -87,8 +87,23 @@ def build_emulator(force: bool = False) -> str:
     return EMUL_LIB
 
 
+CLI = os.path.join(ROOT, "rocoder_b200", "rocoder_gpu")
+
+
+def build_cli(force: bool = False) -> str:
+    """tools/rocoder_gpu.cpp: the reference's CLI flags for the file-to-file path"""
+    src = os.path.join(ROOT, "tools", "rocoder_gpu.cpp")
+    deps = [src, os.path.join(ROOT, "rocoder_b200", "host", "rocoder_audio.hpp"), os.path.join(ROOT, "include", "rocoder_b200.h")]
+    build_product()
+    if force or not _newer(CLI, deps + [LIB]):
+        libdir = os.path.dirname(LIB)
+        _run(["g++", "-O2", "-std=c++17", src, "-o", CLI, "-L", libdir, "-lrocoder_b200", f"-Wl,-rpath,{libdir}", "-lpthread"])
+    return CLI
+
+
 def build_all(force: bool = False) -> None:
     build_product(force)
+    build_cli(force)
     build_oracle(force)
     build_emulator(force)
 
