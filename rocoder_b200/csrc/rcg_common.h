@@ -83,6 +83,23 @@ RCG_HD constexpr int pos_to_bin(int pos) {
     }
 }
 
+// ---- which bin slot a thread of the spectral step owns ----------------------------------------
+// The spectral step walks slots in POSITION order (the forward transform leaves bins digit-reversed):
+// slot c -> position pos = 16*row + kl with kl < 8 (pairs: bins k < H/2) or kl < 4 (half-rate quads:
+// k < H/4).  Rows are 17 cf apart in the padded buffer, so the rows sharing a 16-lane half warp are
+// chosen 8 (resp. 4) apart: their 8 (4) consecutive slots then fall on disjoint 8-byte bank pairs,
+// and so do the partner bins' slots (H-k, Q-k, Q+k), whose rows are the digit complements.
+RCG_HD constexpr int spectral_slot_pos(int log2h, int c) {
+    if (log2h < 8) return (c >> 3) * 16 + (c & 7);   // fewer than 16 rows: plain order
+    const int kl = c & 7, rsel = (c >> 3) & 1, s = (c >> 4) & 7, g = c >> 7;
+    return (16 * g + 8 * rsel + s) * 16 + kl;
+}
+RCG_HD constexpr int spectral_slot_pos_hr(int log2h, int c) {
+    if (log2h < 8) return (c >> 2) * 16 + (c & 3);
+    const int kl = c & 3, rsel = (c >> 2) & 3, s = (c >> 4) & 3, g = c >> 6;
+    return (16 * g + 4 * rsel + s) * 16 + kl;
+}
+
 // shared-memory padding: one cf of padding every 16 keeps stride-16 and stride-1 access
 // patterns of all passes on distinct 8-byte bank pairs.
 RCG_HD constexpr int phys(int i) { return i + (i >> 4); }

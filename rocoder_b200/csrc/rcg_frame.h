@@ -150,8 +150,25 @@ RCG_HD void tw_apply(float& xr, float& xi, float wr, float wi) {
 
 // Multiply element j (1 <= j < R) of a butterfly by w^(m*j) (or its conjugate), w = the pass's
 // principal root, using the table layout tw_scheme() selected.
+// the stored power-of-two exponents of the pow scheme, fetched ahead of the butterfly so that
+// their (L1 / L2) latency overlaps the shared-memory loads and the DFT
+struct TwPre { cf w1, w2, w4, w8; };
+template <int LOG2H, int PASS, int R, bool HR = false>
+RCG_HD TwPre tw_preload(const cf* tw, int m) {
+    constexpr int SCHEME = tw_scheme(LOG2H, PASS, HR);
+    constexpr int M = 1 << make_plan(LOG2H, HR).mlog2[PASS];
+    TwPre p;
+    p.w1 = p.w2 = p.w4 = p.w8 = make_cf(1.0f, 0.0f);
+    if constexpr (SCHEME == kTwPow) {
+        p.w1 = ld_cf(tw + m); p.w2 = ld_cf(tw + M + m);
+        if constexpr (R >= 8) p.w4 = ld_cf(tw + 2 * M + m);
+        if constexpr (R >= 16) p.w8 = ld_cf(tw + 3 * M + m);
+    }
+    return p;
+}
+
 template <int LOG2H, int PASS, bool CONJ, int R, bool HR = false>
-RCG_HD void twiddle_butterfly(float (&xr)[R], float (&xi)[R], const cf* tw, int m) {
+RCG_HD void twiddle_butterfly(float (&xr)[R], float (&xi)[R], const cf* tw, int m, const TwPre& pre) {
     constexpr int SCHEME = tw_scheme(LOG2H, PASS, HR);
     constexpr int M = 1 << make_plan(LOG2H, HR).mlog2[PASS];
     if constexpr (SCHEME == kTwFull) {
@@ -169,21 +186,21 @@ RCG_HD void twiddle_butterfly(float (&xr)[R], float (&xi)[R], const cf* tw, int 
     } else if constexpr (SCHEME == kTwPow) {
         // stored: w1, w2, w4, w8; kept products: w3 = w1 w2, w12 = w8 w4; every other exponent is
         // one product of two of those (depth <= 2 multiplications from correctly rounded tables)
-        const cf w1 = ld_cf(tw + m), w2 = ld_cf(tw + M + m);
+        const cf w1 = pre.w1, w2 = pre.w2;
         tw_apply<CONJ>(xr[1], xi[1], w1.x, w1.y);
         tw_apply<CONJ>(xr[2], xi[2], w2.x, w2.y);
         float w3r, w3i;
         cmul(w1.x, w1.y, w2.x, w2.y, w3r, w3i);
         tw_apply<CONJ>(xr[3], xi[3], w3r, w3i);
         if constexpr (R >= 8) {
-            const cf w4 = ld_cf(tw + 2 * M + m);
+            const cf w4 = pre.w4;
             float tr, ti;
             tw_apply<CONJ>(xr[4], xi[4], w4.x, w4.y);
             cmul(w4.x, w4.y, w1.x, w1.y, tr, ti); tw_apply<CONJ>(xr[5], xi[5], tr, ti);
             cmul(w4.x, w4.y, w2.x, w2.y, tr, ti); tw_apply<CONJ>(xr[6], xi[6], tr, ti);
             cmul(w4.x, w4.y, w3r, w3i, tr, ti);   tw_apply<CONJ>(xr[7], xi[7], tr, ti);
             if constexpr (R >= 16) {
-                const cf w8 = ld_cf(tw + 3 * M + m);
+                const cf w8 = pre.w8;
                 tw_apply<CONJ>(xr[8], xi[8], w8.x, w8.y);
                 cmul(w8.x, w8.y, w1.x, w1.y, tr, ti); tw_apply<CONJ>(xr[9], xi[9], tr, ti);
                 cmul(w8.x, w8.y, w2.x, w2.y, tr, ti); tw_apply<CONJ>(xr[10], xi[10], tr, ti);
@@ -197,6 +214,11 @@ RCG_HD void twiddle_butterfly(float (&xr)[R], float (&xi)[R], const cf* tw, int 
             }
         }
     }
+}
+
+template <int LOG2H, int PASS, bool CONJ, int R, bool HR = false>
+RCG_HD void twiddle_butterfly(float (&xr)[R], float (&xi)[R], const cf* tw, int m) {
+    twiddle_butterfly<LOG2H, PASS, CONJ, R, HR>(xr, xi, tw, m, tw_preload<LOG2H, PASS, R, HR>(tw, m));
 }
 
 // shared-memory offset of butterfly input a relative to input 0: phys(base + a*M) - phys(base)
@@ -291,33 +313,54 @@ RCG_UNROLL(RCG_LOAD_UNROLL)
     }
 }
 
-// ---- one in-place FFT pass (passes 1..NP-1; pass 0 is fused into load / overlap-add) ---------
+// ---- one in-place butterfly of pass PASS >= 1 (pass 0 is fused into load / overlap-add) ---------
+template <int LOG2H, int PASS, bool INV>
+RCG_HD void fft_butterfly(cf* S, const cf* tw_all, int b) {
+    constexpr int RL = make_plan(LOG2H).rlog2[PASS], R = 1 << RL, ML = make_plan(LOG2H).mlog2[PASS], M = 1 << ML;
+    const cf* tw = tw_all + tw_offset(LOG2H, PASS);
+    const int m = b & (M - 1), blk = b >> ML;
+    const TwPre pre = tw_preload<LOG2H, PASS, R>(tw, m);
+    cf* p = S + phys((blk << (ML + RL)) + m);
+    float xr[R], xi[R];
+#pragma unroll
+    for (int a = 0; a < R; a++) {
+        const cf v = p[slot_off<M>(a)];
+        xr[a] = v.x; xi[a] = v.y;
+    }
+    if constexpr (INV) {
+        twiddle_butterfly<LOG2H, PASS, true, R>(xr, xi, tw, m, pre);  // conj twiddle on the inputs (DIT)
+        Dft<R>::run(xi, xr);
+    } else {
+        Dft<R>::run(xr, xi);
+        twiddle_butterfly<LOG2H, PASS, false, R>(xr, xi, tw, m, pre);  // twiddle on the outputs (DIF)
+    }
+#pragma unroll
+    for (int j = 0; j < R; j++) p[slot_off<M>(j)] = make_cf(xr[j], xi[j]);
+}
+
 template <int LOG2H, int PASS, bool INV>
 RCG_HD void phase_fft_pass(cf* S, int t, const cf* tw_all) {
     using C = FrameCfg<LOG2H>;
-    constexpr int RL = make_plan(LOG2H).rlog2[PASS], R = 1 << RL, ML = make_plan(LOG2H).mlog2[PASS], M = 1 << ML;
-    constexpr int NB = C::H / R;
-    const cf* tw = tw_all + tw_offset(LOG2H, PASS);
-    for (int b = t; b < NB; b += C::NT) {
-        const int m = b & (M - 1), blk = b >> ML;
-        cf* p = S + phys((blk << (ML + RL)) + m);
-        float xr[R], xi[R];
-#pragma unroll
-        for (int a = 0; a < R; a++) {
-            const cf v = p[slot_off<M>(a)];
-            xr[a] = v.x; xi[a] = v.y;
-        }
-        if constexpr (INV) {
-            twiddle_butterfly<LOG2H, PASS, true, R>(xr, xi, tw, m);  // conj twiddle on the inputs (DIT)
-            Dft<R>::run(xi, xr);
-        } else {
-            Dft<R>::run(xr, xi);
-            twiddle_butterfly<LOG2H, PASS, false, R>(xr, xi, tw, m);  // twiddle on the outputs (DIF)
-        }
-#pragma unroll
-        for (int j = 0; j < R; j++) p[slot_off<M>(j)] = make_cf(xr[j], xi[j]);
-    }
+    constexpr int NB = C::H >> make_plan(LOG2H).rlog2[PASS];
+    for (int b = t; b < NB; b += C::NT) fft_butterfly<LOG2H, PASS, INV>(S, tw_all, b);
 }
+
+// The last two passes (strides 16 and 1) of a warp's butterflies b .. b+31 touch the same 512
+// elements, so they run as consecutive steps of ONE phase separated by __syncwarp only:
+// step 2i and 2i+1 = the two passes for butterfly index t + NT*i.
+template <int LOG2H, bool INV>
+RCG_HD void fft_tail_step(cf* S, int t, int step, const cf* tw_all) {
+    using C = FrameCfg<LOG2H>;
+    constexpr int NB = C::H / 16;
+    static_assert(make_plan(LOG2H).rlog2[C::NP - 1] == 4 && make_plan(LOG2H).rlog2[C::NP - 2] == 4, "radix-16 tail");
+    const int b = t + C::NT * (step >> 1);
+    if (b >= NB) return;
+    const bool first = (step & 1) == 0;
+    if (first != INV) fft_butterfly<LOG2H, C::NP - 2, INV>(S, tw_all, b);
+    else fft_butterfly<LOG2H, C::NP - 1, INV>(S, tw_all, b);
+}
+template <int LOG2H>
+constexpr int fft_tail_steps() { return 2 * (((FrameCfg<LOG2H>::H / 16) + FrameCfg<LOG2H>::NT - 1) / FrameCfg<LOG2H>::NT); }
 
 // phases are k * 2^-23 * PI with k < 2^23, i.e. in [0, PI): the SFU's sin/cos (abs. error
 // ~2^-21) is accurate far beyond the 1e-4 PCM tolerance and costs 3 instructions instead of ~90
@@ -372,13 +415,11 @@ RCG_HD void pair_fold(cf za, cf zb, cf tw, const uint32_t (&u)[4], float& ar, fl
 template <int LOG2H>
 RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
     using C = FrameCfg<LOG2H>;
-    constexpr int QUARTER = C::RLAST / 4;
     constexpr int Q = C::H / 2;
     const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
     const uint32_t chan = (uint32_t)(channel + prm.channel_offset);
     for (int c = t; c < C::H / 4; c += C::NT) {
-        const int rho = c / QUARTER, kl = c - rho * QUARTER;
-        const int pos = rho * C::RLAST + kl;
+        const int pos = spectral_slot_pos_hr(LOG2H, c);
         const int k = pos_to_bin<LOG2H>(pos);
         uint32_t u[4];
         if (c == 0) {
@@ -432,11 +473,10 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
 template <int LOG2H, int KMUL = 1>
 RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
     using C = FrameCfg<LOG2H>;
-    constexpr int HALF = C::RLAST / 2;
+    static_assert(C::RLAST == 16, "the spectral slot order assumes a radix-16 last pass");
     const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
     for (int c = t; c < C::H / 2; c += C::NT) {
-        const int rho = c / HALF, kl = c - rho * HALF;
-        const int pos = rho * C::RLAST + kl;
+        const int pos = spectral_slot_pos(LOG2H, c);
         const int k = pos_to_bin<LOG2H>(pos);
         uint32_t u[4];
         if (c == 0) {
@@ -478,11 +518,9 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
 template <int LOG2H>
 RCG_HD void phase_spectrum_out(const cf* S, int t, const StretchParams& prm, int channel, long long frame) {
     using C = FrameCfg<LOG2H>;
-    constexpr int HALF = C::RLAST / 2;
     cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * C::W;
     for (int c = t; c < C::H / 2; c += C::NT) {
-        const int rho = c / HALF, kl = c - rho * HALF;
-        const int pos = rho * C::RLAST + kl;
+        const int pos = spectral_slot_pos(LOG2H, c);
         const int k = pos_to_bin<LOG2H>(pos);
         if (c == 0) {
             cf z0 = S[0];
@@ -514,13 +552,11 @@ RCG_HD float cf_norm(cf v) { return sqrtf(v.x * v.x + v.y * v.y); }
 template <int LOG2H>
 RCG_HD void phase_spectral_in(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
     using C = FrameCfg<LOG2H>;
-    constexpr int HALF = C::RLAST / 2;
     const cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * C::W;
     const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
     const uint32_t chan = (uint32_t)(channel + prm.channel_offset);
     for (int c = t; c < C::H / 2; c += C::NT) {
-        const int rho = c / HALF, kl = c - rho * HALF;
-        const int pos = rho * C::RLAST + kl;
+        const int pos = spectral_slot_pos(LOG2H, c);
         const int k = pos_to_bin<LOG2H>(pos);
         uint32_t u[4];
         if (c == 0) {
@@ -631,31 +667,60 @@ RCG_HD void phase_ola(cf* S, int t, const StretchParams& prm, int channel, long 
     else phase_ola_impl<LOG2H, false>(S, t, prm, channel, frame, tail, emit, write_head, load_next);
 }
 
-// ---- half-rate synthesis: inverse DIT pass PASS >= 1 of the Q-point transform ---------------------
-// Logical indices of the hr plan, physical slots of the full layout (expand_hr).
+// ---- half-rate synthesis: inverse DIT butterfly of pass PASS >= 1 of the Q-point transform ------
+// Logical indices of the hr plan, physical slots of the full layout (expand_hr).  For the long-
+// stride pass the butterflies are dealt to lanes with bits 3 and 6 of m swapped, so that the two
+// 8-slot rows a 16-lane half warp touches are 8 rows apart (disjoint bank pairs).
 template <int LOG2H, int PASS>
-RCG_HD void phase_fft_pass_hr(cf* S, int t, const cf* tw_all) {
-    using C = FrameCfg<LOG2H>;
+RCG_HD void fft_butterfly_hr(cf* S, const cf* tw_all, int b) {
     constexpr PlanDesc P = make_plan(LOG2H, true);
     constexpr int RL = P.rlog2[PASS], R = 1 << RL, ML = P.mlog2[PASS], M = 1 << ML;
-    constexpr int NB = (C::H / 2) / R;
     constexpr int STRIDE = (M == 1) ? 1 : 2 * M;   // physical stride between butterfly inputs
     static_assert(M == 1 || M >= 8, "hr pass strides are 1 or multiples of 8");
     const cf* tw = tw_all + tw_offset(LOG2H, PASS, true);
-    for (int b = t; b < NB; b += C::NT) {
-        const int m = b & (M - 1), blk = b >> ML;
-        cf* p = S + phys(expand_hr((blk << (ML + RL)) + m));
-        float xr[R], xi[R];
+    int m = b & (M - 1);
+    const int blk = b >> ML;
+    if constexpr (M >= 128) m = (m & ~0x48) | ((m & 0x08) << 3) | ((m & 0x40) >> 3);
+    const TwPre pre = tw_preload<LOG2H, PASS, R, true>(tw, m);
+    cf* p = S + phys(expand_hr((blk << (ML + RL)) + m));
+    float xr[R], xi[R];
 #pragma unroll
-        for (int a = 0; a < R; a++) {
-            const cf v = p[slot_off<STRIDE>(a)];
-            xr[a] = v.x; xi[a] = v.y;
-        }
-        twiddle_butterfly<LOG2H, PASS, true, R, true>(xr, xi, tw, m);
-        Dft<R>::run(xi, xr);
-#pragma unroll
-        for (int j = 0; j < R; j++) p[slot_off<STRIDE>(j)] = make_cf(xr[j], xi[j]);
+    for (int a = 0; a < R; a++) {
+        const cf v = p[slot_off<STRIDE>(a)];
+        xr[a] = v.x; xi[a] = v.y;
     }
+    twiddle_butterfly<LOG2H, PASS, true, R, true>(xr, xi, tw, m, pre);
+    Dft<R>::run(xi, xr);
+#pragma unroll
+    for (int j = 0; j < R; j++) p[slot_off<STRIDE>(j)] = make_cf(xr[j], xi[j]);
+}
+
+template <int LOG2H, int PASS>
+RCG_HD void phase_fft_pass_hr(cf* S, int t, const cf* tw_all) {
+    using C = FrameCfg<LOG2H>;
+    constexpr int NB = (C::H / 2) >> make_plan(LOG2H, true).rlog2[PASS];
+    for (int b = t; b < NB; b += C::NT) fft_butterfly_hr<LOG2H, PASS>(S, tw_all, b);
+}
+
+// hr tail: the radix-8 last pass works on rows of 8 slots; the radix-16 pass before it on blocks
+// of 16 rows.  A warp's 32 radix-16 butterflies (index 32w'..32w'+31) cover rows 64w'..64w'+63,
+// so step 2i = those 64 radix-8 butterflies (two per lane), step 2i+1 = the radix-16 ones.
+template <int LOG2H>
+RCG_HD void fft_tail_step_hr(cf* S, int t, int step, const cf* tw_all) {
+    using C = FrameCfg<LOG2H>;
+    constexpr int NB_PREV = (C::H / 2) / 16, NB_LAST = (C::H / 2) / 8;
+    const int b = t + C::NT * (step >> 1);
+    if ((step & 1) == 0) {
+        const int b1 = 64 * (b >> 5) + (b & 31);
+        if (b1 < NB_LAST) fft_butterfly_hr<LOG2H, C::NP - 1>(S, tw_all, b1);
+        if (b1 + 32 < NB_LAST) fft_butterfly_hr<LOG2H, C::NP - 1>(S, tw_all, b1 + 32);
+    } else if (b < NB_PREV) {
+        fft_butterfly_hr<LOG2H, C::NP - 2>(S, tw_all, b);
+    }
+}
+template <int LOG2H>
+constexpr int fft_tail_steps_hr() {
+    return 2 * ((((FrameCfg<LOG2H>::H / 2) / 16) + FrameCfg<LOG2H>::NT - 1) / FrameCfg<LOG2H>::NT);
 }
 
 // value i of the staged half-rate block (packed pairs at the hr slots)
@@ -781,20 +846,45 @@ RCG_HD void phase_resample(const cf* S, int t, const StretchParams& prm, int cha
     }
 }
 
-template <int LOG2H, int PASS, class Exec>
-RCG_HD void fft_inv_hr(Exec& ex, cf* S, const StretchParams& prm, bool work) {
-    if constexpr (PASS >= 1) {
+// Exec::par(f) runs f(t) for every thread of the frame lane followed by a block barrier;
+// Exec::par_steps(n, f) runs f(step, t) for step = 0..n-1 with a warp barrier after every step
+// (only intra-warp dependencies between steps) and a block barrier at the end.
+template <int LOG2H, bool INV, int PASS, int LAST, class Exec>
+RCG_HD void fft_range(Exec& ex, cf* S, const StretchParams& prm, bool work) {   // passes PASS..LAST one by one
+    if constexpr (INV ? PASS >= LAST : PASS <= LAST) {
+        ex.par([&](int t) { if (work) phase_fft_pass<LOG2H, PASS, INV>(S, t, prm.tw); });
+        fft_range<LOG2H, INV, INV ? PASS - 1 : PASS + 1, LAST>(ex, S, prm, work);
+    }
+}
+template <int LOG2H, int PASS, int LAST, class Exec>
+RCG_HD void fft_range_hr(Exec& ex, cf* S, const StretchParams& prm, bool work) {
+    if constexpr (PASS >= LAST) {
         ex.par([&](int t) { if (work) phase_fft_pass_hr<LOG2H, PASS>(S, t, prm.tw); });
-        fft_inv_hr<LOG2H, PASS - 1>(ex, S, prm, work);
+        fft_range_hr<LOG2H, PASS - 1, LAST>(ex, S, prm, work);
     }
 }
 
-template <int LOG2H, bool INV, int PASS, class Exec>
+// forward passes 1..NP-1 / inverse passes NP-1..1 of the full plan
+template <int LOG2H, bool INV, class Exec>
 RCG_HD void fft_all(Exec& ex, cf* S, const StretchParams& prm, bool work) {
     using C = FrameCfg<LOG2H>;
-    if constexpr (PASS >= 1 && PASS < C::NP) {
-        ex.par([&](int t) { if (work) phase_fft_pass<LOG2H, PASS, INV>(S, t, prm.tw); });
-        fft_all<LOG2H, INV, INV ? PASS - 1 : PASS + 1>(ex, S, prm, work);
+    if constexpr (C::NP >= 3) {
+        if constexpr (!INV) fft_range<LOG2H, false, 1, C::NP - 3>(ex, S, prm, work);
+        ex.par_steps(fft_tail_steps<LOG2H>(), [&](int step, int t) { if (work) fft_tail_step<LOG2H, INV>(S, t, step, prm.tw); });
+        if constexpr (INV) fft_range<LOG2H, true, C::NP - 3, 1>(ex, S, prm, work);
+    } else {
+        fft_range<LOG2H, INV, INV ? C::NP - 1 : 1, INV ? 1 : C::NP - 1>(ex, S, prm, work);
+    }
+}
+// inverse passes NP-1..1 of the half-rate plan
+template <int LOG2H, class Exec>
+RCG_HD void fft_inv_hr(Exec& ex, cf* S, const StretchParams& prm, bool work) {
+    using C = FrameCfg<LOG2H>;
+    if constexpr (C::NP >= 3) {
+        ex.par_steps(fft_tail_steps_hr<LOG2H>(), [&](int step, int t) { if (work) fft_tail_step_hr<LOG2H>(S, t, step, prm.tw); });
+        fft_range_hr<LOG2H, C::NP - 3, 1>(ex, S, prm, work);
+    } else {
+        fft_range_hr<LOG2H, C::NP - 1, 1>(ex, S, prm, work);
     }
 }
 
@@ -841,17 +931,17 @@ RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, f
         const bool load_next = fuse && work && (it + 1 < n_iter) && (f + 1 < f1);
         if (spectrum_in) {
             ex.par([&](int t) { if (work) phase_spectral_in<LOG2H>(S, t, prm, channel, f); });
-            fft_all<LOG2H, true, C::NP - 1>(ex, S, prm, work);
+            fft_all<LOG2H, true>(ex, S, prm, work);
         } else {
             if (!fuse) ex.par([&](int t) { if (work) phase_load<LOG2H>(S, t, prm, channel, f); });
             if (!bypass) {
-                fft_all<LOG2H, false, 1>(ex, S, prm, work);
+                fft_all<LOG2H, false>(ex, S, prm, work);
                 if (half_rate) {
                     ex.par([&](int t) { if (work) phase_spectral_hr<LOG2H>(S, t, prm, channel, f); });
-                    fft_inv_hr<LOG2H, C::NP - 1>(ex, S, prm, work);
+                    fft_inv_hr<LOG2H>(ex, S, prm, work);
                 } else {
                     ex.par([&](int t) { if (work) phase_spectral<LOG2H>(S, t, prm, channel, f); });
-                    fft_all<LOG2H, true, C::NP - 1>(ex, S, prm, work);
+                    fft_all<LOG2H, true>(ex, S, prm, work);
                 }
             }
         }
@@ -886,7 +976,7 @@ RCG_HD void run_analysis_item(Exec& ex, cf* S, const StretchParams& prm, int ite
         const long long f = f0 + it;
         const bool work = active && f < prm.frame_end;
         ex.par([&](int t) { if (work) phase_load<LOG2H>(S, t, prm, channel, f); });
-        fft_all<LOG2H, false, 1>(ex, S, prm, work);
+        fft_all<LOG2H, false>(ex, S, prm, work);
         ex.par([&](int t) { if (work) phase_spectrum_out<LOG2H>(S, t, prm, channel, f); });
     }
 }

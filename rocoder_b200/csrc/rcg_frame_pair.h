@@ -64,12 +64,10 @@ RCG_HD void pair_phase_load(cf* S, int r, int t, const StretchParams& prm, const
 RCG_HD void pair_phase_spectral_odd(cf* S, int t, const StretchParams& prm, const PairTables& pt, int channel,
                                     long long frame) {
     using C = FrameCfg<kPairLog2HL>;
-    constexpr int HALF = C::RLAST / 2;
     const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
     const uint32_t chan = (uint32_t)(channel + prm.channel_offset);
     for (int c = t; c < kPairHL / 2; c += C::NT) {
-        const int rho = c / HALF, kl = c - rho * HALF;
-        const int pos = rho * C::RLAST + kl;
+        const int pos = spectral_slot_pos(kPairLog2HL, c);
         const int j = pos_to_bin<kPairLog2HL>(pos);
         const int k = 2 * j + 1;
         const int pa = phys(pos), pb = phys(bin_to_pos<kPairLog2HL>(kPairHL - 1 - j));

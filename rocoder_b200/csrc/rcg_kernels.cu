@@ -25,6 +25,16 @@ struct DeviceExec {
         f(t);
         __syncthreads();
     }
+    // steps that only depend on each other within a warp: warp barriers in between, one block
+    // barrier at the end
+    template <class F>
+    __device__ __forceinline__ void par_steps(int n, F f) {
+        for (int s = 0; s < n; s++) {
+            f(s, t);
+            __syncwarp();
+        }
+        __syncthreads();
+    }
 };
 
 #ifndef RCG_MIN_CTAS

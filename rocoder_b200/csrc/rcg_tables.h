@@ -76,12 +76,11 @@ inline std::vector<cf> host_pass_twiddles(int log2h) {
 // exp(-2 pi i k / W) for the bin k the spectral step's pair slot c owns
 inline std::vector<cf> host_spectral_twiddles(int log2h) {
     const PlanDesc d = make_plan(log2h);
-    const int H = 1 << log2h, RL = 1 << d.rlog2[d.npasses - 1], HALF = RL / 2;
+    const int H = 1 << log2h;
     std::vector<cf> tw((size_t)H / 2);
     const double two_pi = 6.283185307179586476925286766559;
     for (int c = 0; c < H / 2; c++) {
-        int rho = c / HALF, kl = c - rho * HALF;
-        int k = rt_pos_to_bin(d, rho * RL + kl);
+        int k = rt_pos_to_bin(d, spectral_slot_pos(log2h, c));
         double a = -two_pi * (double)k / (double)(2 * H);
         tw[c] = make_cf((float)cos(a), (float)sin(a));
     }
@@ -92,12 +91,11 @@ inline std::vector<cf> host_spectral_twiddles(int log2h) {
 // spectral step's order: c -> (rho, kl), kl < 4, position rho*16 + kl)
 inline std::vector<cf> host_spectral_twiddles_hr(int log2h) {
     const PlanDesc d = make_plan(log2h);
-    const int H = 1 << log2h, RL = 1 << d.rlog2[d.npasses - 1], QUARTER = RL / 4;
+    const int H = 1 << log2h;
     std::vector<cf> tw((size_t)std::max(H / 4, 1));
     const double two_pi = 6.283185307179586476925286766559;
     for (int c = 0; c < H / 4; c++) {
-        int rho = c / QUARTER, kl = c - rho * QUARTER;
-        int k = rt_pos_to_bin(d, rho * RL + kl);
+        int k = rt_pos_to_bin(d, spectral_slot_pos_hr(log2h, c));
         double a = -two_pi * (double)k / (double)(2 * H);
         tw[c] = make_cf((float)cos(a), (float)sin(a));
     }
@@ -118,12 +116,11 @@ inline std::vector<cf> host_pair_cross_twiddles(int log2h) {
 inline std::vector<cf> host_pair_spectral_twiddles(int log2h, int odd) {
     const int log2hl = log2h - 1;
     const PlanDesc d = make_plan(log2hl);
-    const int HL = 1 << log2hl, RL = 1 << d.rlog2[d.npasses - 1], HALF = RL / 2;
+    const int HL = 1 << log2hl;
     std::vector<cf> tw((size_t)HL / 2);
     const double two_pi = 6.283185307179586476925286766559;
     for (int c = 0; c < HL / 2; c++) {
-        int rho = c / HALF, kl = c - rho * HALF;
-        int j = rt_pos_to_bin(d, rho * RL + kl);
+        int j = rt_pos_to_bin(d, spectral_slot_pos(log2hl, c));
         double a = -two_pi * (double)(2 * j + odd) / (double)(4 * HL);
         tw[c] = make_cf((float)cos(a), (float)sin(a));
     }

@@ -24,6 +24,20 @@ struct HostExec {
         if (g_reverse_threads) for (int t = nt - 1; t >= 0; t--) f(t);
         else for (int t = 0; t < nt; t++) f(t);
     }
+    // warp by warp: all steps of one warp before the next warp starts, so any dependency that
+    // crosses a warp boundary between steps shows up as a wrong result
+    template <class F>
+    void par_steps(int n, F f) {
+        const int nw = (nt + 31) / 32;
+        for (int wi = 0; wi < nw; wi++) {
+            const int w = g_reverse_threads ? nw - 1 - wi : wi;
+            for (int s = 0; s < n; s++)
+                for (int li = 0; li < 32; li++) {
+                    const int l = g_reverse_threads ? 31 - li : li;
+                    if (w * 32 + l < nt) f(s, w * 32 + l);
+                }
+        }
+    }
 };
 
 static int g_disable_half_rate = 0;
