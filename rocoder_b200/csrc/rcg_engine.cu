@@ -185,6 +185,7 @@ struct rcg_engine {
     PhiloxKeys keys{};
     uint64_t seed = 0;
     float *d_window = nullptr, *d_env = nullptr, *d_scratch = nullptr, *d_window_even = nullptr, *d_env_even = nullptr;
+    float* d_lerp_ratio = nullptr;
     cf *d_tw = nullptr, *d_spec_tw = nullptr, *d_spec_tw_hr = nullptr;
     bool pair = false;        // W = 65536: a frame across a 2-CTA cluster
     PairTables pt{};
@@ -289,6 +290,13 @@ extern "C" int rcg_create(const rcg_config* cfg, rcg_engine** out) {
         TRY_E(cudaMemcpy(e->d_pair_odd, so.data(), so.size() * sizeof(cf), cudaMemcpyHostToDevice));
     }
     std::vector<float> we = host_decimate2(window), ee = host_decimate2(env);
+    {   // j as f32 / factor as f32, resampler.rs:29
+        const int q = cfg->pitch_multiple < 0 ? -cfg->pitch_multiple : 1;
+        std::vector<float> ratio(128, 0.0f);
+        for (int j = 0; j < q && j < 128; j++) ratio[j] = (float)j / (float)q;
+        TRY_E(cudaMalloc(&e->d_lerp_ratio, ratio.size() * sizeof(float)));
+        TRY_E(cudaMemcpy(e->d_lerp_ratio, ratio.data(), ratio.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     TRY_E(cudaMalloc(&e->d_window_even, we.size() * sizeof(float)));
     TRY_E(cudaMalloc(&e->d_env_even, ee.size() * sizeof(float)));
     TRY_E(cudaMalloc(&e->d_spec_tw_hr, stw_hr.size() * sizeof(cf)));
@@ -329,7 +337,7 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     if (e->d2h) cudaStreamSynchronize(e->d2h);
     if (e->h2d) cudaStreamSynchronize(e->h2d);
     cudaFree(e->d_window); cudaFree(e->d_env); cudaFree(e->d_tw); cudaFree(e->d_spec_tw); cudaFree(e->d_scratch);
-    cudaFree(e->d_window_even); cudaFree(e->d_env_even); cudaFree(e->d_spec_tw_hr);
+    cudaFree(e->d_window_even); cudaFree(e->d_env_even); cudaFree(e->d_spec_tw_hr); cudaFree(e->d_lerp_ratio);
     cudaFree(e->d_pair_cross); cudaFree(e->d_pair_even); cudaFree(e->d_pair_odd);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_tail_pp[0]); cudaFree(e->d_tail_pp[1]);
     cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_spec);
@@ -375,6 +383,7 @@ static void fill_params(const rcg_engine* e, StretchParams& p) {
     memset(&p, 0, sizeof(p));
     p.window = e->d_window; p.env = e->d_env; p.tw = e->d_tw; p.spec_tw = e->d_spec_tw;
     p.spec_tw_hr = e->d_spec_tw_hr; p.window_even = e->d_window_even; p.env_even = e->d_env_even;
+    p.lerp_ratio = e->d_lerp_ratio;
     p.tail_scratch = e->d_scratch;
     p.channels = (int)e->cfg.channels;
     p.step = (int)e->plan.sample_step_len;

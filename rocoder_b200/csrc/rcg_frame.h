@@ -70,6 +70,7 @@ struct StretchParams {
     const cf* spec_tw_hr;   // [H/4] the same in the half-rate quad order
     const float* window_even;  // [H]   window[2i]   (half-rate synthesis)
     const float* env_even;     // [H/2] env[2i]
+    const float* lerp_ratio;   // [|p|] j / |p| as f32 (resampler.rs:29), for pitch < -1
     float* tail_scratch;    // [work lanes][H] carried second half window (stretcher.rs:101-102)
     const float* tail_in;   // optional [channels][H]: second half of frame frame_begin-1
     float* tail_out;        // optional [channels][H]: second half of frame frame_end-1
@@ -834,14 +835,20 @@ RCG_HD void phase_resample(const cf* S, int t, const StretchParams& prm, int cha
             out[o - prm.out_origin] = frame_value(S, i);
         }
     } else if (p < -1) {
+        // resample_slower (resampler.rs:20-35): out[i*q + j] = z[i] + (z[i+1] - z[i]) * (j / q).
+        // (i, j) advance by (NT / q, NT % q) per iteration: no integer division in the loop; the
+        // q ratios j/q come from a host-computed table (same IEEE division as the reference).
         const int q = -p;
         const int n = (prm.samples_needed - 1) * q;
         float* dst = out + (frame * (long long)n - prm.out_origin);
+        const int di = C::NT / q, dj = C::NT - di * q;
+        int i = t / q, j = t - i * q;
         for (int tt = t; tt < n; tt += C::NT) {
-            const int i = tt / q, j = tt - i * q;
             const float cur = frame_value(S, i), nxt = frame_value(S, i + 1);
-            const float ratio = RCG_DIV((float)j, (float)q);
+            const float ratio = prm.lerp_ratio[j];
             dst[tt] = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), ratio));
+            i += di; j += dj;
+            if (j >= q) { j -= q; i++; }
         }
     }
 }

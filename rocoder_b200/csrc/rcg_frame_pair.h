@@ -138,10 +138,13 @@ RCG_HD void pair_phase_resample(const float* stage, int t, const StretchParams& 
         const int q = -p;
         const int n = (prm.samples_needed - 1) * q;
         float* dst = out + (frame * (long long)n - prm.out_origin);
+        const int di = C::NT / q, dj = C::NT - di * q;
+        int i = t / q, j = t - i * q;
         for (int tt = t; tt < n; tt += C::NT) {
-            const int i = tt / q, j = tt - i * q;
             const float cur = stage[i], nxt = stage[i + 1];
-            dst[tt] = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), RCG_DIV((float)j, (float)q)));
+            dst[tt] = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), prm.lerp_ratio[j]));
+            i += di; j += dj;
+            if (j >= q) { j -= q; i++; }
         }
     }
 }

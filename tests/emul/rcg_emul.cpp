@@ -41,6 +41,12 @@ struct HostExec {
 };
 
 static int g_disable_half_rate = 0;
+static std::vector<float> lerp_table(int pitch) {
+    const int q = pitch < 0 ? -pitch : 1;
+    std::vector<float> r(128, 0.0f);
+    for (int j = 0; j < q && j < 128; j++) r[j] = (float)j / (float)q;
+    return r;
+}
 static int g_no_fuse = 0;
 
 template <int LOG2H>
@@ -55,6 +61,8 @@ static int emul_run(StretchParams prm) {
     std::vector<float> we = host_decimate2(window), ee = host_decimate2(env);
     prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.spec_tw = stw.data();
     prm.spec_tw_hr = stw_hr.data(); prm.window_even = we.data(); prm.env_even = ee.data();
+    std::vector<float> lr = lerp_table(prm.pitch);
+    prm.lerp_ratio = lr.data();
     if (use_half_rate(prm.pitch, prm.flags) && !g_disable_half_rate) prm.flags |= kFlagHalfRate;
     if (g_no_fuse) prm.flags |= kFlagNoFuse;
     std::vector<cf> S(C::SMEM_CF);
@@ -91,6 +99,8 @@ static int emul_run_pair(StretchParams prm) {
     std::vector<cf> cross = host_pair_cross_twiddles(kPairLog2HL + 1);
     std::vector<cf> se = host_pair_spectral_twiddles(kPairLog2HL + 1, 0), so = host_pair_spectral_twiddles(kPairLog2HL + 1, 1);
     prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data();
+    std::vector<float> lr = lerp_table(prm.pitch);
+    prm.lerp_ratio = lr.data();
     std::vector<float> scratch(3 * (size_t)kPairH);
     PairTables pt{cross.data(), se.data(), so.data(), scratch.data()};
     std::vector<cf> S0(C::SMEM_CF), S1(C::SMEM_CF);
@@ -106,6 +116,8 @@ static int emul_boundary_pair(StretchParams prm, const float* head, const float*
     std::vector<float> env(kPairH), stage(kPairH);
     host_crossfade_compensation(env.data(), kPairH);
     prm.env = env.data();
+    std::vector<float> lr = lerp_table(prm.pitch);
+    prm.lerp_ratio = lr.data();
     HostExec ex{C::NT};
     for (int c = 0; c < prm.channels; c++) run_boundary_pair(ex, prm, c, head, tail_prev, stage.data());
     return 0;
@@ -118,6 +130,8 @@ static int emul_boundary(StretchParams prm, const float* head, const float* tail
     host_crossfade_compensation(env.data(), C::H);
     std::vector<float> ee = host_decimate2(env);
     prm.env = env.data(); prm.env_even = ee.data();
+    std::vector<float> lr = lerp_table(prm.pitch);
+    prm.lerp_ratio = lr.data();
     if (use_half_rate(prm.pitch, prm.flags) && !g_disable_half_rate) prm.flags |= kFlagHalfRate;
     std::vector<cf> S(C::SMEM_CF);
     HostExec ex{C::NT};
@@ -191,6 +205,8 @@ static int emul_plugin(StretchParams prm, apply_fn fn) {
     host_crossfade_compensation(env.data(), H);
     std::vector<cf> tw = host_pass_twiddles(LOG2H), stw = host_spectral_twiddles(LOG2H);
     prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.spec_tw = stw.data();
+    std::vector<float> lr = lerp_table(prm.pitch);
+    prm.lerp_ratio = lr.data();
     const long long nf = prm.frame_end - prm.frame_begin;
     std::vector<cf> spec((size_t)prm.channels * nf * W);
     prm.spectrum = spec.data(); prm.spec_frame0 = prm.frame_begin; prm.spec_frames = nf;
