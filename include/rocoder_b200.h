@@ -175,6 +175,13 @@ typedef int (*rcg_apply_fn)(size_t elapsed_ms, const float *in_re_im, size_t n_b
 int rcg_push_frequency_kernel(rcg_engine *e, rcg_apply_fn fn);
 /* dlopen(path) and push its `apply` symbol (hotswapper.rs:85-86 + fft.rs:93-94) */
 int rcg_load_frequency_kernel(rcg_engine *e, const char *so_path);
+/* Device form of the same contract: CUDA source defining
+ *     __device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, const float2 *spectrum)
+ * which returns the output value of `bin` given the frame's whole W-bin input spectrum.  Compiled
+ * with NVRTC for sm_100a (the compile-and-swap role of hotswapper.rs:58-86); the spectra then never
+ * leave HBM.  A compile error returns RCG_ERR_PLUGIN and keeps the previous kernel
+ * (hotswapper.rs:36-42). */
+int rcg_push_device_frequency_kernel(rcg_engine *e, const char *cuda_source);
 int rcg_frequency_kernel_count(const rcg_engine *e, uint32_t *n);
 
 /* -- helpers ------------------------------------------------------------------------------ */

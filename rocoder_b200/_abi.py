@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
         "rcg_is_done": (C.c_int, [C.c_void_p, C.c_uint32, P(C.c_int)]),
         "rcg_push_frequency_kernel": (C.c_int, [C.c_void_p, APPLY_FN]),
         "rcg_load_frequency_kernel": (C.c_int, [C.c_void_p, C.c_char_p]),
+        "rcg_push_device_frequency_kernel": (C.c_int, [C.c_void_p, C.c_char_p]),
         "rcg_frequency_kernel_count": (C.c_int, [C.c_void_p, P(C.c_uint32)]),
         "rcg_host_alloc": (C.c_int, [P(C.c_void_p), C.c_size_t]),
         "rcg_host_free": (C.c_int, [C.c_void_p]),

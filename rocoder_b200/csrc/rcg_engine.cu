@@ -174,6 +174,14 @@ struct ChannelState {
     int tail_cur = 0;
 };
 
+// one entry of the frequency-kernel stack (fft.rs:22 `kernels: Vec<Library>`): a host `apply`
+// or a device `apply` compiled with NVRTC
+struct FreqKernel {
+    rcg_apply_fn host = nullptr;
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t dev = nullptr;
+};
+
 struct rcg_engine {
     rcg_config cfg{};
     rcg_plan_info plan{};
@@ -201,12 +209,12 @@ struct rcg_engine {
     float *d_sin = nullptr, *d_sout = nullptr, *h_sout = nullptr;
     size_t d_sin_cap = 0, d_sout_cap = 0, h_sout_cap = 0;
     // plugin path buffers: spectra of one batch of frames, device + pinned host
-    cf *d_spec = nullptr, *h_spec = nullptr;
+    cf *d_spec = nullptr, *h_spec = nullptr, *d_spec2 = nullptr;
     size_t spec_cap = 0;  // in cf
     float* d_plug_tail[2] = {nullptr, nullptr};
     std::vector<float> plug_tmp;
     // plugins (fft.rs:22: kernels: Vec<Library>)
-    std::vector<rcg_apply_fn> kernels;
+    std::vector<FreqKernel> kernels;
     bool had_kernels = false;  // a kernel was pushed at some point (even if all have since failed)
     std::vector<void*> libs;
 };
@@ -340,7 +348,8 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     cudaFree(e->d_window_even); cudaFree(e->d_env_even); cudaFree(e->d_spec_tw_hr); cudaFree(e->d_lerp_ratio);
     cudaFree(e->d_pair_cross); cudaFree(e->d_pair_even); cudaFree(e->d_pair_odd);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_tail_pp[0]); cudaFree(e->d_tail_pp[1]);
-    cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_spec);
+    cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_spec); cudaFree(e->d_spec2);
+    for (auto& k : e->kernels) if (k.lib) cudaLibraryUnload(k.lib);
     cudaFree(e->d_plug_tail[0]); cudaFree(e->d_plug_tail[1]);
     if (e->h_spec) cudaFreeHost(e->h_spec);
     if (e->h_sout) cudaFreeHost(e->h_sout);
@@ -452,11 +461,11 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
 // fft.rs:101-106: a failing kernel is dropped for good, the previous one is tried, and with none
 // left the spectrum passes through unchanged.
 static void apply_kernels(rcg_engine* e, float* spectrum, size_t n_bins) {
-    while (!e->kernels.empty()) {
+    while (!e->kernels.empty() && e->kernels.back().host) {
         const size_t ms = (size_t)std::chrono::duration_cast<std::chrono::milliseconds>(
                               std::chrono::system_clock::now().time_since_epoch()).count();  // fft.rs:89-92
         e->plug_tmp.resize(2 * n_bins);
-        if (e->kernels.back()(ms, spectrum, n_bins, e->plug_tmp.data()) == 0) {
+        if (e->kernels.back().host(ms, spectrum, n_bins, e->plug_tmp.data()) == 0) {
             memcpy(spectrum, e->plug_tmp.data(), 2 * n_bins * sizeof(float));
             return;
         }
@@ -478,7 +487,9 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
         cudaFree(e->d_spec); e->d_spec = nullptr;
         if (e->h_spec) cudaFreeHost(e->h_spec);
         e->h_spec = nullptr; e->spec_cap = 0;
+        cudaFree(e->d_spec2); e->d_spec2 = nullptr;
         CUDA_TRY(cudaMalloc(&e->d_spec, need * sizeof(cf)));
+        CUDA_TRY(cudaMalloc(&e->d_spec2, need * sizeof(cf)));
         CUDA_TRY(cudaMallocHost(&e->h_spec, need * sizeof(cf)));
         e->spec_cap = need;
     }
@@ -512,6 +523,26 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
         if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "analysis kernel launch failed: %s", cudaGetErrorString(ce));
         e->launches++;
         const size_t bytes = (size_t)channels * nframes * W * sizeof(cf);
+        cf* synth_src = e->d_spec;
+        bool on_device = false;
+        while (!e->kernels.empty() && e->kernels.back().dev) {
+            // device `apply`: the spectra never leave HBM -- analysis -> apply kernel -> synthesis
+            const unsigned n_bins = (unsigned)W;
+            const unsigned long long n_fr = (unsigned long long)channels * nframes;
+            const unsigned long long ms = (unsigned long long)std::chrono::duration_cast<std::chrono::milliseconds>(
+                                              std::chrono::system_clock::now().time_since_epoch()).count();
+            const cf* in_p = e->d_spec;
+            cf* out_p = e->d_spec2;
+            void* args[] = {(void*)&in_p, (void*)&out_p, (void*)&n_bins, (void*)&n_fr, (void*)&ms};
+            const unsigned long long total = n_fr * n_bins;
+            const unsigned blocks = (unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)e->sm_count * 16);
+            cudaError_t le = cudaLaunchKernel((const void*)e->kernels.back().dev, dim3(blocks), dim3(256), args, 0, stream);
+            if (le == cudaSuccess) { e->launches++; synth_src = e->d_spec2; on_device = true; break; }
+            (void)cudaGetLastError();
+            cudaLibraryUnload(e->kernels.back().lib);
+            e->kernels.pop_back();   // unusable kernel: fall back to the previous one (fft.rs:101-106)
+        }
+        if (!on_device) {
         CUDA_TRY(cudaMemcpyAsync(e->h_spec, e->d_spec, bytes, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         // reference order (stretcher_processor.rs:62-70): call by call, channel by channel, frame by frame
@@ -524,6 +555,7 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
                     apply_kernels(e, reinterpret_cast<float*>(e->h_spec + ((size_t)c * nframes + fi) * W), W);
                 }
         CUDA_TRY(cudaMemcpyAsync(e->d_spec, e->h_spec, bytes, cudaMemcpyHostToDevice, stream));
+        }
         rcg_segment b = s;
         b.first_call = c0; b.n_calls = nb;
         b.d_out = s.d_out + (c0 - s.first_call) * e->plan.out_len_per_call;
@@ -532,7 +564,7 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
         b.d_head_out = first ? s.d_head_out : nullptr;
         b.flags = first ? s.flags : 0u;
         pp ^= 1;
-        SpectrumRef ref{e->d_spec, a0, f1 - a0};
+        SpectrumRef ref{synth_src, a0, f1 - a0};
         int rc = launch_segment(e, b, channels, stream, channel_offset, &ref);
         if (rc) return rc;
         CUDA_TRY(cudaStreamSynchronize(stream));  // the spectrum buffer is reused by the next batch
@@ -769,7 +801,9 @@ static int check_kernel_push(rcg_engine* e) {
 extern "C" int rcg_push_frequency_kernel(rcg_engine* e, rcg_apply_fn fn) {
     if (!e || !fn) return fail(RCG_ERR_INVALID_ARG, "null argument");
     if (int rc = check_kernel_push(e)) return rc;
-    e->kernels.push_back(fn);
+    FreqKernel k;
+    k.host = fn;
+    e->kernels.push_back(k);
     e->had_kernels = true;
     return RCG_OK;
 }
@@ -784,10 +818,93 @@ extern "C" int rcg_load_frequency_kernel(rcg_engine* e, const char* so_path) {
         return fail(RCG_ERR_PLUGIN, "%s has no `apply` symbol", so_path);
     }
     e->libs.push_back(lib);
-    e->kernels.push_back((rcg_apply_fn)sym);
+    FreqKernel k;
+    k.host = (rcg_apply_fn)sym;
+    e->kernels.push_back(k);
     e->had_kernels = true;
     return RCG_OK;
 }
+// ---- device frequency kernels: CUDA source -> NVRTC -> cubin for sm_100a -----------------------------
+// (the role of hotswapper.rs:58-86, which shells out to rustc; libnvrtc is loaded on first use so
+// that the library itself has no NVRTC dependency)
+namespace {
+typedef void* nvrtcProgram_t;
+struct Nvrtc {
+    void* lib = nullptr;
+    int (*create)(nvrtcProgram_t*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*compile)(nvrtcProgram_t, int, const char* const*) = nullptr;
+    int (*log_size)(nvrtcProgram_t, size_t*) = nullptr;
+    int (*get_log)(nvrtcProgram_t, char*) = nullptr;
+    int (*cubin_size)(nvrtcProgram_t, size_t*) = nullptr;
+    int (*get_cubin)(nvrtcProgram_t, char*) = nullptr;
+    int (*destroy)(nvrtcProgram_t*) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"};
+        for (const char* n : names) if ((lib = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+        if (!lib) return false;
+        create = (decltype(create))dlsym(lib, "nvrtcCreateProgram");
+        compile = (decltype(compile))dlsym(lib, "nvrtcCompileProgram");
+        log_size = (decltype(log_size))dlsym(lib, "nvrtcGetProgramLogSize");
+        get_log = (decltype(get_log))dlsym(lib, "nvrtcGetProgramLog");
+        cubin_size = (decltype(cubin_size))dlsym(lib, "nvrtcGetCUBINSize");
+        get_cubin = (decltype(get_cubin))dlsym(lib, "nvrtcGetCUBIN");
+        destroy = (decltype(destroy))dlsym(lib, "nvrtcDestroyProgram");
+        return create && compile && log_size && get_log && cubin_size && get_cubin && destroy;
+    }
+} g_nvrtc;
+
+const char* kDeviceWrapper = R"(
+extern "C" __global__ void rcg_apply_kernel(const float2* in, float2* out, unsigned n_bins,
+                                            unsigned long long n_frames, unsigned long long elapsed_ms) {
+    const unsigned long long total = n_frames * n_bins;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long f = i / n_bins;
+        const unsigned b = (unsigned)(i - f * n_bins);
+        out[i] = apply((size_t)elapsed_ms, b, n_bins, in + f * n_bins);
+    }
+}
+)";
+}  // namespace
+
+extern "C" int rcg_push_device_frequency_kernel(rcg_engine* e, const char* cuda_source) {
+    if (!e || !cuda_source) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (int rc = check_kernel_push(e)) return rc;
+    if (e->pair) return fail(RCG_ERR_PLUGIN, "frequency kernels are not supported at window_len 65536 yet");
+    CUDA_TRY(cudaSetDevice(e->device));
+    if (!g_nvrtc.load()) return fail(RCG_ERR_PLUGIN, "libnvrtc could not be loaded: %s", dlerror());
+    const std::string src = std::string(cuda_source) + kDeviceWrapper;
+    nvrtcProgram_t prog = nullptr;
+    if (g_nvrtc.create(&prog, src.c_str(), "frequency_kernel.cu", 0, nullptr, nullptr) != 0)
+        return fail(RCG_ERR_PLUGIN, "nvrtcCreateProgram failed");
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device"};
+    const int cr = g_nvrtc.compile(prog, 3, opts);
+    if (cr != 0) {   // compile failure keeps the previous kernel (hotswapper.rs:36-42)
+        size_t n = 0;
+        g_nvrtc.log_size(prog, &n);
+        std::string log(n + 1, '\0');
+        if (n) g_nvrtc.get_log(prog, &log[0]);
+        g_nvrtc.destroy(&prog);
+        return fail(RCG_ERR_PLUGIN, "device frequency kernel failed to compile: %.400s", log.c_str());
+    }
+    size_t cn = 0;
+    g_nvrtc.cubin_size(prog, &cn);
+    std::vector<char> cubin(cn);
+    g_nvrtc.get_cubin(prog, cubin.data());
+    g_nvrtc.destroy(&prog);
+    FreqKernel k;
+    CUDA_TRY(cudaLibraryLoadData(&k.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    cudaError_t ke = cudaLibraryGetKernel(&k.dev, k.lib, "rcg_apply_kernel");
+    if (ke != cudaSuccess) {
+        cudaLibraryUnload(k.lib);
+        return fail(RCG_ERR_PLUGIN, "compiled frequency kernel has no entry point: %s", cudaGetErrorString(ke));
+    }
+    e->kernels.push_back(k);
+    e->had_kernels = true;
+    return RCG_OK;
+}
+
 extern "C" int rcg_frequency_kernel_count(const rcg_engine* e, uint32_t* n) {
     if (!e || !n) return fail(RCG_ERR_INVALID_ARG, "null argument");
     *n = (uint32_t)e->kernels.size();

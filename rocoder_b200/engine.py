@@ -222,6 +222,11 @@ class Engine:
         check(lib().rcg_push_frequency_kernel(self._h, cb))
         del W
 
+    def push_device_frequency_kernel(self, cuda_source: str) -> None:
+        """CUDA source defining `__device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins,
+        const float2* spectrum)`; compiled with NVRTC for sm_100a, spectra stay in HBM."""
+        check(lib().rcg_push_device_frequency_kernel(self._h, cuda_source.encode()))
+
     def load_frequency_kernel(self, so_path: str) -> None:
         check(lib().rcg_load_frequency_kernel(self._h, so_path.encode()))
 
