@@ -140,7 +140,26 @@ def cpu_leg(target_seconds: float, native: bool = True):
     per_call = t / max(made, 1)
     calls = int(max(40, min(target_seconds / per_call, ol.expected_counts(x.size, FACTOR, PITCH, WINDOW)[0] - 1)))
     t, made, outs = run(calls)
+    # all cores, one independent replica each (ctypes drops the GIL): labelled separately -- the
+    # reference itself drives every channel from ONE thread (stretcher_processor.rs:55-71)
+    ncores = os.cpu_count() or 1
+    rep_calls = max(20, calls // 4)
+    sinks = [np.zeros(WINDOW * 2, np.float32) for _ in range(ncores)]
+    outs_r = [C.c_size_t() for _ in range(ncores)]
+
+    def rep(i):
+        L.ro_bench_channel(x.ctypes.data_as(ol.PF), x.size, SAMPLE_RATE, FACTOR, 1.0, PITCH, WINDOW, SEED, i, rep_calls,
+                           sinks[i].ctypes.data_as(ol.PF), C.byref(outs_r[i]))
+    ths = [threading.Thread(target=rep, args=(i,)) for i in range(ncores)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    t_rep = time.perf_counter() - t0
+    replica_value = sum(o.value for o in outs_r) / t_rep / 1e6
     return {"value": outs / t / 1e6, "unit": "Msamples/s", "cores": 1,
+            "replica_value": replica_value, "replica_cores": ncores,
             "kind": "port",
             "sample": f"first {made} calls ({made * 4} frames, {outs} output samples) of channel 0 of the workload, "
                       f"{t:.1f} s on 1 thread (the reference DSP loop is single-threaded); "
@@ -258,6 +277,7 @@ def run_ours(args):
     traffic, traffic_src = measured_traffic() if world == 1 else (None, None)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     flops = frames * CHANNELS * (2 * 5 * WINDOW * 14 + 20 * WINDOW)
+    fp32_peak = rb.measure_fp32_peak() if rank == 0 else None
 
     # end to end through the C ABI with pinned host buffers (rank-local 10 minutes)
     e2e_in = rb.PinnedBuffer((CHANNELS, N_IN))
@@ -296,6 +316,8 @@ def run_ours(args):
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "stretch_kernel<13>",
                          "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                          "fp32_tflops_algorithmic": flops / (k_ms * 1e-3) / 1e12,
+                         "fp32_peak_tflops_measured": fp32_peak,
+                         "fp32_frac_algorithmic": (flops / (k_ms * 1e-3) / 1e12 / fp32_peak) if fp32_peak else None,
                          "note": "compute(FP32/shared-memory)-bound path: see DESIGN.md for why frac is capped"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 4 * CHANNELS * N_IN,

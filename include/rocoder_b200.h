@@ -184,9 +184,22 @@ int rcg_load_frequency_kernel(rcg_engine *e, const char *so_path);
 int rcg_push_device_frequency_kernel(rcg_engine *e, const char *cuda_source);
 int rcg_frequency_kernel_count(const rcg_engine *e, uint32_t *n);
 
+/* -- fade in / out (`-x`): what the reference's live Mixer applies (mixer.rs:132-190 with
+ * math::sqrt_interp, math.rs:33-40); not applied in file mode by the reference (main.rs:195-204) and
+ * therefore not by rcg_process_all either.  Multiplies d_audio[c * stride + k], k < n, by the gain of
+ * output position first_pos + k: sqrt(r) over the first fade_s seconds, 1, then sqrt(1 - r) over the
+ * last fade_s seconds before expected_total_samples (= (n_in * factor) as usize, main.rs:154), 0 after. */
+int rcg_fade_in_out(float *d_audio, int64_t stride, uint32_t channels, uint64_t n, uint64_t first_pos,
+                    float fade_s, uint32_t sample_rate, uint64_t expected_total_samples, void *stream);
+/* [host] the keyframe positions Mixer::fade_in_out computes (mixer.rs:179-190) */
+int rcg_fade_keyframes(float fade_s, uint32_t sample_rate, uint64_t expected_total_samples, uint64_t *fade_n,
+                       uint64_t *start_n, uint64_t *end_n);
+
 /* -- helpers ------------------------------------------------------------------------------ */
 int rcg_host_alloc(void **ptr, size_t bytes); /* pinned host memory */
 int rcg_host_free(void *ptr);
+/* FP32 FMA throughput of the current device, TFLOP/s: the measured compute-roofline denominator */
+int rcg_measure_fp32_peak(double *tflops, int reps);
 /* kernels launched by this engine so far */
 int rcg_launch_count(const rcg_engine *e, uint64_t *n);
 

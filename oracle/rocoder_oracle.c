@@ -69,6 +69,39 @@ size_t ro_resample_len(size_t n, int factor) {
     return 0;
 }
 
+/* ---------------------------------------------------------------- fades ---------- */
+/* Mixer::dur_to_sample (mixer.rs:147-149): (dur.as_secs_f32() * sample_rate as f32) as usize */
+static uint64_t ro_dur_to_sample(float secs, uint32_t sr) { return ro_f32_to_usize(secs * (float)sr); }
+
+/* Mixer::fade_in_out (mixer.rs:179-190): fade in from 0 s; fade out starts at total_dur - fade where
+ * total_dur = Duration::from_secs_f32(expected_total_samples as f32 / sample_rate as f32) */
+void ro_fade_keyframes(float fade_s, uint32_t sr, uint64_t expected_total, uint64_t *fade_n, uint64_t *start_n,
+                       uint64_t *end_n) {
+    float total_s = (float)expected_total / (float)sr;
+    /* Durations hold integer nanoseconds; from_secs_f32 rounds to them, subtraction is exact */
+    double total_ns = floor((double)total_s * 1e9 + 0.5), fade_ns = floor((double)fade_s * 1e9 + 0.5);
+    double start_ns = total_ns - fade_ns;
+    if (start_ns < 0) start_ns = 0; /* the reference would panic on Duration underflow */
+    *fade_n = ro_dur_to_sample((float)(fade_ns / 1e9), sr);
+    *start_n = ro_dur_to_sample((float)(start_ns / 1e9), sr);
+    *end_n = ro_dur_to_sample((float)((start_ns + fade_ns) / 1e9), sr);
+}
+
+/* Layer::current_amp (mixer.rs:132-145) with keyframes pruned as playback passes them (:107-120) */
+float ro_fade_gain(uint64_t pos, float fade_s, uint32_t sr, uint64_t expected_total) {
+    uint64_t fade_n, start_n, end_n;
+    ro_fade_keyframes(fade_s, sr, expected_total, &fade_n, &start_n, &end_n);
+    const uint64_t kp[4] = {0, fade_n, start_n, end_n};
+    const float kv[4] = {0.0f, 1.0f, 1.0f, 0.0f};
+    /* the active pair is the last one whose `next` position has not been passed */
+    int i = 0;
+    while (i < 2 && kp[i + 1] < pos) i++;
+    if (pos > kp[3]) return kv[3];
+    if (kp[i + 1] == kp[i]) return kv[i + 1];
+    float progress = (float)(pos - kp[i]) / (float)(kp[i + 1] - kp[i]);
+    return ro_sqrt_interp(kv[i], kv[i + 1], progress);
+}
+
 /* ---------------------------------------------------------------- phase source --- */
 
 void ro_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {

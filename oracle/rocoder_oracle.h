@@ -155,6 +155,14 @@ long ro_process_all_f64(uint32_t channels, uint32_t sample_rate, const float *co
 int ro_expected_counts(size_t n_in, float factor, int pitch_multiple, size_t window_len,
                        size_t *calls, size_t *frames, size_t *out_len);
 
+/* ---- fade in / out of live playback (`-x`; mixer.rs:132-190, main.rs:154, player_processor.rs) ----
+ * Gain the Mixer applies to output sample `pos` after fade_in_out(Some(fade), Some(fade)) with
+ * expected_total_samples = (n_in * factor) as usize: keyframes (0, 0.0), (fade_n, 1.0),
+ * (start_n, 1.0), (end_n, 0.0) interpolated with math::sqrt_interp. */
+float ro_fade_gain(uint64_t pos, float fade_s, uint32_t sample_rate, uint64_t expected_total_samples);
+void ro_fade_keyframes(float fade_s, uint32_t sample_rate, uint64_t expected_total_samples,
+                       uint64_t *fade_n, uint64_t *start_n, uint64_t *end_n);
+
 /* time a bounded sample: run `max_calls` calls (0 = all) of one channel; returns
  * calls made.  Used by bench.py's cpu_baseline leg only. */
 long ro_bench_channel(const float *in, size_t n_in, uint32_t sample_rate, float factor,

@@ -18,6 +18,9 @@
 #ifndef RCG_OLA_UNROLL
 #define RCG_OLA_UNROLL 2
 #endif
+#ifndef RCG_STREAM_POLICY
+#define RCG_STREAM_POLICY 0
+#endif
 #ifndef RCG_FUSE_OLA_LOAD
 #define RCG_FUSE_OLA_LOAD 0   // measured slower on B200 (9.1 vs 8.0 ms on config 2): off by default
 #endif
@@ -120,7 +123,17 @@ RCG_HD float ld_stream(const float* p) {
 }
 RCG_HD cf ld_stream2(const float* p) {  // p must be 8-byte aligned
 #if defined(__CUDA_ARCH__)
+#if RCG_STREAM_POLICY
+    // keep the streams out of L1 (the twiddle tables live there) but pinned in L2: L1 no-allocate
+    // plus an explicit L2 evict_last policy (without it no_allocate loads are evict-first in L2)
+    unsigned long long pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    cf r;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(pol));
+    return r;
+#else
     return __ldg(reinterpret_cast<const float2*>(p));
+#endif
 #else
     return make_cf(p[0], p[1]);
 #endif

@@ -79,6 +79,25 @@ def channel_bound(window_len: int, sample_rate: int, buffer_dur_s: float) -> int
     return b.value
 
 
+def fade_in_out(d_audio, fade_s: float, sample_rate: int, expected_total_samples: int, first_pos: int = 0,
+                stream: Optional[int] = None) -> None:
+    """`-x` fade of the reference's live mixer (mixer.rs:132-190) applied in place to a CUDA tensor [C, n]"""
+    check(lib().rcg_fade_in_out(d_audio.data_ptr(), d_audio.stride(0), d_audio.shape[0], d_audio.shape[1], first_pos,
+                                fade_s, sample_rate, expected_total_samples, _stream(stream) if stream is not None else None))
+
+
+def fade_keyframes(fade_s: float, sample_rate: int, expected_total_samples: int):
+    a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    check(lib().rcg_fade_keyframes(fade_s, sample_rate, expected_total_samples, C.byref(a), C.byref(b), C.byref(c)))
+    return a.value, b.value, c.value
+
+
+def measure_fp32_peak(reps: int = 5) -> float:
+    v = C.c_double()
+    check(lib().rcg_measure_fp32_peak(C.byref(v), reps))
+    return v.value
+
+
 class PinnedBuffer:
     """float32 host buffer in page-locked memory (rcg_host_alloc)."""
 
@@ -241,5 +260,5 @@ class Engine:
         return n.value
 
 
-__all__ = ["Engine", "PinnedBuffer", "RcgError", "WouldBlock", "hanning", "hanning_crossfade_compensation",
+__all__ = ["Engine", "PinnedBuffer", "fade_in_out", "fade_keyframes", "measure_fp32_peak", "RcgError", "WouldBlock", "hanning", "hanning_crossfade_compensation",
            "plan", "expected_counts", "channel_bound", "phase"]

@@ -78,6 +78,9 @@ def oracle(path: str | None = None) -> C.CDLL:
     L.ro_bench_channel.restype = C.c_long
     L.ro_bench_channel.argtypes = [PF, C.c_size_t, C.c_uint32, C.c_float, C.c_float, C.c_int, C.c_size_t,
                                    C.c_uint64, C.c_uint32, C.c_size_t, PF, C.POINTER(C.c_size_t)]
+    L.ro_fade_gain.restype = C.c_float
+    L.ro_fade_gain.argtypes = [C.c_uint64, C.c_float, C.c_uint32, C.c_uint64]
+    L.ro_fade_keyframes.argtypes = [C.c_float, C.c_uint32, C.c_uint64] + [C.POINTER(C.c_uint64)] * 3
     if path is None:
         _oracle = L
     return L
