@@ -18,6 +18,9 @@
 #ifndef RCG_OLA_UNROLL
 #define RCG_OLA_UNROLL 2
 #endif
+#ifndef RCG_TW_EVICT_LAST
+#define RCG_TW_EVICT_LAST 0
+#endif
 #ifndef RCG_STREAM_POLICY
 #define RCG_STREAM_POLICY 0
 #endif
@@ -140,7 +143,13 @@ RCG_HD cf ld_stream2(const float* p) {  // p must be 8-byte aligned
 }
 RCG_HD cf ld_cf(const cf* p) {
 #if defined(__CUDA_ARCH__)
+#if RCG_TW_EVICT_LAST
+    cf r;   // tables: ask L1 to keep them ahead of the streaming input / window / envelope lines
+    asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+#else
     return __ldg(p);
+#endif
 #else
     return *p;
 #endif

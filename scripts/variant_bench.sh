@@ -6,7 +6,7 @@ for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
   out=gpurun_out/variants/lib_${name}.so
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC -shared \
-       -DRCG_ONLY_LOG2H=13 $flags -o $out rocoder_b200/csrc/rcg_kernels.cu rocoder_b200/csrc/rcg_engine.cu -ldl 2> gpurun_out/variants/${name}.build.log \
+       -DRCG_ONLY_LOG2H=13 $flags -o $out rocoder_b200/csrc/*.cu -ldl 2> gpurun_out/variants/${name}.build.log \
     || { echo "{\"tag\": \"$name\", \"error\": \"build failed\"}"; continue; }
   RCG_LIB=$out python scripts/kernel_time.py --tag "$name" $KT_ARGS 2>> gpurun_out/variants/${name}.build.log
 done
