@@ -210,7 +210,7 @@ struct rcg_engine {
     size_t d_sin_cap = 0, d_sout_cap = 0, h_sout_cap = 0;
     // plugin path buffers: spectra of one batch of frames, device + pinned host
     cf *d_spec = nullptr, *h_spec = nullptr, *d_spec2 = nullptr;
-    size_t spec_cap = 0;  // in cf
+    size_t spec_cap = 0, h_spec_cap = 0;  // in cf
     float* d_plug_tail[2] = {nullptr, nullptr};
     std::vector<float> plug_tmp;
     // plugins (fft.rs:22: kernels: Vec<Library>)
@@ -478,19 +478,19 @@ static void apply_kernels(rcg_engine* e, float* spectrum, size_t n_bins) {
 static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream,
                                int channel_offset) {
     const uint64_t k = e->plan.frames_per_call, W = e->plan.window_len, H = W / 2;
-    const uint64_t budget_cf = (uint64_t)256 << 17;  // 256 MiB of spectra per batch
+    // spectra per batch: 256 MiB when they visit the host, 1 GiB when a device kernel keeps them in HBM
+    const bool dev_top = !e->kernels.empty() && e->kernels.back().dev;
+    const uint64_t budget_cf = (uint64_t)(dev_top ? 1024 : 256) << 17;
     uint64_t fpb = std::max<uint64_t>(k + 1, budget_cf / ((uint64_t)channels * W));  // frames/channel/batch
     uint64_t cpb = std::max<uint64_t>(1, (fpb - 1) / k);
     fpb = cpb * k + 1;
     const size_t need = (size_t)channels * fpb * W;
     if (e->spec_cap < need) {
         cudaFree(e->d_spec); e->d_spec = nullptr;
-        if (e->h_spec) cudaFreeHost(e->h_spec);
-        e->h_spec = nullptr; e->spec_cap = 0;
+        e->spec_cap = 0;
         cudaFree(e->d_spec2); e->d_spec2 = nullptr;
         CUDA_TRY(cudaMalloc(&e->d_spec, need * sizeof(cf)));
         CUDA_TRY(cudaMalloc(&e->d_spec2, need * sizeof(cf)));
-        CUDA_TRY(cudaMallocHost(&e->h_spec, need * sizeof(cf)));
         e->spec_cap = need;
     }
     for (int i = 0; i < 2; i++)
@@ -543,6 +543,12 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
             e->kernels.pop_back();   // unusable kernel: fall back to the previous one (fft.rs:101-106)
         }
         if (!on_device) {
+        if (e->h_spec_cap < need) {   // pinned staging only when spectra really visit the host
+            if (e->h_spec) cudaFreeHost(e->h_spec);
+            e->h_spec = nullptr; e->h_spec_cap = 0;
+            CUDA_TRY(cudaMallocHost(&e->h_spec, need * sizeof(cf)));
+            e->h_spec_cap = need;
+        }
         CUDA_TRY(cudaMemcpyAsync(e->h_spec, e->d_spec, bytes, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         // reference order (stretcher_processor.rs:62-70): call by call, channel by channel, frame by frame
@@ -567,7 +573,7 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
         SpectrumRef ref{synth_src, a0, f1 - a0};
         int rc = launch_segment(e, b, channels, stream, channel_offset, &ref);
         if (rc) return rc;
-        CUDA_TRY(cudaStreamSynchronize(stream));  // the spectrum buffer is reused by the next batch
+        // (the next batch reuses the spectrum buffers in stream order: no host synchronisation needed)
     }
     return RCG_OK;
 }
