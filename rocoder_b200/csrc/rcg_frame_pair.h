@@ -35,17 +35,26 @@ RCG_HD cf pair_cross_tw(const cf* tab, int n) {
 }
 
 // ---- LOAD + cross-CTA radix-2 DIF stage ---------------------------------------------------------
-RCG_HD void pair_phase_load(cf* S, int r, int t, const StretchParams& prm, const PairTables& pt, int channel,
-                            long long frame) {
+// FAST: the whole frame lies inside the input and is 8-byte aligned -> branch-free float2 loads that
+// the compiler batches across unrolled iterations
+template <bool FAST>
+RCG_HD void pair_phase_load_impl(cf* S, int r, int t, const StretchParams& prm, const PairTables& pt, const float* in,
+                                 long long base, bool bypass) {
     using C = FrameCfg<kPairLog2HL>;
-    const float* in = prm.in + (long long)channel * prm.in_stride;
-    const long long base = frame * (long long)prm.step - prm.in_origin;
-    const bool bypass = prm.flags & kFlagBypass;
     auto sample = [&](long long i) { return (i >= 0 && i < prm.in_valid) ? ld_stream(in + i) : 0.0f; };
+RCG_UNROLL(4)
     for (int n = t; n < kPairHL; n += C::NT) {
         const cf wa = ld_stream2(prm.window + 2 * n), wb = ld_stream2(prm.window + kPairH + 2 * n);
-        const float a0 = RCG_MUL(sample(base + 2 * n), wa.x), a1 = RCG_MUL(sample(base + 2 * n + 1), wa.y);
-        const float b0 = RCG_MUL(sample(base + kPairH + 2 * n), wb.x), b1 = RCG_MUL(sample(base + kPairH + 2 * n + 1), wb.y);
+        cf xa, xb;
+        if constexpr (FAST) {
+            xa = ld_stream2(in + base + 2 * n);
+            xb = ld_stream2(in + base + kPairH + 2 * n);
+        } else {
+            xa = make_cf(sample(base + 2 * n), sample(base + 2 * n + 1));
+            xb = make_cf(sample(base + kPairH + 2 * n), sample(base + kPairH + 2 * n + 1));
+        }
+        const float a0 = RCG_MUL(xa.x, wa.x), a1 = RCG_MUL(xa.y, wa.y);
+        const float b0 = RCG_MUL(xb.x, wb.x), b1 = RCG_MUL(xb.y, wb.y);
         cf v;
         if (bypass) {
             v = r == 0 ? make_cf(a0, a1) : make_cf(b0, b1);
@@ -58,6 +67,16 @@ RCG_HD void pair_phase_load(cf* S, int r, int t, const StretchParams& prm, const
         }
         S[phys(n)] = v;
     }
+}
+RCG_HD void pair_phase_load(cf* S, int r, int t, const StretchParams& prm, const PairTables& pt, int channel,
+                            long long frame) {
+    const float* in = prm.in + (long long)channel * prm.in_stride;
+    const long long base = frame * (long long)prm.step - prm.in_origin;
+    const bool bypass = prm.flags & kFlagBypass;
+    const bool fast = base >= 0 && base + kPairW <= prm.in_valid &&
+                      (reinterpret_cast<unsigned long long>(in + base) & 7ull) == 0;
+    if (fast) pair_phase_load_impl<true>(S, r, t, prm, pt, in, base, bypass);
+    else pair_phase_load_impl<false>(S, r, t, prm, pt, in, base, bypass);
 }
 
 // ---- SPECTRAL, odd bins (CTA 1): k = 2j+1 pairs with H-k = 2(HL-1-j)+1; no self-paired bins ----
@@ -93,6 +112,7 @@ RCG_HD void pair_phase_ola(const cf* S, const cf* peer, int r, int t, const Stre
     const bool bypass = prm.flags & kFlagBypass;
     float* out = prm.out + (long long)channel * prm.out_stride;
     const float scale = bypass ? 1.0f : prm.inv_w;
+RCG_UNROLL(2)
     for (int n = t; n < kPairHL; n += C::NT) {
         float zr, zi;
         if (bypass) {
@@ -109,10 +129,10 @@ RCG_HD void pair_phase_ola(const cf* S, const cf* peer, int r, int t, const Stre
         if (r == 0) {
             const cf wa = ld_stream2(prm.window + 2 * n);
             const float y0 = RCG_MUL(RCG_MUL(zr, scale), wa.x), y1 = RCG_MUL(RCG_MUL(zi, scale), wa.y);
+            const cf old = ld_pair(tail_old + 2 * n);      // unconditional: no branches around loads
+            const cf e = ld_stream2(prm.env + 2 * n);
             if (write_head) st_pair(prm.head_out + (long long)channel * kPairH + 2 * n, y0, y1);
             if (emit) {
-                const cf old = ld_pair(tail_old + 2 * n);
-                const cf e = ld_stream2(prm.env + 2 * n);
                 const float z0 = RCG_MUL(RCG_MUL(RCG_ADD(y0, old.x), e.x), prm.amp);
                 const float z1 = RCG_MUL(RCG_MUL(RCG_ADD(y1, old.y), e.y), prm.amp);
                 if (prm.pitch == 1) st_pair(out + (frame * (long long)kPairH + 2 * n - prm.out_origin), z0, z1);
@@ -151,12 +171,22 @@ RCG_HD void pair_phase_resample(const float* stage, int t, const StretchParams& 
 
 // Exec for the pair: par(f) runs f(r, t) for every thread of both CTAs, then a CTA barrier;
 // par_cluster(f) ends in a cluster barrier (release/acquire) instead.  bufs[r] is CTA r's buffer.
-template <int PASS, bool INV, class Exec>
-RCG_HD void pair_fft_all(Exec& ex, cf* const (&bufs)[2], const StretchParams& prm, bool work) {
-    if constexpr (PASS >= 0 && PASS < FrameCfg<kPairLog2HL>::NP) {
+// passes FIRST..LAST of the local transform one by one (each ends in a CTA barrier)
+template <int PASS, int LAST, bool INV, class Exec>
+RCG_HD void pair_fft_range(Exec& ex, cf* const (&bufs)[2], const StretchParams& prm, bool work) {
+    if constexpr (INV ? PASS >= LAST : PASS <= LAST) {
         ex.par([&](int r, int t) { if (work) phase_fft_pass<kPairLog2HL, PASS, INV>(bufs[r], t, prm.tw); });
-        pair_fft_all<INV ? PASS - 1 : PASS + 1, INV>(ex, bufs, prm, work);
+        pair_fft_range<INV ? PASS - 1 : PASS + 1, LAST, INV>(ex, bufs, prm, work);
     }
+}
+// all passes 0..NP-1 (forward) / NP-1..0 (inverse); the last two run as one warp-synchronous phase
+template <bool INV, class Exec>
+RCG_HD void pair_fft_all(Exec& ex, cf* const (&bufs)[2], const StretchParams& prm, bool work) {
+    constexpr int NP = FrameCfg<kPairLog2HL>::NP;
+    if constexpr (!INV) pair_fft_range<0, NP - 3, false>(ex, bufs, prm, work);
+    ex.par_steps(fft_tail_steps<kPairLog2HL>(),
+                 [&](int step, int r, int t) { if (work) fft_tail_step<kPairLog2HL, INV>(bufs[r], t, step, prm.tw); });
+    if constexpr (INV) pair_fft_range<NP - 3, 0, true>(ex, bufs, prm, work);
 }
 
 template <class Exec>
@@ -191,7 +221,7 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], const StretchPara
         const bool emit = work && !is_halo && !head;
         ex.par([&](int r, int t) { if (work) pair_phase_load(bufs[r], r, t, prm, pt, channel, f); });
         if (!bypass) {
-            pair_fft_all<0, false>(ex, bufs, prm, work);
+            pair_fft_all<false>(ex, bufs, prm, work);
             ex.par([&](int r, int t) {
                 if (!work) return;
                 if (r == 0) {
@@ -202,7 +232,7 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], const StretchPara
                     pair_phase_spectral_odd(bufs[1], t, prm, pt, channel, f);
                 }
             });
-            pair_fft_all<C::NP - 1, true>(ex, bufs, prm, work);
+            pair_fft_all<true>(ex, bufs, prm, work);
         }
         ex.cluster_sync();   // both halves of the inverse are complete
         ex.par_cluster([&](int r, int t) {   // ends in a cluster barrier: peers are done reading, tails are visible

@@ -93,6 +93,14 @@ struct PairDeviceExec {
         __syncthreads();
     }
     template <class F>
+    __device__ __forceinline__ void par_steps(int n, F f) {
+        for (int s = 0; s < n; s++) {
+            f(s, r, t);
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+    template <class F>
     __device__ __forceinline__ void par_cluster(F f) {
         f(r, t);
         __threadfence();            // carried half windows travel through global memory

@@ -86,6 +86,17 @@ struct PairHostExec {
         }
     }
     template <class F>
+    void par_steps(int n, F f) {   // warp by warp, like HostExec::par_steps
+        const int nw = (nt + 31) / 32;
+        for (int r = 0; r < 2; r++)
+            for (int wi = 0; wi < nw; wi++) {
+                const int w = g_reverse_threads ? nw - 1 - wi : wi;
+                for (int s = 0; s < n; s++)
+                    for (int l = 0; l < 32; l++)
+                        if (w * 32 + l < nt) f(s, r, w * 32 + l);
+            }
+    }
+    template <class F>
     void par_cluster(F f) { par(f); }
     void cluster_sync() {}
 };
