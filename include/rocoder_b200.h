@@ -103,6 +103,10 @@ typedef struct rcg_engine rcg_engine;
 int rcg_create(const rcg_config *cfg, rcg_engine **out);
 void rcg_destroy(rcg_engine *e);
 int rcg_get_plan(const rcg_engine *e, rcg_plan_info *out);
+/* The `window: Vec<f32>` argument of Stretcher::new (stretcher.rs:36) when it is not the Hann window
+ * of main.rs:131 (e.g. windows::rectangular, windows.rs:12-14).  len must equal window_len; call
+ * before any processing. */
+int rcg_set_window(rcg_engine *e, const float *window, size_t len);
 
 /* -- batched, host buffers: what main.rs:133-160 + AudioBus::into_audio (audio.rs:152-172)
  * do for a whole file.  in[c] holds n_in samples of channel c (the one chunk main.rs:148

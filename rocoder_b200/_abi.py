@@ -95,6 +95,7 @@ def lib() -> C.CDLL:
         "rcg_abi_version": (C.c_int, []),
         "rcg_create": (C.c_int, [P(rcg_config), P(C.c_void_p)]),
         "rcg_destroy": (None, [C.c_void_p]),
+        "rcg_set_window": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "rcg_get_plan": (C.c_int, [C.c_void_p, P(rcg_plan_info)]),
         "rcg_process_all": (C.c_int, [C.c_void_p, P(C.c_void_p), C.c_uint64, P(C.c_void_p), C.c_uint64, P(C.c_uint64)]),
         "rcg_process_segment": (C.c_int, [C.c_void_p, P(rcg_segment)]),

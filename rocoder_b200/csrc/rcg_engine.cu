@@ -362,6 +362,19 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     delete e;
 }
 
+// Stretcher::new takes `window: Vec<f32>` (stretcher.rs:36); main.rs:131 always passes
+// windows::hanning(len), which rcg_create installs.  This replaces it (e.g. windows::rectangular).
+extern "C" int rcg_set_window(rcg_engine* e, const float* window, size_t len) {
+    if (!e || !window) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (len != e->cfg.window_len) return fail(RCG_ERR_INVALID_ARG, "window has %zu samples, engine window_len is %u", len, e->cfg.window_len);
+    if (e->launches > 0) return fail(RCG_ERR_STATE, "the window must be set before processing starts");
+    CUDA_TRY(cudaSetDevice(e->device));
+    std::vector<float> w(window, window + len), we = host_decimate2(w);
+    CUDA_TRY(cudaMemcpy(e->d_window, w.data(), len * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(e->d_window_even, we.data(), we.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return RCG_OK;
+}
+
 extern "C" int rcg_get_plan(const rcg_engine* e, rcg_plan_info* out) {
     if (!e || !out) return fail(RCG_ERR_INVALID_ARG, "null argument");
     *out = e->plan;

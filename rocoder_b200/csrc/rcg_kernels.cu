@@ -23,7 +23,11 @@ struct DeviceExec {
     template <class F>
     __device__ __forceinline__ void par(F f) {
         f(t);
+#ifdef RCG_EXPERIMENT_NO_BLOCK_BARRIERS   // timing experiment only: results are wrong
+        __syncwarp();
+#else
         __syncthreads();
+#endif
     }
     // steps that only depend on each other within a warp: warp barriers in between, one block
     // barrier at the end

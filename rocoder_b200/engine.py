@@ -155,6 +155,11 @@ class Engine:
     def __exit__(self, *a):
         self.close()
 
+    def set_window(self, window) -> None:
+        """replace the Hann window (the `window: Vec<f32>` argument of Stretcher::new)"""
+        w = np.ascontiguousarray(window, dtype=np.float32)
+        check(lib().rcg_set_window(self._h, w.ctypes.data, w.size))
+
     # -- batched ---------------------------------------------------------------------------
     def expected_counts(self, n_in: int):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -97,9 +97,13 @@ class Stretcher:
     """
 
     def __init__(self, spec: AudioSpec, input: Receiver, factor: float, amplitude: float, pitch_multiple: int,
-                 window_len: int, buffer_dur: float = 1.0, frequency_kernel_src=None, *, channel: int = 0,
+                 window_len, buffer_dur: float = 1.0, frequency_kernel_src=None, *, channel: int = 0,
                  seed: int = 0, device: int = 0, flags: int = 0):
         assert pitch_multiple != 0  # stretcher.rs:40
+        window = None
+        if not isinstance(window_len, (int, np.integer)):   # `window: Vec<f32>` given explicitly
+            window = np.ascontiguousarray(window_len, dtype=np.float32)
+            window_len = int(window.size)
         self.spec = spec
         self.input = input
         self.window_len = window_len
@@ -107,6 +111,8 @@ class Stretcher:
         self.channel = channel
         self._engine = Engine(1, spec.sample_rate, window_len, factor, amplitude, pitch_multiple, buffer_dur, seed,
                               device, flags, first_channel=channel)
+        if window is not None:
+            self._engine.set_window(window)
         p = self._engine.plan
         self.half_window_len = p["half_window_len"]
         self.samples_needed_per_window = p["samples_needed_per_window"]

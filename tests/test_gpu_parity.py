@@ -284,3 +284,30 @@ def test_window_65536_streaming_and_segments():
         while not e.is_done(0):
             wins.append(e.next_window(0))
     assert np.array_equal(np.concatenate(wins), whole[0])
+
+
+def test_custom_window_vector():
+    """Stretcher::new takes `window: Vec<f32>` (stretcher.rs:36); the reference's own tests pass a
+    rectangular one (stretcher.rs:174, windows.rs:12-14)"""
+    n, f, p, W = 9000, 2.0, 1, 1024
+    x = _input(n, channels=1, seed=4)
+    rect = np.ones(W, np.float32)
+    s = ol.OracleStretcher(f, p, W, window=rect, precision=64)
+    s.set_philox(3, 0)
+    s.send(x[0]); s.close()
+    ref = []
+    while not s.is_done():
+        ref.append(s.next_window())
+    ref = np.concatenate(ref)
+    with rb.Engine(1, 44100, W, f, 1.0, p, seed=3) as e:
+        e.set_window(rect)
+        got = e.process_all(x)[0]
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-3 and ol.snr_db(ref, got) > 100.0   # rectangular frames are ~10x louder
+    tx, rx = rb.unbounded()
+    st = rb.Stretcher(rb.AudioSpec(1, 44100), rx, f, 1.0, p, rect, 1.0, None, seed=3)
+    tx.send(x[0]); tx.drop()
+    wins = []
+    while not st.is_done():
+        wins.append(st.next_window())
+    assert np.array_equal(np.concatenate(wins), got)
