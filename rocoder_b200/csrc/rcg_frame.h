@@ -537,45 +537,69 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
 }
 
 // ---- plugin path, analysis side: real-FFT split -> the full W-bin spectrum the reference hands
-// to `apply` (fft.rs:87: every bin of the complex FFT of the real windowed frame)
+// to `apply` (fft.rs:87: every bin of the complex FFT of the real windowed frame).
+// Two phases so that HBM sees coalesced, natural-order writes although the transform leaves the
+// bins digit-reversed: (1) pair threads replace Z[k], Z[H-k] by X[k], X[H-k] in place (position
+// order, conflict free); (2) after a barrier the spectrum is copied out in natural bin order
+// (the digit-reversing gather is paid in shared-memory bank conflicts, not in DRAM sectors).
 template <int LOG2H>
-RCG_HD void phase_spectrum_out(const cf* S, int t, const StretchParams& prm, int channel, long long frame) {
+RCG_HD void phase_spectrum_split(cf* S, int t, const StretchParams& prm) {
     using C = FrameCfg<LOG2H>;
-    cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * C::W;
     for (int c = t; c < C::H / 2; c += C::NT) {
         const int pos = spectral_slot_pos(LOG2H, c);
         const int k = pos_to_bin<LOG2H>(pos);
         if (c == 0) {
-            cf z0 = S[0];
-            X[0] = make_cf(z0.x + z0.y, 0.0f);
-            X[C::H] = make_cf(z0.x - z0.y, 0.0f);
-            cf zq = S[phys(bin_to_pos<LOG2H>(C::H / 2))];
-            X[C::H / 2] = make_cf(zq.x, -zq.y);
-            X[C::H + C::H / 2] = zq;
+            const cf z0 = S[0];
+            S[0] = make_cf(z0.x + z0.y, z0.x - z0.y);                 // (X[0], X[H]): both real
+            const int pq = phys(bin_to_pos<LOG2H>(C::H / 2));
+            const cf zq = S[pq];
+            S[pq] = make_cf(zq.x, -zq.y);                             // X[H/2] = conj(Z[H/2])
             continue;
         }
-        const cf za = S[phys(pos)], zb = S[phys(bin_to_pos<LOG2H>(C::H - k))];
+        const int pa = phys(pos), pb = phys(bin_to_pos<LOG2H>(C::H - k));
+        const cf za = S[pa], zb = S[pb];
         const cf tw = ld_cf(prm.spec_tw + c);
         float pr = za.x + zb.x, pi = za.y - zb.y, qr = za.x - zb.x, qi = za.y + zb.y;
         float tqr = tw.x * qr - tw.y * qi, tqi = tw.x * qi + tw.y * qr;
         float ur = tqi, ui = -tqr;
-        float xkr = 0.5f * (pr + ur), xki = 0.5f * (pi + ui);   // X[k]
-        float xbr = 0.5f * (pr - ur), xbi = 0.5f * (pi - ui);   // conj(X[H-k])
-        X[k] = make_cf(xkr, xki);
-        X[C::W - k] = make_cf(xkr, -xki);
-        X[C::H - k] = make_cf(xbr, -xbi);
-        X[C::H + k] = make_cf(xbr, xbi);
+        S[pa] = make_cf(0.5f * (pr + ur), 0.5f * (pi + ui));          // X[k]
+        S[pb] = make_cf(0.5f * (pr - ur), -(0.5f * (pi - ui)));       // X[H-k]
+    }
+}
+template <int LOG2H>
+RCG_HD void phase_spectrum_copyout(const cf* S, int t, const StretchParams& prm, int channel, long long frame) {
+    using C = FrameCfg<LOG2H>;
+    cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * C::W;
+    for (int b = t; b < C::H; b += C::NT) {
+        const cf v = S[phys(bin_to_pos<LOG2H>(b))];
+        if (b == 0) {
+            X[0] = make_cf(v.x, 0.0f);
+            X[C::H] = make_cf(v.y, 0.0f);
+        } else {
+            X[b] = v;
+            X[C::W - b] = make_cf(v.x, -v.y);    // the spectrum of a real frame is Hermitian
+        }
     }
 }
 
 RCG_HD float cf_norm(cf v) { return sqrtf(v.x * v.x + v.y * v.y); }
 
 // ---- plugin path, synthesis side: |apply(X)[k]| for each of the W bins (only the norm of the
-// plugin's output survives, fft.rs:67) -> random phase -> Hermitian fold -> inverse pre-pass
+// plugin's output survives, fft.rs:67) -> random phase -> Hermitian fold -> inverse pre-pass.
+// Again two phases: (1) natural-order, coalesced read of the plugin output; the slot of bin b < H
+// receives (|P[b]|, |P[W-b]|) (slot 0: (|P[0]|, |P[H]|)); (2) pair threads in position order.
+template <int LOG2H>
+RCG_HD void phase_mags_copyin(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
+    using C = FrameCfg<LOG2H>;
+    const cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * C::W;
+    for (int b = t; b < C::H; b += C::NT) {
+        const cf lo = X[b], hi = X[b == 0 ? C::H : C::W - b];
+        S[phys(bin_to_pos<LOG2H>(b))] = make_cf(cf_norm(lo), cf_norm(hi));
+    }
+}
 template <int LOG2H>
 RCG_HD void phase_spectral_in(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
     using C = FrameCfg<LOG2H>;
-    const cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * C::W;
     const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
     const uint32_t chan = (uint32_t)(channel + prm.channel_offset);
     for (int c = t; c < C::H / 2; c += C::NT) {
@@ -583,23 +607,27 @@ RCG_HD void phase_spectral_in(cf* S, int t, const StretchParams& prm, int channe
         const int k = pos_to_bin<LOG2H>(pos);
         uint32_t u[4];
         if (c == 0) {
+            const cf m0h = S[0];                                     // (|P[0]|, |P[H]|)
             philox4x32_10(0u, f_lo, f_hi, chan, prm.keys, u);
             float s, c0, ch;
             sincos_phase(phase_from_u32(u[0]), s, c0);
             sincos_phase(phase_from_u32(u[2]), s, ch);
-            float y0 = cf_norm(X[0]) * c0, yh = cf_norm(X[C::H]) * ch;
+            float y0 = m0h.x * c0, yh = m0h.y * ch;
             S[0] = make_cf(y0 + yh, y0 - yh);
+            const int pq = phys(bin_to_pos<LOG2H>(C::H / 2));
+            const cf mq = S[pq];                                     // (|P[H/2]|, |P[3H/2]|)
             philox4x32_10((uint32_t)(C::H / 2), f_lo, f_hi, chan, prm.keys, u);
             float sa, ca, sb, cb;
             sincos_phase(phase_from_u32(u[0]), sa, ca);
             sincos_phase(phase_from_u32(u[1]), sb, cb);
-            float ma = cf_norm(X[C::H / 2]), mb = cf_norm(X[C::H + C::H / 2]);
-            S[phys(bin_to_pos<LOG2H>(C::H / 2))] = make_cf(ma * ca + mb * cb, -(ma * sa - mb * sb));
+            S[pq] = make_cf(mq.x * ca + mq.y * cb, -(mq.x * sa - mq.y * sb));
             continue;
         }
+        const int pa = phys(pos), pb = phys(bin_to_pos<LOG2H>(C::H - k));
+        const cf ma = S[pa], mb = S[pb];                             // (|P[k]|, |P[W-k]|), (|P[H-k]|, |P[H+k]|)
         const cf tw = ld_cf(prm.spec_tw + c);
         philox4x32_10((uint32_t)k, f_lo, f_hi, chan, prm.keys, u);
-        const float m0 = cf_norm(X[k]), m1 = cf_norm(X[C::W - k]), m2 = cf_norm(X[C::H - k]), m3 = cf_norm(X[C::H + k]);
+        const float m0 = ma.x, m1 = ma.y, m2 = mb.x, m3 = mb.y;
         float s0, c0, s1, c1, s2, c2, s3, c3;
         sincos_phase(phase_from_u32(u[0]), s0, c0);
         sincos_phase(phase_from_u32(u[1]), s1, c1);
@@ -609,8 +637,8 @@ RCG_HD void phase_spectral_in(cf* S, int t, const StretchParams& prm, int channe
         float ybr = 0.5f * (m2 * c2 + m3 * c3), ybi = 0.5f * (m2 * s2 - m3 * s3);
         float ar = ykr + ybr, ai = yki - ybi, br = ykr - ybr, bi = yki + ybi;
         float cr = -(tw.x * bi - tw.y * br), ci = tw.x * br + tw.y * bi;
-        S[phys(pos)] = make_cf(ar + cr, ai + ci);
-        S[phys(bin_to_pos<LOG2H>(C::H - k))] = make_cf(ar - cr, -(ai - ci));
+        S[pa] = make_cf(ar + cr, ai + ci);
+        S[pb] = make_cf(ar - cr, -(ai - ci));
     }
 }
 
@@ -959,6 +987,7 @@ RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, f
         const bool work = active && (is_halo ? halo : f < f1);
         const bool load_next = fuse && work && (it + 1 < n_iter) && (f + 1 < f1);
         if (spectrum_in) {
+            ex.par([&](int t) { if (work) phase_mags_copyin<LOG2H>(S, t, prm, channel, f); });
             ex.par([&](int t) { if (work) phase_spectral_in<LOG2H>(S, t, prm, channel, f); });
             fft_all<LOG2H, true>(ex, S, prm, work);
         } else {
@@ -1006,7 +1035,8 @@ RCG_HD void run_analysis_item(Exec& ex, cf* S, const StretchParams& prm, int ite
         const bool work = active && f < prm.frame_end;
         ex.par([&](int t) { if (work) phase_load<LOG2H>(S, t, prm, channel, f); });
         fft_all<LOG2H, false>(ex, S, prm, work);
-        ex.par([&](int t) { if (work) phase_spectrum_out<LOG2H>(S, t, prm, channel, f); });
+        ex.par([&](int t) { if (work) phase_spectrum_split<LOG2H>(S, t, prm); });
+        ex.par([&](int t) { if (work) phase_spectrum_copyout<LOG2H>(S, t, prm, channel, f); });
     }
 }
 

@@ -107,3 +107,16 @@ def test_product_does_not_reference_the_oracle():
     import subprocess
     out = subprocess.run(["ldd", rb.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out and "emul" not in out
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: the header must compile as C99 and as C++"""
+    import subprocess
+    src = tmp_path / "t.c"
+    src.write_text('#include "rocoder_b200.h"\nint main(void) { rcg_config c; c.struct_size = sizeof c; return rcg_abi_version() == RCG_ABI_VERSION ? 0 : (int)c.struct_size; }\n')
+    inc = os.path.join(ol.ROOT, "include")
+    libdir = os.path.dirname(rb.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(tmp_path / "t"),
+                           "-L", libdir, "-lrocoder_b200", f"-Wl,-rpath,{libdir}"])
+    assert subprocess.run([str(tmp_path / "t")]).returncode == 0
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-I", inc, "-x", "c++", os.path.join(inc, "rocoder_b200.hpp")])
