@@ -13,6 +13,8 @@ typedef float2 cf;
 #define RCG_HD inline
 #define RCG_D inline
 struct alignas(8) cf { float x, y; };
+struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 #endif
 
 RCG_HD cf make_cf(float x, float y) { cf r; r.x = x; r.y = y; return r; }

@@ -194,6 +194,8 @@ struct rcg_engine {
     uint64_t seed = 0;
     float *d_window = nullptr, *d_env = nullptr, *d_scratch = nullptr, *d_window_even = nullptr, *d_env_even = nullptr;
     float* d_lerp_ratio = nullptr;
+    uint2* d_pair_tab = nullptr;
+    uint4* d_quad_tab = nullptr;
     cf *d_tw = nullptr, *d_spec_tw = nullptr, *d_spec_tw_hr = nullptr;
     bool pair = false;        // W = 65536: a frame across a 2-CTA cluster
     PairTables pt{};
@@ -298,6 +300,14 @@ extern "C" int rcg_create(const rcg_config* cfg, rcg_engine** out) {
         TRY_E(cudaMemcpy(e->d_pair_odd, so.data(), so.size() * sizeof(cf), cudaMemcpyHostToDevice));
     }
     std::vector<float> we = host_decimate2(window), ee = host_decimate2(env);
+    {   // frame-invariant slot-index tables of the spectral steps
+        std::vector<uint2> ptab = host_pair_table(plan_log2h);
+        std::vector<uint4> qtab = host_quad_table(plan_log2h);
+        TRY_E(cudaMalloc(&e->d_pair_tab, ptab.size() * sizeof(uint2)));
+        TRY_E(cudaMalloc(&e->d_quad_tab, qtab.size() * sizeof(uint4)));
+        TRY_E(cudaMemcpy(e->d_pair_tab, ptab.data(), ptab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+        TRY_E(cudaMemcpy(e->d_quad_tab, qtab.data(), qtab.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    }
     {   // j as f32 / factor as f32, resampler.rs:29
         const int q = cfg->pitch_multiple < 0 ? -cfg->pitch_multiple : 1;
         std::vector<float> ratio(128, 0.0f);
@@ -346,6 +356,7 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     if (e->h2d) cudaStreamSynchronize(e->h2d);
     cudaFree(e->d_window); cudaFree(e->d_env); cudaFree(e->d_tw); cudaFree(e->d_spec_tw); cudaFree(e->d_scratch);
     cudaFree(e->d_window_even); cudaFree(e->d_env_even); cudaFree(e->d_spec_tw_hr); cudaFree(e->d_lerp_ratio);
+    cudaFree(e->d_pair_tab); cudaFree(e->d_quad_tab);
     cudaFree(e->d_pair_cross); cudaFree(e->d_pair_even); cudaFree(e->d_pair_odd);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_tail_pp[0]); cudaFree(e->d_tail_pp[1]);
     cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_spec); cudaFree(e->d_spec2);
@@ -406,6 +417,7 @@ static void fill_params(const rcg_engine* e, StretchParams& p) {
     p.window = e->d_window; p.env = e->d_env; p.tw = e->d_tw; p.spec_tw = e->d_spec_tw;
     p.spec_tw_hr = e->d_spec_tw_hr; p.window_even = e->d_window_even; p.env_even = e->d_env_even;
     p.lerp_ratio = e->d_lerp_ratio;
+    p.pair_tab = e->d_pair_tab; p.quad_tab = e->d_quad_tab;
     p.tail_scratch = e->d_scratch;
     p.channels = (int)e->cfg.channels;
     p.step = (int)e->plan.sample_step_len;

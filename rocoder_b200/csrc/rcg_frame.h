@@ -77,6 +77,8 @@ struct StretchParams {
     const float* window_even;  // [H]   window[2i]   (half-rate synthesis)
     const float* env_even;     // [H/2] env[2i]
     const float* lerp_ratio;   // [|p|] j / |p| as f32 (resampler.rs:29), for pitch < -1
+    const uint4* quad_tab;     // [H/4] half-rate spectral step: {pa | pb<<16, pc | pd<<16, k, 0} (padded slot indices)
+    const uint2* pair_tab;     // [H/2] full-rate spectral step: {pa | pb<<16, k}
     float* tail_scratch;    // [work lanes][H] carried second half window (stretcher.rs:101-102)
     const float* tail_in;   // optional [channels][H]: second half of frame frame_begin-1
     float* tail_out;        // optional [channels][H]: second half of frame frame_end-1
@@ -150,6 +152,20 @@ RCG_HD cf ld_cf(const cf* p) {
 #else
     return __ldg(p);
 #endif
+#else
+    return *p;
+#endif
+}
+RCG_HD uint4 ld_u4(const uint4* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+RCG_HD uint2 ld_u2(const uint2* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
 #else
     return *p;
 #endif
@@ -442,8 +458,6 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
     const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
     const uint32_t chan = (uint32_t)(channel + prm.channel_offset);
     for (int c = t; c < C::H / 4; c += C::NT) {
-        const int pos = spectral_slot_pos_hr(LOG2H, c);
-        const int k = pos_to_bin<LOG2H>(pos);
         uint32_t u[4];
         if (c == 0) {
             // E[0] = Y[0] + Y[H] (both real), E[Q] = 2 Re Y[Q]
@@ -471,14 +485,17 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
             S[ph] = make_cf(2.0f * ar, -2.0f * ai);
             continue;
         }
-        const int pa = phys(pos), pc = phys(bin_to_pos<LOG2H>(Q - k));
-        const cf za = S[pa], zb = S[phys(bin_to_pos<LOG2H>(C::H - k))];
-        const cf zc = S[pc], zd = S[phys(bin_to_pos<LOG2H>(Q + k))];
+        // slot indices of bins k, H-k, Q-k, Q+k and k itself: frame-invariant, precomputed on the host
+        const uint4 qt = ld_u4(prm.quad_tab + c);
+        const int pa = (int)(qt.x & 0xFFFFu), pc = (int)(qt.y & 0xFFFFu);
+        const cf za = S[pa], zb = S[qt.x >> 16];
+        const cf zc = S[pc], zd = S[qt.y >> 16];
         const cf tw = ld_cf(prm.spec_tw_hr + c);  // exp(-2 pi i k / W)
         float ar, ai, er, ei, br, bi;
-        philox4x32_10((uint32_t)k, f_lo, f_hi, chan, prm.keys, u);
+        const uint32_t k = qt.z;
+        philox4x32_10(k, f_lo, f_hi, chan, prm.keys, u);
         pair_fold(za, zb, tw, u, ar, ai, br, bi);                              // E[k]
-        philox4x32_10((uint32_t)(Q - k), f_lo, f_hi, chan, prm.keys, u);
+        philox4x32_10((uint32_t)Q - k, f_lo, f_hi, chan, prm.keys, u);
         pair_fold(zc, zd, make_cf(-tw.y, -tw.x), u, er, ei, br, bi);          // E[Q-k]; exp(-2 pi i (Q-k)/W) = -i conj(tw)
         // A2 = E[k] + conj(E[Q-k]), B2 = E[k] - conj(E[Q-k]), C2 = i conj(t2) B2, t2 = exp(-2 pi i k/H) = tw^2
         const float a2r = ar + er, a2i = ai - ei, b2r = ar - er, b2i = ai + ei;
@@ -499,8 +516,6 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
     static_assert(C::RLAST == 16, "the spectral slot order assumes a radix-16 last pass");
     const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
     for (int c = t; c < C::H / 2; c += C::NT) {
-        const int pos = spectral_slot_pos(LOG2H, c);
-        const int k = pos_to_bin<LOG2H>(pos);
         uint32_t u[4];
         if (c == 0) {
             // k = 0: bins 0 and H are real: X[0] = a + b, X[H] = a - b
@@ -523,10 +538,11 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
             S[pq] = make_cf(mq * (ca + cb), -(mq * (sa - sb)));
             continue;
         }
-        const int pa = phys(pos), pb = phys(bin_to_pos<LOG2H>(C::H - k));
+        const uint2 pt = ld_u2(prm.pair_tab + c);   // frame-invariant slot indices of bins k, H-k and k itself
+        const int pa = (int)(pt.x & 0xFFFFu), pb = (int)(pt.x >> 16);
         const cf za = S[pa], zb = S[pb];
         const cf tw = ld_cf(prm.spec_tw + c);  // exp(-2 pi i k / W)
-        philox4x32_10((uint32_t)(k * KMUL), f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
+        philox4x32_10(pt.y * (uint32_t)KMUL, f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
         // A = Y[k] + conj(Y[H-k]), B = Y[k] - conj(Y[H-k]), Cc = i conj(t) B
         float ar, ai, br, bi;
         pair_fold(za, zb, tw, u, ar, ai, br, bi);

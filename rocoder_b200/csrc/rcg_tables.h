@@ -127,6 +127,36 @@ inline std::vector<cf> host_pair_spectral_twiddles(int log2h, int odd) {
     return tw;
 }
 
+// frame-invariant index tables of the spectral steps: padded shared-memory slot indices of the bins
+// a pair / quad thread touches, and the pair's bin number
+inline std::vector<uint2> host_pair_table(int log2h) {
+    const PlanDesc d = make_plan(log2h);
+    const int H = 1 << log2h;
+    std::vector<uint2> tab((size_t)H / 2);
+    for (int c = 0; c < H / 2; c++) {
+        const int pos = spectral_slot_pos(log2h, c), k = rt_pos_to_bin(d, pos);
+        const unsigned pa = (unsigned)phys(pos), pb = (unsigned)phys(rt_bin_to_pos(d, (H - k) % H));
+        tab[c].x = pa | (pb << 16);
+        tab[c].y = (unsigned)k;
+    }
+    return tab;
+}
+inline std::vector<uint4> host_quad_table(int log2h) {
+    const PlanDesc d = make_plan(log2h);
+    const int H = 1 << log2h, Q = H / 2;
+    std::vector<uint4> tab((size_t)std::max(H / 4, 1));
+    for (int c = 0; c < H / 4; c++) {
+        const int pos = spectral_slot_pos_hr(log2h, c), k = rt_pos_to_bin(d, pos);
+        const unsigned pa = (unsigned)phys(pos), pb = (unsigned)phys(rt_bin_to_pos(d, (H - k) % H));
+        const unsigned pc = (unsigned)phys(rt_bin_to_pos(d, (Q - k + H) % H)), pd = (unsigned)phys(rt_bin_to_pos(d, Q + k));
+        tab[c].x = pa | (pb << 16);
+        tab[c].y = pc | (pd << 16);
+        tab[c].z = (unsigned)k;
+        tab[c].w = 0;
+    }
+    return tab;
+}
+
 // even samples of a table (half-rate synthesis reads window[2i], env[2i])
 inline std::vector<float> host_decimate2(const std::vector<float>& v) {
     std::vector<float> o((v.size() + 1) / 2);

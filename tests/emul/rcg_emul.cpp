@@ -63,6 +63,9 @@ static int emul_run(StretchParams prm) {
     prm.spec_tw_hr = stw_hr.data(); prm.window_even = we.data(); prm.env_even = ee.data();
     std::vector<float> lr = lerp_table(prm.pitch);
     prm.lerp_ratio = lr.data();
+    std::vector<uint2> ptab = host_pair_table(LOG2H);
+    std::vector<uint4> qtab = host_quad_table(LOG2H);
+    prm.pair_tab = ptab.data(); prm.quad_tab = qtab.data();
     if (use_half_rate(prm.pitch, prm.flags) && !g_disable_half_rate) prm.flags |= kFlagHalfRate;
     if (g_no_fuse) prm.flags |= kFlagNoFuse;
     std::vector<cf> S(C::SMEM_CF);
@@ -112,6 +115,8 @@ static int emul_run_pair(StretchParams prm) {
     prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data();
     std::vector<float> lr = lerp_table(prm.pitch);
     prm.lerp_ratio = lr.data();
+    std::vector<uint2> ptab = host_pair_table(kPairLog2HL);
+    prm.pair_tab = ptab.data();
     std::vector<float> scratch(3 * (size_t)kPairH);
     PairTables pt{cross.data(), se.data(), so.data(), scratch.data()};
     std::vector<cf> S0(C::SMEM_CF), S1(C::SMEM_CF);
