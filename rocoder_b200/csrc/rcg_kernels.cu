@@ -18,7 +18,11 @@ namespace cg = cooperative_groups;
 
 namespace rcg {
 
-struct DeviceExec {
+// WARP_LOCAL: a frame lane is at most one warp (W <= 1024), so the frames sharing a CTA never
+// exchange data and every phase boundary is a warp barrier: the lanes drift apart and overlap their
+// memory and compute phases instead of marching in lockstep.
+template <bool WARP_LOCAL>
+struct DeviceExecT {
     int t;
     template <class F>
     __device__ __forceinline__ void par(F f) {
@@ -26,7 +30,7 @@ struct DeviceExec {
 #ifdef RCG_EXPERIMENT_NO_BLOCK_BARRIERS   // timing experiment only: results are wrong
         __syncwarp();
 #else
-        __syncthreads();
+        if constexpr (WARP_LOCAL) __syncwarp(); else __syncthreads();
 #endif
     }
     // steps that only depend on each other within a warp: warp barriers in between, one block
@@ -37,9 +41,10 @@ struct DeviceExec {
             f(s, t);
             __syncwarp();
         }
-        __syncthreads();
+        if constexpr (!WARP_LOCAL) __syncthreads();
     }
 };
+using DeviceExec = DeviceExecT<false>;
 
 #ifndef RCG_MIN_CTAS
 #define RCG_MIN_CTAS 3
@@ -53,7 +58,11 @@ stretch_kernel(const __grid_constant__ StretchParams prm, int n_items) {
     using C = FrameCfg<LOG2H>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x / C::NT;
-    DeviceExec ex{(int)(threadIdx.x % C::NT)};
+#ifdef RCG_NO_WARP_LOCAL
+    DeviceExecT<false> ex{(int)(threadIdx.x % C::NT)};
+#else
+    DeviceExecT<(C::NT <= 32)> ex{(int)(threadIdx.x % C::NT)};
+#endif
     cf* S = reinterpret_cast<cf*>(smem_raw) + lane * C::SMEM_CF;
     float* tail = prm.tail_scratch + ((long long)blockIdx.x * C::FPC + lane) * C::H;
     const int n_groups = (n_items + C::FPC - 1) / C::FPC;
