@@ -21,17 +21,25 @@ namespace rcg {
 // WARP_LOCAL: a frame lane is at most one warp (W <= 1024), so the frames sharing a CTA never
 // exchange data and every phase boundary is a warp barrier: the lanes drift apart and overlap their
 // memory and compute phases instead of marching in lockstep.
-template <bool WARP_LOCAL>
+// Otherwise, when several multi-warp frame lanes share a CTA (W = 2048, 4096), each lane
+// synchronises on its own named barrier (bar.sync id, NT) for the same reason.
+template <bool WARP_LOCAL, int LANE_THREADS = 0>
 struct DeviceExecT {
     int t;
-    template <class F>
-    __device__ __forceinline__ void par(F f) {
-        f(t);
+    int lane = 0;
+    __device__ __forceinline__ void lane_barrier() {
 #ifdef RCG_EXPERIMENT_NO_BLOCK_BARRIERS   // timing experiment only: results are wrong
         __syncwarp();
 #else
-        if constexpr (WARP_LOCAL) __syncwarp(); else __syncthreads();
+        if constexpr (WARP_LOCAL) __syncwarp();
+        else if constexpr (LANE_THREADS > 0) asm volatile("bar.sync %0, %1;" ::"r"(lane + 1), "r"(LANE_THREADS) : "memory");
+        else __syncthreads();
 #endif
+    }
+    template <class F>
+    __device__ __forceinline__ void par(F f) {
+        f(t);
+        lane_barrier();
     }
     // steps that only depend on each other within a warp: warp barriers in between, one block
     // barrier at the end
@@ -41,7 +49,7 @@ struct DeviceExecT {
             f(s, t);
             __syncwarp();
         }
-        if constexpr (!WARP_LOCAL) __syncthreads();
+        if constexpr (!WARP_LOCAL) lane_barrier();
     }
 };
 using DeviceExec = DeviceExecT<false>;
@@ -61,7 +69,8 @@ stretch_kernel(const __grid_constant__ StretchParams prm, int n_items) {
 #ifdef RCG_NO_WARP_LOCAL
     DeviceExecT<false> ex{(int)(threadIdx.x % C::NT)};
 #else
-    DeviceExecT<(C::NT <= 32)> ex{(int)(threadIdx.x % C::NT)};
+    // frame lanes of one CTA are independent: warp barriers (<= 1 warp per lane) or one named barrier per lane
+    DeviceExecT<(C::NT <= 32), (C::NT > 32 && C::FPC > 1) ? C::NT : 0> ex{(int)(threadIdx.x % C::NT), lane};
 #endif
     cf* S = reinterpret_cast<cf*>(smem_raw) + lane * C::SMEM_CF;
     float* tail = prm.tail_scratch + ((long long)blockIdx.x * C::FPC + lane) * C::H;
