@@ -16,6 +16,9 @@ SMALL_CASES = [
     (50000, 2.0, -4, 8192),
     (6000, 2.5, 5, 512),
     (2048, 1.0, 1, 1024),       # exactly two windows
+    (8000, 1.0, 7, 256),        # large odd harmonic: 14 frames per call
+    (8000, 7.0, -7, 512),       # deep subharmonic: S = 74 of 256 finished samples kept per call
+    (5000, 1.0, 12, 128),       # even, non power of two (half-rate path with a decimating gather)
 ]
 LARGE_CASES = [
     (70000, 8.0, 2, 16384),     # BASELINE config 2's flags
