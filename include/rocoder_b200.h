@@ -187,6 +187,21 @@ int rcg_load_frequency_kernel(rcg_engine *e, const char *so_path);
  * (hotswapper.rs:36-42). */
 int rcg_push_device_frequency_kernel(rcg_engine *e, const char *cuda_source);
 int rcg_frequency_kernel_count(const rcg_engine *e, uint32_t *n);
+/* hotswapper::hotswap(path) (hotswapper.rs:14-33, called from ReFFT::new, fft.rs:31-35): build `path` now on
+ * the calling thread, then poll it every poll_ms (0 = the reference's 100 ms, hotswapper.rs:12) on a background
+ * thread and build it again whenever it is modified.  Each successful build is queued and becomes the newest
+ * kernel at the start of the next batch of frames (fft.rs:78-81 polls without blocking before every frame); a
+ * failed build changes nothing (hotswapper.rs:36-42) and its compiler output is kept for rcg_watch_log.  Built by
+ * suffix: .cu = device `apply` via NVRTC; .c/.cc/.cpp = host `apply` via `$RCG_CXX|gcc|g++ -O3 -shared -fPIC`
+ * (the reference shells out to rustc, hotswapper.rs:60-72); .so = dlopen.  One watched file per engine, as in
+ * the reference.  Must be called before processing starts when the pitch multiple is even. */
+int rcg_watch_frequency_kernel(rcg_engine *e, const char *path, uint32_t poll_ms);
+/* take queued builds now (also done by every process / next_window call); *swapped = kernels installed */
+int rcg_poll_frequency_kernels(rcg_engine *e, uint32_t *swapped);
+/* builds that succeeded / failed on the watcher so far, and kernels installed from it */
+int rcg_watch_stats(const rcg_engine *e, uint32_t *builds_ok, uint32_t *builds_failed, uint32_t *swaps);
+/* compiler output of the last failed build ("" after a success) */
+int rcg_watch_log(const rcg_engine *e, char *buf, size_t cap);
 
 /* -- fade in / out (`-x`): what the reference's live Mixer applies (mixer.rs:132-190 with
  * math::sqrt_interp, math.rs:33-40); not applied in file mode by the reference (main.rs:195-204) and

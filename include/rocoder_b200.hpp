@@ -133,7 +133,8 @@ class Stretcher {
 
     // Stretcher::new (stretcher.rs:30-39).  `window_len` stands for `window: Vec<f32>` (the engine
     // builds windows::hanning(window_len), what main.rs:131 passes); frequency_kernel_src is the
-    // path of a shared object exporting the C-ABI `apply`, or empty.  channel / seed / device are
+    // path of a kernel file (.cu / .c / .cpp source or a .so exporting the C-ABI `apply`) that is built,
+    // watched and hot-swapped like ReFFT::new does (fft.rs:31-35, hotswapper.rs:14-33), or empty.  channel / seed / device are
     // the additions: phases are drawn from a counter-based generator keyed by them.
     Stretcher(AudioSpec spec_, Receiver<std::vector<float>> input, float factor, float amplitude,
               int8_t pitch_multiple, size_t window_len, std::chrono::duration<float> buffer_dur,
@@ -156,7 +157,7 @@ class Stretcher {
         cfg_.first_channel = channel;
         check(rcg_create(&cfg_, &engine_));
         check(rcg_get_plan(engine_, &plan_));
-        if (!frequency_kernel_src.empty()) check(rcg_load_frequency_kernel(engine_, frequency_kernel_src.c_str()));
+        if (!frequency_kernel_src.empty()) check(rcg_watch_frequency_kernel(engine_, frequency_kernel_src.c_str(), 0));
     }
     Stretcher(Stretcher&& o) noexcept
         : spec(o.spec), input_(std::move(o.input_)), engine_(o.engine_), cfg_(o.cfg_), plan_(o.plan_),

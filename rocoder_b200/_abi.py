@@ -109,6 +109,10 @@ def lib() -> C.CDLL:
         "rcg_load_frequency_kernel": (C.c_int, [C.c_void_p, C.c_char_p]),
         "rcg_push_device_frequency_kernel": (C.c_int, [C.c_void_p, C.c_char_p]),
         "rcg_frequency_kernel_count": (C.c_int, [C.c_void_p, P(C.c_uint32)]),
+        "rcg_watch_frequency_kernel": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32]),
+        "rcg_poll_frequency_kernels": (C.c_int, [C.c_void_p, P(C.c_uint32)]),
+        "rcg_watch_stats": (C.c_int, [C.c_void_p, P(C.c_uint32), P(C.c_uint32), P(C.c_uint32)]),
+        "rcg_watch_log": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t]),
         "rcg_fade_in_out": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint32, C.c_uint64, C.c_uint64, C.c_float, C.c_uint32,
                                       C.c_uint64, C.c_void_p]),
         "rcg_fade_keyframes": (C.c_int, [C.c_float, C.c_uint32, C.c_uint64, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)]),

@@ -12,11 +12,14 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <memory>
+#include <mutex>
 #include <random>
 #include <string>
 #include <vector>
 
 #include "../../include/rocoder_b200.h"
+#include "rcg_hotswap.h"
 #include "rcg_kernels.h"
 #include "rcg_tables.h"
 
@@ -219,7 +222,11 @@ struct rcg_engine {
     std::vector<FreqKernel> kernels;
     bool had_kernels = false;  // a kernel was pushed at some point (even if all have since failed)
     std::vector<void*> libs;
+    // hotswapper.rs:14-33: watched source file, builds queued for the next batch
+    std::unique_ptr<rcg::KernelWatcher> watcher;
+    uint32_t swaps = 0;
 };
+static int drain_watcher(rcg_engine* e, uint32_t* swapped);
 
 static int pick_run_len(uint64_t frames_per_channel, uint32_t channels, int slots) {
     // minimise waves * (frames per item + 1 halo frame)
@@ -350,6 +357,7 @@ extern "C" int rcg_create(const rcg_config* cfg, rcg_engine** out) {
 
 extern "C" void rcg_destroy(rcg_engine* e) {
     if (!e) return;
+    e->watcher.reset();   // joins the polling thread
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->d2h) cudaStreamSynchronize(e->d2h);
@@ -604,6 +612,8 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
 }
 
 static int run_segment(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream, int channel_offset) {
+    if (e->watcher)   // fft.rs:78-81: take what the hot-swapper has built, without blocking
+        if (int rc = drain_watcher(e, nullptr)) return rc;
     if (e->pair && !e->kernels.empty())
         return fail(RCG_ERR_PLUGIN, "frequency kernels are not supported at window_len 65536 yet");
     if (!e->kernels.empty() && !(e->cfg.flags & RCG_FLAG_BYPASS_RESYNTH))
@@ -899,31 +909,38 @@ extern "C" __global__ void rcg_apply_kernel(const float2* in, float2* out, unsig
 )";
 }  // namespace
 
-extern "C" int rcg_push_device_frequency_kernel(rcg_engine* e, const char* cuda_source) {
-    if (!e || !cuda_source) return fail(RCG_ERR_INVALID_ARG, "null argument");
-    if (int rc = check_kernel_push(e)) return rc;
-    if (e->pair) return fail(RCG_ERR_PLUGIN, "frequency kernels are not supported at window_len 65536 yet");
-    CUDA_TRY(cudaSetDevice(e->device));
-    if (!g_nvrtc.load()) return fail(RCG_ERR_PLUGIN, "libnvrtc could not be loaded: %s", dlerror());
-    const std::string src = std::string(cuda_source) + kDeviceWrapper;
+// user source -> cubin for sm_100a; no CUDA context needed (runs on the watcher thread too)
+static bool compile_device_source(const std::string& user_src, std::vector<char>& cubin, std::string& log) {
+    static std::mutex load_mutex;
+    {
+        std::lock_guard<std::mutex> g(load_mutex);
+        if (!g_nvrtc.load()) { log = std::string("libnvrtc could not be loaded: ") + (dlerror() ? dlerror() : ""); return false; }
+    }
+    const std::string src = user_src + kDeviceWrapper;
     nvrtcProgram_t prog = nullptr;
-    if (g_nvrtc.create(&prog, src.c_str(), "frequency_kernel.cu", 0, nullptr, nullptr) != 0)
-        return fail(RCG_ERR_PLUGIN, "nvrtcCreateProgram failed");
+    if (g_nvrtc.create(&prog, src.c_str(), "frequency_kernel.cu", 0, nullptr, nullptr) != 0) {
+        log = "nvrtcCreateProgram failed";
+        return false;
+    }
     const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device"};
     const int cr = g_nvrtc.compile(prog, 3, opts);
-    if (cr != 0) {   // compile failure keeps the previous kernel (hotswapper.rs:36-42)
+    if (cr != 0) {
         size_t n = 0;
         g_nvrtc.log_size(prog, &n);
-        std::string log(n + 1, '\0');
+        log.assign(n + 1, '\0');
         if (n) g_nvrtc.get_log(prog, &log[0]);
         g_nvrtc.destroy(&prog);
-        return fail(RCG_ERR_PLUGIN, "device frequency kernel failed to compile: %.400s", log.c_str());
+        return false;
     }
     size_t cn = 0;
     g_nvrtc.cubin_size(prog, &cn);
-    std::vector<char> cubin(cn);
+    cubin.resize(cn);
     g_nvrtc.get_cubin(prog, cubin.data());
     g_nvrtc.destroy(&prog);
+    return true;
+}
+
+static int install_cubin(rcg_engine* e, const std::vector<char>& cubin) {
     FreqKernel k;
     CUDA_TRY(cudaLibraryLoadData(&k.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     cudaError_t ke = cudaLibraryGetKernel(&k.dev, k.lib, "rcg_apply_kernel");
@@ -933,6 +950,79 @@ extern "C" int rcg_push_device_frequency_kernel(rcg_engine* e, const char* cuda_
     }
     e->kernels.push_back(k);
     e->had_kernels = true;
+    return RCG_OK;
+}
+
+extern "C" int rcg_push_device_frequency_kernel(rcg_engine* e, const char* cuda_source) {
+    if (!e || !cuda_source) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (int rc = check_kernel_push(e)) return rc;
+    if (e->pair) return fail(RCG_ERR_PLUGIN, "frequency kernels are not supported at window_len 65536 yet");
+    CUDA_TRY(cudaSetDevice(e->device));
+    std::vector<char> cubin;
+    std::string log;
+    if (!compile_device_source(cuda_source, cubin, log))   // compile failure keeps the previous kernel (hotswapper.rs:36-42)
+        return fail(RCG_ERR_PLUGIN, "device frequency kernel failed to compile: %.400s", log.c_str());
+    return install_cubin(e, cubin);
+}
+
+// ---- hot swap from a watched file (hotswapper.rs:14-33 + fft.rs:78-81) ------------------------------
+static int drain_watcher(rcg_engine* e, uint32_t* swapped) {
+    uint32_t n = 0;
+    rcg::BuiltKernel b;
+    int status = RCG_OK;
+    while (e->watcher->try_recv(b)) {
+        if (b.host) {
+            e->libs.push_back(b.dl);       // every library stays loaded (fft.rs:22)
+            FreqKernel k;
+            k.host = (rcg_apply_fn)b.host;
+            e->kernels.push_back(k);
+            e->had_kernels = true;
+            n++;
+        } else {
+            CUDA_TRY(cudaSetDevice(e->device));
+            const int rc = install_cubin(e, b.cubin);
+            if (rc) status = rc; else n++;
+        }
+        b = rcg::BuiltKernel();
+    }
+    e->swaps += n;
+    if (swapped) *swapped = n;
+    return status;
+}
+
+extern "C" int rcg_watch_frequency_kernel(rcg_engine* e, const char* path, uint32_t poll_ms) {
+    if (!e || !path) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (e->watcher) return fail(RCG_ERR_STATE, "this engine already watches %s", e->watcher->path().c_str());
+    if (int rc = check_kernel_push(e)) return rc;
+    if (e->pair) return fail(RCG_ERR_PLUGIN, "frequency kernels are not supported at window_len 65536 yet");
+    if (rcg::KernelWatcher::kind_of(path) == rcg::KernelWatcher::kUnknown)
+        return fail(RCG_ERR_PLUGIN, "frequency kernel %s: want a .cu, .c, .cc, .cpp or .so file", path);
+    // from here on this engine runs the full-rate path: a kernel may arrive between any two batches
+    e->had_kernels = true;
+    e->watcher.reset(new rcg::KernelWatcher(path, poll_ms, compile_device_source));
+    e->watcher->start();   // first build happens here, on the caller's thread (hotswapper.rs:17)
+    return drain_watcher(e, nullptr);
+}
+
+extern "C" int rcg_poll_frequency_kernels(rcg_engine* e, uint32_t* swapped) {
+    if (!e) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (swapped) *swapped = 0;
+    if (!e->watcher) return RCG_OK;
+    return drain_watcher(e, swapped);
+}
+
+extern "C" int rcg_watch_stats(const rcg_engine* e, uint32_t* builds_ok, uint32_t* builds_failed, uint32_t* swaps) {
+    if (!e) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (builds_ok) *builds_ok = e->watcher ? e->watcher->builds_ok() : 0;
+    if (builds_failed) *builds_failed = e->watcher ? e->watcher->builds_failed() : 0;
+    if (swaps) *swaps = e->swaps;
+    return RCG_OK;
+}
+
+extern "C" int rcg_watch_log(const rcg_engine* e, char* buf, size_t cap) {
+    if (!e || !buf || !cap) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    const std::string log = e->watcher ? e->watcher->last_log() : std::string();
+    snprintf(buf, cap, "%s", log.c_str());
     return RCG_OK;
 }
 

@@ -254,6 +254,27 @@ class Engine:
     def load_frequency_kernel(self, so_path: str) -> None:
         check(lib().rcg_load_frequency_kernel(self._h, so_path.encode()))
 
+    def watch_frequency_kernel(self, path: str, poll_ms: int = 0) -> None:
+        """hotswapper::hotswap (reference hotswapper.rs:14-33): build `path` (.cu / .c / .cpp / .so) now,
+        rebuild it whenever it changes (polled every poll_ms, 0 = 100 ms) and swap each good build in at
+        the start of the next batch; a failed build keeps the current kernel."""
+        check(lib().rcg_watch_frequency_kernel(self._h, str(path).encode(), poll_ms))
+
+    def poll_frequency_kernels(self) -> int:
+        n = C.c_uint32()
+        check(lib().rcg_poll_frequency_kernels(self._h, C.byref(n)))
+        return n.value
+
+    def watch_stats(self) -> dict:
+        ok, bad, sw = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib().rcg_watch_stats(self._h, C.byref(ok), C.byref(bad), C.byref(sw)))
+        return {"builds_ok": ok.value, "builds_failed": bad.value, "swaps": sw.value}
+
+    def watch_log(self) -> str:
+        buf = C.create_string_buffer(4096)
+        check(lib().rcg_watch_log(self._h, buf, len(buf)))
+        return buf.value.decode(errors="replace")
+
     def frequency_kernel_count(self) -> int:
         n = C.c_uint32()
         check(lib().rcg_frequency_kernel_count(self._h, C.byref(n)))

@@ -92,8 +92,9 @@ class Stretcher:
 
     Stretcher::new(spec, input, factor, amplitude, pitch_multiple, window, buffer_dur,
     frequency_kernel_src) -- `window` is given by its length (the engine builds the Hann
-    window of main.rs:131 itself); `frequency_kernel_src` is a path to a shared object
-    exporting the C-ABI `apply` (see include/rocoder_b200.h), or a Python callable.
+    window of main.rs:131 itself); `frequency_kernel_src` is the path of a kernel file (.cu / .c / .cpp
+    source, or a .so exporting the C-ABI `apply`, see include/rocoder_b200.h) that is built, watched
+    and hot-swapped as ReFFT::new does (fft.rs:31-35, hotswapper.rs:14-33), or a Python callable.
     """
 
     def __init__(self, spec: AudioSpec, input: Receiver, factor: float, amplitude: float, pitch_multiple: int,
@@ -127,7 +128,7 @@ class Stretcher:
             if callable(frequency_kernel_src):
                 self._engine.push_frequency_kernel(frequency_kernel_src)
             else:
-                self._engine.load_frequency_kernel(str(frequency_kernel_src))
+                self._engine.watch_frequency_kernel(str(frequency_kernel_src))
 
     # stretcher.rs:78
     def is_done(self) -> bool:

@@ -43,7 +43,8 @@ static void usage() {
         "  -a, --amplitude <x>        Output amplitude [1]\n"
         "  -i, --input <path>         A .wav file ('-' for stdin)\n"
         "      --rotate-channels      Rotate the input audio channels\n"
-        "      --freq-kernel <path>   Frequency kernel: a .so exporting the C-ABI `apply`, or a .c/.cpp source\n"
+        "      --freq-kernel <path>   Frequency kernel, rebuilt and swapped in whenever the file changes: a .cu\n"
+        "                             (device `apply`), .c/.cpp (host `apply`) or .so exporting the C-ABI `apply`\n"
         "  -x, --fade <dur>           (live playback only in the reference; accepted and ignored)\n"
         "  -s, --start <dur>          Start time in input audio (hh:mm:ss.ss)\n"
         "  -d, --duration <dur>       Duration to use from input audio (hh:mm:ss.ss)\n"
@@ -83,14 +84,6 @@ static bool parse(int argc, char** argv, Opt& o) {
     return true;
 }
 
-static std::string compile_kernel(const std::string& src) {
-    // the hot-swapper's compile step (hotswapper.rs:58-86) with the host C/C++ compiler
-    std::string so = src + ".rocoder.so";
-    std::string cmd = "g++ -O3 -shared -fPIC -o '" + so + "' '" + src + "' 2>&1";
-    if (std::system(cmd.c_str()) != 0) throw AudioError("frequency kernel compilation failed: " + src);
-    return so;
-}
-
 int main(int argc, char** argv) {
     try {
         Opt opt;
@@ -125,9 +118,16 @@ int main(int argc, char** argv) {
         rcg_engine* eng = nullptr;
         if (rcg_create(&cfg, &eng) != RCG_OK) throw AudioError(rcg_last_error());
         if (!opt.freq_kernel.empty()) {
-            std::string so = opt.freq_kernel;
-            if (so.size() < 3 || so.substr(so.size() - 3) != ".so") so = compile_kernel(so);
-            if (rcg_load_frequency_kernel(eng, so.c_str()) != RCG_OK) throw AudioError(rcg_last_error());
+            // ReFFT::new -> hotswapper::hotswap (fft.rs:31-35): build now, rebuild and swap whenever the file changes
+            if (rcg_watch_frequency_kernel(eng, opt.freq_kernel.c_str(), 0) != RCG_OK) throw AudioError(rcg_last_error());
+            uint32_t n = 0, bad = 0;
+            rcg_frequency_kernel_count(eng, &n);
+            rcg_watch_stats(eng, nullptr, &bad, nullptr);
+            if (n == 0 && bad) {   // like the reference: warn and pass frames through until a build succeeds
+                char log[2048];
+                rcg_watch_log(eng, log, sizeof log);
+                fprintf(stderr, "warning: failed to compile %s\n%s\n", opt.freq_kernel.c_str(), log);
+            }
         }
         uint64_t calls = 0, frames = 0, out_len = 0;
         if (rcg_expected_counts(&cfg, n_in, &calls, &frames, &out_len) != RCG_OK) throw AudioError(rcg_last_error());
