@@ -552,7 +552,7 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
         p.n_runs = (int)((nframes + p.run_len - 1) / p.run_len);
         const long long items = (long long)p.n_runs * channels;
         const int grid = (int)std::min<long long>((items + e->geo.frames_per_cta - 1) / e->geo.frames_per_cta, e->max_grid);
-        cudaError_t ce = launch_analysis(e->log2w, p, grid, stream);
+        cudaError_t ce = e->pair ? launch_analysis_pair(p, e->pt, grid, stream) : launch_analysis(e->log2w, p, grid, stream);
         if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "analysis kernel launch failed: %s", cudaGetErrorString(ce));
         e->launches++;
         const size_t bytes = (size_t)channels * nframes * W * sizeof(cf);
@@ -614,8 +614,6 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
 static int run_segment(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream, int channel_offset) {
     if (e->watcher)   // fft.rs:78-81: take what the hot-swapper has built, without blocking
         if (int rc = drain_watcher(e, nullptr)) return rc;
-    if (e->pair && !e->kernels.empty())
-        return fail(RCG_ERR_PLUGIN, "frequency kernels are not supported at window_len 65536 yet");
     if (!e->kernels.empty() && !(e->cfg.flags & RCG_FLAG_BYPASS_RESYNTH))
         return run_segment_plugins(e, s, channels, stream, channel_offset);
     return launch_segment(e, s, channels, stream, channel_offset);
@@ -956,7 +954,6 @@ static int install_cubin(rcg_engine* e, const std::vector<char>& cubin) {
 extern "C" int rcg_push_device_frequency_kernel(rcg_engine* e, const char* cuda_source) {
     if (!e || !cuda_source) return fail(RCG_ERR_INVALID_ARG, "null argument");
     if (int rc = check_kernel_push(e)) return rc;
-    if (e->pair) return fail(RCG_ERR_PLUGIN, "frequency kernels are not supported at window_len 65536 yet");
     CUDA_TRY(cudaSetDevice(e->device));
     std::vector<char> cubin;
     std::string log;
@@ -994,7 +991,6 @@ extern "C" int rcg_watch_frequency_kernel(rcg_engine* e, const char* path, uint3
     if (!e || !path) return fail(RCG_ERR_INVALID_ARG, "null argument");
     if (e->watcher) return fail(RCG_ERR_STATE, "this engine already watches %s", e->watcher->path().c_str());
     if (int rc = check_kernel_push(e)) return rc;
-    if (e->pair) return fail(RCG_ERR_PLUGIN, "frequency kernels are not supported at window_len 65536 yet");
     if (rcg::KernelWatcher::kind_of(path) == rcg::KernelWatcher::kUnknown)
         return fail(RCG_ERR_PLUGIN, "frequency kernel %s: want a .cu, .c, .cc, .cpp or .so file", path);
     // from here on this engine runs the full-rate path: a kernel may arrive between any two batches

@@ -613,7 +613,8 @@ RCG_HD void phase_mags_copyin(cf* S, int t, const StretchParams& prm, int channe
         S[phys(bin_to_pos<LOG2H>(b))] = make_cf(cf_norm(lo), cf_norm(hi));
     }
 }
-template <int LOG2H>
+// KMUL: as in phase_spectral (2 for the even-bin half of a CTA pair)
+template <int LOG2H, int KMUL = 1>
 RCG_HD void phase_spectral_in(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
     using C = FrameCfg<LOG2H>;
     const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
@@ -632,7 +633,7 @@ RCG_HD void phase_spectral_in(cf* S, int t, const StretchParams& prm, int channe
             S[0] = make_cf(y0 + yh, y0 - yh);
             const int pq = phys(bin_to_pos<LOG2H>(C::H / 2));
             const cf mq = S[pq];                                     // (|P[H/2]|, |P[3H/2]|)
-            philox4x32_10((uint32_t)(C::H / 2), f_lo, f_hi, chan, prm.keys, u);
+            philox4x32_10((uint32_t)(C::H / 2 * KMUL), f_lo, f_hi, chan, prm.keys, u);
             float sa, ca, sb, cb;
             sincos_phase(phase_from_u32(u[0]), sa, ca);
             sincos_phase(phase_from_u32(u[1]), sb, cb);
@@ -642,7 +643,7 @@ RCG_HD void phase_spectral_in(cf* S, int t, const StretchParams& prm, int channe
         const int pa = phys(pos), pb = phys(bin_to_pos<LOG2H>(C::H - k));
         const cf ma = S[pa], mb = S[pb];                             // (|P[k]|, |P[W-k]|), (|P[H-k]|, |P[H+k]|)
         const cf tw = ld_cf(prm.spec_tw + c);
-        philox4x32_10((uint32_t)k, f_lo, f_hi, chan, prm.keys, u);
+        philox4x32_10((uint32_t)(k * KMUL), f_lo, f_hi, chan, prm.keys, u);
         const float m0 = ma.x, m1 = ma.y, m2 = mb.x, m3 = mb.y;
         float s0, c0, s1, c1, s2, c2, s3, c3;
         sincos_phase(phase_from_u32(u[0]), s0, c0);

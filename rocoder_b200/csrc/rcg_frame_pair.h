@@ -102,6 +102,78 @@ RCG_HD void pair_phase_spectral_odd(cf* S, int t, const StretchParams& prm, cons
     }
 }
 
+// ---- frequency-kernel path (fft.rs:76-108) at W = 65536 ------------------------------------------------
+// Same two-phase scheme as rcg_frame.h: bins k and H-k have the same parity, so the real-FFT split, the
+// copy-out of X[k] / X[W-k] and the magnitude copy-in all stay inside the CTA that owns the parity.
+// CTA r owns global bins k = 2b + r, b = local bin.
+RCG_HD void pair_phase_spectrum_split_odd(cf* S, int t, const PairTables& pt) {
+    using C = FrameCfg<kPairLog2HL>;
+    for (int c = t; c < kPairHL / 2; c += C::NT) {
+        const int pos = spectral_slot_pos(kPairLog2HL, c);
+        const int j = pos_to_bin<kPairLog2HL>(pos);
+        const int pa = phys(pos), pb = phys(bin_to_pos<kPairLog2HL>(kPairHL - 1 - j));
+        const cf za = S[pa], zb = S[pb];
+        const cf tw = ld_cf(pt.spec_tw_odd + c);
+        float pr = za.x + zb.x, pi = za.y - zb.y, qr = za.x - zb.x, qi = za.y + zb.y;
+        float tqr = tw.x * qr - tw.y * qi, tqi = tw.x * qi + tw.y * qr;
+        float ur = tqi, ui = -tqr;
+        S[pa] = make_cf(0.5f * (pr + ur), 0.5f * (pi + ui));          // X[k], k = 2j+1
+        S[pb] = make_cf(0.5f * (pr - ur), -(0.5f * (pi - ui)));       // X[H-k]
+    }
+}
+RCG_HD void pair_phase_spectrum_copyout(const cf* S, int r, int t, const StretchParams& prm, int channel, long long frame) {
+    using C = FrameCfg<kPairLog2HL>;
+    cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * kPairW;
+    for (int b = t; b < kPairHL; b += C::NT) {
+        const cf v = S[phys(bin_to_pos<kPairLog2HL>(b))];
+        const int k = 2 * b + r;
+        if (k == 0) {
+            X[0] = make_cf(v.x, 0.0f);
+            X[kPairH] = make_cf(v.y, 0.0f);
+        } else {
+            X[k] = v;
+            X[kPairW - k] = make_cf(v.x, -v.y);
+        }
+    }
+}
+RCG_HD void pair_phase_mags_copyin(cf* S, int r, int t, const StretchParams& prm, int channel, long long frame) {
+    using C = FrameCfg<kPairLog2HL>;
+    const cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * kPairW;
+    for (int b = t; b < kPairHL; b += C::NT) {
+        const int k = 2 * b + r;
+        const cf lo = X[k], hi = X[k == 0 ? kPairH : kPairW - k];
+        S[phys(bin_to_pos<kPairLog2HL>(b))] = make_cf(cf_norm(lo), cf_norm(hi));
+    }
+}
+// odd bins, magnitudes from the kernel's output: slot of k holds (|P[k]|, |P[W-k]|)
+RCG_HD void pair_phase_spectral_in_odd(cf* S, int t, const StretchParams& prm, const PairTables& pt, int channel,
+                                       long long frame) {
+    using C = FrameCfg<kPairLog2HL>;
+    const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
+    const uint32_t chan = (uint32_t)(channel + prm.channel_offset);
+    for (int c = t; c < kPairHL / 2; c += C::NT) {
+        const int pos = spectral_slot_pos(kPairLog2HL, c);
+        const int j = pos_to_bin<kPairLog2HL>(pos);
+        const int k = 2 * j + 1;
+        const int pa = phys(pos), pb = phys(bin_to_pos<kPairLog2HL>(kPairHL - 1 - j));
+        const cf ma = S[pa], mb = S[pb];
+        const cf tw = ld_cf(pt.spec_tw_odd + c);
+        uint32_t u[4];
+        philox4x32_10((uint32_t)k, f_lo, f_hi, chan, prm.keys, u);
+        float s0, c0, s1, c1, s2, c2, s3, c3;
+        sincos_phase(phase_from_u32(u[0]), s0, c0);
+        sincos_phase(phase_from_u32(u[1]), s1, c1);
+        sincos_phase(phase_from_u32(u[2]), s2, c2);
+        sincos_phase(phase_from_u32(u[3]), s3, c3);
+        float ykr = 0.5f * (ma.x * c0 + ma.y * c1), yki = 0.5f * (ma.x * s0 - ma.y * s1);
+        float ybr = 0.5f * (mb.x * c2 + mb.y * c3), ybi = 0.5f * (mb.x * s2 - mb.y * s3);
+        float ar = ykr + ybr, ai = yki - ybi, br = ykr - ybr, bi = yki + ybi;
+        float cr = -(tw.x * bi - tw.y * br), ci = tw.x * br + tw.y * bi;
+        S[pa] = make_cf(ar + cr, ai + ci);
+        S[pb] = make_cf(ar - cr, -(ai - ci));
+    }
+}
+
 // ---- cross-CTA radix-2 DIT stage + overlap-add -------------------------------------------------------
 // CTA 0: first half window: /W * window, + carried half, * envelope * amp, emit (pitch 1) or stage
 // in global memory for the resampling gather.  CTA 1: second half window -> carried buffer.
@@ -203,6 +275,7 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], const StretchPara
     const bool have_tail_in = first_run && prm.tail_in != nullptr && f0 > 0;
     const bool halo = active && f0 > 0 && !defer && !have_tail_in;
     const bool bypass = prm.flags & kFlagBypass;
+    const bool spectrum_in = prm.flags & kFlagSpectrumIn;
     float* tails[2] = {scratch, scratch + kPairH};
     float* stage = scratch + 2 * kPairH;
     // carried half window for the first iteration lives in tails[0]
@@ -219,6 +292,20 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], const StretchPara
         const bool work = active && (is_halo ? halo : f < f1);
         const bool head = work && defer && f == f0;
         const bool emit = work && !is_halo && !head;
+        if (spectrum_in) {
+            ex.par([&](int r, int t) { if (work) pair_phase_mags_copyin(bufs[r], r, t, prm, channel, f); });
+            ex.par([&](int r, int t) {
+                if (!work) return;
+                if (r == 0) {
+                    StretchParams pe = prm;
+                    pe.spec_tw = pt.spec_tw_even;
+                    phase_spectral_in<kPairLog2HL, 2>(bufs[0], t, pe, channel, f);
+                } else {
+                    pair_phase_spectral_in_odd(bufs[1], t, prm, pt, channel, f);
+                }
+            });
+            pair_fft_all<true>(ex, bufs, prm, work);
+        } else {
         ex.par([&](int r, int t) { if (work) pair_phase_load(bufs[r], r, t, prm, pt, channel, f); });
         if (!bypass) {
             pair_fft_all<false>(ex, bufs, prm, work);
@@ -233,6 +320,7 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], const StretchPara
                 }
             });
             pair_fft_all<true>(ex, bufs, prm, work);
+        }
         }
         ex.cluster_sync();   // both halves of the inverse are complete
         ex.par_cluster([&](int r, int t) {   // ends in a cluster barrier: peers are done reading, tails are visible
@@ -250,6 +338,32 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], const StretchPara
             float* dst = prm.tail_out + (long long)channel * kPairH;
             for (int i = t; i < kPairH; i += C::NT) dst[i] = last[i];
         });
+    }
+}
+
+// frequency-kernel path: analysis of a run of frames; the two CTAs never exchange data here
+template <class Exec>
+RCG_HD void run_analysis_item_pair(Exec& ex, cf* const (&bufs)[2], const StretchParams& prm, const PairTables& pt,
+                                   int item, bool active) {
+    const int channel = active ? item / prm.n_runs : 0;
+    const int run = active ? item - channel * prm.n_runs : 0;
+    const long long f0 = prm.frame_begin + (long long)run * prm.run_len;
+    for (int it = 0; it < prm.run_len; it++) {
+        const long long f = f0 + it;
+        const bool work = active && f < prm.frame_end;
+        ex.par([&](int r, int t) { if (work) pair_phase_load(bufs[r], r, t, prm, pt, channel, f); });
+        pair_fft_all<false>(ex, bufs, prm, work);
+        ex.par([&](int r, int t) {
+            if (!work) return;
+            if (r == 0) {
+                StretchParams pe = prm;
+                pe.spec_tw = pt.spec_tw_even;
+                phase_spectrum_split<kPairLog2HL>(bufs[0], t, pe);
+            } else {
+                pair_phase_spectrum_split_odd(bufs[1], t, pt);
+            }
+        });
+        ex.par([&](int r, int t) { if (work) pair_phase_spectrum_copyout(bufs[r], r, t, prm, channel, f); });
     }
 }
 

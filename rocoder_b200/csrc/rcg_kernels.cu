@@ -147,6 +147,18 @@ stretch_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_cons
     cluster.sync();  // no CTA may exit while its peer can still read its shared memory
 }
 
+// frequency-kernel path at W = 65536, analysis half: each CTA of the pair writes the bins of its parity
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FrameCfg<kPairLog2HL>::NT, 1)
+analysis_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, int n_items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int r = (int)cg::this_cluster().block_rank();
+    cf* S = reinterpret_cast<cf*>(smem_raw);
+    cf* bufs[2] = {S, S};   // only bufs[r] is touched: no data crosses the pair in this kernel
+    PairDeviceExec ex{r, (int)threadIdx.x};
+    const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
+    for (int item = cid; item < n_items; item += ncl) run_analysis_item_pair(ex, bufs, prm, pt, item, true);
+}
+
 __global__ void __launch_bounds__(FrameCfg<kPairLog2HL>::NT)
 boundary_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, const float* head,
                      const float* tail_prev) {
@@ -161,7 +173,16 @@ cudaError_t pair_geometry(LaunchGeometry* g) {
     g->frames_per_cta = 1;
     g->smem_bytes = (size_t)C::SMEM_CF * sizeof(cf);
     g->max_ctas_per_sm = 1;
+    cudaError_t e = cudaFuncSetAttribute(analysis_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(stretch_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
+}
+cudaError_t launch_analysis_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream) {
+    using C = FrameCfg<kPairLog2HL>;
+    const int n_items = prm.channels * prm.n_runs;
+    if (n_items <= 0) return cudaSuccess;
+    analysis_pair_kernel<<<2 * n_clusters, C::NT, (size_t)C::SMEM_CF * sizeof(cf), stream>>>(prm, pt, n_items);
+    return cudaGetLastError();
 }
 cudaError_t launch_stretch_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream) {
     using C = FrameCfg<kPairLog2HL>;

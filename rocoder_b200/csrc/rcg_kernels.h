@@ -28,6 +28,7 @@ cudaError_t launch_boundary(int log2w, const StretchParams& prm, const float* he
 // (and per channel for the boundary kernel)
 cudaError_t pair_geometry(LaunchGeometry* g);
 cudaError_t launch_stretch_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream);
+cudaError_t launch_analysis_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream);
 cudaError_t launch_boundary_pair(const StretchParams& prm, const PairTables& pt, const float* head, const float* tail_prev,
                                  cudaStream_t stream);
 

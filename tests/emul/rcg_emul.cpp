@@ -241,6 +241,41 @@ static int emul_plugin(StretchParams prm, apply_fn fn) {
     return 0;
 }
 
+// the same at W = 65536 (CTA pair)
+static int emul_plugin_pair(StretchParams prm, apply_fn fn) {
+    using C = FrameCfg<kPairLog2HL>;
+    std::vector<float> window(kPairW), env(kPairH);
+    host_hanning(window.data(), kPairW);
+    host_crossfade_compensation(env.data(), kPairH);
+    std::vector<cf> tw = host_pass_twiddles(kPairLog2HL);
+    std::vector<cf> cross = host_pair_cross_twiddles(kPairLog2HL + 1);
+    std::vector<cf> se = host_pair_spectral_twiddles(kPairLog2HL + 1, 0), so = host_pair_spectral_twiddles(kPairLog2HL + 1, 1);
+    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data();
+    std::vector<float> lr = lerp_table(prm.pitch);
+    prm.lerp_ratio = lr.data();
+    std::vector<uint2> ptab = host_pair_table(kPairLog2HL);
+    prm.pair_tab = ptab.data();
+    std::vector<float> scratch(3 * (size_t)kPairH);
+    PairTables pt{cross.data(), se.data(), so.data(), scratch.data()};
+    const long long nf = prm.frame_end - prm.frame_begin;
+    std::vector<cf> spec((size_t)prm.channels * nf * kPairW);
+    prm.spectrum = spec.data(); prm.spec_frame0 = prm.frame_begin; prm.spec_frames = nf;
+    std::vector<cf> S0(C::SMEM_CF), S1(C::SMEM_CF);
+    cf* bufs[2] = {S0.data(), S1.data()};
+    std::vector<float> tmp(2 * (size_t)kPairW);
+    PairHostExec ex{C::NT};
+    const int items = prm.channels * prm.n_runs;
+    for (int item = 0; item < items; item++) run_analysis_item_pair(ex, bufs, prm, pt, item, true);
+    for (long long f = 0; f < nf; f++)
+        for (int c = 0; c < prm.channels; c++) {
+            float* x = reinterpret_cast<float*>(spec.data() + ((size_t)c * nf + f) * kPairW);
+            if (fn && fn(1234, x, kPairW, tmp.data()) == 0) memcpy(x, tmp.data(), sizeof(float) * 2 * kPairW);
+        }
+    prm.flags |= kFlagSpectrumIn;
+    for (int item = 0; item < items; item++) run_work_item_pair(ex, bufs, prm, pt, item, scratch.data(), true);
+    return 0;
+}
+
 extern "C" {
 int rcg_emul_stretch_plugin(int log2w, const float* in, long long in_stride, long long in_valid, float* out,
                             long long out_stride, long long frame_end, int run_len, int channels, int step,
@@ -254,6 +289,7 @@ int rcg_emul_stretch_plugin(int log2w, const float* in, long long in_stride, lon
     p.channels = channels; p.step = step; p.pitch = pitch; p.samples_needed = samples_needed;
     p.amp = amp; p.inv_w = 1.0f / (float)(1 << log2w);
     p.keys = make_philox_keys(seed);
+    if (log2w == 16) return emul_plugin_pair(p, fn);
     switch (log2w - 1) {
 #define CASE(L) case L: return emul_plugin<L>(p, fn);
         CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)

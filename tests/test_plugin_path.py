@@ -13,12 +13,22 @@ def _input(n, seed=1):
 
 
 CASES = [(6000, 2.0, 1, 256), (9000, 3.0, 2, 1024), (7000, 4.0, -2, 512), (40000, 2.0, 1, 16384)]
+PAIR_CASES = [(150000, 2.0, 1, 65536), (150000, 3.0, 2, 65536), (150000, 2.0, -2, 65536)]   # frame across a CTA pair
 PLUGS = [plugins.amplitude_x2, plugins.lowpass_asymmetric, plugins.tilt]
 
 
 @pytest.mark.parametrize("n,f,p,W", CASES[:3])
 @pytest.mark.parametrize("plug", PLUGS, ids=lambda f: f.__name__)
 def test_emulated_plugin_path_matches_oracle(n, f, p, W, plug):
+    x = _input(n)
+    ref = ol.process_all(x, f, p, W, seed=4, precision=64, plugin=plug)
+    got = ol.emul_process_all_plugin(x, f, p, W, plug, seed=4)
+    assert np.abs(got - ref).max() <= 1e-4 and ol.snr_db(ref, got) > 100.0
+
+
+@pytest.mark.parametrize("n,f,p,W", PAIR_CASES)
+@pytest.mark.parametrize("plug", [plugins.lowpass_asymmetric, plugins.tilt], ids=lambda f: f.__name__)
+def test_emulated_plugin_path_matches_oracle_w65536(n, f, p, W, plug):
     x = _input(n)
     ref = ol.process_all(x, f, p, W, seed=4, precision=64, plugin=plug)
     got = ol.emul_process_all_plugin(x, f, p, W, plug, seed=4)
@@ -56,7 +66,7 @@ def test_oracle_plugin_panic_falls_back():
 
 # ---------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,f,p,W", CASES)
+@pytest.mark.parametrize("n,f,p,W", CASES + PAIR_CASES)
 @pytest.mark.parametrize("plug", PLUGS, ids=lambda f: f.__name__)
 def test_gpu_plugin_path_matches_oracle(n, f, p, W, plug):
     import ctypes as C
@@ -139,7 +149,7 @@ __device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, const 
 @pytest.mark.gpu
 @pytest.mark.parametrize("src,host", [(DEVICE_X2, plugins.amplitude_x2), (DEVICE_TILT, plugins.tilt),
                                       (DEVICE_LOWPASS, plugins.lowpass_asymmetric)], ids=["x2", "tilt", "lowpass"])
-@pytest.mark.parametrize("n,f,p,W", [(9000, 3.0, 2, 1024), (60000, 2.0, 1, 16384)])
+@pytest.mark.parametrize("n,f,p,W", [(9000, 3.0, 2, 1024), (60000, 2.0, 1, 16384), (150000, 3.0, 2, 65536)])
 def test_gpu_device_frequency_kernel_matches_oracle(src, host, n, f, p, W):
     """NVRTC-compiled device `apply` (spectra stay in HBM) == the oracle with the same host kernel"""
     import rocoder_b200 as rb
