@@ -207,6 +207,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local)
+    numa = rb.bind_host_thread(local) if not os.environ.get("RCG_NO_NUMA_BIND") else -1   # pinned buffers next to the GPU
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -321,7 +322,8 @@ def run_ours(args):
                          "note": "compute(FP32/shared-memory)-bound path: see DESIGN.md for why frac is capped"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 4 * CHANNELS * N_IN,
-                    "d2h_bytes_per_step": 4 * CHANNELS * e2e_len, "ms_per_step": e2e_ms, "checksum": checksum},
+                    "d2h_bytes_per_step": 4 * CHANNELS * e2e_len, "ms_per_step": e2e_ms, "checksum": checksum,
+                    "host_numa_node_rank0": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }))

@@ -217,6 +217,11 @@ int rcg_fade_keyframes(float fade_s, uint32_t sample_rate, uint64_t expected_tot
 /* -- helpers ------------------------------------------------------------------------------ */
 int rcg_host_alloc(void **ptr, size_t bytes); /* pinned host memory */
 int rcg_host_free(void *ptr);
+/* [host] pin the calling thread to the CPUs of the NUMA node `device` is attached to (never widening the
+ * current affinity mask), so that pinned buffers allocated afterwards sit next to the GPU.  *numa_node = the
+ * node bound to, or -1 when the box exposes no NUMA information (then nothing changes).  Optional: call it once
+ * per rank before rcg_host_alloc / rcg_create on multi-socket, multi-GPU boxes. */
+int rcg_bind_host_thread(int device, int *numa_node);
 /* FP32 FMA throughput of the current device, TFLOP/s: the measured compute-roofline denominator */
 int rcg_measure_fp32_peak(double *tflops, int reps);
 /* kernels launched by this engine so far */

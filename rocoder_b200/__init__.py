@@ -6,7 +6,7 @@ StretcherProcessor interface.  There is no CPU fallback: without librocoder_b200
 without an sm_100 GPU the engine raises.
 """
 from ._abi import (RCG_FLAG_BYPASS_RESYNTH, RCG_FLAG_RANDOM_SEED, RcgError, WouldBlock, LIB_PATH)
-from .engine import (Engine, PinnedBuffer, channel_bound, expected_counts, fade_in_out, fade_keyframes, hanning, measure_fp32_peak,
+from .engine import (Engine, PinnedBuffer, bind_host_thread, channel_bound, expected_counts, fade_in_out, fade_keyframes, hanning, measure_fp32_peak,
                      hanning_crossfade_compensation, phase, plan)
 from .stretcher import (AudioBus, AudioSpec, Disconnected, Receiver, Sender, Stretcher, StretcherProcessor,
                         bounded, stretch, unbounded)

@@ -118,6 +118,7 @@ def lib() -> C.CDLL:
         "rcg_fade_keyframes": (C.c_int, [C.c_float, C.c_uint32, C.c_uint64, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)]),
         "rcg_measure_fp32_peak": (C.c_int, [P(C.c_double), C.c_int]),
         "rcg_host_alloc": (C.c_int, [P(C.c_void_p), C.c_size_t]),
+        "rcg_bind_host_thread": (C.c_int, [C.c_int, P(C.c_int)]),
         "rcg_host_free": (C.c_int, [C.c_void_p]),
         "rcg_launch_count": (C.c_int, [C.c_void_p, P(C.c_uint64)]),
     }

@@ -121,3 +121,53 @@ extern "C" int rcg_measure_fp32_peak(double* tflops, int reps) {
     *tflops = best;
     return cudaGetLastError() == cudaSuccess ? RCG_OK : RCG_ERR_CUDA;
 }
+
+// ---- NUMA placement of the calling thread ---------------------------------------------------------------
+// Pinned staging buffers are allocated on the NUMA node the calling thread runs on; on a multi-socket box a
+// buffer on the far socket halves the host<->device rate of every copy through it.  This pins the calling
+// thread (and hence its later rcg_host_alloc / cudaMallocHost pages) to the CPUs of the node the GPU hangs off.
+#include <sched.h>
+
+#include <cctype>
+#include <cstdio>
+#include <cstring>
+
+static bool read_line(const char* path, char* buf, size_t cap) {
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    const bool ok = fgets(buf, (int)cap, f) != nullptr;
+    fclose(f);
+    return ok;
+}
+
+extern "C" int rcg_bind_host_thread(int device, int* numa_node) {
+    if (numa_node) *numa_node = -1;
+    char bus[64] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return RCG_ERR_NO_DEVICE;
+    }
+    for (char* c = bus; *c; c++) *c = (char)tolower((unsigned char)*c);
+    char path[160], line[4096];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    int node = -1;
+    if (!read_line(path, line, sizeof line) || sscanf(line, "%d", &node) != 1 || node < 0) return RCG_OK;  // no NUMA info: leave as is
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    if (!read_line(path, line, sizeof line)) return RCG_OK;
+    cpu_set_t allowed, want;
+    CPU_ZERO(&want);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return RCG_OK;
+    int n_want = 0;
+    for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {   // "0-31,64-95"
+        int a = 0, b = 0;
+        const int got = sscanf(tok, "%d-%d", &a, &b);
+        if (got < 1) continue;
+        if (got == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; c++)
+            if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &want); n_want++; }   // never widen a cgroup / taskset mask
+    }
+    if (n_want == 0) return RCG_OK;
+    if (sched_setaffinity(0, sizeof want, &want) != 0) return RCG_OK;
+    if (numa_node) *numa_node = node;
+    return RCG_OK;
+}

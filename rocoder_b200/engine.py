@@ -92,6 +92,13 @@ def fade_keyframes(fade_s: float, sample_rate: int, expected_total_samples: int)
     return a.value, b.value, c.value
 
 
+def bind_host_thread(device: int = 0) -> int:
+    """Pin the calling thread to the NUMA node of `device` (rcg_bind_host_thread); returns the node or -1."""
+    node = C.c_int(-1)
+    check(lib().rcg_bind_host_thread(device, C.byref(node)))
+    return node.value
+
+
 def measure_fp32_peak(reps: int = 5) -> float:
     v = C.c_double()
     check(lib().rcg_measure_fp32_peak(C.byref(v), reps))
@@ -286,5 +293,5 @@ class Engine:
         return n.value
 
 
-__all__ = ["Engine", "PinnedBuffer", "fade_in_out", "fade_keyframes", "measure_fp32_peak", "RcgError", "WouldBlock", "hanning", "hanning_crossfade_compensation",
+__all__ = ["Engine", "PinnedBuffer", "bind_host_thread", "fade_in_out", "fade_keyframes", "measure_fp32_peak", "RcgError", "WouldBlock", "hanning", "hanning_crossfade_compensation",
            "plan", "expected_counts", "channel_bound", "phase"]
