@@ -29,6 +29,9 @@
 #endif
 #define RCG_PRAGMA(x) _Pragma(#x)
 #define RCG_UNROLL(n) RCG_PRAGMA(unroll n)
+#ifndef RCG_SPECTRUM_PREFETCH
+#define RCG_SPECTRUM_PREFETCH 0
+#endif
 
 #if defined(__CUDA_ARCH__)
 #define RCG_MUL(a, b) __fmul_rn((a), (b))
@@ -166,6 +169,17 @@ RCG_HD uint4 ld_u4(const uint4* p) {
 RCG_HD uint2 ld_u2(const uint2* p) {
 #if defined(__CUDA_ARCH__)
     return __ldg(p);
+#else
+    return *p;
+#endif
+}
+// single-use stream (spectra of the frequency-kernel path): keep it out of L1, where the twiddle tables, window
+// and envelope live, and let L2 drop it first (what L1::no_allocate means to L2 on sm_100, see above)
+RCG_HD cf ld_once(const cf* p) {
+#if defined(__CUDA_ARCH__)
+    cf r;
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
 #else
     return *p;
 #endif
@@ -582,35 +596,73 @@ RCG_HD void phase_spectrum_split(cf* S, int t, const StretchParams& prm) {
         S[pb] = make_cf(0.5f * (pr - ur), -(0.5f * (pi - ui)));       // X[H-k]
     }
 }
+// Which bin the i-th element of a natural-order sweep over the H bin slots stands for.  The transform
+// leaves bin k at a position whose low 4 bits are k's top 4 bits, so 32 consecutive bins share one
+// shared-memory bank pair (a 32-way conflict).  Instead a warp covers 8 values of k's top bits times 4
+// consecutive bins: 8 distinct bank pairs (4 wavefronts instead of 32) while each group of 4 lanes still
+// moves one whole 32-byte sector of the spectrum in HBM.
+template <int LOG2H>
+RCG_HD constexpr int sweep_bin(int i) {
+    using C = FrameCfg<LOG2H>;
+    if constexpr (LOG2H < 9 || C::NT < 32) {
+        return i;
+    } else {
+        constexpr int HS = LOG2H - 4;   // k >> HS = the digit of the last pass = position bits 0..3
+        const int r = i >> 5;
+        return (i & 3) | ((r & ((1 << (HS - 2)) - 1)) << 2) | (((i >> 2) & 7) << HS) | ((r >> (HS - 2)) << (LOG2H - 1));
+    }
+}
 template <int LOG2H>
 RCG_HD void phase_spectrum_copyout(const cf* S, int t, const StretchParams& prm, int channel, long long frame) {
     using C = FrameCfg<LOG2H>;
     cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * C::W;
-    for (int b = t; b < C::H; b += C::NT) {
+RCG_UNROLL(4)
+    for (int i = t; i < C::H; i += C::NT) {
+        const int b = sweep_bin<LOG2H>(i);
         const cf v = S[phys(bin_to_pos<LOG2H>(b))];
-        if (b == 0) {
-            X[0] = make_cf(v.x, 0.0f);
-            X[C::H] = make_cf(v.y, 0.0f);
-        } else {
-            X[b] = v;
-            X[C::W - b] = make_cf(v.x, -v.y);    // the spectrum of a real frame is Hermitian
-        }
+        // bin 0 holds (X[0], X[H]), both real; otherwise the spectrum of a real frame is Hermitian
+        X[b] = make_cf(v.x, b == 0 ? 0.0f : v.y);
+        X[b == 0 ? C::H : C::W - b] = make_cf(b == 0 ? v.y : v.x, b == 0 ? 0.0f : -v.y);
     }
 }
 
-RCG_HD float cf_norm(cf v) { return sqrtf(v.x * v.x + v.y * v.y); }
+RCG_HD float cf_norm(cf v) { return fast_sqrt(v.x * v.x + v.y * v.y); }
 
 // ---- plugin path, synthesis side: |apply(X)[k]| for each of the W bins (only the norm of the
 // plugin's output survives, fft.rs:67) -> random phase -> Hermitian fold -> inverse pre-pass.
 // Again two phases: (1) natural-order, coalesced read of the plugin output; the slot of bin b < H
 // receives (|P[b]|, |P[W-b]|) (slot 0: (|P[0]|, |P[H]|)); (2) pair threads in position order.
+RCG_HD void prefetch_l2(const void* p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
+// pf_next (RCG_SPECTRUM_PREFETCH, off: measured slower, 1.40 vs 1.20 ms on config 5): also pull the next frame's
+// spectrum (the one this lane reads in its next iteration) into L2
 template <int LOG2H>
-RCG_HD void phase_mags_copyin(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
+RCG_HD void phase_mags_copyin(cf* S, int t, const StretchParams& prm, int channel, long long frame, bool pf_next) {
     using C = FrameCfg<LOG2H>;
     const cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * C::W;
-    for (int b = t; b < C::H; b += C::NT) {
-        const cf lo = X[b], hi = X[b == 0 ? C::H : C::W - b];
-        S[phys(bin_to_pos<LOG2H>(b))] = make_cf(cf_norm(lo), cf_norm(hi));
+    if (RCG_SPECTRUM_PREFETCH && pf_next)
+        for (int l = t; l < C::W / 16; l += C::NT) prefetch_l2(X + C::W + 16 * l);   // 128-byte lines
+    // all loads of a batch are issued before the first use: the sweep is bound by HBM latency otherwise
+    constexpr int ITERS = C::H / C::NT, U = ITERS % 8 == 0 ? 8 : (ITERS % 4 == 0 ? 4 : 1);
+    static_assert(C::H % C::NT == 0, "bins per thread");
+    for (int i0 = t; i0 < C::H; i0 += C::NT * U) {
+        cf lo[U], hi[U];
+RCG_UNROLL(U)
+        for (int u = 0; u < U; u++) {
+            const int b = sweep_bin<LOG2H>(i0 + u * C::NT);
+            lo[u] = ld_once(X + b);
+            hi[u] = ld_once(X + (b == 0 ? C::H : C::W - b));
+        }
+RCG_UNROLL(U)
+        for (int u = 0; u < U; u++) {
+            const int b = sweep_bin<LOG2H>(i0 + u * C::NT);
+            S[phys(bin_to_pos<LOG2H>(b))] = make_cf(cf_norm(lo[u]), cf_norm(hi[u]));
+        }
     }
 }
 // KMUL: as in phase_spectral (2 for the even-bin half of a CTA pair)
@@ -620,8 +672,6 @@ RCG_HD void phase_spectral_in(cf* S, int t, const StretchParams& prm, int channe
     const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
     const uint32_t chan = (uint32_t)(channel + prm.channel_offset);
     for (int c = t; c < C::H / 2; c += C::NT) {
-        const int pos = spectral_slot_pos(LOG2H, c);
-        const int k = pos_to_bin<LOG2H>(pos);
         uint32_t u[4];
         if (c == 0) {
             const cf m0h = S[0];                                     // (|P[0]|, |P[H]|)
@@ -640,7 +690,8 @@ RCG_HD void phase_spectral_in(cf* S, int t, const StretchParams& prm, int channe
             S[pq] = make_cf(mq.x * ca + mq.y * cb, -(mq.x * sa - mq.y * sb));
             continue;
         }
-        const int pa = phys(pos), pb = phys(bin_to_pos<LOG2H>(C::H - k));
+        const uint2 pt = ld_u2(prm.pair_tab + c);   // slot indices of bins k, H-k and k itself (as in phase_spectral)
+        const int pa = (int)(pt.x & 0xFFFFu), pb = (int)(pt.x >> 16), k = (int)pt.y;
         const cf ma = S[pa], mb = S[pb];                             // (|P[k]|, |P[W-k]|), (|P[H-k]|, |P[H+k]|)
         const cf tw = ld_cf(prm.spec_tw + c);
         philox4x32_10((uint32_t)(k * KMUL), f_lo, f_hi, chan, prm.keys, u);
@@ -964,7 +1015,9 @@ RCG_HD void fft_inv_hr(Exec& ex, cf* S, const StretchParams& prm, bool work) {
 
 // ---- the frame loop of one work item (a run of consecutive frames of one channel) --------
 // Exec::par(f) runs f(t) for every thread of the frame lane followed by a barrier.
-template <int LOG2H, class Exec>
+// SPEC_IN: the frequency-kernel synthesis (kFlagSpectrumIn) as its own instantiation, so that its phases
+// do not weigh on the register allocation of the fused kernel.
+template <int LOG2H, bool SPEC_IN = false, class Exec>
 RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, float* tail, bool active) {
     using C = FrameCfg<LOG2H>;
     const int channel = active ? item / prm.n_runs : 0;
@@ -985,9 +1038,9 @@ RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, f
         const float* src = have_tail_in ? prm.tail_in + (long long)channel * C::H : nullptr;
         for (int i = t; i < C::H; i += C::NT) tail[i] = src ? src[i] : 0.0f;
     });
-    const bool half_rate = prm.flags & kFlagHalfRate;
+    const bool half_rate = !SPEC_IN && (prm.flags & kFlagHalfRate);
     const bool bypass = prm.flags & kFlagBypass;
-    const bool spectrum_in = prm.flags & kFlagSpectrumIn;
+    constexpr bool spectrum_in = SPEC_IN;
     // Load of frame f+1 fused into the overlap-add phase of frame f: possible when that phase leaves
     // nothing staged in shared memory (pitch 1, or pitch 2 on the half-rate path).
     const bool fuse = RCG_FUSE_OLA_LOAD && !(prm.flags & kFlagNoFuse) && !bypass && !spectrum_in &&
@@ -1003,8 +1056,9 @@ RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, f
         const bool is_halo = (it == 0);
         const bool work = active && (is_halo ? halo : f < f1);
         const bool load_next = fuse && work && (it + 1 < n_iter) && (f + 1 < f1);
-        if (spectrum_in) {
-            ex.par([&](int t) { if (work) phase_mags_copyin<LOG2H>(S, t, prm, channel, f); });
+        if constexpr (spectrum_in) {
+            const bool pf = work && f + 1 < f1;
+            ex.par([&](int t) { if (work) phase_mags_copyin<LOG2H>(S, t, prm, channel, f, pf); });
             ex.par([&](int t) { if (work) phase_spectral_in<LOG2H>(S, t, prm, channel, f); });
             fft_all<LOG2H, true>(ex, S, prm, work);
         } else {

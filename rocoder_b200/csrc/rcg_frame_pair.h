@@ -141,7 +141,7 @@ RCG_HD void pair_phase_mags_copyin(cf* S, int r, int t, const StretchParams& prm
     const cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * kPairW;
     for (int b = t; b < kPairHL; b += C::NT) {
         const int k = 2 * b + r;
-        const cf lo = X[k], hi = X[k == 0 ? kPairH : kPairW - k];
+        const cf lo = ld_once(X + k), hi = ld_once(X + (k == 0 ? kPairH : kPairW - k));
         S[phys(bin_to_pos<kPairLog2HL>(b))] = make_cf(cf_norm(lo), cf_norm(hi));
     }
 }

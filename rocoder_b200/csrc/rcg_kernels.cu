@@ -60,7 +60,7 @@ using DeviceExec = DeviceExecT<false>;
 template <int LOG2H>
 constexpr int min_ctas() { return LOG2H >= 14 ? 1 : RCG_MIN_CTAS; }
 
-template <int LOG2H>
+template <int LOG2H, bool SPEC_IN = false>
 __global__ void __launch_bounds__(FrameCfg<LOG2H>::NT * FrameCfg<LOG2H>::FPC, min_ctas<LOG2H>())
 stretch_kernel(const __grid_constant__ StretchParams prm, int n_items) {
     using C = FrameCfg<LOG2H>;
@@ -77,7 +77,7 @@ stretch_kernel(const __grid_constant__ StretchParams prm, int n_items) {
     const int n_groups = (n_items + C::FPC - 1) / C::FPC;
     for (int g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const int item = g * C::FPC + lane;
-        run_work_item<LOG2H>(ex, S, prm, item, tail, item < n_items);
+        run_work_item<LOG2H, SPEC_IN>(ex, S, prm, item, tail, item < n_items);
     }
 }
 
@@ -203,8 +203,11 @@ static cudaError_t geometry_t(LaunchGeometry* g) {
     g->threads = C::NT * C::FPC;
     g->frames_per_cta = C::FPC;
     g->smem_bytes = (size_t)C::FPC * C::SMEM_CF * sizeof(cf);
-    cudaError_t e = cudaFuncSetAttribute(stretch_kernel<LOG2H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(stretch_kernel<LOG2H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)g->smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(stretch_kernel<LOG2H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)g->smem_bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(analysis_kernel<LOG2H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)g->smem_bytes);
@@ -213,7 +216,7 @@ static cudaError_t geometry_t(LaunchGeometry* g) {
                              (int)(C::SMEM_CF * sizeof(cf)));
     if (e != cudaSuccess) return e;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stretch_kernel<LOG2H>, g->threads, g->smem_bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stretch_kernel<LOG2H, false>, g->threads, g->smem_bytes);
     g->max_ctas_per_sm = n;
     return e;
 }
@@ -223,7 +226,10 @@ static cudaError_t launch_t(const StretchParams& prm, int grid, cudaStream_t str
     using C = FrameCfg<LOG2H>;
     const int n_items = prm.channels * prm.n_runs;
     if (n_items <= 0) return cudaSuccess;
-    stretch_kernel<LOG2H><<<grid, C::NT * C::FPC, (size_t)C::FPC * C::SMEM_CF * sizeof(cf), stream>>>(prm, n_items);
+    if (prm.flags & kFlagSpectrumIn)
+        stretch_kernel<LOG2H, true><<<grid, C::NT * C::FPC, (size_t)C::FPC * C::SMEM_CF * sizeof(cf), stream>>>(prm, n_items);
+    else
+        stretch_kernel<LOG2H, false><<<grid, C::NT * C::FPC, (size_t)C::FPC * C::SMEM_CF * sizeof(cf), stream>>>(prm, n_items);
     return cudaGetLastError();
 }
 

@@ -223,6 +223,8 @@ static int emul_plugin(StretchParams prm, apply_fn fn) {
     prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.spec_tw = stw.data();
     std::vector<float> lr = lerp_table(prm.pitch);
     prm.lerp_ratio = lr.data();
+    std::vector<uint2> ptab = host_pair_table(LOG2H);
+    prm.pair_tab = ptab.data();
     const long long nf = prm.frame_end - prm.frame_begin;
     std::vector<cf> spec((size_t)prm.channels * nf * W);
     prm.spectrum = spec.data(); prm.spec_frame0 = prm.frame_begin; prm.spec_frames = nf;
@@ -237,7 +239,7 @@ static int emul_plugin(StretchParams prm, apply_fn fn) {
             if (fn && fn(1234, x, W, tmp.data()) == 0) memcpy(x, tmp.data(), sizeof(float) * 2 * W);
         }
     prm.flags |= kFlagSpectrumIn;
-    for (int item = 0; item < items; item++) run_work_item<LOG2H>(ex, S.data(), prm, item, tail.data(), true);
+    for (int item = 0; item < items; item++) run_work_item<LOG2H, true>(ex, S.data(), prm, item, tail.data(), true);
     return 0;
 }
 
