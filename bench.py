@@ -64,32 +64,82 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs"""
+    """SM clock and throttle reasons sampled WHILE the timed region runs: NVML from a thread every 2 ms (a
+    default run's timed region is ~70 ms, shorter than one `nvidia-smi -lms` period), nvidia-smi as fallback."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+        self.sm, self.mask, self.max_mhz = [], 0, None
+        self.rows, self.proc, self.thread, self.nvml, self.handle = [], None, None, None, None
+        self.stop_flag = threading.Event()
+        self.source = None
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        self.nvml = pynvml
+        try:   # CUDA_VISIBLE_DEVICES can renumber devices: go by PCI address
+            pr = torch.cuda.get_device_properties(self.gpu)
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            return pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            return pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
 
     def start(self):
         try:
+            self.handle = self._nvml_handle()
+            self.max_mhz = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.handle, self.nvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.handle = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _sample(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            self.mask |= int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            self.mask |= int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+
+    def _poll(self):
+        while not self.stop_flag.is_set():
+            try:
+                self._sample()
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self) -> dict:
+        """call while the GPU is still busy with the timed region's last step or right at its end"""
+        if self.handle is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=1.0)
+            reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(self.sm), "reasons": reasons, "source": "nvml"}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no NVML, no nvidia-smi"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
@@ -104,11 +154,14 @@ class ClockSampler:
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------------
 # CPU legs: the ONLY place bench.py touches oracle/ (as the timed baseline, never as the product)
+_CPU_CACHE = {}
+
+
 def cpu_leg(target_seconds: float, native: bool = True):
     """time the oracle (port of the reference's single-threaded DSP loop, stretcher_processor.rs:55-71)
     on a bounded sample of the workload: the first calls of channel 0"""
@@ -125,8 +178,10 @@ def cpu_leg(target_seconds: float, native: bool = True):
         except Exception:
             path = None
     L = ol.oracle(path) if path else ol.oracle()
-    secs = 60
-    x = noise_chirp(SAMPLE_RATE * secs, SAMPLE_RATE, 1, seed=0)[0]
+    secs = 600   # the workload's own 10 minutes of channel 0; the sample is its first `calls` calls
+    if "x" not in _CPU_CACHE:
+        _CPU_CACHE["x"] = noise_chirp(SAMPLE_RATE * secs, SAMPLE_RATE, 1, seed=0)[0]
+    x = _CPU_CACHE["x"]
     sink = np.zeros(WINDOW * 2, np.float32)
     n_out = C.c_size_t()
 
@@ -314,7 +369,7 @@ def run_ours(args):
                        "frames_per_gpu": frames * CHANNELS, "l2": "inputs+outputs larger than L2 (0.23 GB in, 1.84 GB out per step)",
                        "exchange": "channels x W/2 fp32 carried half window, rank r -> r+1, NCCL p2p" if world > 1 else "none"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "stretch_kernel<13>",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "stretch_kernel<13, false>",
                          "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                          "fp32_tflops_algorithmic": flops / (k_ms * 1e-3) / 1e12,
                          "fp32_peak_tflops_measured": fp32_peak,
