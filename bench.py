@@ -193,8 +193,12 @@ def cpu_leg(target_seconds: float, native: bool = True):
 
     t, made, outs = run(40)  # probe
     per_call = t / max(made, 1)
-    calls = int(max(40, min(target_seconds / per_call, ol.expected_counts(x.size, FACTOR, PITCH, WINDOW)[0] - 1)))
+    max_calls = ol.expected_counts(x.size, FACTOR, PITCH, WINDOW)[0] - 1
+    calls = int(max(40, min(target_seconds / per_call, max_calls)))
     t, made, outs = run(calls)
+    if t < 0.75 * target_seconds and calls < max_calls:   # the probe over-estimated the cost per call: one more pass
+        calls = int(min(calls * target_seconds / max(t, 1e-3), max_calls))
+        t, made, outs = run(calls)
     # all cores, one independent replica each (ctypes drops the GIL): labelled separately -- the
     # reference itself drives every channel from ONE thread (stretcher_processor.rs:55-71)
     ncores = os.cpu_count() or 1
