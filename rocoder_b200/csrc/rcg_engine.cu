@@ -480,8 +480,9 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
     p.run_len = pick_run_len(nframes, (uint32_t)channels, slots);
     p.n_runs = (int)((nframes + p.run_len - 1) / p.run_len);
     const long long items = (long long)p.n_runs * channels;
-    const int groups = (int)((items + e->geo.frames_per_cta - 1) / e->geo.frames_per_cta);
-    const int grid = std::min(groups, e->max_grid);
+    // one item per CTA first (every SM busy), frame lanes double up only once the CTAs run out; W = 65536
+    // counts clusters (frames_per_cta = 1)
+    const int grid = (int)std::min<long long>(items, e->max_grid);
     cudaError_t ce = e->pair ? launch_stretch_pair(p, e->pt, grid, stream) : launch_stretch(e->log2w, p, grid, stream);
     if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "stretch kernel launch failed: %s", cudaGetErrorString(ce));
     e->launches++;
@@ -551,7 +552,7 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
         p.run_len = (int)std::max<uint64_t>(1, (nframes * channels + slots - 1) / slots);
         p.n_runs = (int)((nframes + p.run_len - 1) / p.run_len);
         const long long items = (long long)p.n_runs * channels;
-        const int grid = (int)std::min<long long>((items + e->geo.frames_per_cta - 1) / e->geo.frames_per_cta, e->max_grid);
+        const int grid = (int)std::min<long long>(items, e->max_grid);
         cudaError_t ce = e->pair ? launch_analysis_pair(p, e->pt, grid, stream) : launch_analysis(e->log2w, p, grid, stream);
         if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "analysis kernel launch failed: %s", cudaGetErrorString(ce));
         e->launches++;

@@ -115,6 +115,8 @@ struct FrameCfg {
     static constexpr int FPC = frames_per_cta(LOG2H);
     static constexpr int SMEM_CF = padded_len(H);  // per frame lane
     static constexpr int RLAST = 1 << make_plan(LOG2H).rlog2[NP - 1];
+    static constexpr bool TW_SMEM = tw_in_smem(LOG2H);   // prm.tw of the kernels points into shared memory
+    static constexpr int TW_CF = tw_total(LOG2H);
 };
 
 // ---- global loads ---------------------------------------------------------------------
@@ -158,6 +160,12 @@ RCG_HD cf ld_cf(const cf* p) {
 #else
     return *p;
 #endif
+}
+// pass twiddles: read-only global tables, or the CTA's shared-memory copy (FrameCfg::TW_SMEM)
+template <int LOG2H>
+RCG_HD cf ld_tw(const cf* p) {
+    if constexpr (FrameCfg<LOG2H>::TW_SMEM) return *p;
+    else return ld_cf(p);
 }
 RCG_HD uint4 ld_u4(const uint4* p) {
 #if defined(__CUDA_ARCH__)
@@ -213,9 +221,9 @@ RCG_HD TwPre tw_preload(const cf* tw, int m) {
     TwPre p;
     p.w1 = p.w2 = p.w4 = p.w8 = make_cf(1.0f, 0.0f);
     if constexpr (SCHEME == kTwPow) {
-        p.w1 = ld_cf(tw + m); p.w2 = ld_cf(tw + M + m);
-        if constexpr (R >= 8) p.w4 = ld_cf(tw + 2 * M + m);
-        if constexpr (R >= 16) p.w8 = ld_cf(tw + 3 * M + m);
+        p.w1 = ld_tw<LOG2H>(tw + m); p.w2 = ld_tw<LOG2H>(tw + M + m);
+        if constexpr (R >= 8) p.w4 = ld_tw<LOG2H>(tw + 2 * M + m);
+        if constexpr (R >= 16) p.w8 = ld_tw<LOG2H>(tw + 3 * M + m);
     }
     return p;
 }
@@ -227,12 +235,12 @@ RCG_HD void twiddle_butterfly(float (&xr)[R], float (&xi)[R], const cf* tw, int 
     if constexpr (SCHEME == kTwFull) {
 #pragma unroll
         for (int j = 1; j < R; j++) {
-            const cf w = ld_cf(tw + (j - 1) * M + m);
+            const cf w = ld_tw<LOG2H>(tw + (j - 1) * M + m);
             tw_apply<CONJ>(xr[j], xi[j], w.x, w.y);
         }
     } else if constexpr (SCHEME == kTwTwoLevel) {
         static_assert(SCHEME != kTwTwoLevel || R == 2, "two-level tables serve radix-2 passes");
-        const cf a = ld_cf(tw + (m >> 6)), b = ld_cf(tw + M / 64 + (m & 63));
+        const cf a = ld_tw<LOG2H>(tw + (m >> 6)), b = ld_tw<LOG2H>(tw + M / 64 + (m & 63));
         float wr, wi;
         cmul(a.x, a.y, b.x, b.y, wr, wi);
         tw_apply<CONJ>(xr[1], xi[1], wr, wi);
