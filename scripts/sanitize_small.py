@@ -9,7 +9,7 @@ import rocoder_b200 as rb
 
 rng = np.random.default_rng(0)
 def inp(ch, n): return ((rng.random((ch, n), dtype=np.float32) * 2 - 1) * 0.5).astype(np.float32)
-cases = [(2, 40000, 2.0, 1, 16384), (2, 40000, 4.0, 2, 16384), (2, 30000, 3.0, -3, 4096), (2, 9000, 2.0, 4, 1024),
+cases = [(2, 40000, 2.0, 1, 16384), (2, 40000, 4.0, 2, 16384), (2, 700000, 2.0, 2, 16384), (2, 650000, 2.0, -2, 16384), (2, 30000, 3.0, -3, 4096), (2, 9000, 2.0, 4, 1024),
          (1, 3000, 2.0, 2, 64), (2, 200000, 2.0, 1, 65536), (2, 200000, 2.0, -2, 65536)]
 for ch, n, f, p, W in cases:
     with rb.Engine(ch, 48000, W, f, 1.0, p, seed=1) as e:
@@ -37,6 +37,11 @@ with rb.Engine(2, 48000, 1024, 2.0, 1.0, 1, seed=1) as e:
 with rb.Engine(2, 48000, 1024, 2.0, 1.0, 2, seed=1) as e:
     e.push_device_frequency_kernel("__device__ float2 apply(size_t t, unsigned b, unsigned n, const float2* s) { return s[b]; }")
     e.process_all(inp(2, 9000))
+for W, n in ((16384, 120000), (65536, 300000)):   # frequency-kernel path at the large windows (three lanes per CTA; CTA pair)
+    with rb.Engine(2, 48000, W, 2.0, 1.0, 1, seed=1) as e:
+        e.push_device_frequency_kernel("__device__ float2 apply(size_t t, unsigned b, unsigned n, const float2* s) { return s[b]; }")
+        assert np.isfinite(e.process_all(inp(2, n))).all()
+    print("ok plugin", W, flush=True)
 d = torch.randn(2, 50000, device="cuda")
 rb.fade_in_out(d, 0.25, 48000, 50000, stream=1)
 torch.cuda.synchronize()
