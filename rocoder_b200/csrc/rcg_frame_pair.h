@@ -12,6 +12,15 @@
 #pragma once
 #include "rcg_frame.h"
 
+// unroll factors of the two phases that wait on global / distributed-shared loads (512 threads per CTA, one
+// CTA per SM: 128 registers per thread are available)
+#ifndef RCG_PAIR_LOAD_UNROLL
+#define RCG_PAIR_LOAD_UNROLL 4
+#endif
+#ifndef RCG_PAIR_OLA_UNROLL
+#define RCG_PAIR_OLA_UNROLL 2
+#endif
+
 namespace rcg {
 
 constexpr int kPairLog2HL = 14;              // local transform: 16384 points
@@ -42,7 +51,7 @@ RCG_HD void pair_phase_load_impl(cf* S, int r, int t, const StretchParams& prm, 
                                  long long base, bool bypass) {
     using C = FrameCfg<kPairLog2HL>;
     auto sample = [&](long long i) { return (i >= 0 && i < prm.in_valid) ? ld_stream(in + i) : 0.0f; };
-RCG_UNROLL(4)
+RCG_UNROLL(RCG_PAIR_LOAD_UNROLL)
     for (int n = t; n < kPairHL; n += C::NT) {
         const cf wa = ld_stream2(prm.window + 2 * n), wb = ld_stream2(prm.window + kPairH + 2 * n);
         cf xa, xb;
@@ -184,7 +193,7 @@ RCG_HD void pair_phase_ola(const cf* S, const cf* peer, int r, int t, const Stre
     const bool bypass = prm.flags & kFlagBypass;
     float* out = prm.out + (long long)channel * prm.out_stride;
     const float scale = bypass ? 1.0f : prm.inv_w;
-RCG_UNROLL(2)
+RCG_UNROLL(RCG_PAIR_OLA_UNROLL)
     for (int n = t; n < kPairHL; n += C::NT) {
         float zr, zi;
         if (bypass) {

@@ -13,6 +13,7 @@
 #include <cooperative_groups.h>
 
 #include "rcg_frame_pair.h"
+#include "rcg_frame_quad.h"
 
 namespace cg = cooperative_groups;
 
@@ -209,6 +210,48 @@ analysis_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_con
     for (int item = cid; item < n_items; item += ncl) run_analysis_item_pair(ex, bufs, prm, pt, item, true);
 }
 
+// ---- W = 65536, fused path: a frame across a 4-CTA cluster (rcg_frame_quad.h) -----------------------------
+struct QuadDeviceExec {
+    int r, t;
+    template <class F>
+    __device__ __forceinline__ void par(F f) {
+        f(r, t);
+        __syncthreads();
+    }
+    template <class F>
+    __device__ __forceinline__ void par_steps(int n, F f) {
+        for (int s = 0; s < n; s++) {
+            f(s, r, t);
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+    template <class F>
+    __device__ __forceinline__ void par_cluster(F f) {
+        f(r, t);
+        __threadfence();            // carried half windows and the staged block travel through global memory
+        cg::this_cluster().sync();  // barrier.cluster arrive.release / wait.acquire
+    }
+    __device__ __forceinline__ void cluster_sync() { cg::this_cluster().sync(); }
+};
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FrameCfg<kQuadLog2HL>::NT, 3)
+stretch_quad_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ QuadTables qt, int n_items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int r = (int)cluster.block_rank();
+    cf* S = reinterpret_cast<cf*>(smem_raw);
+    cf* bufs[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) bufs[q] = cluster.map_shared_rank(S, q);   // peers' quarters, through DSMEM
+    bufs[r] = S;
+    QuadDeviceExec ex{r, (int)threadIdx.x};
+    const int cid = blockIdx.x / 4, ncl = gridDim.x / 4;
+    float* scratch = qt.scratch + (long long)cid * 3 * kPairH;
+    for (int item = cid; item < n_items; item += ncl) run_work_item_quad(ex, bufs, prm, qt, item, scratch, true);
+    cluster.sync();  // no CTA may exit while a peer can still read its shared memory
+}
+
 __global__ void __launch_bounds__(FrameCfg<kPairLog2HL>::NT)
 boundary_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, const float* head,
                      const float* tail_prev) {
@@ -226,6 +269,30 @@ cudaError_t pair_geometry(LaunchGeometry* g) {
     cudaError_t e = cudaFuncSetAttribute(analysis_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(stretch_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
+}
+// max_clusters: how many 4-CTA clusters the device keeps resident
+cudaError_t quad_geometry(int* max_clusters) {
+    using C = FrameCfg<kQuadLog2HL>;
+    const size_t smem = (size_t)C::SMEM_CF * sizeof(cf);
+    cudaError_t e = cudaFuncSetAttribute(stretch_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * 1024);
+    cfg.blockDim = dim3(C::NT);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 4; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(max_clusters, stretch_quad_kernel, &cfg);
+}
+cudaError_t launch_stretch_quad(const StretchParams& prm, const QuadTables& qt, int n_clusters, cudaStream_t stream) {
+    using C = FrameCfg<kQuadLog2HL>;
+    const int n_items = prm.channels * prm.n_runs;
+    if (n_items <= 0) return cudaSuccess;
+    stretch_quad_kernel<<<4 * n_clusters, C::NT, (size_t)C::SMEM_CF * sizeof(cf), stream>>>(prm, qt, n_items);
+    return cudaGetLastError();
 }
 cudaError_t launch_analysis_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream) {
     using C = FrameCfg<kPairLog2HL>;

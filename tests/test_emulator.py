@@ -159,10 +159,20 @@ def test_phases_are_race_free(n, f, p, W):
     assert np.array_equal(a, b) and np.array_equal(b0, b1)
 
 
+@pytest.fixture(params=["quad", "pair"])
+def layout_65536(request):
+    """W = 65536 fused path: 4-CTA cluster (rcg_frame_quad.h, what the engine launches) or the CTA pair
+    (rcg_frame_pair.h, kept for the frequency-kernel path and as the fallback)"""
+    ol.emulator().rcg_emul_use_pair(1 if request.param == "pair" else 0)
+    yield request.param
+    ol.emulator().rcg_emul_use_pair(0)
+
+
 @pytest.mark.parametrize("f,p,n", [(2.0, 1, 300000), (4.0, 2, 200000), (3.0, -3, 200000), (1.0, 3, 150000)])
-def test_window_65536_cta_pair(f, p, n):
-    """W = 65536 splits a frame across a 2-CTA cluster (even / odd bins, DSMEM exchange of the last
-    radix-2 stage): bit-exact indexing, PCM within tolerance, order-independent phases"""
+def test_window_65536_clusters(f, p, n, layout_65536):
+    """W = 65536 splits a frame across a thread-block cluster (bin classes mod 2 or mod 4, DSMEM exchange of
+    the outer radix stage and, on four CTAs, of the partner bins of classes 1 and 3): bit-exact indexing, PCM
+    within tolerance, order-independent phases"""
     W = 65536
     x = _input(n, seed=p + 7)
     assert np.array_equal(ol.emul_process_all(x, f, p, W, bypass=True), ol.process_all(x, f, p, W, mode=ol.RO_PHASE_BYPASS))
@@ -177,7 +187,7 @@ def test_window_65536_cta_pair(f, p, n):
     assert np.array_equal(got, again)
 
 
-def test_window_65536_segments():
+def test_window_65536_segments(layout_65536):
     f, p, W, n = 2.0, 1, 65536, 500000
     x = _input(n, seed=3)
     calls, _, out_len = ol.expected_counts(n, f, p, W)
