@@ -33,7 +33,7 @@ struct DeviceExecT {
         __syncwarp();
 #else
         if constexpr (WARP_LOCAL) __syncwarp();
-        else if constexpr (LANE_THREADS > 0) asm volatile("bar.sync %0, %1;" ::"r"(lane + 1), "r"(LANE_THREADS) : "memory");
+        else if constexpr (LANE_THREADS > 0) asm volatile("bar.sync %0, %1;" ::"r"(lane + 1), "n"(LANE_THREADS) : "memory");
         else __syncthreads();
 #endif
     }
