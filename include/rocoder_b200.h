@@ -193,7 +193,9 @@ int rcg_frequency_kernel_count(const rcg_engine *e, uint32_t *n);
  * kernel at the start of the next batch of frames (fft.rs:78-81 polls without blocking before every frame); a
  * failed build changes nothing (hotswapper.rs:36-42) and its compiler output is kept for rcg_watch_log.  Built by
  * suffix: .cu = device `apply` via NVRTC; .c/.cc/.cpp = host `apply` via `$RCG_CXX|gcc|g++ -O3 -shared -fPIC`
- * (the reference shells out to rustc, hotswapper.rs:60-72); .so = dlopen.  One watched file per engine, as in
+ * (the reference shells out to rustc, hotswapper.rs:60-72); .so = dlopen; .rs = a kernel written for the reference
+ * (Rust-ABI `apply`, README.md:108-113) plus an appended C-ABI shim, via `$RCG_RUSTC|rustc --crate-type cdylib` when a Rust
+ * compiler is installed.  One watched file per engine, as in
  * the reference.  Must be called before processing starts when the pitch multiple is even. */
 int rcg_watch_frequency_kernel(rcg_engine *e, const char *path, uint32_t poll_ms);
 /* take queued builds now (also done by every process / next_window call); *swapped = kernels installed */

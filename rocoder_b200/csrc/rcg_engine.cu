@@ -1027,7 +1027,7 @@ extern "C" int rcg_watch_frequency_kernel(rcg_engine* e, const char* path, uint3
     if (e->watcher) return fail(RCG_ERR_STATE, "this engine already watches %s", e->watcher->path().c_str());
     if (int rc = check_kernel_push(e)) return rc;
     if (rcg::KernelWatcher::kind_of(path) == rcg::KernelWatcher::kUnknown)
-        return fail(RCG_ERR_PLUGIN, "frequency kernel %s: want a .cu, .c, .cc, .cpp or .so file", path);
+        return fail(RCG_ERR_PLUGIN, "frequency kernel %s: want a .cu, .c, .cc, .cpp, .so or .rs file", path);
     // from here on this engine runs the full-rate path: a kernel may arrive between any two batches
     e->had_kernels = true;
     e->watcher.reset(new rcg::KernelWatcher(path, poll_ms, compile_device_source));

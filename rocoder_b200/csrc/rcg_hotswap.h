@@ -11,6 +11,10 @@
 //   .cu            -> cubin via the callback (NVRTC in the engine), a device `apply`
 //   .c .cc .cpp    -> `$RCG_CXX (default g++) -O3 -shared -fPIC` into a temp .so, dlopen, host `apply`
 //   .so            -> dlopen of a private copy of the file, host `apply`
+//   .rs            -> a kernel written for the reference itself (`#[no_mangle] pub fn apply(usize, Vec<(f32, f32)>)
+//                     -> Vec<(f32, f32)>`, README.md:108-113): the source plus a C-ABI shim is built with
+//                     `$RCG_RUSTC (default rustc) -C opt-level=3 --crate-type cdylib` (hotswapper.rs:60-72 uses
+//                     `--crate-type dylib`), when a Rust compiler is installed; a panic maps to a non-zero return
 #pragma once
 #include <dlfcn.h>
 #include <fcntl.h>
@@ -58,7 +62,7 @@ class KernelWatcher {
     KernelWatcher(const KernelWatcher&) = delete;
     KernelWatcher& operator=(const KernelWatcher&) = delete;
 
-    enum Kind { kUnknown, kDeviceSource, kHostSource, kSharedObject };
+    enum Kind { kUnknown, kDeviceSource, kHostSource, kSharedObject, kRustSource };
     static Kind kind_of(const std::string& p) {
         auto ends = [&](const char* s) {
             const size_t n = strlen(s);
@@ -67,6 +71,7 @@ class KernelWatcher {
         if (ends(".cu")) return kDeviceSource;
         if (ends(".c") || ends(".cc") || ends(".cpp") || ends(".cxx")) return kHostSource;
         if (ends(".so")) return kSharedObject;
+        if (ends(".rs")) return kRustSource;
         return kUnknown;
     }
 
@@ -204,16 +209,36 @@ class KernelWatcher {
         unlink(logfile.c_str());
         return ok;
     }
-    bool open_library(const std::string& so, BuiltKernel& b, std::string& log) {
+    bool open_library(const std::string& so, BuiltKernel& b, std::string& log, const char* symbol = "apply") {
         void* lib = dlopen(so.c_str(), RTLD_NOW | RTLD_LOCAL);
         if (!lib) { log = std::string("dlopen: ") + dlerror(); return false; }
-        void* sym = dlsym(lib, "apply");   // fft.rs:93-94
-        if (!sym) { log = so + " has no `apply` symbol"; dlclose(lib); return false; }
+        void* sym = dlsym(lib, symbol);   // fft.rs:93-94
+        if (!sym) { log = so + " has no `" + symbol + "` symbol"; dlclose(lib); return false; }
         b.dl = lib;
         b.host = (host_apply_fn)sym;
         return true;
     }
 
+  public:
+    // C-ABI entry appended to a reference-style Rust kernel: same contract as rcg_apply_fn, built over the user's
+    // `apply` (fft.rs:93: fn(usize, Vec<(f32, f32)>) -> Vec<(f32, f32)>); catch_unwind is what fft.rs:88 does
+    static const char* rust_shim() {
+        return "// ---- appended by rocoder_b200: C-ABI entry over `apply` ----\n"
+               "#[no_mangle]\n"
+               "pub unsafe extern \"C\" fn rcg_apply(elapsed_ms: usize, input: *const f32, n_bins: usize, output: *mut f32) -> i32 {\n"
+               "    let inp: Vec<(f32, f32)> = (0..n_bins).map(|i| (*input.add(2 * i), *input.add(2 * i + 1))).collect();\n"
+               "    match std::panic::catch_unwind(move || apply(elapsed_ms, inp)) {\n"
+               "        Ok(v) => {\n"
+               "            if v.len() != n_bins { return 2; }\n"
+               "            for (i, c) in v.iter().enumerate() { *output.add(2 * i) = c.0; *output.add(2 * i + 1) = c.1; }\n"
+               "            0\n"
+               "        }\n"
+               "        Err(_) => 1,\n"
+               "    }\n"
+               "}\n";
+    }
+
+  private:
     // hotswapper.rs:52-86
     bool compile(BuiltKernel& b, std::string& log) {
         switch (kind_of(path_)) {
@@ -247,8 +272,25 @@ class KernelWatcher {
                 unlink(so.c_str());
                 return ok;
             }
+            case kRustSource: {
+                std::string src;
+                if (!read_file(path_, src)) { log = "cannot read " + path_; return false; }
+                const std::string rs = temp_path(".rs"), so = temp_path(".so");
+                if (rs.empty() || so.empty()) { log = "mkstemps failed"; return false; }
+                {
+                    std::ofstream o(rs, std::ios::binary | std::ios::trunc);
+                    o << src << "\n" << rust_shim();
+                }
+                const char* rustc = getenv("RCG_RUSTC");
+                std::vector<std::string> argv = {rustc && *rustc ? rustc : "rustc", "-A", "warnings", "-C", "opt-level=3",
+                                                 "--crate-type", "cdylib", "--crate-name", "rcg_kernel", rs, "-o", so};
+                bool ok = run_tool(argv, log) && open_library(so, b, log, "rcg_apply");
+                unlink(rs.c_str());
+                unlink(so.c_str());
+                return ok;
+            }
             default:
-                log = "unknown frequency-kernel file type (want .cu, .c, .cc, .cpp or .so): " + path_;
+                log = "unknown frequency-kernel file type (want .cu, .c, .cc, .cpp, .so or .rs): " + path_;
                 return false;
         }
     }

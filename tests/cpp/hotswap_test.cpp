@@ -92,7 +92,7 @@ int main(int argc, char** argv) {
         rcg::KernelWatcher w(src, 20, nullptr);
         w.start();
         CHECK(w.builds_failed() == 1 && w.last_log().find("apply") != std::string::npos);
-        CHECK(rcg::KernelWatcher::kind_of("k.rs") == rcg::KernelWatcher::kUnknown);
+        CHECK(rcg::KernelWatcher::kind_of("k.txt") == rcg::KernelWatcher::kUnknown);
         CHECK(rcg::KernelWatcher::kind_of("a/b.cu") == rcg::KernelWatcher::kDeviceSource);
         CHECK(rcg::KernelWatcher::kind_of("x.so") == rcg::KernelWatcher::kSharedObject);
     }
@@ -129,6 +129,39 @@ int main(int argc, char** argv) {
         CHECK(system(("gcc -shared -fPIC -o " + so + ".new " + c1 + " && mv " + so + ".new " + so).c_str()) == 0);
         CHECK(wait_for([&] { return w.builds_ok() >= 2; }));
         CHECK(w.try_recv(b) && gain_of(b) == 6.0f && gain_of(a) == 4.0f);
+    }
+    {   // .rs: the user's source plus the C-ABI shim goes to $RCG_RUSTC; `rcg_apply` of the result is the kernel.
+        // No Rust compiler exists here: a stand-in script checks what it is handed and builds a C body instead.
+        const std::string rs = dir + "/k.rs", fake = dir + "/fake_rustc.sh", seen = dir + "/seen.rs";
+        write_file(rs, "#[no_mangle]\npub fn apply(_t: usize, input: Vec<(f32, f32)>) -> Vec<(f32, f32)> {\n"
+                       "    input.iter().map(|c| (c.0 * 2.0, c.1 * 2.0)).collect()\n}\n");
+        write_file(fake, "#!/bin/sh\n# args: -A warnings -C opt-level=3 --crate-type cdylib --crate-name rcg_kernel <src> -o <out>\n"
+                         "[ \"$6\" = cdylib ] || exit 3\nsrc=\"$9\"; out=\"${11}\"\ncp \"$src\" " + seen + "\n"
+                         "grep -q 'pub fn apply' \"$src\" || exit 4\ngrep -q 'extern \"C\" fn rcg_apply' \"$src\" || exit 5\n"
+                         "printf '#include <stddef.h>\\nint rcg_apply(size_t t, const float* i, size_t n, float* o) { for (size_t k = 0; k < 2 * n; k++) o[k] = i[k] * 2.0f; return 0; }\\n' > \"$src.c\"\n"
+                         "gcc -shared -fPIC -o \"$out\" \"$src.c\"; rc=$?; rm -f \"$src.c\"; exit $rc\n");
+        chmod(fake.c_str(), 0755);
+        setenv("RCG_RUSTC", fake.c_str(), 1);
+        {
+            rcg::KernelWatcher w(rs, 20, nullptr);
+            w.start();
+            rcg::BuiltKernel a;
+            CHECK(w.builds_ok() == 1);
+            if (w.builds_ok() != 1) printf("log: %s\n", w.last_log().c_str());
+            CHECK(w.try_recv(a) && gain_of(a) == 2.0f);
+            std::ifstream f(seen);
+            std::stringstream ss; ss << f.rdbuf();
+            CHECK(ss.str().find("catch_unwind") != std::string::npos && ss.str().find("input.iter().map") != std::string::npos);
+        }
+        setenv("RCG_RUSTC", "/nonexistent/rustc", 1);   // no compiler: a failed build, nothing else
+        {
+            rcg::KernelWatcher w(rs, 20, nullptr);
+            w.start();
+            rcg::BuiltKernel a;
+            CHECK(w.builds_failed() == 1 && !w.try_recv(a) && !w.last_log().empty());
+        }
+        unsetenv("RCG_RUSTC");
+        CHECK(rcg::KernelWatcher::kind_of("k.rs") == rcg::KernelWatcher::kRustSource);
     }
     if (g_fail) return 1;
     printf("hotswap_test: ok\n");

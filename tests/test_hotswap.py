@@ -121,14 +121,32 @@ def test_gpu_watch_starts_without_a_working_kernel(tmp_path):
 def test_gpu_watch_rejects_unknown_file_type_and_late_start(tmp_path):
     import rocoder_b200 as rb
     x = _input(9000)
-    (tmp_path / "k.rs").write_text("fn apply() {}\n")
+    (tmp_path / "k.txt").write_text("fn apply() {}\n")
     (tmp_path / "k.c").write_text(_host_src(2.0))
     with rb.Engine(2, 48000, 1024, 2.0, 1.0, 2, seed=4) as e:
         with pytest.raises(rb.RcgError):
-            e.watch_frequency_kernel(str(tmp_path / "k.rs"))
+            e.watch_frequency_kernel(str(tmp_path / "k.txt"))
         e.process_all(x)   # the half-rate path has now run: the carried half window is even samples only
         with pytest.raises(rb.RcgError):
             e.watch_frequency_kernel(str(tmp_path / "k.c"))
+
+
+@pytest.mark.gpu
+def test_gpu_rust_kernel_without_a_rust_compiler(tmp_path, monkeypatch):
+    """a reference-style .rs kernel is accepted; with no rustc the build fails like any other failed build
+    (hotswapper.rs:36-42) and frames pass through (fft.rs:82-85).  The shim itself is checked on CPU
+    (tests/cpp/hotswap_test.cpp)."""
+    import rocoder_b200 as rb
+    monkeypatch.setenv("RCG_RUSTC", "/nonexistent/rustc")
+    x = _input(9000)
+    path = tmp_path / "kernel.rs"
+    path.write_text("#[no_mangle]\npub fn apply(_t: usize, input: Vec<(f32, f32)>) -> Vec<(f32, f32)> { input }\n")
+    with rb.Engine(2, 48000, 1024, 2.0, 1.0, 1, seed=4) as plain:
+        base = plain.process_all(x)
+    with rb.Engine(2, 48000, 1024, 2.0, 1.0, 1, seed=4) as e:
+        e.watch_frequency_kernel(str(path), poll_ms=20)
+        assert e.frequency_kernel_count() == 0 and e.watch_stats()["builds_failed"] == 1 and e.watch_log() != ""
+        assert np.abs(e.process_all(x) - base).max() < 2e-6
 
 
 @pytest.mark.gpu

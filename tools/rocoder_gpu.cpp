@@ -44,7 +44,8 @@ static void usage() {
         "  -i, --input <path>         A .wav file ('-' for stdin)\n"
         "      --rotate-channels      Rotate the input audio channels\n"
         "      --freq-kernel <path>   Frequency kernel, rebuilt and swapped in whenever the file changes: a .cu\n"
-        "                             (device `apply`), .c/.cpp (host `apply`) or .so exporting the C-ABI `apply`\n"
+        "                             (device `apply`), .c/.cpp (host `apply`), .so exporting the C-ABI `apply`, or a\n"
+        "                             reference-style .rs kernel (needs rustc)\n"
         "  -x, --fade <dur>           (live playback only in the reference; accepted and ignored)\n"
         "  -s, --start <dur>          Start time in input audio (hh:mm:ss.ss)\n"
         "  -d, --duration <dur>       Duration to use from input audio (hh:mm:ss.ss)\n"
