@@ -254,7 +254,26 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
+def ensure_built():
+    """The CUDA library normally travels with the tree (__graft_entry__.build()).  If it is absent, local rank 0
+    compiles it (nvcc, sm_100a) and the other ranks wait: building the product, never replacing it."""
+    from rocoder_b200 import build
+    ok = build.LIB + ".built"
+    if os.path.exists(build.LIB):
+        return
+    if int(os.environ.get("LOCAL_RANK", "0")) == 0:
+        build.build_product()
+        open(ok, "w").write("ok\n")
+        return
+    t0 = time.time()
+    while not os.path.exists(ok):
+        if time.time() - t0 > 900:
+            raise SystemExit("bench.py: librocoder_b200.so was not built")
+        time.sleep(1.0)
+
+
 def run_ours(args):
+    ensure_built()
     import torch
     import rocoder_b200 as rb
     from rocoder_b200.sharding import TimeShardedStretch, input_span
