@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Randomised parity sweep of the CUDA path against the oracle: random window, factor, pitch multiple, input
+length and channel count inside the reference's valid domain (1 <= step <= W, p not in {0, -1}).
+Index path bit-exact (bypass mode), PCM within the north-star tolerance of the fp64 arbiter, batch == streaming.
+usage: python scripts/fuzz_parity.py [n_cases] [seed]"""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import oracle_lib as ol
+import rocoder_b200 as rb
+
+n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+bad = []
+done = 0
+while done < n_cases:
+    W = int(2 ** rng.integers(6, 17))
+    p = int(rng.choice([1, 1, 2, 2, 3, 4, 5, 6, 8, -2, -2, -3, -3, -4, -5, -7]))
+    f = float(np.float32(rng.choice([0.5, 0.75, 1.0, 1.0, 1.5, 2.0, 2.5, 3.0, 4.0, 8.0, 20.0, rng.uniform(0.5, 12.0)])))
+    try:
+        c = ol.constants(f, p, W)
+    except Exception:
+        continue
+    step = c["sample_step_len"]
+    if not (1 <= step <= W):
+        continue
+    ch = int(rng.choice([1, 2, 2, 3, 8]))
+    frames_target = int(rng.integers(1, 40 if W >= 16384 else 120))
+    n = int(rng.integers(0, W + frames_target * step + 1))
+    if n * c["pitch_shifted_factor"] * ch > 6e6:     # keep the oracle in seconds
+        continue
+    x = ((rng.random((ch, n), dtype=np.float32) * 2 - 1) * 0.5).astype(np.float32)
+    seed = int(rng.integers(0, 2 ** 40))
+    tag = dict(W=W, p=p, f=f, ch=ch, n=n, seed=seed)
+    try:
+        want_b = ol.process_all(x, f, p, W, mode=ol.RO_PHASE_BYPASS)
+        ref = ol.process_all(x, f, p, W, seed=seed, precision=64)
+        with rb.Engine(ch, 48000, W, f, 1.0, p, flags=rb.RCG_FLAG_BYPASS_RESYNTH) as e:
+            got_b = e.process_all(x)
+        with rb.Engine(ch, 48000, W, f, 1.0, p, seed=seed) as e:
+            got = e.process_all(x)
+        ok_b = got_b.shape == want_b.shape and np.array_equal(got_b, want_b)
+        err = float(np.abs(got - ref).max()) if ref.size else 0.0
+        ok_p = got.shape == ref.shape and np.isfinite(got).all() and err <= 1e-4 and (not ref.any() or ol.snr_db(ref, got) > 100.0)
+        ok_s = True
+        if done % 4 == 0 and n > 0:      # streaming next_window == batch, bit for bit
+            with rb.Engine(ch, 48000, W, f, 1.0, p, seed=seed, max_lookahead_calls=int(rng.integers(1, 6))) as e:
+                for cc in range(ch):
+                    cut = int(rng.integers(0, n + 1))
+                    e.send(cc, x[cc, :cut]); e.send(cc, x[cc, cut:]); e.close_input(cc)
+                outs = [[] for _ in range(ch)]
+                while not e.is_done(0):
+                    for cc in range(ch):
+                        outs[cc].append(e.next_window(cc))
+                st = np.stack([np.concatenate(o) for o in outs])
+            ok_s = st.shape == got.shape and np.array_equal(st, got)
+        if not (ok_b and ok_p and ok_s):
+            bad.append(dict(tag, index_exact=bool(ok_b), pcm_ok=bool(ok_p), stream_ok=bool(ok_s), max_abs=err))
+            print("FAIL", json.dumps(bad[-1]), flush=True)
+    except Exception as ex:   # noqa
+        bad.append(dict(tag, error=repr(ex)[:300]))
+        print("ERROR", json.dumps(bad[-1]), flush=True)
+    done += 1
+    if done % 20 == 0:
+        print(f"{done} cases, {len(bad)} failures", flush=True)
+print(json.dumps({"cases": done, "failures": len(bad), "failed": bad[:20]}))
+sys.exit(1 if bad else 0)
