@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Randomised parity sweep of the CUDA path against the oracle: random window, factor, pitch multiple, input
 length and channel count inside the reference's valid domain (1 <= step <= W, p not in {0, -1}).
-Index path bit-exact (bypass mode), PCM within the north-star tolerance of the fp64 arbiter, batch == streaming.
+Index path bit-exact (bypass mode), PCM within the north-star tolerance of the fp64 arbiter, batch == streaming,
+batch == time-sharded segments (halo recompute / tail chaining / deferred boundary) at random cut points.
 usage: python scripts/fuzz_parity.py [n_cases] [seed]"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -14,6 +15,7 @@ n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bad = []
 done = 0
+n_stream = n_segments = 0
 while done < n_cases:
     W = int(2 ** rng.integers(6, 17))
     p = int(rng.choice([1, 1, 2, 2, 3, 4, 5, 6, 8, -2, -2, -3, -3, -4, -5, -7]))
@@ -45,6 +47,7 @@ while done < n_cases:
         ok_p = got.shape == ref.shape and np.isfinite(got).all() and err <= 1e-4 and (not ref.any() or ol.snr_db(ref, got) > 100.0)
         ok_s = True
         if done % 4 == 0 and n > 0:      # streaming next_window == batch, bit for bit
+            n_stream += 1
             with rb.Engine(ch, 48000, W, f, 1.0, p, seed=seed, max_lookahead_calls=int(rng.integers(1, 6))) as e:
                 for cc in range(ch):
                     cut = int(rng.integers(0, n + 1))
@@ -55,8 +58,43 @@ while done < n_cases:
                         outs[cc].append(e.next_window(cc))
                 st = np.stack([np.concatenate(o) for o in outs])
             ok_s = st.shape == got.shape and np.array_equal(st, got)
-        if not (ok_b and ok_p and ok_s):
-            bad.append(dict(tag, index_exact=bool(ok_b), pcm_ok=bool(ok_p), stream_ok=bool(ok_s), max_abs=err))
+        ok_g = True
+        calls = ol.expected_counts(n, f, p, W)[0]
+        if done % 3 == 0 and calls >= 3 and got.shape[1] % 2 == 0:
+            # time sharding: random cut points; halo recompute, tail chaining and deferred boundary == one shot
+            import torch
+            n_segments += 1
+            k, olen, H = c["frames_per_call"], c["out_len_per_call"], W // 2
+            cuts = sorted(set([0, calls] + [int(v) for v in rng.integers(1, calls, size=int(rng.integers(1, 4)))]))
+            dx = torch.from_numpy(x).cuda()
+            st_ = torch.cuda.current_stream().cuda_stream
+            with rb.Engine(ch, 48000, W, f, 1.0, p, seed=seed) as e:
+                res = []
+                out = torch.full((ch, got.shape[1]), float("nan"), device="cuda")
+                for c0, c1 in zip(cuts[:-1], cuts[1:]):
+                    s0 = max(c0 * k - 1, 0) * step
+                    s0 -= s0 % 2   # float2 loads want an even origin
+                    seg = dx[:, s0:].contiguous() if (n - s0) % 2 == 0 else torch.nn.functional.pad(dx[:, s0:], (0, 1)).contiguous()
+                    e.process_segment(seg, seg.stride(0), s0, n - s0, out[:, c0 * olen:], out.stride(0), c0, c1 - c0, stream=st_)
+                torch.cuda.synchronize(); res.append(out.cpu().numpy())
+                out = torch.full((ch, got.shape[1]), float("nan"), device="cuda")
+                tails = [torch.zeros(ch, H, device="cuda") for _ in cuts]
+                for i, (c0, c1) in enumerate(zip(cuts[:-1], cuts[1:])):
+                    e.process_segment(dx, dx.stride(0), 0, n, out[:, c0 * olen:], out.stride(0), c0, c1 - c0,
+                                      tail_in=tails[i] if c0 else None, tail_out=tails[i + 1], stream=st_)
+                torch.cuda.synchronize(); res.append(out.cpu().numpy())
+                out = torch.full((ch, got.shape[1]), float("nan"), device="cuda")
+                heads = [torch.zeros(ch, H, device="cuda") for _ in cuts]
+                tails = [torch.zeros(ch, H, device="cuda") for _ in cuts]
+                for i, (c0, c1) in enumerate(zip(cuts[:-1], cuts[1:])):
+                    e.process_segment(dx, dx.stride(0), 0, n, out[:, c0 * olen:], out.stride(0), c0, c1 - c0,
+                                      tail_out=tails[i], head_out=heads[i], defer_first=c0 > 0, stream=st_)
+                for i, c0 in enumerate(cuts[1:-1], start=1):
+                    e.finish_boundary(out[:, c0 * olen:], out.stride(0), c0, heads[i], tails[i - 1], stream=st_)
+                torch.cuda.synchronize(); res.append(out.cpu().numpy())
+            ok_g = all(np.array_equal(r, got) for r in res)
+        if not (ok_b and ok_p and ok_s and ok_g):
+            bad.append(dict(tag, index_exact=bool(ok_b), pcm_ok=bool(ok_p), stream_ok=bool(ok_s), segments_ok=bool(ok_g), max_abs=err))
             print("FAIL", json.dumps(bad[-1]), flush=True)
     except Exception as ex:   # noqa
         bad.append(dict(tag, error=repr(ex)[:300]))
@@ -64,5 +102,5 @@ while done < n_cases:
     done += 1
     if done % 20 == 0:
         print(f"{done} cases, {len(bad)} failures", flush=True)
-print(json.dumps({"cases": done, "failures": len(bad), "failed": bad[:20]}))
+print(json.dumps({"cases": done, "streaming_checks": n_stream, "segment_checks": n_segments, "failures": len(bad), "failed": bad[:20]}))
 sys.exit(1 if bad else 0)
