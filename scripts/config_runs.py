@@ -110,12 +110,25 @@ def main():
         else:
             total_out = float(my_out)
         bytes_alg = 4.0 * (cfg["ch"] * n + total_out)
+        # end to end through rcg_process_all with pinned host buffers (1 GPU, outputs up to 4 GB)
+        e2e_ms = None
+        if os.environ.get("RCG_E2E") and world == 1 and total_out * 4 <= 4e9:
+            import time
+            hin, hout = rb.PinnedBuffer((ch, n)), rb.PinnedBuffer((ch, out_len))
+            hin.array[:] = x.cpu().numpy()
+            for _ in range(2):
+                eng.process_all_into(hin.array, hout.array)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                eng.process_all_into(hin.array, hout.array)
+            e2e_ms = (time.perf_counter() - t0) * 1e3 / 3
+            del hin, hout
         if rank == 0:
             print(json.dumps({"config": cfg["name"], "n_gpus": world, "W": cfg["W"], "f": cfg["f"], "p": cfg["p"],
                               "channels": cfg["ch"], "seconds_of_audio": cfg["secs"], "frames": frames * cfg["ch"],
                               "out_samples": total_out, "ms": ms, "out_Msamples_s": total_out / ms / 1e3,
                               "realtime_x": cfg["secs"] / (ms * 1e-3), "hbm_GBs_algorithmic": bytes_alg / ms / 1e6,
-                              "sharding": shard if world > 1 else "none", "finite": bool(torch.isfinite(out[:, ::997]).all())}),
+                              "sharding": shard if world > 1 else "none", "e2e_ms": e2e_ms, "finite": bool(torch.isfinite(out[:, ::997]).all())}),
                   flush=True)
         del x, out, eng
         torch.cuda.empty_cache()
