@@ -186,13 +186,21 @@ int rcg_load_frequency_kernel(rcg_engine *e, const char *so_path);
  * leave HBM.  A compile error returns RCG_ERR_PLUGIN and keeps the previous kernel
  * (hotswapper.rs:36-42). */
 int rcg_push_device_frequency_kernel(rcg_engine *e, const char *cuda_source);
+/* Bin-local device form: CUDA source defining
+ *     __device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, float2 x)
+ * for kernels whose output bin depends on the same input bin only (the README's example, README.md:121-129, every
+ * bin times a constant, is one).  NVRTC builds the whole stretch kernel around it for this engine's window size
+ * (a few seconds): |apply(X[k])| is evaluated in registers inside the fused spectral step -- only the norm of a
+ * kernel's output survives, fft.rs:67 -- so no spectrum ever exists in memory and a frame costs what it costs
+ * without a kernel.  Window lengths up to 32768; same stack / fall-back rules as the other forms. */
+int rcg_push_local_device_frequency_kernel(rcg_engine *e, const char *cuda_source);
 int rcg_frequency_kernel_count(const rcg_engine *e, uint32_t *n);
 /* hotswapper::hotswap(path) (hotswapper.rs:14-33, called from ReFFT::new, fft.rs:31-35): build `path` now on
  * the calling thread, then poll it every poll_ms (0 = the reference's 100 ms, hotswapper.rs:12) on a background
  * thread and build it again whenever it is modified.  Each successful build is queued and becomes the newest
  * kernel at the start of the next batch of frames (fft.rs:78-81 polls without blocking before every frame); a
  * failed build changes nothing (hotswapper.rs:36-42) and its compiler output is kept for rcg_watch_log.  Built by
- * suffix: .cu = device `apply` via NVRTC; .c/.cc/.cpp = host `apply` via `$RCG_CXX|gcc|g++ -O3 -shared -fPIC`
+ * suffix: .cu = device `apply` via NVRTC (`*.local.cu` = the bin-local form, fused into the stretch kernel); .c/.cc/.cpp = host `apply` via `$RCG_CXX|gcc|g++ -O3 -shared -fPIC`
  * (the reference shells out to rustc, hotswapper.rs:60-72); .so = dlopen; .rs = a kernel written for the reference
  * (Rust-ABI `apply`, README.md:108-113) plus an appended C-ABI shim, via `$RCG_RUSTC|rustc --crate-type cdylib` when a Rust
  * compiler is installed.  One watched file per engine, as in

@@ -108,6 +108,7 @@ def lib() -> C.CDLL:
         "rcg_push_frequency_kernel": (C.c_int, [C.c_void_p, APPLY_FN]),
         "rcg_load_frequency_kernel": (C.c_int, [C.c_void_p, C.c_char_p]),
         "rcg_push_device_frequency_kernel": (C.c_int, [C.c_void_p, C.c_char_p]),
+        "rcg_push_local_device_frequency_kernel": (C.c_int, [C.c_void_p, C.c_char_p]),
         "rcg_frequency_kernel_count": (C.c_int, [C.c_void_p, P(C.c_uint32)]),
         "rcg_watch_frequency_kernel": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32]),
         "rcg_poll_frequency_kernels": (C.c_int, [C.c_void_p, P(C.c_uint32)]),

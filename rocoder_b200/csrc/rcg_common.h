@@ -1,13 +1,23 @@
 // rcg_common.h -- types and the compile-time FFT plan shared by the sm_100a kernels,
 // the host table builder and the host-side emulator used by the CPU tests.
 #pragma once
+#if defined(__CUDACC_RTC__)
+// NVRTC (frequency kernels fused into the stretch kernel at run time, rcg_jit.*): no host headers
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef int int32_t;
+typedef long long int64_t;
+#else
 #include <stdint.h>
 #include <math.h>
+#endif
 
 #if defined(__CUDACC__)
 #define RCG_HD __host__ __device__ __forceinline__
 #define RCG_D __device__ __forceinline__
+#if !defined(__CUDACC_RTC__)
 #include <cuda_runtime.h>
+#endif
 typedef float2 cf;
 #else
 #define RCG_HD inline

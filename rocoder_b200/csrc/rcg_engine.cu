@@ -183,7 +183,8 @@ struct ChannelState {
 struct FreqKernel {
     rcg_apply_fn host = nullptr;
     cudaLibrary_t lib = nullptr;
-    cudaKernel_t dev = nullptr;
+    cudaKernel_t dev = nullptr;     // gather form: runs on the spectra in HBM between analysis and synthesis
+    cudaKernel_t fused = nullptr;   // bin-local form: the whole stretch kernel with the user's apply compiled in
 };
 
 struct rcg_engine {
@@ -470,7 +471,7 @@ static void fill_params(const rcg_engine* e, StretchParams& p) {
 struct SpectrumRef { cf* spectrum; long long frame0, frames; };
 
 static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream,
-                          int channel_offset = 0, const SpectrumRef* spec = nullptr) {
+                          int channel_offset = 0, const SpectrumRef* spec = nullptr, cudaKernel_t fused = nullptr) {
     if (s.n_calls == 0) return RCG_OK;
     auto misaligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) != 0; };
     // float2 stores: the carried / head buffers always; the output only where it is written
@@ -515,9 +516,19 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
     // one item per CTA first (every SM busy), frame lanes double up only once the CTAs run out; W = 65536
     // counts clusters (frames_per_cta = 1)
     const int grid = (int)std::min<long long>(items, max_grid);
-    cudaError_t ce = quad      ? launch_stretch_quad(p, e->qt, grid, stream)
-                     : e->pair ? launch_stretch_pair(p, e->pt, grid, stream)
-                               : launch_stretch(e->log2w, p, grid, stream);
+    cudaError_t ce;
+    if (fused) {   // the stretch kernel NVRTC built around a bin-local frequency kernel (same geometry as the fused one)
+        p.elapsed_ms = (unsigned long long)std::chrono::duration_cast<std::chrono::milliseconds>(
+                           std::chrono::system_clock::now().time_since_epoch()).count();   // fft.rs:89-92
+        int n_items = (int)items;
+        void* args[] = {(void*)&p, (void*)&n_items};
+        ce = items > 0 ? cudaLaunchKernel((const void*)fused, dim3(grid), dim3(e->geo.threads), args, e->geo.smem_bytes, stream)
+                       : cudaSuccess;
+    } else {
+        ce = quad      ? launch_stretch_quad(p, e->qt, grid, stream)
+             : e->pair ? launch_stretch_pair(p, e->pt, grid, stream)
+                       : launch_stretch(e->log2w, p, grid, stream);
+    }
     if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "stretch kernel launch failed: %s", cudaGetErrorString(ce));
     e->launches++;
     return RCG_OK;
@@ -649,8 +660,14 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
 static int run_segment(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream, int channel_offset) {
     if (e->watcher)   // fft.rs:78-81: take what the hot-swapper has built, without blocking
         if (int rc = drain_watcher(e, nullptr)) return rc;
-    if (!e->kernels.empty() && !(e->cfg.flags & RCG_FLAG_BYPASS_RESYNTH))
-        return run_segment_plugins(e, s, channels, stream, channel_offset);
+    while (!e->kernels.empty() && !(e->cfg.flags & RCG_FLAG_BYPASS_RESYNTH)) {
+        if (!e->kernels.back().fused) return run_segment_plugins(e, s, channels, stream, channel_offset);
+        // newest kernel is bin-local: one fused launch, no spectra in memory
+        if (launch_segment(e, s, channels, stream, channel_offset, nullptr, e->kernels.back().fused) == RCG_OK) return RCG_OK;
+        (void)cudaGetLastError();
+        cudaLibraryUnload(e->kernels.back().lib);
+        e->kernels.pop_back();   // unusable kernel: fall back to the previous one (fft.rs:101-106)
+    }
     return launch_segment(e, s, channels, stream, channel_offset);
 }
 
@@ -997,6 +1014,68 @@ extern "C" int rcg_push_device_frequency_kernel(rcg_engine* e, const char* cuda_
     return install_cubin(e, cubin);
 }
 
+// ---- bin-local device kernels: NVRTC builds the whole stretch kernel around the user's apply ----------------
+#include "rcg_jit_sources.inc"
+
+static bool compile_fused_source(const std::string& user_src, int log2h, std::vector<char>& cubin, std::string& log) {
+    static std::mutex load_mutex;
+    {
+        std::lock_guard<std::mutex> g(load_mutex);
+        if (!g_nvrtc.load()) { log = "libnvrtc could not be loaded"; return false; }
+    }
+    const std::string src = user_src + "\n#define RCG_JIT_LOG2H " + std::to_string(log2h) + "\n#include \"rcg_jit_entry.h\"\n";
+    const int n_headers = (int)(sizeof(kJitHeaderNames) / sizeof(kJitHeaderNames[0]));
+    nvrtcProgram_t prog = nullptr;
+    if (g_nvrtc.create(&prog, src.c_str(), "fused_frequency_kernel.cu", n_headers, kJitHeaderSources, kJitHeaderNames) != 0) {
+        log = "nvrtcCreateProgram failed";
+        return false;
+    }
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device"};
+    const int cr = g_nvrtc.compile(prog, 3, opts);
+    if (cr != 0) {
+        size_t n = 0;
+        g_nvrtc.log_size(prog, &n);
+        log.assign(n + 1, '\0');
+        if (n) g_nvrtc.get_log(prog, &log[0]);
+        g_nvrtc.destroy(&prog);
+        return false;
+    }
+    size_t cn = 0;
+    g_nvrtc.cubin_size(prog, &cn);
+    cubin.resize(cn);
+    g_nvrtc.get_cubin(prog, cubin.data());
+    g_nvrtc.destroy(&prog);
+    return true;
+}
+
+static int install_fused_cubin(rcg_engine* e, const std::vector<char>& cubin) {
+    FreqKernel k;
+    CUDA_TRY(cudaLibraryLoadData(&k.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    cudaError_t ke = cudaLibraryGetKernel(&k.fused, k.lib, "rcg_jit_stretch");
+    if (ke == cudaSuccess)
+        ke = cudaFuncSetAttribute((const void*)k.fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->geo.smem_bytes);
+    if (ke != cudaSuccess) {
+        (void)cudaGetLastError();
+        cudaLibraryUnload(k.lib);
+        return fail(RCG_ERR_PLUGIN, "fused frequency kernel could not be loaded: %s", cudaGetErrorString(ke));
+    }
+    e->kernels.push_back(k);
+    e->had_kernels = true;
+    return RCG_OK;
+}
+
+extern "C" int rcg_push_local_device_frequency_kernel(rcg_engine* e, const char* cuda_source) {
+    if (!e || !cuda_source) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (int rc = check_kernel_push(e)) return rc;
+    if (e->pair) return fail(RCG_ERR_PLUGIN, "bin-local frequency kernels are not fused at window_len 65536: push the gather form");
+    CUDA_TRY(cudaSetDevice(e->device));
+    std::vector<char> cubin;
+    std::string log;
+    if (!compile_fused_source(cuda_source, e->log2w - 1, cubin, log))   // compile failure keeps the previous kernel
+        return fail(RCG_ERR_PLUGIN, "bin-local frequency kernel failed to compile: %.400s", log.c_str());
+    return install_fused_cubin(e, cubin);
+}
+
 // ---- hot swap from a watched file (hotswapper.rs:14-33 + fft.rs:78-81) ------------------------------
 static int drain_watcher(rcg_engine* e, uint32_t* swapped) {
     uint32_t n = 0;
@@ -1012,7 +1091,7 @@ static int drain_watcher(rcg_engine* e, uint32_t* swapped) {
             n++;
         } else {
             CUDA_TRY(cudaSetDevice(e->device));
-            const int rc = install_cubin(e, b.cubin);
+            const int rc = b.local ? install_fused_cubin(e, b.cubin) : install_cubin(e, b.cubin);
             if (rc) status = rc; else n++;
         }
         b = rcg::BuiltKernel();
@@ -1030,7 +1109,14 @@ extern "C" int rcg_watch_frequency_kernel(rcg_engine* e, const char* path, uint3
         return fail(RCG_ERR_PLUGIN, "frequency kernel %s: want a .cu, .c, .cc, .cpp, .so or .rs file", path);
     // from here on this engine runs the full-rate path: a kernel may arrive between any two batches
     e->had_kernels = true;
-    e->watcher.reset(new rcg::KernelWatcher(path, poll_ms, compile_device_source));
+    const int log2h = e->log2w - 1;
+    const bool pair = e->pair;
+    e->watcher.reset(new rcg::KernelWatcher(path, poll_ms,
+        [log2h, pair](const std::string& src, bool local, std::vector<char>& cubin, std::string& log) {
+            if (!local) return compile_device_source(src, cubin, log);
+            if (pair) { log = "bin-local frequency kernels are not fused at window_len 65536"; return false; }
+            return compile_fused_source(src, log2h, cubin, log);
+        }));
     e->watcher->start();   // first build happens here, on the caller's thread (hotswapper.rs:17)
     return drain_watcher(e, nullptr);
 }

@@ -103,6 +103,7 @@ struct StretchParams {
     cf* spectrum;
     long long spec_frame0;
     long long spec_frames;  // frames per channel in the buffer
+    unsigned long long elapsed_ms;  // what a fused bin-local frequency kernel receives (fft.rs:89-92)
     PhiloxKeys keys;
 };
 
@@ -442,27 +443,53 @@ RCG_HD float fast_sqrt(float v) {
 #endif
 }
 
+#if defined(RCG_PLUGIN_LOCAL)
+// |apply(X[bin])| of the bin-local frequency kernel compiled into this translation unit (only the norm of a
+// kernel's output survives, fft.rs:67)
+struct StretchParams;
+RCG_HD float plugin_mag_raw(unsigned long long ms, uint32_t bin, uint32_t n_bins, float xr, float xi) {
+    const float2 p = apply((size_t)ms, (unsigned)bin, (unsigned)n_bins, make_float2(xr, xi));
+    return fast_sqrt(p.x * p.x + p.y * p.y);
+}
+#define plugin_mag(prm, bin, n_bins, xr, xi) plugin_mag_raw((prm).elapsed_ms, (bin), (n_bins), (xr), (xi))
+#endif
+
 // One bin pair (kk, H-kk) of the half-size forward transform: real-FFT split -> magnitudes of
 // bins kk and H-kk -> the four random phases of bins {kk, W-kk, H-kk, H+kk} (one Philox block)
 // -> Hermitian fold.  Returns A = Y[kk] + conj(Y[H-kk]) and B = Y[kk] - conj(Y[H-kk]) where
 // Y[k] = |X[k]| (e^{i phi_k} + e^{-i phi_{W-k}}) / 2 is the Hermitian part of the reference's
 // W-bin spectrum (fft.rs:65-68): the real part of its inverse FFT is the inverse of Y.
-RCG_HD void pair_fold(cf za, cf zb, cf tw, const uint32_t (&u)[4], float& ar, float& ai, float& br, float& bi) {
+// kk = the pair's bin number, n_bins = W: only read when a bin-local frequency kernel is fused in (RCG_PLUGIN_LOCAL,
+// rcg_jit_entry.h): the magnitudes are then those of the kernel's output for the four bins.
+RCG_HD void pair_fold(cf za, cf zb, cf tw, const uint32_t (&u)[4], float& ar, float& ai, float& br, float& bi,
+                      const StretchParams& prm, uint32_t kk, uint32_t n_bins) {
     // P = za + conj(zb), Q = za - conj(zb), U = -i t Q;  X[kk] = (P + U)/2, conj(X[H-kk]) = (P - U)/2
     float pr = za.x + zb.x, pi = za.y - zb.y, qr = za.x - zb.x, qi = za.y + zb.y;
     float tqr = tw.x * qr - tw.y * qi, tqi = tw.x * qi + tw.y * qr;
     float ur = tqi, ui = -tqr;
     float xkr = pr + ur, xki = pi + ui;   // halves folded into the 0.25 below
     float xbr = pr - ur, xbi = pi - ui;
-    float mk = fast_sqrt(xkr * xkr + xki * xki), mb = fast_sqrt(xbr * xbr + xbi * xbi);
     float s0, c0, s1, c1, s2, c2, s3, c3;
     sincos_phase(phase_from_u32(u[0]), s0, c0);  // bin kk
     sincos_phase(phase_from_u32(u[1]), s1, c1);  // bin W - kk
     sincos_phase(phase_from_u32(u[2]), s2, c2);  // bin H - kk
     sincos_phase(phase_from_u32(u[3]), s3, c3);  // bin H + kk
+#if defined(RCG_PLUGIN_LOCAL)
+    // X[kk] = (xk)/2, X[W-kk] = conj X[kk]; X[H-kk] = conj(xb)/2, X[H+kk] = conj X[H-kk]  (real input frame)
+    const uint32_t hh = n_bins >> 1;
+    const float m0 = plugin_mag(prm, kk, n_bins, 0.5f * xkr, 0.5f * xki);
+    const float m1 = plugin_mag(prm, n_bins - kk, n_bins, 0.5f * xkr, -0.5f * xki);
+    const float m2 = plugin_mag(prm, hh - kk, n_bins, 0.5f * xbr, -0.5f * xbi);
+    const float m3 = plugin_mag(prm, hh + kk, n_bins, 0.5f * xbr, 0.5f * xbi);
+    float ykr = 0.5f * (m0 * c0 + m1 * c1), yki = 0.5f * (m0 * s0 - m1 * s1);
+    float ybr = 0.5f * (m2 * c2 + m3 * c3), ybi = 0.5f * (m2 * s2 - m3 * s3);
+#else
+    (void)prm; (void)kk; (void)n_bins;
+    float mk = fast_sqrt(xkr * xkr + xki * xki), mb = fast_sqrt(xbr * xbr + xbi * xbi);
     float hk = 0.25f * mk, hb = 0.25f * mb;
     float ykr = hk * (c0 + c1), yki = hk * (s0 - s1);
     float ybr = hb * (c2 + c3), ybi = hb * (s2 - s3);
+#endif
     ar = ykr + ybr; ai = yki - ybi; br = ykr - ybr; bi = yki + ybi;
 }
 
@@ -485,25 +512,34 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
             // E[0] = Y[0] + Y[H] (both real), E[Q] = 2 Re Y[Q]
             cf z0 = S[0];
             philox4x32_10(0u, f_lo, f_hi, chan, prm.keys, u);
+#if defined(RCG_PLUGIN_LOCAL)
+            float m0 = plugin_mag(prm, 0u, (uint32_t)C::W, z0.x + z0.y, 0.0f), mh = plugin_mag(prm, (uint32_t)C::H, (uint32_t)C::W, z0.x - z0.y, 0.0f);
+#else
             float m0 = fabsf(z0.x + z0.y), mh = fabsf(z0.x - z0.y);
+#endif
             float s, c0, ch;
             sincos_phase(phase_from_u32(u[0]), s, c0);
             sincos_phase(phase_from_u32(u[2]), s, ch);
             const float e0 = m0 * c0 + mh * ch;
             cf zq = S[phys(bin_to_pos<LOG2H>(Q))];
             philox4x32_10((uint32_t)Q, f_lo, f_hi, chan, prm.keys, u);
-            float mq = fast_sqrt(zq.x * zq.x + zq.y * zq.y);
             float ca, cb;
             sincos_phase(phase_from_u32(u[0]), s, ca);
             sincos_phase(phase_from_u32(u[1]), s, cb);
+#if defined(RCG_PLUGIN_LOCAL)   // X[Q] = conj(Z[Q]), X[W-Q] = Z[Q]
+            const float eq = plugin_mag(prm, (uint32_t)Q, (uint32_t)C::W, zq.x, -zq.y) * ca +
+                             plugin_mag(prm, (uint32_t)(C::W - Q), (uint32_t)C::W, zq.x, zq.y) * cb;
+#else
+            float mq = fast_sqrt(zq.x * zq.x + zq.y * zq.y);
             const float eq = mq * (ca + cb);
+#endif
             S[0] = make_cf(e0 + eq, e0 - eq);
             // k = Q/2 pairs with itself: Z''[Q/2] = 2 conj(E[Q/2]); its twiddle is exp(-i pi/4)
             const int ph = phys(bin_to_pos<LOG2H>(Q / 2));
             const cf za = S[ph], zb = S[phys(bin_to_pos<LOG2H>(C::H - Q / 2))];
             philox4x32_10((uint32_t)(Q / 2), f_lo, f_hi, chan, prm.keys, u);
             float ar, ai, br, bi;
-            pair_fold(za, zb, make_cf(0.70710678118654752f, -0.70710678118654752f), u, ar, ai, br, bi);
+            pair_fold(za, zb, make_cf(0.70710678118654752f, -0.70710678118654752f), u, ar, ai, br, bi, prm, (uint32_t)(Q / 2), (uint32_t)C::W);
             S[ph] = make_cf(2.0f * ar, -2.0f * ai);
             continue;
         }
@@ -516,9 +552,9 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
         float ar, ai, er, ei, br, bi;
         const uint32_t k = qt.z;
         philox4x32_10(k, f_lo, f_hi, chan, prm.keys, u);
-        pair_fold(za, zb, tw, u, ar, ai, br, bi);                              // E[k]
+        pair_fold(za, zb, tw, u, ar, ai, br, bi, prm, k, (uint32_t)C::W);                              // E[k]
         philox4x32_10((uint32_t)Q - k, f_lo, f_hi, chan, prm.keys, u);
-        pair_fold(zc, zd, make_cf(-tw.y, -tw.x), u, er, ei, br, bi);          // E[Q-k]; exp(-2 pi i (Q-k)/W) = -i conj(tw)
+        pair_fold(zc, zd, make_cf(-tw.y, -tw.x), u, er, ei, br, bi, prm, (uint32_t)Q - k, (uint32_t)C::W);   // E[Q-k]; exp(-2 pi i (Q-k)/W) = -i conj(tw)
         // A2 = E[k] + conj(E[Q-k]), B2 = E[k] - conj(E[Q-k]), C2 = i conj(t2) B2, t2 = exp(-2 pi i k/H) = tw^2
         const float a2r = ar + er, a2i = ai - ei, b2r = ar - er, b2i = ai + ei;
         const float t2r = tw.x * tw.x - tw.y * tw.y, t2i = 2.0f * tw.x * tw.y;
@@ -543,7 +579,12 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
             // k = 0: bins 0 and H are real: X[0] = a + b, X[H] = a - b
             cf z0 = S[0];
             philox4x32_10(0u, f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
+#if defined(RCG_PLUGIN_LOCAL)
+            float m0 = plugin_mag(prm, 0u, (uint32_t)(C::W * KMUL), z0.x + z0.y, 0.0f);
+            float mh = plugin_mag(prm, (uint32_t)(C::H * KMUL), (uint32_t)(C::W * KMUL), z0.x - z0.y, 0.0f);
+#else
             float m0 = fabsf(z0.x + z0.y), mh = fabsf(z0.x - z0.y);
+#endif
             float s, c0, ch;
             sincos_phase(phase_from_u32(u[0]), s, c0);
             sincos_phase(phase_from_u32(u[2]), s, ch);
@@ -553,11 +594,17 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
             const int pq = phys(bin_to_pos<LOG2H>(C::H / 2));
             cf zq = S[pq];
             philox4x32_10((uint32_t)(C::H / 2 * KMUL), f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
-            float mq = fast_sqrt(zq.x * zq.x + zq.y * zq.y);
             float sa, ca, sb, cb;
             sincos_phase(phase_from_u32(u[0]), sa, ca);
             sincos_phase(phase_from_u32(u[1]), sb, cb);
+#if defined(RCG_PLUGIN_LOCAL)   // X[H/2] = conj(Z[H/2]), X[W - H/2] = Z[H/2]
+            const float ma = plugin_mag(prm, (uint32_t)(C::H / 2 * KMUL), (uint32_t)(C::W * KMUL), zq.x, -zq.y);
+            const float mb = plugin_mag(prm, (uint32_t)((C::W - C::H / 2) * KMUL), (uint32_t)(C::W * KMUL), zq.x, zq.y);
+            S[pq] = make_cf(ma * ca + mb * cb, -(ma * sa - mb * sb));
+#else
+            float mq = fast_sqrt(zq.x * zq.x + zq.y * zq.y);
             S[pq] = make_cf(mq * (ca + cb), -(mq * (sa - sb)));
+#endif
             continue;
         }
         const uint2 pt = ld_u2(prm.pair_tab + c);   // frame-invariant slot indices of bins k, H-k and k itself
@@ -567,7 +614,7 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
         philox4x32_10(pt.y * (uint32_t)KMUL, f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
         // A = Y[k] + conj(Y[H-k]), B = Y[k] - conj(Y[H-k]), Cc = i conj(t) B
         float ar, ai, br, bi;
-        pair_fold(za, zb, tw, u, ar, ai, br, bi);
+        pair_fold(za, zb, tw, u, ar, ai, br, bi, prm, pt.y * (uint32_t)KMUL, (uint32_t)(C::W * KMUL));
         float cr = -(tw.x * bi - tw.y * br), ci = tw.x * br + tw.y * bi;
         S[pa] = make_cf(ar + cr, ai + ci);      // Z'[k]   = A + Cc
         S[pb] = make_cf(ar - cr, -(ai - ci));   // Z'[H-k] = conj(A - Cc)

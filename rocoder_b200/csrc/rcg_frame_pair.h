@@ -104,7 +104,7 @@ RCG_HD void pair_phase_spectral_odd(cf* S, int t, const StretchParams& prm, cons
         uint32_t u[4];
         philox4x32_10((uint32_t)k, f_lo, f_hi, chan, prm.keys, u);
         float ar, ai, br, bi;
-        pair_fold(za, zb, tw, u, ar, ai, br, bi);
+        pair_fold(za, zb, tw, u, ar, ai, br, bi, prm, (uint32_t)k, (uint32_t)kPairW);
         const float cr = -(tw.x * bi - tw.y * br), ci = tw.x * br + tw.y * bi;
         S[pa] = make_cf(ar + cr, ai + ci);
         S[pb] = make_cf(ar - cr, -(ai - ci));

@@ -118,7 +118,7 @@ RCG_HD void quad_phase_spectral_rest(cf* own, cf* other, int r, int t, const Str
         uint32_t u[4];
         philox4x32_10((uint32_t)k, f_lo, f_hi, chan, prm.keys, u);
         float ar, ai, br, bi;
-        pair_fold(za, zb, tw, u, ar, ai, br, bi);
+        pair_fold(za, zb, tw, u, ar, ai, br, bi, prm, (uint32_t)k, (uint32_t)kPairW);
         const float cr = -(tw.x * bi - tw.y * br), ci = tw.x * br + tw.y * bi;
         own[pa] = make_cf(ar + cr, ai + ci);
         other[pb] = make_cf(ar - cr, -(ai - ci));

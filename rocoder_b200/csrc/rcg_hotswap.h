@@ -8,7 +8,8 @@
 //
 // Host-only C++ (no CUDA types): device sources are handed to a compile callback that returns a cubin.
 // What a build produces, by suffix of the watched path:
-//   .cu            -> cubin via the callback (NVRTC in the engine), a device `apply`
+//   .cu            -> cubin via the callback (NVRTC in the engine), a device `apply`; `*.local.cu` is the bin-local
+//                     form that the engine fuses into the stretch kernel itself
 //   .c .cc .cpp    -> `$RCG_CXX (default g++) -O3 -shared -fPIC` into a temp .so, dlopen, host `apply`
 //   .so            -> dlopen of a private copy of the file, host `apply`
 //   .rs            -> a kernel written for the reference itself (`#[no_mangle] pub fn apply(usize, Vec<(f32, f32)>)
@@ -49,10 +50,12 @@ struct BuiltKernel {
     void* dl = nullptr;           // dlopen handle (host kernels); owned by whoever pops it
     host_apply_fn host = nullptr;
     std::vector<char> cubin;      // device kernels
+    bool local = false;           // device kernel of the bin-local form, fused into the stretch kernel
 };
 
 // source text -> cubin; returns false and fills `log` on a compile error
-typedef std::function<bool(const std::string& src, std::vector<char>& cubin, std::string& log)> DeviceCompileFn;
+// local: the bin-local form `float2 apply(size_t, unsigned bin, unsigned n_bins, float2 x)` (file *.local.cu)
+typedef std::function<bool(const std::string& src, bool local, std::vector<char>& cubin, std::string& log)> DeviceCompileFn;
 
 class KernelWatcher {
   public:
@@ -73,6 +76,12 @@ class KernelWatcher {
         if (ends(".so")) return kSharedObject;
         if (ends(".rs")) return kRustSource;
         return kUnknown;
+    }
+
+    static bool is_local_device_source(const std::string& p) {
+        const char* suf = ".local.cu";
+        const size_t n = strlen(suf);
+        return p.size() >= n && p.compare(p.size() - n, n, suf) == 0;
     }
 
     // hotswapper.rs:17 + :20-30: first attempt on the calling thread, then the polling thread
@@ -246,7 +255,8 @@ class KernelWatcher {
                 std::string src;
                 if (!read_file(path_, src)) { log = "cannot read " + path_; return false; }
                 if (!dev_) { log = "no device compiler"; return false; }
-                return dev_(src, b.cubin, log);
+                b.local = is_local_device_source(path_);
+                return dev_(src, b.local, b.cubin, log);
             }
             case kHostSource: {
                 const std::string so = temp_path(".so");   // tempfile::Builder::new().suffix(".so") (:58)

@@ -1,0 +1,22 @@
+// rcg_jit_entry.h -- entry point of the translation unit NVRTC builds when a BIN-LOCAL frequency kernel is fused
+// into the stretch kernel (rcg_push_local_device_frequency_kernel).  The engine prepends the user's source, which
+// defines
+//     __device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, float2 x)
+// (the reference's `apply`, fft.rs:93, restricted to kernels whose output bin depends on the same input bin only --
+// the README's own example, README.md:121-129, is one), and defines RCG_JIT_LOG2H = log2(W) - 1.  Because only
+// the norm of a kernel's output survives (fft.rs:67), the fused spectral step evaluates |apply(X[k])| in
+// registers: the spectra never exist in memory and the frame costs what it costs without a kernel.
+#pragma once
+#define RCG_PLUGIN_LOCAL 1
+#include "rcg_kernel_body.h"
+
+extern "C" __global__ void
+__launch_bounds__(rcg::FrameCfg<RCG_JIT_LOG2H>::NT * rcg::FrameCfg<RCG_JIT_LOG2H>::FPC, rcg::min_ctas<RCG_JIT_LOG2H>())
+rcg_jit_stretch(const __grid_constant__ rcg::StretchParams prm, int n_items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if constexpr (rcg::FrameCfg<RCG_JIT_LOG2H>::TW_SMEM)
+        rcg::stretch_body<RCG_JIT_LOG2H, false>(rcg::with_smem_twiddles<RCG_JIT_LOG2H>(prm, reinterpret_cast<cf*>(smem_raw)),
+                                                n_items, smem_raw);
+    else
+        rcg::stretch_body<RCG_JIT_LOG2H, false>(prm, n_items, smem_raw);
+}

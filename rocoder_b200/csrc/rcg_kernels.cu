@@ -14,104 +14,12 @@
 
 #include "rcg_frame_pair.h"
 #include "rcg_frame_quad.h"
+#include "rcg_kernel_body.h"
 
 namespace cg = cooperative_groups;
 
 namespace rcg {
 
-// WARP_LOCAL: a frame lane is at most one warp (W <= 1024), so the frames sharing a CTA never
-// exchange data and every phase boundary is a warp barrier: the lanes drift apart and overlap their
-// memory and compute phases instead of marching in lockstep.
-// Otherwise, when several multi-warp frame lanes share a CTA (W = 2048, 4096), each lane
-// synchronises on its own named barrier (bar.sync id, NT) for the same reason.
-template <bool WARP_LOCAL, int LANE_THREADS = 0>
-struct DeviceExecT {
-    int t;
-    int lane = 0;
-    __device__ __forceinline__ void lane_barrier() {
-#ifdef RCG_EXPERIMENT_NO_BLOCK_BARRIERS   // timing experiment only: results are wrong
-        __syncwarp();
-#else
-        if constexpr (WARP_LOCAL) __syncwarp();
-        else if constexpr (LANE_THREADS > 0) asm volatile("bar.sync %0, %1;" ::"r"(lane + 1), "n"(LANE_THREADS) : "memory");
-        else __syncthreads();
-#endif
-    }
-    template <class F>
-    __device__ __forceinline__ void par(F f) {
-        f(t);
-        lane_barrier();
-    }
-    // steps that only depend on each other within a warp: warp barriers in between, one block
-    // barrier at the end
-    template <class F>
-    __device__ __forceinline__ void par_steps(int n, F f) {
-        for (int s = 0; s < n; s++) {
-            f(s, t);
-            __syncwarp();
-        }
-        if constexpr (!WARP_LOCAL) lane_barrier();
-    }
-};
-using DeviceExec = DeviceExecT<false>;
-
-#ifndef RCG_MIN_CTAS
-#define RCG_MIN_CTAS 3
-#endif
-
-// FrameCfg::TW_SMEM: the CTA copies the pass twiddle tables behind its frame buffers once (the CTAs are
-// persistent) and the frame code reads them from there
-template <int LOG2H>
-__device__ __forceinline__ StretchParams with_smem_twiddles(const StretchParams& prm, cf* smem_base) {
-    using C = FrameCfg<LOG2H>;
-    StretchParams p = prm;
-    if constexpr (C::TW_SMEM) {
-        cf* tw = smem_base + C::FPC * C::SMEM_CF;
-        for (int i = threadIdx.x; i < C::TW_CF; i += blockDim.x) tw[i] = __ldg(prm.tw + i);
-        __syncthreads();
-        p.tw = tw;
-    }
-    return p;
-}
-template <int LOG2H>
-constexpr size_t kernel_smem_bytes() {
-    using C = FrameCfg<LOG2H>;
-    return ((size_t)C::FPC * C::SMEM_CF + (C::TW_SMEM ? C::TW_CF : 0)) * sizeof(cf);
-}
-template <int LOG2H>
-constexpr int min_ctas() { return (LOG2H >= 14 || FrameCfg<LOG2H>::TW_SMEM) ? 1 : RCG_MIN_CTAS; }
-
-template <int LOG2H, bool SPEC_IN>
-__device__ __forceinline__ void stretch_body(const StretchParams& prm, int n_items, unsigned char* smem_raw) {
-    using C = FrameCfg<LOG2H>;
-    const int lane = threadIdx.x / C::NT;
-#ifdef RCG_NO_WARP_LOCAL
-    DeviceExecT<false> ex{(int)(threadIdx.x % C::NT)};
-#else
-    // frame lanes of one CTA are independent: warp barriers (<= 1 warp per lane) or one named barrier per lane
-    DeviceExecT<(C::NT <= 32), (C::NT > 32 && C::FPC > 1) ? C::NT : 0> ex{(int)(threadIdx.x % C::NT), lane};
-#endif
-    cf* S = reinterpret_cast<cf*>(smem_raw) + lane * C::SMEM_CF;
-    float* tail = prm.tail_scratch + ((long long)blockIdx.x * C::FPC + lane) * C::H;
-    // A full round gives CTA c the FPC neighbouring items r * per_round + c * FPC + l (neighbouring runs of a
-    // channel share input and tables in L1 / L2: 6.77 vs 6.95 ms on config 2); a partial last round spreads its items
-    // over the CTAs first, item r * per_round + l * grid + c, so that a small job keeps every SM busy before any
-    // CTA runs a second lane.  The trip count is uniform over the CTA.
-    const int per_round = (int)gridDim.x * C::FPC;
-    const int rounds = (n_items + per_round - 1) / per_round;
-    for (int r = 0; r < rounds; r++) {
-        const int first = r * per_round;
-#if defined(RCG_ITEM_MAP) && RCG_ITEM_MAP == 1   // experiments: always grouped / always spread
-        const bool full = true;
-#elif defined(RCG_ITEM_MAP) && RCG_ITEM_MAP == 2
-        const bool full = false;
-#else
-        const bool full = n_items - first >= per_round;
-#endif
-        const int item = first + (full ? (int)blockIdx.x * C::FPC + lane : lane * (int)gridDim.x + (int)blockIdx.x);
-        run_work_item<LOG2H, SPEC_IN>(ex, S, prm, item, tail, item < n_items);
-    }
-}
 template <int LOG2H, bool SPEC_IN = false>
 __global__ void __launch_bounds__(FrameCfg<LOG2H>::NT * FrameCfg<LOG2H>::FPC, min_ctas<LOG2H>())
 stretch_kernel(const __grid_constant__ StretchParams prm, int n_items) {

@@ -258,6 +258,11 @@ class Engine:
         const float2* spectrum)`; compiled with NVRTC for sm_100a, spectra stay in HBM."""
         check(lib().rcg_push_device_frequency_kernel(self._h, cuda_source.encode()))
 
+    def push_local_device_frequency_kernel(self, cuda_source: str) -> None:
+        """CUDA source defining the bin-local form `__device__ float2 apply(size_t elapsed_ms, unsigned bin,
+        unsigned n_bins, float2 x)`; NVRTC builds the stretch kernel around it, no spectra in memory."""
+        check(lib().rcg_push_local_device_frequency_kernel(self._h, cuda_source.encode()))
+
     def load_frequency_kernel(self, so_path: str) -> None:
         check(lib().rcg_load_frequency_kernel(self._h, so_path.encode()))
 

@@ -24,6 +24,13 @@ __device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, const 
 """
 
 
+LOCAL_X2 = """
+__device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, float2 x) {
+    return make_float2(x.x * 2.0f, x.y * 2.0f);
+}
+"""
+
+
 def synth(channels, n, rate, dev, seed, offset=0):
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -74,7 +81,10 @@ def main():
         eng = rb.Engine(max(ch, 1), cfg["rate"], cfg["W"], cfg["f"], 1.0, cfg["p"], seed=1234, device=local,
                         first_channel=first_channel)
         if cfg.get("plugin"):
-            eng.push_device_frequency_kernel(DEVICE_X2)
+            if os.environ.get("RCG_PLUGIN_FORM", "local") == "local":   # bin-local form: fused into the stretch kernel
+                eng.push_local_device_frequency_kernel(LOCAL_X2)
+            else:
+                eng.push_device_frequency_kernel(DEVICE_X2)
         calls, frames, out_len = eng.expected_counts(n)
         if shard == "time" and world > 1:
             job = TimeShardedStretch(eng, eng.plan, ch, calls, rank, world, dev)

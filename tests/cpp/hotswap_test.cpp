@@ -95,12 +95,15 @@ int main(int argc, char** argv) {
         CHECK(rcg::KernelWatcher::kind_of("k.txt") == rcg::KernelWatcher::kUnknown);
         CHECK(rcg::KernelWatcher::kind_of("a/b.cu") == rcg::KernelWatcher::kDeviceSource);
         CHECK(rcg::KernelWatcher::kind_of("x.so") == rcg::KernelWatcher::kSharedObject);
+        CHECK(rcg::KernelWatcher::kind_of("gain.local.cu") == rcg::KernelWatcher::kDeviceSource);
+        CHECK(rcg::KernelWatcher::is_local_device_source("a/gain.local.cu") && !rcg::KernelWatcher::is_local_device_source("gain.cu"));
     }
     {   // device source: text reaches the compile callback, cubin comes back
         const std::string src = dir + "/k.cu";
         write_file(src, "AAA");
         int calls = 0;
-        rcg::KernelWatcher w(src, 20, [&](const std::string& s, std::vector<char>& cubin, std::string& log) {
+        rcg::KernelWatcher w(src, 20, [&](const std::string& s, bool local, std::vector<char>& cubin, std::string& log) {
+            CHECK(!local);
             calls++;
             if (s == "bad") { log = "syntax error"; return false; }
             cubin.assign(s.begin(), s.end());

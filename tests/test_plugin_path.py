@@ -175,3 +175,78 @@ def test_gpu_device_kernel_compile_error_keeps_previous():
         got = e.process_all(x)
     ref = ol.process_all(x, 2.0, 1, 1024, seed=4, precision=64, plugin=plugins.amplitude_x2)
     assert np.abs(got - ref).max() <= 1e-4
+
+
+LOCAL_X2 = """
+__device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, float2 x) {
+    return make_float2(x.x * 2.0f, x.y * 2.0f);        // README.md:121-129
+}
+"""
+LOCAL_TILT = """
+float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, float2 v) {   // -default-device
+    float g = 0.25f + (float)bin / (float)n_bins;
+    return make_float2((v.x * 0.6f - v.y * 0.8f) * g, (v.x * 0.8f + v.y * 0.6f) * g);
+}
+"""
+LOCAL_LOWPASS = """
+__device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, float2 x) {
+    return bin < n_bins / 8 ? x : make_float2(0.0f, 0.0f);
+}
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("src,host", [(LOCAL_X2, plugins.amplitude_x2), (LOCAL_TILT, plugins.tilt),
+                                      (LOCAL_LOWPASS, plugins.lowpass_asymmetric)], ids=["x2", "tilt", "lowpass"])
+@pytest.mark.parametrize("n,f,p,W", [(3000, 2.0, 1, 64), (9000, 3.0, 2, 1024), (20000, 4.0, -2, 4096), (60000, 2.0, 1, 16384),
+                                     (150000, 2.0, 3, 32768)])
+def test_gpu_fused_local_frequency_kernel_matches_oracle(src, host, n, f, p, W):
+    """bin-local device `apply` compiled INTO the stretch kernel by NVRTC: one launch, no spectra in memory, same
+    result as the oracle calling the equivalent host kernel on the full spectrum (non-Hermitian outputs included)"""
+    import rocoder_b200 as rb
+    x = _input(n)
+    ref = ol.process_all(x, f, p, W, seed=4, precision=64, plugin=host)
+    with rb.Engine(2, 48000, W, f, 1.0, p, seed=4) as e:
+        e.push_local_device_frequency_kernel(src)
+        assert e.frequency_kernel_count() == 1
+        l0 = e.launch_count()
+        got = e.process_all(x)
+        assert e.launch_count() - l0 <= 2          # the fused kernel (per chunk), not analysis + apply + synthesis
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-4 and ol.snr_db(ref, got) > 100.0
+
+
+@pytest.mark.gpu
+def test_gpu_fused_local_kernel_errors_and_stack():
+    import rocoder_b200 as rb
+    x = _input(9000)
+    ref2 = ol.process_all(x, 2.0, 1, 1024, seed=4, precision=64, plugin=plugins.amplitude_x2)
+    with rb.Engine(2, 48000, 1024, 2.0, 1.0, 1, seed=4) as e:
+        e.push_device_frequency_kernel(DEVICE_TILT)                   # older kernel, gather form
+        e.push_local_device_frequency_kernel(LOCAL_X2)                # newest kernel wins (fft.rs:82 `kernels.last()`)
+        with pytest.raises(rb.RcgError) as ei:
+            e.push_local_device_frequency_kernel("float2 apply(int oops) { return nothing; }")
+        assert ei.value.status == 9 and e.frequency_kernel_count() == 2
+        got = e.process_all(x)
+    assert np.abs(got - ref2).max() <= 1e-4
+    with rb.Engine(2, 48000, 65536, 2.0, 1.0, 1, seed=4) as e:
+        with pytest.raises(rb.RcgError):
+            e.push_local_device_frequency_kernel(LOCAL_X2)            # not fused at W = 65536
+
+
+@pytest.mark.gpu
+def test_gpu_fused_local_kernel_streaming_equals_batch():
+    import rocoder_b200 as rb
+    x = _input(30000)
+    with rb.Engine(2, 48000, 2048, 3.0, 1.0, 1, seed=4) as e:
+        e.push_local_device_frequency_kernel(LOCAL_TILT)
+        batch = e.process_all(x)
+    with rb.Engine(2, 48000, 2048, 3.0, 1.0, 1, seed=4, max_lookahead_calls=3) as e:
+        e.push_local_device_frequency_kernel(LOCAL_TILT)
+        for c in range(2):
+            e.send(c, x[c]); e.close_input(c)
+        outs = [[], []]
+        while not e.is_done(0):
+            for c in range(2):
+                outs[c].append(e.next_window(c))
+    assert np.array_equal(np.stack([np.concatenate(o) for o in outs]), batch)
