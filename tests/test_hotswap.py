@@ -61,7 +61,13 @@ def _gain_plugin(g):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("suffix,src", [(".c", _host_src), (".cu", _dev_src)], ids=["host", "device"])
+def _local_src(gain):
+    return ("__device__ float2 apply(size_t ms, unsigned bin, unsigned n, float2 x) {\n"
+            f"  return make_float2(x.x * {gain:.1f}f, x.y * {gain:.1f}f);\n}}\n")
+
+
+@pytest.mark.parametrize("suffix,src", [(".c", _host_src), (".cu", _dev_src), (".local.cu", _local_src)],
+                         ids=["host", "device", "device-local"])
 @pytest.mark.parametrize("p", [1, 2])
 def test_gpu_hot_swap_from_watched_file(tmp_path, suffix, src, p):
     import rocoder_b200 as rb
