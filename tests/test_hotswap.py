@@ -60,12 +60,12 @@ def _gain_plugin(g):
     return plug
 
 
-@pytest.mark.gpu
 def _local_src(gain):
     return ("__device__ float2 apply(size_t ms, unsigned bin, unsigned n, float2 x) {\n"
             f"  return make_float2(x.x * {gain:.1f}f, x.y * {gain:.1f}f);\n}}\n")
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("suffix,src", [(".c", _host_src), (".cu", _dev_src), (".local.cu", _local_src)],
                          ids=["host", "device", "device-local"])
 @pytest.mark.parametrize("p", [1, 2])
