@@ -227,7 +227,10 @@ struct rcg_engine {
     std::vector<float> plug_tmp;
     // plugins (fft.rs:22: kernels: Vec<Library>)
     std::vector<FreqKernel> kernels;
-    bool had_kernels = false;  // a kernel was pushed at some point (even if all have since failed)
+    // a kernel that needs the spectra in memory (host or gather form), or a watched file, was installed at some
+    // point (even if all have since failed): the engine then stays on the full-rate path.  Fused bin-local
+    // kernels do not set it -- they run inside the stretch kernel, half-rate synthesis included.
+    bool had_kernels = false;
     std::vector<void*> libs;
     // hotswapper.rs:14-33: watched source file, builds queued for the next batch
     std::unique_ptr<rcg::KernelWatcher> watcher;
@@ -444,10 +447,11 @@ extern "C" int rcg_synchronize(rcg_engine* e) {
 }
 
 // Even pitch multiples keep only even output samples (resampler.rs:15-18): the synthesis side
-// then runs at half size.  Not with frequency kernels loaded (that path keeps the full layout), so
-// the carried half windows of fused and plugin launches are never mixed within one engine state.
+// then runs at half size.  Not once a frequency kernel that works on spectra in memory was loaded (that path
+// keeps the full layout), so the carried half windows of fused and plugin launches are never mixed within one
+// engine state.
 static bool engine_half_rate(const rcg_engine* e) {
-    return use_half_rate(e->cfg.pitch_multiple, 0u) && e->kernels.empty() && !e->had_kernels && !e->pair;
+    return use_half_rate(e->cfg.pitch_multiple, 0u) && !e->had_kernels && !e->pair;
 }
 
 static void fill_params(const rcg_engine* e, StretchParams& p) {
@@ -1060,13 +1064,11 @@ static int install_fused_cubin(rcg_engine* e, const std::vector<char>& cubin) {
         return fail(RCG_ERR_PLUGIN, "fused frequency kernel could not be loaded: %s", cudaGetErrorString(ke));
     }
     e->kernels.push_back(k);
-    e->had_kernels = true;
     return RCG_OK;
 }
 
 extern "C" int rcg_push_local_device_frequency_kernel(rcg_engine* e, const char* cuda_source) {
     if (!e || !cuda_source) return fail(RCG_ERR_INVALID_ARG, "null argument");
-    if (int rc = check_kernel_push(e)) return rc;
     if (e->pair) return fail(RCG_ERR_PLUGIN, "bin-local frequency kernels are not fused at window_len 65536: push the gather form");
     CUDA_TRY(cudaSetDevice(e->device));
     std::vector<char> cubin;

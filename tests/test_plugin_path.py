@@ -235,6 +235,25 @@ def test_gpu_fused_local_kernel_errors_and_stack():
 
 
 @pytest.mark.gpu
+def test_gpu_fused_local_kernel_keeps_half_rate_and_can_follow_processing():
+    """a bin-local kernel runs inside the stretch kernel, so the even-pitch half-rate path stays on and the kernel
+    may be pushed after audio was processed; a gather-form kernel may not (the carried half window differs)"""
+    import rocoder_b200 as rb
+    x = _input(40000)
+    f, p, W = 8.0, 2, 4096
+    ref = ol.process_all(x, f, p, W, seed=4, precision=64, plugin=plugins.tilt)
+    with rb.Engine(2, 48000, W, f, 1.0, p, seed=4) as e:
+        plain = e.process_all(x)                                      # half-rate fused path
+        e.push_local_device_frequency_kernel(LOCAL_TILT)              # allowed after processing
+        got = e.process_all(x)
+        with pytest.raises(rb.RcgError) as ei:
+            e.push_device_frequency_kernel(DEVICE_TILT)
+        assert ei.value.status == 10
+    assert np.abs(got - ref).max() <= 1e-4 and ol.snr_db(ref, got) > 100.0
+    assert not np.array_equal(got, plain)
+
+
+@pytest.mark.gpu
 def test_gpu_fused_local_kernel_streaming_equals_batch():
     import rocoder_b200 as rb
     x = _input(30000)
