@@ -42,6 +42,12 @@ for W, n in ((16384, 120000), (65536, 300000)):   # frequency-kernel path at the
         e.push_device_frequency_kernel("__device__ float2 apply(size_t t, unsigned b, unsigned n, const float2* s) { return s[b]; }")
         assert np.isfinite(e.process_all(inp(2, n))).all()
     print("ok plugin", W, flush=True)
+LOCAL = "__device__ float2 apply(size_t t, unsigned b, unsigned n, float2 x) { return make_float2(x.x * 0.5f, x.y * (b & 1 ? 2.0f : 1.0f)); }"
+for W, n, p in ((16384, 120000, 2), (16384, 120000, -2), (1024, 9000, 1), (64, 3000, 3)):   # bin-local kernels fused by NVRTC
+    with rb.Engine(2, 48000, W, 2.0, 1.0, p, seed=1) as e:
+        e.push_local_device_frequency_kernel(LOCAL)
+        assert np.isfinite(e.process_all(inp(2, n))).all()
+    print("ok fused local plugin", W, p, flush=True)
 d = torch.randn(2, 50000, device="cuda")
 rb.fade_in_out(d, 0.25, 48000, 50000, stream=1)
 torch.cuda.synchronize()
