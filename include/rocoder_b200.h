@@ -192,7 +192,7 @@ int rcg_push_device_frequency_kernel(rcg_engine *e, const char *cuda_source);
  * bin times a constant, is one).  NVRTC builds the whole stretch kernel around it for this engine's window size
  * (a few seconds): |apply(X[k])| is evaluated in registers inside the fused spectral step -- only the norm of a
  * kernel's output survives, fft.rs:67 -- so no spectrum ever exists in memory and a frame costs what it costs
- * without a kernel.  Window lengths up to 32768; same stack / fall-back rules as the other forms. */
+ * without a kernel.  Same stack / fall-back rules as the other forms. */
 int rcg_push_local_device_frequency_kernel(rcg_engine *e, const char *cuda_source);
 int rcg_frequency_kernel_count(const rcg_engine *e, uint32_t *n);
 /* hotswapper::hotswap(path) (hotswapper.rs:14-33, called from ReFFT::new, fft.rs:31-35): build `path` now on

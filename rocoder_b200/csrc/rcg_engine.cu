@@ -511,7 +511,7 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
                     p.frame_begin);
     const uint64_t nframes = (uint64_t)(p.frame_end - p.frame_begin);
     // W = 65536: the fused path on 4-CTA clusters, frequency-kernel synthesis on the CTA pair
-    const bool quad = e->pair && !spec && e->quad_clusters > 0;
+    const bool quad = e->pair && !spec && !fused && e->quad_clusters > 0;
     const int max_grid = quad ? e->quad_clusters : e->max_grid;
     const int slots = max_grid * e->geo.frames_per_cta;
     p.run_len = pick_run_len(nframes, (uint32_t)channels, slots);
@@ -526,8 +526,10 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
                            std::chrono::system_clock::now().time_since_epoch()).count();   // fft.rs:89-92
         int n_items = (int)items;
         void* args[] = {(void*)&p, (void*)&n_items};
-        ce = items > 0 ? cudaLaunchKernel((const void*)fused, dim3(grid), dim3(e->geo.threads), args, e->geo.smem_bytes, stream)
-                       : cudaSuccess;
+        void* pair_args[] = {(void*)&p, (void*)&e->pt, (void*)&n_items};   // W = 65536: `grid` counts 2-CTA clusters
+        ce = items <= 0 ? cudaSuccess
+             : e->pair  ? cudaLaunchKernel((const void*)fused, dim3(2 * grid), dim3(e->geo.threads), pair_args, e->geo.smem_bytes, stream)
+                        : cudaLaunchKernel((const void*)fused, dim3(grid), dim3(e->geo.threads), args, e->geo.smem_bytes, stream);
     } else {
         ce = quad      ? launch_stretch_quad(p, e->qt, grid, stream)
              : e->pair ? launch_stretch_pair(p, e->pt, grid, stream)
@@ -1069,7 +1071,6 @@ static int install_fused_cubin(rcg_engine* e, const std::vector<char>& cubin) {
 
 extern "C" int rcg_push_local_device_frequency_kernel(rcg_engine* e, const char* cuda_source) {
     if (!e || !cuda_source) return fail(RCG_ERR_INVALID_ARG, "null argument");
-    if (e->pair) return fail(RCG_ERR_PLUGIN, "bin-local frequency kernels are not fused at window_len 65536: push the gather form");
     CUDA_TRY(cudaSetDevice(e->device));
     std::vector<char> cubin;
     std::string log;
@@ -1112,12 +1113,9 @@ extern "C" int rcg_watch_frequency_kernel(rcg_engine* e, const char* path, uint3
     // from here on this engine runs the full-rate path: a kernel may arrive between any two batches
     e->had_kernels = true;
     const int log2h = e->log2w - 1;
-    const bool pair = e->pair;
     e->watcher.reset(new rcg::KernelWatcher(path, poll_ms,
-        [log2h, pair](const std::string& src, bool local, std::vector<char>& cubin, std::string& log) {
-            if (!local) return compile_device_source(src, cubin, log);
-            if (pair) { log = "bin-local frequency kernels are not fused at window_len 65536"; return false; }
-            return compile_fused_source(src, log2h, cubin, log);
+        [log2h](const std::string& src, bool local, std::vector<char>& cubin, std::string& log) {
+            return local ? compile_fused_source(src, log2h, cubin, log) : compile_device_source(src, cubin, log);
         }));
     e->watcher->start();   // first build happens here, on the caller's thread (hotswapper.rs:17)
     return drain_watcher(e, nullptr);

@@ -10,6 +10,14 @@
 #define RCG_PLUGIN_LOCAL 1
 #include "rcg_kernel_body.h"
 
+#if RCG_JIT_LOG2H == 15   // W = 65536: the CTA-pair kernel (rcg_frame_pair.h)
+#include "rcg_pair_body.h"
+extern "C" __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(rcg::FrameCfg<rcg::kPairLog2HL>::NT, 1)
+rcg_jit_stretch(const __grid_constant__ rcg::StretchParams prm, const __grid_constant__ rcg::PairTables pt, int n_items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    rcg::stretch_pair_body(prm, pt, n_items, smem_raw);
+}
+#else
 extern "C" __global__ void
 __launch_bounds__(rcg::FrameCfg<RCG_JIT_LOG2H>::NT * rcg::FrameCfg<RCG_JIT_LOG2H>::FPC, rcg::min_ctas<RCG_JIT_LOG2H>())
 rcg_jit_stretch(const __grid_constant__ rcg::StretchParams prm, int n_items) {
@@ -20,3 +28,4 @@ rcg_jit_stretch(const __grid_constant__ rcg::StretchParams prm, int n_items) {
     else
         rcg::stretch_body<RCG_JIT_LOG2H, false>(prm, n_items, smem_raw);
 }
+#endif

@@ -15,6 +15,7 @@
 #include "rcg_frame_pair.h"
 #include "rcg_frame_quad.h"
 #include "rcg_kernel_body.h"
+#include "rcg_pair_body.h"
 
 namespace cg = cooperative_groups;
 
@@ -66,51 +67,18 @@ boundary_kernel(const __grid_constant__ StretchParams prm, const float* head, co
 }
 
 // ---- W = 65536: a frame across a 2-CTA cluster (rcg_frame_pair.h) -------------------------------
-struct PairDeviceExec {
-    int r, t;
-    template <class F>
-    __device__ __forceinline__ void par(F f) {
-        f(r, t);
-        __syncthreads();
-    }
-    template <class F>
-    __device__ __forceinline__ void par_steps(int n, F f) {
-        for (int s = 0; s < n; s++) {
-            f(s, r, t);
-            __syncwarp();
-        }
-        __syncthreads();
-    }
-    template <class F>
-    __device__ __forceinline__ void par_cluster(F f) {
-        f(r, t);
-        __threadfence();            // carried half windows travel through global memory
-        cg::this_cluster().sync();  // barrier.cluster arrive.release / wait.acquire
-    }
-    __device__ __forceinline__ void cluster_sync() { cg::this_cluster().sync(); }
-};
-
+// PairDeviceExec, stretch_pair_body: rcg_pair_body.h (shared with the NVRTC translation unit)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FrameCfg<kPairLog2HL>::NT, 1)
 stretch_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, int n_items) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int r = (int)cluster.block_rank();
-    cf* S = reinterpret_cast<cf*>(smem_raw);
-    cf* bufs[2];
-    bufs[r] = S;
-    bufs[r ^ 1] = cluster.map_shared_rank(S, r ^ 1);   // the peer's half, read through DSMEM
-    PairDeviceExec ex{r, (int)threadIdx.x};
-    const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
-    float* scratch = pt.scratch + (long long)cid * 3 * kPairH;
-    for (int item = cid; item < n_items; item += ncl) run_work_item_pair(ex, bufs, prm, pt, item, scratch, true);
-    cluster.sync();  // no CTA may exit while its peer can still read its shared memory
+    stretch_pair_body(prm, pt, n_items, smem_raw);
 }
 
 // frequency-kernel path at W = 65536, analysis half: each CTA of the pair writes the bins of its parity
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FrameCfg<kPairLog2HL>::NT, 1)
 analysis_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, int n_items) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int r = (int)cg::this_cluster().block_rank();
+    const int r = (int)cluster_cta_rank();
     cf* S = reinterpret_cast<cf*>(smem_raw);
     cf* bufs[2] = {S, S};   // only bufs[r] is touched: no data crosses the pair in this kernel
     PairDeviceExec ex{r, (int)threadIdx.x};

@@ -1,0 +1,66 @@
+// rcg_pair_body.h -- W = 65536: the body of the CTA-pair stretch kernel (rcg_frame_pair.h) and its barrier
+// flavours.  Shared by rcg_kernels.cu and by the translation unit NVRTC builds when a bin-local frequency kernel
+// is fused in (rcg_jit_entry.h), so the cluster operations are spelled in PTX instead of cooperative_groups
+// (NVRTC sees no toolkit headers).  Device code only.
+#pragma once
+#include "rcg_frame_pair.h"
+
+namespace rcg {
+
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// generic address of `p` (a shared-memory address of this CTA) in the shared memory of CTA `rank` of the cluster
+template <class T>
+__device__ __forceinline__ T* cluster_map_shared(T* p, unsigned rank) {
+    unsigned long long out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)p), "r"(rank));
+    return reinterpret_cast<T*>(out);
+}
+// all threads of all CTAs of the cluster; release / acquire: shared-memory writes before it are visible to
+// distributed-shared-memory reads after it
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+struct PairDeviceExec {
+    int r, t;
+    template <class F>
+    __device__ __forceinline__ void par(F f) {
+        f(r, t);
+        __syncthreads();
+    }
+    template <class F>
+    __device__ __forceinline__ void par_steps(int n, F f) {
+        for (int s = 0; s < n; s++) {
+            f(s, r, t);
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+    template <class F>
+    __device__ __forceinline__ void par_cluster(F f) {
+        f(r, t);
+        __threadfence();     // carried half windows travel through global memory
+        cluster_barrier();
+    }
+    __device__ __forceinline__ void cluster_sync() { cluster_barrier(); }
+};
+
+__device__ __forceinline__ void stretch_pair_body(const StretchParams& prm, const PairTables& pt, int n_items,
+                                                  unsigned char* smem_raw) {
+    const int r = (int)cluster_cta_rank();
+    cf* S = reinterpret_cast<cf*>(smem_raw);
+    cf* bufs[2];
+    bufs[r] = S;
+    bufs[r ^ 1] = cluster_map_shared(S, (unsigned)(r ^ 1));   // the peer's half, read through DSMEM
+    PairDeviceExec ex{r, (int)threadIdx.x};
+    const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
+    float* scratch = pt.scratch + (long long)cid * 3 * kPairH;
+    for (int item = cid; item < n_items; item += ncl) run_work_item_pair(ex, bufs, prm, pt, item, scratch, true);
+    cluster_barrier();  // no CTA may exit while its peer can still read its shared memory
+}
+
+}  // namespace rcg

@@ -42,7 +42,7 @@ def test_embedded_headers_equal_the_sources():
         assert text == open(os.path.join(CSRC, name)).read(), name
 
 
-@pytest.mark.parametrize("log2h", [5, 8, 11, 13, 14])
+@pytest.mark.parametrize("log2h", [5, 8, 11, 13, 14, 15])
 def test_fused_translation_unit_compiles_with_nvrtc(log2h):
     nv = _nvrtc()
     hdr = _embedded_headers()
