@@ -21,14 +21,19 @@ namespace cg = cooperative_groups;
 
 namespace rcg {
 
-template <int LOG2H, bool SPEC_IN = false>
+template <int LOG2H, bool SPEC_IN = false, int MODE = 0>
 __global__ void __launch_bounds__(FrameCfg<LOG2H>::NT * FrameCfg<LOG2H>::FPC, min_ctas<LOG2H>())
-stretch_kernel(const __grid_constant__ StretchParams prm, int n_items) {
+stretch_kernel(const __grid_constant__ StretchParams prm_in, int n_items) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    if constexpr (FrameCfg<LOG2H>::TW_SMEM)
-        stretch_body<LOG2H, SPEC_IN>(with_smem_twiddles<LOG2H>(prm, reinterpret_cast<cf*>(smem_raw)), n_items, smem_raw);
-    else
-        stretch_body<LOG2H, SPEC_IN>(prm, n_items, smem_raw);
+    if constexpr (MODE == 0 && !FrameCfg<LOG2H>::TW_SMEM) {
+        stretch_body<LOG2H, SPEC_IN>(prm_in, n_items, smem_raw);
+    } else {
+        const StretchParams prm = with_mode_constants<MODE>(prm_in);
+        if constexpr (FrameCfg<LOG2H>::TW_SMEM)
+            stretch_body<LOG2H, SPEC_IN>(with_smem_twiddles<LOG2H>(prm, reinterpret_cast<cf*>(smem_raw)), n_items, smem_raw);
+        else
+            stretch_body<LOG2H, SPEC_IN>(prm, n_items, smem_raw);
+    }
 }
 
 // plugin path, analysis half: frames -> full complex spectra in HBM for the host `apply` call
@@ -196,12 +201,14 @@ static cudaError_t geometry_t(LaunchGeometry* g) {
     g->threads = C::NT * C::FPC;
     g->frames_per_cta = C::FPC;
     g->smem_bytes = kernel_smem_bytes<LOG2H>();
-    cudaError_t e = cudaFuncSetAttribute(stretch_kernel<LOG2H, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)g->smem_bytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(stretch_kernel<LOG2H, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)g->smem_bytes);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
+    const void* kernels[] = {(const void*)stretch_kernel<LOG2H, false, 0>, (const void*)stretch_kernel<LOG2H, false, 1>,
+                             (const void*)stretch_kernel<LOG2H, false, 2>, (const void*)stretch_kernel<LOG2H, false, 3>,
+                             (const void*)stretch_kernel<LOG2H, true, 0>};
+    for (const void* k : kernels) {
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
+        if (e != cudaSuccess) return e;
+    }
     e = cudaFuncSetAttribute(analysis_kernel<LOG2H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)g->smem_bytes);
     if (e != cudaSuccess) return e;
@@ -209,7 +216,7 @@ static cudaError_t geometry_t(LaunchGeometry* g) {
                              (int)(C::SMEM_CF * sizeof(cf)));
     if (e != cudaSuccess) return e;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stretch_kernel<LOG2H, false>, g->threads, g->smem_bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stretch_kernel<LOG2H, false, 0>, g->threads, g->smem_bytes);
     g->max_ctas_per_sm = n;
     return e;
 }
@@ -219,10 +226,18 @@ static cudaError_t launch_t(const StretchParams& prm, int grid, cudaStream_t str
     using C = FrameCfg<LOG2H>;
     const int n_items = prm.channels * prm.n_runs;
     if (n_items <= 0) return cudaSuccess;
-    if (prm.flags & kFlagSpectrumIn)
-        stretch_kernel<LOG2H, true><<<grid, C::NT * C::FPC, kernel_smem_bytes<LOG2H>(), stream>>>(prm, n_items);
-    else
-        stretch_kernel<LOG2H, false><<<grid, C::NT * C::FPC, kernel_smem_bytes<LOG2H>(), stream>>>(prm, n_items);
+    const dim3 block(C::NT * C::FPC);
+    const size_t smem = kernel_smem_bytes<LOG2H>();
+    if (prm.flags & kFlagSpectrumIn) {
+        stretch_kernel<LOG2H, true, 0><<<grid, block, smem, stream>>>(prm, n_items);
+    } else {
+        switch (stretch_mode_of(prm.pitch, prm.flags)) {   // same arithmetic, scalar configuration folded in
+            case 1: stretch_kernel<LOG2H, false, 1><<<grid, block, smem, stream>>>(prm, n_items); break;
+            case 2: stretch_kernel<LOG2H, false, 2><<<grid, block, smem, stream>>>(prm, n_items); break;
+            case 3: stretch_kernel<LOG2H, false, 3><<<grid, block, smem, stream>>>(prm, n_items); break;
+            default: stretch_kernel<LOG2H, false, 0><<<grid, block, smem, stream>>>(prm, n_items); break;
+        }
+    }
     return cudaGetLastError();
 }
 
