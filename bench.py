@@ -392,7 +392,7 @@ def run_ours(args):
                        "frames_per_gpu": frames * CHANNELS, "l2": "inputs+outputs larger than L2 (0.23 GB in, 1.84 GB out per step)",
                        "exchange": "channels x W/2 fp32 carried half window, rank r -> r+1, NCCL p2p" if world > 1 else "none"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "stretch_kernel<13, false>",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "stretch_kernel<13, false, 1>",
                          "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                          "fp32_tflops_algorithmic": flops / (k_ms * 1e-3) / 1e12,
                          "fp32_peak_tflops_measured": fp32_peak,
