@@ -8,7 +8,11 @@ HDRS := $(wildcard rocoder_b200/csrc/*.h) include/rocoder_b200.h
 
 all: rocoder_b200/librocoder_b200.so rocoder_b200/rocoder_gpu
 
-rocoder_b200/librocoder_b200.so: $(CSRC) $(HDRS)
+# text of the kernel headers, embedded for the run-time (NVRTC) build of fused frequency kernels
+rocoder_b200/csrc/rcg_jit_sources.inc: $(HDRS) rocoder_b200/build.py
+	python -c "from rocoder_b200 import build; build.generate_jit_sources()"
+
+rocoder_b200/librocoder_b200.so: $(CSRC) $(HDRS) rocoder_b200/csrc/rcg_jit_sources.inc
 	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC) -ldl
 
 rocoder_b200/rocoder_gpu: tools/rocoder_gpu.cpp rocoder_b200/host/rocoder_audio.hpp rocoder_b200/librocoder_b200.so
@@ -19,6 +23,6 @@ test-infra:
 	g++ -O2 -std=c++17 -fPIC -shared -ffp-contract=off -o tests/emul/librcg_emul.so tests/emul/rcg_emul.cpp
 
 clean:
-	rm -f rocoder_b200/librocoder_b200.so rocoder_b200/rocoder_gpu tests/emul/librcg_emul.so
+	rm -f rocoder_b200/librocoder_b200.so rocoder_b200/rocoder_gpu tests/emul/librcg_emul.so rocoder_b200/csrc/rcg_jit_sources.inc
 	$(MAKE) -C oracle clean
 .PHONY: all test-infra clean
