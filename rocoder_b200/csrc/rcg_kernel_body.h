@@ -88,6 +88,9 @@ __device__ __forceinline__ StretchParams with_mode_constants(const StretchParams
     if constexpr (MODE == 1) { p.pitch = 2; p.flags = (in.flags & kFlagDeferFirst) | kFlagHalfRate; }
     if constexpr (MODE == 2) { p.pitch = 1; p.flags = in.flags & kFlagDeferFirst; }
     if constexpr (MODE == 3) { p.flags = in.flags & kFlagDeferFirst; }
+#if defined(RCG_EXP_MODE3_PITCH)   // experiment: what a run-time (NVRTC) specialisation on the exact pitch would buy
+    if constexpr (MODE == 3) { p.pitch = RCG_EXP_MODE3_PITCH; }
+#endif
     return p;
 }
 
