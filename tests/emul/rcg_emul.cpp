@@ -7,6 +7,20 @@
 #include <cstring>
 #include <vector>
 
+#if defined(RCG_EMUL_LOCAL_PLUGIN)
+// Second build of this file (librcg_emul_local.so): the hook that fuses a bin-local frequency kernel into the
+// spectral step (RCG_PLUGIN_LOCAL, rcg_jit_entry.h) executed on the host, with the `tilt` kernel of
+// tests/plugins.py standing in for the user's source.
+#include "../../rocoder_b200/csrc/rcg_common.h"
+typedef cf float2;
+static inline float2 make_float2(float x, float y) { return make_cf(x, y); }
+static inline float2 apply(size_t, unsigned bin, unsigned n_bins, float2 v) {
+    const float g = 0.25f + (float)bin / (float)n_bins;
+    return make_float2((v.x * 0.6f - v.y * 0.8f) * g, (v.x * 0.8f + v.y * 0.6f) * g);
+}
+#define RCG_PLUGIN_LOCAL 1
+#endif
+
 #include "../../rocoder_b200/csrc/rcg_frame.h"
 #include "../../rocoder_b200/csrc/rcg_frame_pair.h"
 #include "../../rocoder_b200/csrc/rcg_frame_quad.h"

@@ -207,21 +207,36 @@ def resample(x: np.ndarray, p: int) -> np.ndarray:
 
 
 # ---- host emulator of the kernel phases -------------------------------------------------------
+_emul_local = None
+
+
+def _declare_emulator(E):
+    E.rcg_emul_stretch.argtypes = [C.c_int, PF, C.c_longlong, C.c_longlong, C.c_longlong, PF, C.c_longlong,
+                                   C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_float, C.c_ulonglong, C.c_uint, C.c_int, PF, PF, PF]
+    E.rcg_emul_boundary.argtypes = [C.c_int, PF, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
+                                    C.c_int, C.c_float, PF, PF]
+    E.rcg_emul_stretch_plugin.argtypes = [C.c_int, PF, C.c_longlong, C.c_longlong, PF, C.c_longlong,
+                                          C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                          C.c_ulonglong, APPLY_FN]
+    return E
+
+
 def emulator() -> C.CDLL:
     global _emul
     if _emul is None:
         from rocoder_b200 import build
-        E = C.CDLL(build.build_emulator())
-        E.rcg_emul_stretch.argtypes = [C.c_int, PF, C.c_longlong, C.c_longlong, C.c_longlong, PF, C.c_longlong,
-                                       C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
-                                       C.c_int, C.c_float, C.c_ulonglong, C.c_uint, C.c_int, PF, PF, PF]
-        E.rcg_emul_boundary.argtypes = [C.c_int, PF, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
-                                        C.c_int, C.c_float, PF, PF]
-        E.rcg_emul_stretch_plugin.argtypes = [C.c_int, PF, C.c_longlong, C.c_longlong, PF, C.c_longlong,
-                                              C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                              C.c_ulonglong, APPLY_FN]
-        _emul = E
+        _emul = _declare_emulator(C.CDLL(build.build_emulator()))
     return _emul
+
+
+def emulator_local_plugin() -> C.CDLL:
+    """the emulator built with the fused bin-local frequency-kernel hook (`tilt` compiled in)"""
+    global _emul_local
+    if _emul_local is None:
+        from rocoder_b200 import build
+        _emul_local = _declare_emulator(C.CDLL(build.build_emulator_local_plugin()))
+    return _emul_local
 
 
 def _pf(a):
@@ -231,13 +246,13 @@ def _pf(a):
 def emul_segment(x: np.ndarray, in_origin: int, out: np.ndarray, factor: float, pitch: int, W: int,
                  first_call: int, n_calls: int, seed: int = 0, amplitude: float = 1.0, run_len: int = 5,
                  bypass: bool = False, tail_in=None, tail_out=None, head_out=None, defer_first: bool = False,
-                 first_channel: int = 0):
+                 first_channel: int = 0, lib=None):
     """Run the kernel phases on the host for calls [first_call, first_call+n_calls)."""
     c = constants(factor, pitch, W, amplitude)
     k, olen = c["frames_per_call"], c["out_len_per_call"]
     ch, n = x.shape
     flags = (1 if bypass else 0) | (2 if defer_first else 0)
-    rc = emulator().rcg_emul_stretch(
+    rc = (lib or emulator()).rcg_emul_stretch(
         int(np.log2(W)), _pf(x), x.strides[0] // 4, in_origin, n, _pf(out), out.strides[0] // 4,
         first_call * olen, first_call * k, (first_call + n_calls) * k, run_len, ch, c["sample_step_len"], pitch,
         c["samples_needed_per_window"], c["corrected_amp_factor"], seed, flags, first_channel, _pf(tail_in),
@@ -256,11 +271,11 @@ def emul_boundary(out: np.ndarray, factor: float, pitch: int, W: int, first_call
 
 
 def emul_process_all(x: np.ndarray, factor: float, pitch: int, W: int, seed: int = 0, amplitude: float = 1.0,
-                     run_len: int = 5, bypass: bool = False) -> np.ndarray:
+                     run_len: int = 5, bypass: bool = False, lib=None) -> np.ndarray:
     x = np.ascontiguousarray(x, np.float32)
     calls, _, out_len = expected_counts(x.shape[1], factor, pitch, W)
     out = np.full((x.shape[0], out_len), np.nan, np.float32)
-    emul_segment(x, 0, out, factor, pitch, W, 0, calls, seed, amplitude, run_len, bypass)
+    emul_segment(x, 0, out, factor, pitch, W, 0, calls, seed, amplitude, run_len, bypass, lib=lib)
     return out
 
 

@@ -35,6 +35,27 @@ def test_emulated_plugin_path_matches_oracle_w65536(n, f, p, W, plug):
     assert np.abs(got - ref).max() <= 1e-4 and ol.snr_db(ref, got) > 100.0
 
 
+@pytest.mark.parametrize("n,f,p,W", [(6000, 2.0, 1, 256), (9000, 3.0, 2, 1024), (7000, 4.0, -2, 512), (5000, 1.0, 12, 128),
+                                     (40000, 8.0, 2, 16384), (100, 1.0, 1, 64), (150000, 2.0, 1, 65536)])
+def test_emulated_fused_local_plugin_matches_oracle(n, f, p, W):
+    """the hook that evaluates a bin-local frequency kernel inside the spectral step (what NVRTC compiles into the
+    stretch kernel, rcg_jit_entry.h) executed on the host -- full-rate, half-rate and CTA-pair paths, special bins
+    included -- against the oracle calling the same kernel (`tilt`) on the whole spectrum"""
+    x = _input(n)
+    ref = ol.process_all(x, f, p, W, seed=4, precision=64, plugin=plugins.tilt)
+    ol.emulator().rcg_emul_use_pair(1)      # the fused form at W = 65536 is built on the CTA pair
+    ol.emulator_local_plugin().rcg_emul_use_pair(1)
+    try:
+        got = ol.emul_process_all(x, f, p, W, seed=4, lib=ol.emulator_local_plugin())
+    finally:
+        ol.emulator().rcg_emul_use_pair(0)
+        ol.emulator_local_plugin().rcg_emul_use_pair(0)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-4 and (not ref.any() or ol.snr_db(ref, got) > 100.0)
+    plain = ol.emul_process_all(x, f, p, W, seed=4)
+    assert not np.array_equal(plain, got)
+
+
 def test_identity_plugin_equals_fused_path():
     """pass-through spectra (no kernel loaded yet, fft.rs:82-85) reproduce the fused kernel up to
     the rounding of the two different magnitude formulas"""
