@@ -54,6 +54,14 @@ def test_emulated_fused_local_plugin_matches_oracle(n, f, p, W):
     assert np.abs(got - ref).max() <= 1e-4 and (not ref.any() or ol.snr_db(ref, got) > 100.0)
     plain = ol.emul_process_all(x, f, p, W, seed=4)
     assert not np.array_equal(plain, got)
+    if W <= 16384:   # phases stay order-independent with the hook compiled in
+        E = ol.emulator_local_plugin()
+        E.rcg_emul_reverse_threads(1)
+        try:
+            again = ol.emul_process_all(x, f, p, W, seed=4, lib=E)
+        finally:
+            E.rcg_emul_reverse_threads(0)
+        assert np.array_equal(got, again)
 
 
 def test_identity_plugin_equals_fused_path():
