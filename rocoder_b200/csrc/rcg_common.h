@@ -129,10 +129,7 @@ RCG_HD constexpr int threads_per_frame(int log2h) {
 // W = 16384: three frame lanes share one CTA per SM and ONE copy of the pass twiddle tables in shared memory
 // (3 x 69.6 KB + 17 KB = 226 KB of the 227 KB an SM offers).  With three 1-lane CTAs per SM instead, the
 // carve-out leaves 28 KB of L1 and every twiddle load is an L2 round trip (ncu: 19 % L1 hit rate).
-#ifndef RCG_TW_SMEM
-#define RCG_TW_SMEM 1
-#endif
-RCG_HD constexpr bool tw_in_smem(int log2h) { return RCG_TW_SMEM && log2h == 13; }
+RCG_HD constexpr bool tw_in_smem(int log2h) { return log2h == 13; }
 RCG_HD constexpr int frames_per_cta(int log2h) {
     if (tw_in_smem(log2h)) return 3;
     int nt = threads_per_frame(log2h);

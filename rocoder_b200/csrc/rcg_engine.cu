@@ -205,11 +205,6 @@ struct rcg_engine {
     bool pair = false;        // W = 65536: a frame across a 2-CTA cluster
     PairTables pt{};
     cf *d_pair_cross = nullptr, *d_pair_even = nullptr, *d_pair_odd = nullptr;
-    // W = 65536, fused path: a frame across a 4-CTA cluster (rcg_frame_quad.h); 0 clusters = not available
-    QuadTables qt{};
-    int quad_clusters = 0;
-    cf *d_quad_cross = nullptr, *d_quad_spec = nullptr, *d_quad_tw = nullptr;
-    uint2* d_quad_pair_tab = nullptr;
     cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
     uint64_t launches = 0;
     // process_all buffers (grow only)
@@ -315,27 +310,6 @@ extern "C" int rcg_create(const rcg_config* cfg, rcg_engine** out) {
         TRY_E(cudaMemcpy(e->d_pair_cross, cross.data(), cross.size() * sizeof(cf), cudaMemcpyHostToDevice));
         TRY_E(cudaMemcpy(e->d_pair_even, se.data(), se.size() * sizeof(cf), cudaMemcpyHostToDevice));
         TRY_E(cudaMemcpy(e->d_pair_odd, so.data(), so.size() * sizeof(cf), cudaMemcpyHostToDevice));
-        // Opt-in (RCG_QUAD=1): the fused path on 4-CTA clusters (rcg_frame_quad.h).  Measured slower than the pair
-        // on config 3 (6.07 vs 5.15 ms): 104 resident clusters instead of 74, but every CTA loads the whole frame,
-        // the last stage reads three remote quarters per output and a frame crosses four cluster barriers.
-        int qc = 0;
-        const char* want_quad = getenv("RCG_QUAD");
-        if (want_quad && want_quad[0] == '1' && quad_geometry(&qc) == cudaSuccess && qc >= e->sm_count / 2) {
-            std::vector<cf> qcross = host_quad_cross_twiddles(e->log2w - 1), qspec = host_quad_spectral_twiddles(e->log2w - 1);
-            std::vector<cf> qtw = host_pass_twiddles(kQuadLog2HL);
-            std::vector<uint2> qptab = host_pair_table(kQuadLog2HL);
-            TRY_E(cudaMalloc(&e->d_quad_cross, qcross.size() * sizeof(cf)));
-            TRY_E(cudaMalloc(&e->d_quad_spec, qspec.size() * sizeof(cf)));
-            TRY_E(cudaMalloc(&e->d_quad_tw, qtw.size() * sizeof(cf)));
-            TRY_E(cudaMalloc(&e->d_quad_pair_tab, qptab.size() * sizeof(uint2)));
-            TRY_E(cudaMemcpy(e->d_quad_cross, qcross.data(), qcross.size() * sizeof(cf), cudaMemcpyHostToDevice));
-            TRY_E(cudaMemcpy(e->d_quad_spec, qspec.data(), qspec.size() * sizeof(cf), cudaMemcpyHostToDevice));
-            TRY_E(cudaMemcpy(e->d_quad_tw, qtw.data(), qtw.size() * sizeof(cf), cudaMemcpyHostToDevice));
-            TRY_E(cudaMemcpy(e->d_quad_pair_tab, qptab.data(), qptab.size() * sizeof(uint2), cudaMemcpyHostToDevice));
-            e->quad_clusters = qc;
-        } else {
-            (void)cudaGetLastError();
-        }
     }
     std::vector<float> we = host_decimate2(window), ee = host_decimate2(env);
     {   // frame-invariant slot-index tables of the spectral steps
@@ -363,11 +337,10 @@ extern "C" int rcg_create(const rcg_config* cfg, rcg_engine** out) {
     TRY_E(cudaMalloc(&e->d_env, H * sizeof(float)));
     TRY_E(cudaMalloc(&e->d_tw, std::max<size_t>(tw.size(), 1) * sizeof(cf)));
     TRY_E(cudaMalloc(&e->d_spec_tw, stw.size() * sizeof(cf)));
-    const size_t scratch_floats = e->pair ? (size_t)std::max<int>(std::max(e->max_grid, e->quad_clusters), (int)cfg->channels) * 3 * H
+    const size_t scratch_floats = e->pair ? (size_t)std::max<int>(e->max_grid, (int)cfg->channels) * 3 * H
                                           : (size_t)e->max_grid * e->geo.frames_per_cta * H;
     TRY_E(cudaMalloc(&e->d_scratch, scratch_floats * sizeof(float)));
     e->pt = PairTables{e->d_pair_cross, e->d_pair_even, e->d_pair_odd, e->d_scratch};
-    e->qt = QuadTables{e->d_quad_cross, e->d_quad_spec, e->d_quad_tw, e->d_quad_pair_tab, e->d_scratch};
     TRY_E(cudaMemcpy(e->d_window, window.data(), W * sizeof(float), cudaMemcpyHostToDevice));
     TRY_E(cudaMemcpy(e->d_env, env.data(), H * sizeof(float), cudaMemcpyHostToDevice));
     TRY_E(cudaMemcpy(e->d_tw, tw.data(), tw.size() * sizeof(cf), cudaMemcpyHostToDevice));
@@ -398,7 +371,6 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     cudaFree(e->d_window_even); cudaFree(e->d_env_even); cudaFree(e->d_spec_tw_hr); cudaFree(e->d_lerp_ratio);
     cudaFree(e->d_pair_tab); cudaFree(e->d_quad_tab);
     cudaFree(e->d_pair_cross); cudaFree(e->d_pair_even); cudaFree(e->d_pair_odd);
-    cudaFree(e->d_quad_cross); cudaFree(e->d_quad_spec); cudaFree(e->d_quad_tw); cudaFree(e->d_quad_pair_tab);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_tail_pp[0]); cudaFree(e->d_tail_pp[1]);
     cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_spec); cudaFree(e->d_spec2);
     for (auto& k : e->kernels) if (k.lib) cudaLibraryUnload(k.lib);
@@ -510,9 +482,7 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
         return fail(RCG_ERR_INVALID_ARG, "segment starts at frame %lld but its input starts past the halo frame",
                     p.frame_begin);
     const uint64_t nframes = (uint64_t)(p.frame_end - p.frame_begin);
-    // W = 65536: the fused path on 4-CTA clusters, frequency-kernel synthesis on the CTA pair
-    const bool quad = e->pair && !spec && !fused && e->quad_clusters > 0;
-    const int max_grid = quad ? e->quad_clusters : e->max_grid;
+    const int max_grid = e->max_grid;
     const int slots = max_grid * e->geo.frames_per_cta;
     p.run_len = pick_run_len(nframes, (uint32_t)channels, slots);
     p.n_runs = (int)((nframes + p.run_len - 1) / p.run_len);
@@ -531,9 +501,7 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
              : e->pair  ? cudaLaunchKernel((const void*)fused, dim3(2 * grid), dim3(e->geo.threads), pair_args, e->geo.smem_bytes, stream)
                         : cudaLaunchKernel((const void*)fused, dim3(grid), dim3(e->geo.threads), args, e->geo.smem_bytes, stream);
     } else {
-        ce = quad      ? launch_stretch_quad(p, e->qt, grid, stream)
-             : e->pair ? launch_stretch_pair(p, e->pt, grid, stream)
-                       : launch_stretch(e->log2w, p, grid, stream);
+        ce = e->pair ? launch_stretch_pair(p, e->pt, grid, stream) : launch_stretch(e->log2w, p, grid, stream);
     }
     if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "stretch kernel launch failed: %s", cudaGetErrorString(ce));
     e->launches++;

@@ -11,27 +11,11 @@
 #include "rcg_dft.h"
 #include "rcg_philox.h"
 
-// tuning knobs (scripts/variant_bench.sh builds variants with -D...)
-#ifndef RCG_LOAD_UNROLL
+// unroll factors of the load and overlap-add loops (measured: 1..8 within 1 % of each other)
 #define RCG_LOAD_UNROLL 4
-#endif
-#ifndef RCG_OLA_UNROLL
 #define RCG_OLA_UNROLL 2
-#endif
-#ifndef RCG_TW_EVICT_LAST
-#define RCG_TW_EVICT_LAST 0
-#endif
-#ifndef RCG_STREAM_POLICY
-#define RCG_STREAM_POLICY 0
-#endif
-#ifndef RCG_FUSE_OLA_LOAD
-#define RCG_FUSE_OLA_LOAD 0   // measured slower on B200 (9.1 vs 8.0 ms on config 2): off by default
-#endif
 #define RCG_PRAGMA(x) _Pragma(#x)
 #define RCG_UNROLL(n) RCG_PRAGMA(unroll n)
-#ifndef RCG_SPECTRUM_PREFETCH
-#define RCG_SPECTRUM_PREFETCH 0
-#endif
 
 #if defined(__CUDA_ARCH__)
 #define RCG_MUL(a, b) __fmul_rn((a), (b))
@@ -51,7 +35,6 @@ enum : uint32_t {
     kFlagBypass = 1u,      // test hook: resynth(s)[n] = (s[n]*w[n])*w[n]  (no FFT, no phases)
     kFlagDeferFirst = 2u,  // do not emit block frame_begin; write its raw first half to head_out
     kFlagSpectrumIn = 4u,  // plugin path: magnitudes come from prm.spectrum (plugin output), not the FFT
-    kFlagNoFuse = 16u,     // tuning / test hook: keep load and overlap-add as separate phases
     kFlagHalfRate = 8u,    // even pitch multiple > 0: only even output samples survive the decimation
                            // (resampler.rs:15-18), so the synthesis side runs at half size
 };
@@ -134,30 +117,14 @@ RCG_HD float ld_stream(const float* p) {
 }
 RCG_HD cf ld_stream2(const float* p) {  // p must be 8-byte aligned
 #if defined(__CUDA_ARCH__)
-#if RCG_STREAM_POLICY
-    // keep the streams out of L1 (the twiddle tables live there) but pinned in L2: L1 no-allocate
-    // plus an explicit L2 evict_last policy (without it no_allocate loads are evict-first in L2)
-    unsigned long long pol;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    cf r;
-    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(r.x), "=f"(r.y) : "l"(p), "l"(pol));
-    return r;
-#else
     return __ldg(reinterpret_cast<const float2*>(p));
-#endif
 #else
     return make_cf(p[0], p[1]);
 #endif
 }
 RCG_HD cf ld_cf(const cf* p) {
 #if defined(__CUDA_ARCH__)
-#if RCG_TW_EVICT_LAST
-    cf r;   // tables: ask L1 to keep them ahead of the streaming input / window / envelope lines
-    asm("ld.global.nc.L1::evict_last.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-    return r;
-#else
     return __ldg(p);
-#endif
 #else
     return *p;
 #endif
@@ -687,21 +654,10 @@ RCG_HD float cf_norm(cf v) { return fast_sqrt(v.x * v.x + v.y * v.y); }
 // plugin's output survives, fft.rs:67) -> random phase -> Hermitian fold -> inverse pre-pass.
 // Again two phases: (1) natural-order, coalesced read of the plugin output; the slot of bin b < H
 // receives (|P[b]|, |P[W-b]|) (slot 0: (|P[0]|, |P[H]|)); (2) pair threads in position order.
-RCG_HD void prefetch_l2(const void* p) {
-#if defined(__CUDA_ARCH__)
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-#else
-    (void)p;
-#endif
-}
-// pf_next (RCG_SPECTRUM_PREFETCH, off: measured slower, 1.40 vs 1.20 ms on config 5): also pull the next frame's
-// spectrum (the one this lane reads in its next iteration) into L2
 template <int LOG2H>
-RCG_HD void phase_mags_copyin(cf* S, int t, const StretchParams& prm, int channel, long long frame, bool pf_next) {
+RCG_HD void phase_mags_copyin(cf* S, int t, const StretchParams& prm, int channel, long long frame) {
     using C = FrameCfg<LOG2H>;
     const cf* X = prm.spectrum + ((long long)channel * prm.spec_frames + (frame - prm.spec_frame0)) * C::W;
-    if (RCG_SPECTRUM_PREFETCH && pf_next)
-        for (int l = t; l < C::W / 16; l += C::NT) prefetch_l2(X + C::W + 16 * l);   // 128-byte lines
     // all loads of a batch are issued before the first use: the sweep is bound by HBM latency otherwise
     constexpr int ITERS = C::H / C::NT, U = ITERS % 8 == 0 ? 8 : (ITERS % 4 == 0 ? 4 : 1);
     static_assert(C::H % C::NT == 0, "bins per thread");
@@ -777,24 +733,18 @@ RCG_HD float frame_value(const cf* S, int i) {
 // ((y + tail) * env) * amp.  A thread owns packed outputs n = m + a*M, a < R: those with a < R/2
 // are the first half window (emitted), the others the second half (carried to the next frame);
 // both map onto the same slots of the carried buffer, so no other thread ever touches them.
-// With load_next (pitch 1 only: nothing is staged in the slots) the thread then refills its own
-// slots with the next frame: no barrier is needed in between, and the next frame's global loads
-// are in flight while this frame's half window is finished.
 template <int LOG2H, bool BYPASS>
 RCG_HD void phase_ola_impl(cf* S, int t, const StretchParams& prm, int channel, long long frame,
-                           float* tail, bool emit, bool write_head, bool load_next) {
+                           float* tail, bool emit, bool write_head) {
     using C = FrameCfg<LOG2H>;
     constexpr int RL = make_plan(LOG2H).rlog2[0], R = 1 << RL, ML = make_plan(LOG2H).mlog2[0], M = 1 << ML;
     constexpr int RH = R / 2;
     constexpr bool bypass = BYPASS;
     float* out = prm.out + (long long)channel * prm.out_stride;
     const cf* tw = prm.tw + tw_offset(LOG2H, 0);
-    const LoadCtx<LOG2H> nx = make_load_ctx<LOG2H>(prm, channel, frame + 1);
 RCG_UNROLL(RCG_OLA_UNROLL)
     for (int m = t; m < M; m += C::NT) {
         cf* p = S + phys(m);
-        float nr[R], ni[R];
-        if (load_next) load_fetch<LOG2H, R, false>(nx, prm, m, nr, ni);
         float xr[R], xi[R];
 #pragma unroll
         for (int a = 0; a < R; a++) {
@@ -831,14 +781,13 @@ RCG_UNROLL(RCG_OLA_UNROLL)
                 }
             }
         }
-        if (load_next) load_finish<LOG2H, R>(S, nx, m, nr, ni);
     }
 }
 template <int LOG2H>
 RCG_HD void phase_ola(cf* S, int t, const StretchParams& prm, int channel, long long frame,
-                      float* tail, bool emit, bool write_head, bool load_next = false) {
-    if (prm.flags & kFlagBypass) phase_ola_impl<LOG2H, true>(S, t, prm, channel, frame, tail, emit, write_head, false);
-    else phase_ola_impl<LOG2H, false>(S, t, prm, channel, frame, tail, emit, write_head, load_next);
+                      float* tail, bool emit, bool write_head) {
+    if (prm.flags & kFlagBypass) phase_ola_impl<LOG2H, true>(S, t, prm, channel, frame, tail, emit, write_head);
+    else phase_ola_impl<LOG2H, false>(S, t, prm, channel, frame, tail, emit, write_head);
 }
 
 // ---- half-rate synthesis: inverse DIT butterfly of pass PASS >= 1 of the Q-point transform ------
@@ -906,12 +855,9 @@ RCG_HD float frame_value_hr(const cf* S, int i) {
 // ---- half-rate synthesis: last DIT pass + /W * window + overlap-add + envelope * amp on the even
 // samples only.  ye[i] = y[2i], i < H: i < Q is the emitted half window, the rest is carried.
 // The carried buffer, head_out / tail_in / tail_out then hold even samples ([Q] per channel).
-// With load_next (pitch 2 only) the thread then loads the next frame into the two pass-0
-// butterflies whose slots it owns or nobody uses any more: m1 = its own hr slot, m2 = m1 | 8 (the
-// sibling slot the half-rate inverse never touched).
 template <int LOG2H>
 RCG_HD void phase_ola_hr(cf* S, int t, const StretchParams& prm, int channel, long long frame,
-                         float* tail, bool emit, bool write_head, bool load_next = false) {
+                         float* tail, bool emit, bool write_head) {
     using C = FrameCfg<LOG2H>;
     constexpr PlanDesc P = make_plan(LOG2H, true);
     constexpr int RL = P.rlog2[0], R = 1 << RL, ML = P.mlog2[0], M = 1 << ML;
@@ -935,15 +881,9 @@ RCG_HD void phase_ola_hr(cf* S, int t, const StretchParams& prm, int channel, lo
         return;
     }
     const cf* tw = prm.tw + tw_offset(LOG2H, 0, true);
-    const LoadCtx<LOG2H> nx = make_load_ctx<LOG2H>(prm, channel, frame + 1);
 RCG_UNROLL(RCG_OLA_UNROLL)
     for (int m = t; m < M; m += C::NT) {
         cf* p = S + phys(expand_hr(m));
-        float n1r[R], n1i[R], n2r[R], n2i[R];
-        if (load_next) {
-            load_fetch<LOG2H, R, false>(nx, prm, expand_hr(m), n1r, n1i);
-            load_fetch<LOG2H, R, false>(nx, prm, expand_hr(m) | 8, n2r, n2i);
-        }
         float xr[R], xi[R];
 #pragma unroll
         for (int a = 0; a < R; a++) {
@@ -971,10 +911,6 @@ RCG_UNROLL(RCG_OLA_UNROLL)
                     p[slot_off<STRIDE>(a)] = make_cf(z0, z1);  // staged for the decimating gather
                 }
             }
-        }
-        if (load_next) {
-            load_finish<LOG2H, R>(S, nx, expand_hr(m), n1r, n1i);
-            load_finish<LOG2H, R>(S, nx, expand_hr(m) | 8, n2r, n2i);
         }
     }
 }
@@ -1096,28 +1032,17 @@ RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, f
     const bool half_rate = !SPEC_IN && (prm.flags & kFlagHalfRate);
     const bool bypass = prm.flags & kFlagBypass;
     constexpr bool spectrum_in = SPEC_IN;
-    // Load of frame f+1 fused into the overlap-add phase of frame f: possible when that phase leaves
-    // nothing staged in shared memory (pitch 1, or pitch 2 on the half-rate path).
-    const bool fuse = RCG_FUSE_OLA_LOAD && !(prm.flags & kFlagNoFuse) && !bypass && !spectrum_in &&
-                      (half_rate ? prm.pitch == 2 : prm.pitch == 1);
     const int n_iter = prm.run_len + 1;  // uniform trip count for every lane of the CTA
-    if (fuse) {
-        const bool pro = active && (halo || f0 < f1);
-        const long long first = halo ? f0 - 1 : f0;
-        ex.par([&](int t) { if (pro) phase_load<LOG2H>(S, t, prm, channel, first); });
-    }
     for (int it = 0; it < n_iter; it++) {
         const long long f = f0 - 1 + it;
         const bool is_halo = (it == 0);
         const bool work = active && (is_halo ? halo : f < f1);
-        const bool load_next = fuse && work && (it + 1 < n_iter) && (f + 1 < f1);
         if constexpr (spectrum_in) {
-            const bool pf = work && f + 1 < f1;
-            ex.par([&](int t) { if (work) phase_mags_copyin<LOG2H>(S, t, prm, channel, f, pf); });
+            ex.par([&](int t) { if (work) phase_mags_copyin<LOG2H>(S, t, prm, channel, f); });
             ex.par([&](int t) { if (work) phase_spectral_in<LOG2H>(S, t, prm, channel, f); });
             fft_all<LOG2H, true>(ex, S, prm, work);
         } else {
-            if (!fuse) ex.par([&](int t) { if (work) phase_load<LOG2H>(S, t, prm, channel, f); });
+            ex.par([&](int t) { if (work) phase_load<LOG2H>(S, t, prm, channel, f); });
             if (!bypass) {
                 fft_all<LOG2H, false>(ex, S, prm, work);
                 if (half_rate) {
@@ -1132,11 +1057,11 @@ RCG_HD void run_work_item(Exec& ex, cf* S, const StretchParams& prm, int item, f
         const bool head = work && defer && f == f0;
         const bool emit = work && !is_halo && !head;
         if (half_rate) {
-            ex.par([&](int t) { if (work) phase_ola_hr<LOG2H>(S, t, prm, channel, f, tail, emit, head, load_next); });
+            ex.par([&](int t) { if (work) phase_ola_hr<LOG2H>(S, t, prm, channel, f, tail, emit, head); });
             if (prm.pitch != 2)
                 ex.par([&](int t) { if (emit) phase_resample<LOG2H>(S, t, prm, channel, f); });
         } else {
-            ex.par([&](int t) { if (work) phase_ola<LOG2H>(S, t, prm, channel, f, tail, emit, head, load_next); });
+            ex.par([&](int t) { if (work) phase_ola<LOG2H>(S, t, prm, channel, f, tail, emit, head); });
             if (prm.pitch != 1)
                 ex.par([&](int t) { if (emit) phase_resample<LOG2H>(S, t, prm, channel, f); });
         }

@@ -17,13 +17,9 @@ struct DeviceExecT {
     int t;
     int lane = 0;
     __device__ __forceinline__ void lane_barrier() {
-#ifdef RCG_EXPERIMENT_NO_BLOCK_BARRIERS   // timing experiment only: results are wrong
-        __syncwarp();
-#else
         if constexpr (WARP_LOCAL) __syncwarp();
         else if constexpr (LANE_THREADS > 0) asm volatile("bar.sync %0, %1;" ::"r"(lane + 1), "n"(LANE_THREADS) : "memory");
         else __syncthreads();
-#endif
     }
     template <class F>
     __device__ __forceinline__ void par(F f) {
@@ -43,9 +39,6 @@ struct DeviceExecT {
 };
 using DeviceExec = DeviceExecT<false>;
 
-#ifndef RCG_MIN_CTAS
-#define RCG_MIN_CTAS 3
-#endif
 
 // FrameCfg::TW_SMEM: the CTA copies the pass twiddle tables behind its frame buffers once (the CTAs are
 // persistent) and the frame code reads them from there
@@ -67,7 +60,7 @@ constexpr size_t kernel_smem_bytes() {
     return ((size_t)C::FPC * C::SMEM_CF + (C::TW_SMEM ? C::TW_CF : 0)) * sizeof(cf);
 }
 template <int LOG2H>
-constexpr int min_ctas() { return (LOG2H >= 14 || FrameCfg<LOG2H>::TW_SMEM) ? 1 : RCG_MIN_CTAS; }
+constexpr int min_ctas() { return (LOG2H >= 14 || FrameCfg<LOG2H>::TW_SMEM) ? 1 : 3; }
 
 // MODE: the launch's scalar configuration as compile-time constants.  The frame code reads pitch and flags in
 // many places (which synthesis path, where the overlap-add phase stores, whether a resample phase exists); with
@@ -88,9 +81,6 @@ __device__ __forceinline__ StretchParams with_mode_constants(const StretchParams
     if constexpr (MODE == 1) { p.pitch = 2; p.flags = (in.flags & kFlagDeferFirst) | kFlagHalfRate; }
     if constexpr (MODE == 2) { p.pitch = 1; p.flags = in.flags & kFlagDeferFirst; }
     if constexpr (MODE == 3) { p.flags = in.flags & kFlagDeferFirst; }
-#if defined(RCG_EXP_MODE3_PITCH)   // experiment: what a run-time (NVRTC) specialisation on the exact pitch would buy
-    if constexpr (MODE == 3) { p.pitch = RCG_EXP_MODE3_PITCH; }
-#endif
     return p;
 }
 
@@ -98,12 +88,8 @@ template <int LOG2H, bool SPEC_IN>
 __device__ __forceinline__ void stretch_body(const StretchParams& prm, int n_items, unsigned char* smem_raw) {
     using C = FrameCfg<LOG2H>;
     const int lane = threadIdx.x / C::NT;
-#ifdef RCG_NO_WARP_LOCAL
-    DeviceExecT<false> ex{(int)(threadIdx.x % C::NT)};
-#else
     // frame lanes of one CTA are independent: warp barriers (<= 1 warp per lane) or one named barrier per lane
     DeviceExecT<(C::NT <= 32), (C::NT > 32 && C::FPC > 1) ? C::NT : 0> ex{(int)(threadIdx.x % C::NT), lane};
-#endif
     cf* S = reinterpret_cast<cf*>(smem_raw) + lane * C::SMEM_CF;
     float* tail = prm.tail_scratch + ((long long)blockIdx.x * C::FPC + lane) * C::H;
     // A full round gives CTA c the FPC neighbouring items r * per_round + c * FPC + l (neighbouring runs of a
@@ -114,13 +100,7 @@ __device__ __forceinline__ void stretch_body(const StretchParams& prm, int n_ite
     const int rounds = (n_items + per_round - 1) / per_round;
     for (int r = 0; r < rounds; r++) {
         const int first = r * per_round;
-#if defined(RCG_ITEM_MAP) && RCG_ITEM_MAP == 1   // experiments: always grouped / always spread
-        const bool full = true;
-#elif defined(RCG_ITEM_MAP) && RCG_ITEM_MAP == 2
-        const bool full = false;
-#else
         const bool full = n_items - first >= per_round;
-#endif
         const int item = first + (full ? (int)blockIdx.x * C::FPC + lane : lane * (int)gridDim.x + (int)blockIdx.x);
         run_work_item<LOG2H, SPEC_IN>(ex, S, prm, item, tail, item < n_items);
     }

@@ -8,18 +8,19 @@
 //   -> /W * window -> overlap-add with the carried half window -> envelope * amp -> resample.
 // HBM sees each input sample once per overlapping frame (L2 absorbs the overlap) and each
 // output sample exactly once.  No tensor cores: nothing here is a dense contraction.
+//
+// One source, several translation units so that the window sizes compile in parallel (rocoder_b200/build.py):
+//   -DRCG_TU_LOG2H=L   the kernels and launchers of W = 2^(L+1), L = 5..14
+//   (nothing)          the W = 65536 CTA-pair kernels and the dispatch by window size
 #include "rcg_kernels.h"
 
-#include <cooperative_groups.h>
-
 #include "rcg_frame_pair.h"
-#include "rcg_frame_quad.h"
 #include "rcg_kernel_body.h"
 #include "rcg_pair_body.h"
 
-namespace cg = cooperative_groups;
-
 namespace rcg {
+
+#if defined(RCG_TU_LOG2H)
 
 template <int LOG2H, bool SPEC_IN = false, int MODE = 0>
 __global__ void __launch_bounds__(FrameCfg<LOG2H>::NT * FrameCfg<LOG2H>::FPC, min_ctas<LOG2H>())
@@ -71,132 +72,8 @@ boundary_kernel(const __grid_constant__ StretchParams prm, const float* head, co
     run_boundary<LOG2H>(ex, reinterpret_cast<cf*>(smem_raw), prm, (int)blockIdx.x, head, tail_prev);
 }
 
-// ---- W = 65536: a frame across a 2-CTA cluster (rcg_frame_pair.h) -------------------------------
-// PairDeviceExec, stretch_pair_body: rcg_pair_body.h (shared with the NVRTC translation unit)
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FrameCfg<kPairLog2HL>::NT, 1)
-stretch_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, int n_items) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    stretch_pair_body(prm, pt, n_items, smem_raw);
-}
-
-// frequency-kernel path at W = 65536, analysis half: each CTA of the pair writes the bins of its parity
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FrameCfg<kPairLog2HL>::NT, 1)
-analysis_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, int n_items) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int r = (int)cluster_cta_rank();
-    cf* S = reinterpret_cast<cf*>(smem_raw);
-    cf* bufs[2] = {S, S};   // only bufs[r] is touched: no data crosses the pair in this kernel
-    PairDeviceExec ex{r, (int)threadIdx.x};
-    const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
-    for (int item = cid; item < n_items; item += ncl) run_analysis_item_pair(ex, bufs, prm, pt, item, true);
-}
-
-// ---- W = 65536, fused path: a frame across a 4-CTA cluster (rcg_frame_quad.h) -----------------------------
-struct QuadDeviceExec {
-    int r, t;
-    template <class F>
-    __device__ __forceinline__ void par(F f) {
-        f(r, t);
-        __syncthreads();
-    }
-    template <class F>
-    __device__ __forceinline__ void par_steps(int n, F f) {
-        for (int s = 0; s < n; s++) {
-            f(s, r, t);
-            __syncwarp();
-        }
-        __syncthreads();
-    }
-    template <class F>
-    __device__ __forceinline__ void par_cluster(F f) {
-        f(r, t);
-        __threadfence();            // carried half windows and the staged block travel through global memory
-        cg::this_cluster().sync();  // barrier.cluster arrive.release / wait.acquire
-    }
-    __device__ __forceinline__ void cluster_sync() { cg::this_cluster().sync(); }
-};
-
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FrameCfg<kQuadLog2HL>::NT, 3)
-stretch_quad_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ QuadTables qt, int n_items) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cg::cluster_group cluster = cg::this_cluster();
-    const int r = (int)cluster.block_rank();
-    cf* S = reinterpret_cast<cf*>(smem_raw);
-    cf* bufs[4];
-#pragma unroll
-    for (int q = 0; q < 4; q++) bufs[q] = cluster.map_shared_rank(S, q);   // peers' quarters, through DSMEM
-    bufs[r] = S;
-    QuadDeviceExec ex{r, (int)threadIdx.x};
-    const int cid = blockIdx.x / 4, ncl = gridDim.x / 4;
-    float* scratch = qt.scratch + (long long)cid * 3 * kPairH;
-    for (int item = cid; item < n_items; item += ncl) run_work_item_quad(ex, bufs, prm, qt, item, scratch, true);
-    cluster.sync();  // no CTA may exit while a peer can still read its shared memory
-}
-
-__global__ void __launch_bounds__(FrameCfg<kPairLog2HL>::NT)
-boundary_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, const float* head,
-                     const float* tail_prev) {
-    DeviceExec ex{(int)threadIdx.x};
-    float* stage = pt.scratch + (long long)blockIdx.x * 3 * kPairH + 2 * kPairH;
-    run_boundary_pair(ex, prm, (int)blockIdx.x, head, tail_prev, stage);
-}
-
-cudaError_t pair_geometry(LaunchGeometry* g) {
-    using C = FrameCfg<kPairLog2HL>;
-    g->threads = C::NT;
-    g->frames_per_cta = 1;
-    g->smem_bytes = (size_t)C::SMEM_CF * sizeof(cf);
-    g->max_ctas_per_sm = 1;
-    cudaError_t e = cudaFuncSetAttribute(analysis_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(stretch_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
-}
-// max_clusters: how many 4-CTA clusters the device keeps resident
-cudaError_t quad_geometry(int* max_clusters) {
-    using C = FrameCfg<kQuadLog2HL>;
-    const size_t smem = (size_t)C::SMEM_CF * sizeof(cf);
-    cudaError_t e = cudaFuncSetAttribute(stretch_quad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(4 * 1024);
-    cfg.blockDim = dim3(C::NT);
-    cfg.dynamicSmemBytes = smem;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 4; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    return cudaOccupancyMaxActiveClusters(max_clusters, stretch_quad_kernel, &cfg);
-}
-cudaError_t launch_stretch_quad(const StretchParams& prm, const QuadTables& qt, int n_clusters, cudaStream_t stream) {
-    using C = FrameCfg<kQuadLog2HL>;
-    const int n_items = prm.channels * prm.n_runs;
-    if (n_items <= 0) return cudaSuccess;
-    stretch_quad_kernel<<<4 * n_clusters, C::NT, (size_t)C::SMEM_CF * sizeof(cf), stream>>>(prm, qt, n_items);
-    return cudaGetLastError();
-}
-cudaError_t launch_analysis_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream) {
-    using C = FrameCfg<kPairLog2HL>;
-    const int n_items = prm.channels * prm.n_runs;
-    if (n_items <= 0) return cudaSuccess;
-    analysis_pair_kernel<<<2 * n_clusters, C::NT, (size_t)C::SMEM_CF * sizeof(cf), stream>>>(prm, pt, n_items);
-    return cudaGetLastError();
-}
-cudaError_t launch_stretch_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream) {
-    using C = FrameCfg<kPairLog2HL>;
-    const int n_items = prm.channels * prm.n_runs;
-    if (n_items <= 0) return cudaSuccess;
-    stretch_pair_kernel<<<2 * n_clusters, C::NT, (size_t)C::SMEM_CF * sizeof(cf), stream>>>(prm, pt, n_items);
-    return cudaGetLastError();
-}
-cudaError_t launch_boundary_pair(const StretchParams& prm, const PairTables& pt, const float* head, const float* tail_prev,
-                                 cudaStream_t stream) {
-    boundary_pair_kernel<<<prm.channels, FrameCfg<kPairLog2HL>::NT, 0, stream>>>(prm, pt, head, tail_prev);
-    return cudaGetLastError();
-}
-
 template <int LOG2H>
-static cudaError_t geometry_t(LaunchGeometry* g) {
+cudaError_t geometry_t(LaunchGeometry* g) {
     using C = FrameCfg<LOG2H>;
     g->threads = C::NT * C::FPC;
     g->frames_per_cta = C::FPC;
@@ -222,7 +99,7 @@ static cudaError_t geometry_t(LaunchGeometry* g) {
 }
 
 template <int LOG2H>
-static cudaError_t launch_t(const StretchParams& prm, int grid, cudaStream_t stream) {
+cudaError_t launch_t(const StretchParams& prm, int grid, cudaStream_t stream) {
     using C = FrameCfg<LOG2H>;
     const int n_items = prm.channels * prm.n_runs;
     if (n_items <= 0) return cudaSuccess;
@@ -242,7 +119,7 @@ static cudaError_t launch_t(const StretchParams& prm, int grid, cudaStream_t str
 }
 
 template <int LOG2H>
-static cudaError_t analysis_t(const StretchParams& prm, int grid, cudaStream_t stream) {
+cudaError_t analysis_t(const StretchParams& prm, int grid, cudaStream_t stream) {
     using C = FrameCfg<LOG2H>;
     const int n_items = prm.channels * prm.n_runs;
     if (n_items <= 0) return cudaSuccess;
@@ -251,10 +128,81 @@ static cudaError_t analysis_t(const StretchParams& prm, int grid, cudaStream_t s
 }
 
 template <int LOG2H>
-static cudaError_t boundary_t(const StretchParams& prm, const float* head, const float* tail_prev,
+cudaError_t boundary_t(const StretchParams& prm, const float* head, const float* tail_prev,
                               cudaStream_t stream) {
     using C = FrameCfg<LOG2H>;
     boundary_kernel<LOG2H><<<prm.channels, C::NT, C::SMEM_CF * sizeof(cf), stream>>>(prm, head, tail_prev);
+    return cudaGetLastError();
+}
+
+template cudaError_t geometry_t<RCG_TU_LOG2H>(LaunchGeometry*);
+template cudaError_t launch_t<RCG_TU_LOG2H>(const StretchParams&, int, cudaStream_t);
+template cudaError_t analysis_t<RCG_TU_LOG2H>(const StretchParams&, int, cudaStream_t);
+template cudaError_t boundary_t<RCG_TU_LOG2H>(const StretchParams&, const float*, const float*, cudaStream_t);
+
+#else   // ---- main translation unit ---------------------------------------------------------------------------
+
+// defined by the per-size translation units
+template <int LOG2H> cudaError_t geometry_t(LaunchGeometry* g);
+template <int LOG2H> cudaError_t launch_t(const StretchParams& prm, int grid, cudaStream_t stream);
+template <int LOG2H> cudaError_t analysis_t(const StretchParams& prm, int grid, cudaStream_t stream);
+template <int LOG2H> cudaError_t boundary_t(const StretchParams& prm, const float* head, const float* tail_prev, cudaStream_t stream);
+
+// ---- W = 65536: a frame across a 2-CTA cluster (rcg_frame_pair.h) -------------------------------
+// PairDeviceExec, stretch_pair_body: rcg_pair_body.h (shared with the NVRTC translation unit)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FrameCfg<kPairLog2HL>::NT, 1)
+stretch_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, int n_items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    stretch_pair_body(prm, pt, n_items, smem_raw);
+}
+
+// frequency-kernel path at W = 65536, analysis half: each CTA of the pair writes the bins of its parity
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FrameCfg<kPairLog2HL>::NT, 1)
+analysis_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, int n_items) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int r = (int)cluster_cta_rank();
+    cf* S = reinterpret_cast<cf*>(smem_raw);
+    cf* bufs[2] = {S, S};   // only bufs[r] is touched: no data crosses the pair in this kernel
+    PairDeviceExec ex{r, (int)threadIdx.x};
+    const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
+    for (int item = cid; item < n_items; item += ncl) run_analysis_item_pair(ex, bufs, prm, pt, item, true);
+}
+
+__global__ void __launch_bounds__(FrameCfg<kPairLog2HL>::NT)
+boundary_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, const float* head,
+                     const float* tail_prev) {
+    DeviceExec ex{(int)threadIdx.x};
+    float* stage = pt.scratch + (long long)blockIdx.x * 3 * kPairH + 2 * kPairH;
+    run_boundary_pair(ex, prm, (int)blockIdx.x, head, tail_prev, stage);
+}
+
+cudaError_t pair_geometry(LaunchGeometry* g) {
+    using C = FrameCfg<kPairLog2HL>;
+    g->threads = C::NT;
+    g->frames_per_cta = 1;
+    g->smem_bytes = (size_t)C::SMEM_CF * sizeof(cf);
+    g->max_ctas_per_sm = 1;
+    cudaError_t e = cudaFuncSetAttribute(analysis_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(stretch_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
+}
+cudaError_t launch_analysis_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream) {
+    using C = FrameCfg<kPairLog2HL>;
+    const int n_items = prm.channels * prm.n_runs;
+    if (n_items <= 0) return cudaSuccess;
+    analysis_pair_kernel<<<2 * n_clusters, C::NT, (size_t)C::SMEM_CF * sizeof(cf), stream>>>(prm, pt, n_items);
+    return cudaGetLastError();
+}
+cudaError_t launch_stretch_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream) {
+    using C = FrameCfg<kPairLog2HL>;
+    const int n_items = prm.channels * prm.n_runs;
+    if (n_items <= 0) return cudaSuccess;
+    stretch_pair_kernel<<<2 * n_clusters, C::NT, (size_t)C::SMEM_CF * sizeof(cf), stream>>>(prm, pt, n_items);
+    return cudaGetLastError();
+}
+cudaError_t launch_boundary_pair(const StretchParams& prm, const PairTables& pt, const float* head, const float* tail_prev,
+                                 cudaStream_t stream) {
+    boundary_pair_kernel<<<prm.channels, FrameCfg<kPairLog2HL>::NT, 0, stream>>>(prm, pt, head, tail_prev);
     return cudaGetLastError();
 }
 
@@ -297,5 +245,7 @@ cudaError_t launch_boundary(int log2w, const StretchParams& prm, const float* he
     RCG_DISPATCH(log2w, CALL)
 #undef CALL
 }
+
+#endif  // RCG_TU_LOG2H
 
 }  // namespace rcg

@@ -4,7 +4,6 @@
 
 #include "rcg_frame.h"
 #include "rcg_frame_pair.h"
-#include "rcg_frame_quad.h"
 
 namespace rcg {
 
@@ -32,9 +31,5 @@ cudaError_t launch_stretch_pair(const StretchParams& prm, const PairTables& pt, 
 cudaError_t launch_analysis_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream);
 cudaError_t launch_boundary_pair(const StretchParams& prm, const PairTables& pt, const float* head, const float* tail_prev,
                                  cudaStream_t stream);
-
-// W = 65536, fused path: a frame across a 4-CTA cluster; qt.scratch as for the pair
-cudaError_t quad_geometry(int* max_clusters);
-cudaError_t launch_stretch_quad(const StretchParams& prm, const QuadTables& qt, int n_clusters, cudaStream_t stream);
 
 }  // namespace rcg

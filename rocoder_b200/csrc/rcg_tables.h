@@ -127,35 +127,6 @@ inline std::vector<cf> host_pair_spectral_twiddles(int log2h, int odd) {
     return tw;
 }
 
-// ---- W = 65536, 4-CTA cluster (rcg_frame_quad.h) ---------------------------------------------------
-// [3][HL/64 + 64]: two-level tables for w_H^{r n} = exp(-2 pi i r n / H), n < HL = H/4, r = 1..3
-inline std::vector<cf> host_quad_cross_twiddles(int log2h) {
-    const int H = 1 << log2h, HL = H / 4, len = HL / 64 + 64;
-    std::vector<cf> tw((size_t)3 * len);
-    const double two_pi = 6.283185307179586476925286766559;
-    for (int r = 1; r <= 3; r++) {
-        cf* t = tw.data() + (size_t)(r - 1) * len;
-        for (int a = 0; a < HL / 64; a++) { double x = -two_pi * (double)r * (double)(a * 64) / H; t[a] = make_cf((float)cos(x), (float)sin(x)); }
-        for (int b = 0; b < 64; b++) { double x = -two_pi * (double)r * (double)b / H; t[HL / 64 + b] = make_cf((float)cos(x), (float)sin(x)); }
-    }
-    return tw;
-}
-// [4][HL/2]: exp(-2 pi i (4 j + r) / W) for the local bin j the pair slot c of the HL-point plan owns
-inline std::vector<cf> host_quad_spectral_twiddles(int log2h) {
-    const int log2hl = log2h - 2;
-    const PlanDesc d = make_plan(log2hl);
-    const int HL = 1 << log2hl;
-    std::vector<cf> tw((size_t)4 * (HL / 2));
-    const double two_pi = 6.283185307179586476925286766559;
-    for (int r = 0; r < 4; r++)
-        for (int c = 0; c < HL / 2; c++) {
-            int j = rt_pos_to_bin(d, spectral_slot_pos(log2hl, c));
-            double a = -two_pi * (double)(4 * j + r) / (double)(8 * HL);
-            tw[(size_t)r * (HL / 2) + c] = make_cf((float)cos(a), (float)sin(a));
-        }
-    return tw;
-}
-
 // frame-invariant index tables of the spectral steps: padded shared-memory slot indices of the bins
 // a pair / quad thread touches, and the pair's bin number
 inline std::vector<uint2> host_pair_table(int log2h) {

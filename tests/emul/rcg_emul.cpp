@@ -23,7 +23,6 @@ static inline float2 apply(size_t, unsigned bin, unsigned n_bins, float2 v) {
 
 #include "../../rocoder_b200/csrc/rcg_frame.h"
 #include "../../rocoder_b200/csrc/rcg_frame_pair.h"
-#include "../../rocoder_b200/csrc/rcg_frame_quad.h"
 #include "../../rocoder_b200/csrc/rcg_tables.h"
 
 using namespace rcg;
@@ -32,7 +31,6 @@ using namespace rcg;
 // read what another wrote in the same phase): the tests run every case in ascending and descending
 // thread order and demand identical results, which exposes intra-phase races.
 static int g_reverse_threads = 0;
-static int g_use_pair = 0;   // W = 65536: run the fused path on the CTA pair instead of the 4-CTA cluster
 struct HostExec {
     int nt;
     template <class F>
@@ -63,7 +61,6 @@ static std::vector<float> lerp_table(int pitch) {
     for (int j = 0; j < q && j < 128; j++) r[j] = (float)j / (float)q;
     return r;
 }
-static int g_no_fuse = 0;
 
 template <int LOG2H>
 static int emul_run(StretchParams prm) {
@@ -83,7 +80,6 @@ static int emul_run(StretchParams prm) {
     std::vector<uint4> qtab = host_quad_table(LOG2H);
     prm.pair_tab = ptab.data(); prm.quad_tab = qtab.data();
     if (use_half_rate(prm.pitch, prm.flags) && !g_disable_half_rate) prm.flags |= kFlagHalfRate;
-    if (g_no_fuse) prm.flags |= kFlagNoFuse;
     std::vector<cf> S(C::SMEM_CF);
     std::vector<float> tail(H);
     HostExec ex{C::NT};
@@ -143,54 +139,6 @@ static int emul_run_pair(StretchParams prm) {
     return 0;
 }
 
-// W = 65536, fused path on the 4-CTA cluster (rcg_frame_quad.h)
-struct QuadHostExec {
-    int nt;
-    template <class F>
-    void par(F f) {
-        for (int r = 0; r < 4; r++) {
-            const int rr = g_reverse_threads ? 3 - r : r;
-            if (g_reverse_threads) for (int t = nt - 1; t >= 0; t--) f(rr, t);
-            else for (int t = 0; t < nt; t++) f(rr, t);
-        }
-    }
-    template <class F>
-    void par_steps(int n, F f) {
-        const int nw = (nt + 31) / 32;
-        for (int r = 0; r < 4; r++)
-            for (int wi = 0; wi < nw; wi++) {
-                const int w = g_reverse_threads ? nw - 1 - wi : wi;
-                for (int s = 0; s < n; s++)
-                    for (int l = 0; l < 32; l++)
-                        if (w * 32 + l < nt) f(s, r, w * 32 + l);
-            }
-    }
-    template <class F>
-    void par_cluster(F f) { par(f); }
-    void cluster_sync() {}
-};
-
-static int emul_run_quad(StretchParams prm) {
-    using C = FrameCfg<kQuadLog2HL>;
-    std::vector<float> window(kPairW), env(kPairH);
-    host_hanning(window.data(), kPairW);
-    host_crossfade_compensation(env.data(), kPairH);
-    std::vector<cf> tw = host_pass_twiddles(kQuadLog2HL);
-    std::vector<cf> cross = host_quad_cross_twiddles(kPairLog2HL + 1), spec = host_quad_spectral_twiddles(kPairLog2HL + 1);
-    std::vector<uint2> ptab = host_pair_table(kQuadLog2HL);
-    prm.window = window.data(); prm.env = env.data();
-    std::vector<float> lr = lerp_table(prm.pitch);
-    prm.lerp_ratio = lr.data();
-    std::vector<float> scratch(3 * (size_t)kPairH);
-    QuadTables qt{cross.data(), spec.data(), tw.data(), ptab.data(), scratch.data()};
-    std::vector<cf> S0(C::SMEM_CF), S1(C::SMEM_CF), S2(C::SMEM_CF), S3(C::SMEM_CF);
-    cf* bufs[4] = {S0.data(), S1.data(), S2.data(), S3.data()};
-    QuadHostExec ex{C::NT};
-    const int items = prm.channels * prm.n_runs;
-    for (int item = 0; item < items; item++) run_work_item_quad(ex, bufs, prm, qt, item, scratch.data(), true);
-    return 0;
-}
-
 static int emul_boundary_pair(StretchParams prm, const float* head, const float* tail_prev) {
     using C = FrameCfg<kPairLog2HL>;
     std::vector<float> env(kPairH), stage(kPairH);
@@ -223,10 +171,7 @@ extern "C" {
 
 // force the full-rate synthesis path even for even pitch multiples (A/B checks)
 void rcg_emul_disable_half_rate(int v) { g_disable_half_rate = v; }
-// keep load and overlap-add as separate phases (A/B checks of the fused phase)
-void rcg_emul_no_fuse(int v) { g_no_fuse = v; }
 void rcg_emul_reverse_threads(int v) { g_reverse_threads = v; }
-void rcg_emul_use_pair(int v) { g_use_pair = v; }
 
 // Processes frames [frame_begin, frame_end) of every channel.  See StretchParams.
 int rcg_emul_stretch(int log2w, const float* in, long long in_stride, long long in_origin,
@@ -245,7 +190,7 @@ int rcg_emul_stretch(int log2w, const float* in, long long in_stride, long long 
     p.amp = amp; p.inv_w = 1.0f / (float)(1 << log2w); p.flags = flags;
     p.keys = make_philox_keys(seed);
     p.tail_in = tail_in; p.tail_out = tail_out; p.head_out = head_out;
-    if (log2w == 16) return g_use_pair ? emul_run_pair(p) : emul_run_quad(p);
+    if (log2w == 16) return emul_run_pair(p);
     switch (log2w - 1) {
 #define CASE(L) case L: return emul_run<L>(p);
         CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)

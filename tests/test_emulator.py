@@ -123,24 +123,6 @@ def test_half_rate_synthesis_even_pitch(p, W):
 
 
 @pytest.mark.parametrize("n,f,p,W", [(30000, 4.0, 1, 2048), (40000, 8.0, 2, 4096), (70000, 8.0, 2, 16384),
-                                     (100000, 1.0, 1, 16384), (3000, 2.0, 2, 64), (5000, 1.0, 1, 256),
-                                     (90000, 3.0, 1, 32768), (9000, 2.0, 2, 1024)])
-@pytest.mark.parametrize("run_len", [1, 4, 1000])
-def test_fused_ola_load_phase_is_bit_identical(n, f, p, W, run_len):
-    """pitch 1 / pitch 2 fuse the next frame's load into the overlap-add phase (no barrier between):
-    bit-identical to the separate phases, for every run length (halo frames, ragged last runs)"""
-    x = _input(n, seed=W)
-    fused = ol.emul_process_all(x, f, p, W, seed=5, run_len=run_len)
-    ol.emulator().rcg_emul_no_fuse(1)
-    try:
-        plain = ol.emul_process_all(x, f, p, W, seed=5, run_len=run_len)
-    finally:
-        ol.emulator().rcg_emul_no_fuse(0)
-    assert not np.isnan(fused).any()
-    assert np.array_equal(fused, plain)
-
-
-@pytest.mark.parametrize("n,f,p,W", [(30000, 4.0, 1, 2048), (40000, 8.0, 2, 4096), (70000, 8.0, 2, 16384),
                                      (9000, 20.0, -3, 1024), (6000, 2.5, 5, 512), (9000, 2.0, 4, 1024),
                                      (90000, 3.0, 1, 32768), (3000, 2.0, 2, 64)])
 def test_phases_are_race_free(n, f, p, W):
@@ -159,20 +141,10 @@ def test_phases_are_race_free(n, f, p, W):
     assert np.array_equal(a, b) and np.array_equal(b0, b1)
 
 
-@pytest.fixture(params=["quad", "pair"])
-def layout_65536(request):
-    """W = 65536 fused path: 4-CTA cluster (rcg_frame_quad.h, what the engine launches) or the CTA pair
-    (rcg_frame_pair.h, kept for the frequency-kernel path and as the fallback)"""
-    ol.emulator().rcg_emul_use_pair(1 if request.param == "pair" else 0)
-    yield request.param
-    ol.emulator().rcg_emul_use_pair(0)
-
-
 @pytest.mark.parametrize("f,p,n", [(2.0, 1, 300000), (4.0, 2, 200000), (3.0, -3, 200000), (1.0, 3, 150000)])
-def test_window_65536_clusters(f, p, n, layout_65536):
-    """W = 65536 splits a frame across a thread-block cluster (bin classes mod 2 or mod 4, DSMEM exchange of
-    the outer radix stage and, on four CTAs, of the partner bins of classes 1 and 3): bit-exact indexing, PCM
-    within tolerance, order-independent phases"""
+def test_window_65536_clusters(f, p, n):
+    """W = 65536 splits a frame across a 2-CTA thread-block cluster (even / odd bins, DSMEM exchange of the outer
+    radix-2 stage): bit-exact indexing, PCM within tolerance, order-independent phases"""
     W = 65536
     x = _input(n, seed=p + 7)
     assert np.array_equal(ol.emul_process_all(x, f, p, W, bypass=True), ol.process_all(x, f, p, W, mode=ol.RO_PHASE_BYPASS))
@@ -187,7 +159,7 @@ def test_window_65536_clusters(f, p, n, layout_65536):
     assert np.array_equal(got, again)
 
 
-def test_window_65536_segments(layout_65536):
+def test_window_65536_segments():
     f, p, W, n = 2.0, 1, 65536, 500000
     x = _input(n, seed=3)
     calls, _, out_len = ol.expected_counts(n, f, p, W)

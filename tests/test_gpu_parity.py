@@ -311,20 +311,3 @@ def test_custom_window_vector():
     while not st.is_done():
         wins.append(st.next_window())
     assert np.array_equal(np.concatenate(wins), got)
-
-
-@pytest.mark.parametrize("n,f,p", [(300000, 4.0, 1), (200000, 4.0, 2), (200000, 3.0, -3)])
-def test_window_65536_four_cta_cluster(n, f, p, monkeypatch):
-    """the opt-in 4-CTA-cluster layout of the W = 65536 fused path (rcg_frame_quad.h, RCG_QUAD=1 at rcg_create)
-    against the oracle, and against the default CTA-pair layout on the index path"""
-    W = 65536
-    x = _input(n)
-    pair_bypass = _gpu(x, f, p, W, flags=rb.RCG_FLAG_BYPASS_RESYNTH)
-    monkeypatch.setenv("RCG_QUAD", "1")
-    ref = ol.process_all(x, f, p, W, seed=1234, precision=64)
-    with rb.Engine(2, 48000, W, f, 1.0, p, seed=1234) as e:
-        got = e.process_all(x)
-        launches = e.launch_count()
-    assert launches >= 1 and got.shape == ref.shape
-    assert np.abs(got - ref).max() <= TOL_MAX_ABS and ol.snr_db(ref, got) > TOL_SNR_DB
-    assert np.array_equal(_gpu(x, f, p, W, flags=rb.RCG_FLAG_BYPASS_RESYNTH), pair_bypass)

@@ -43,13 +43,7 @@ def test_emulated_fused_local_plugin_matches_oracle(n, f, p, W):
     included -- against the oracle calling the same kernel (`tilt`) on the whole spectrum"""
     x = _input(n)
     ref = ol.process_all(x, f, p, W, seed=4, precision=64, plugin=plugins.tilt)
-    ol.emulator().rcg_emul_use_pair(1)      # the fused form at W = 65536 is built on the CTA pair
-    ol.emulator_local_plugin().rcg_emul_use_pair(1)
-    try:
-        got = ol.emul_process_all(x, f, p, W, seed=4, lib=ol.emulator_local_plugin())
-    finally:
-        ol.emulator().rcg_emul_use_pair(0)
-        ol.emulator_local_plugin().rcg_emul_use_pair(0)
+    got = ol.emul_process_all(x, f, p, W, seed=4, lib=ol.emulator_local_plugin())
     assert got.shape == ref.shape
     assert np.abs(got - ref).max() <= 1e-4 and (not ref.any() or ol.snr_db(ref, got) > 100.0)
     plain = ol.emul_process_all(x, f, p, W, seed=4)
