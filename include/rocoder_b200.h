@@ -26,7 +26,8 @@
 extern "C" {
 #endif
 
-#define RCG_ABI_VERSION 1
+#define RCG_ABI_VERSION 2
+#define RCG_MAX_DEVICES 16
 
 typedef enum rcg_status {
     RCG_OK = 0,
@@ -45,9 +46,26 @@ typedef enum rcg_status {
 /* flags for rcg_config.flags */
 #define RCG_FLAG_RANDOM_SEED 1u   /* ignore `seed`, draw one from the OS like rand::thread_rng (fft.rs:64) */
 #define RCG_FLAG_BYPASS_RESYNTH 2u /* test hook: resynth(s)[n] = (s[n]*w[n])*w[n]; checks all indexing bit-exactly */
+#define RCG_FLAG_SHARD_HALO 4u     /* multi-device time shards recompute the frame before their first one instead of
+                                      receiving the carried half window from the neighbour device: zero communication,
+                                      bit-identical output; the check of the exchange path (see n_devices) */
+#define RCG_FLAG_SHARD_ALWAYS 8u   /* use every listed device even for jobs too small to gain from it (tests) */
 
-/* Arguments of Stretcher::new (stretcher.rs:30-39) plus the phase seed and the device.
- * The Hann window of main.rs:131 is built internally from window_len. */
+/* Arguments of Stretcher::new (stretcher.rs:30-39) plus the phase seed and the device(s).
+ * The Hann window of main.rs:131 is built internally from window_len.
+ *
+ * Several GPUs behind one engine (n_devices > 1): the reference makes ONE call per file for all channels
+ * (main.rs:133-156) and its channels are independent Stretchers (stretcher_processor.rs:55-71), so
+ * rcg_process_all partitions the job over the listed devices itself -- by channel when the channel count
+ * divides evenly (no communication at all), otherwise by time: contiguous call ranges of every channel, each
+ * device reading its own input span, and ONE exchange per boundary: the carried half window (channels x W/2
+ * floats, stretcher.rs:101-102) goes from device g to g+1 (cudaMemcpyPeerAsync: NVLink peer-to-peer where the
+ * devices are peers) and is added into the first block of g+1 -- there is no phase carry to pass (fft.rs:63-68
+ * draws every phase independently).  Output is bit-identical for every device list.  The same ordinal may be
+ * listed more than once (shards then share that GPU).  Jobs too small to amortise a second device, and jobs with
+ * a host `apply` on top of the kernel stack (it must be called from one thread in the reference's order), run on
+ * devices[0] alone.  Streaming calls are served by device (channel mod n_devices); rcg_process_segment /
+ * rcg_finish_boundary run on the listed device their buffers live on. */
 typedef struct rcg_config {
     uint32_t struct_size;     /* sizeof(rcg_config) */
     uint32_t channels;        /* AudioSpec.channels  (audio.rs:32-37); one Stretcher per channel (main.rs:133-153) */
@@ -62,6 +80,9 @@ typedef struct rcg_config {
     uint32_t flags;
     uint32_t max_lookahead_calls; /* streaming: calls computed per launch when input allows (0 = default 64) */
     uint32_t first_channel;   /* channel index of row 0: Stretcher c of main.rs:133-153 is an engine with channels=1, first_channel=c */
+    /* -- ABI 2 (a struct_size that ends before this line is accepted and means one device) -- */
+    uint32_t n_devices;       /* 0 or 1: `device` alone; > 1: devices[0 .. n_devices) share every rcg_process_all job */
+    int32_t devices[RCG_MAX_DEVICES];
 } rcg_config;
 
 /* The constants Stretcher::new derives (stretcher.rs:40-59), f32 arithmetic, truncating casts. */
@@ -111,9 +132,13 @@ int rcg_set_window(rcg_engine *e, const float *window, size_t len);
 /* -- batched, host buffers: what main.rs:133-160 + AudioBus::into_audio (audio.rs:152-172)
  * do for a whole file.  in[c] holds n_in samples of channel c (the one chunk main.rs:148
  * sends, sender then dropped); out[c] receives the concatenated windows.  Host<->device
- * copies happen inside; pinned buffers (rcg_host_alloc) make them asynchronous. */
+ * copies happen inside; pinned buffers (rcg_host_alloc) make them asynchronous.  With n_devices > 1 every
+ * listed device takes its share (see rcg_config). */
 int rcg_process_all(rcg_engine *e, const float *const *in, uint64_t n_in, float *const *out,
                     uint64_t out_cap, uint64_t *n_out);
+/* How the last rcg_process_all was partitioned: devices used, "channel" / "time" / "none" split (static string),
+ * and the number of carried-half-window exchanges between devices. */
+int rcg_last_partition(const rcg_engine *e, uint32_t *devices_used, const char **split, uint32_t *exchanges);
 
 /* -- batched, device-resident: calls [first_call, first_call + n_calls) of every channel.
  * d_in[c * in_stride + i] is input sample in_origin + i of channel c; samples at or past
@@ -172,7 +197,12 @@ int rcg_is_done(rcg_engine *e, uint32_t channel, int *done);
  * (fft.rs:93, README.md:108-113): in/out are n_bins interleaved (re, im) pairs, the full
  * W-bin unnormalised spectrum in natural order.  Return 0; non-zero stands for a panic:
  * the newest kernel is popped and the frame retried with the previous one, else passed
- * through (fft.rs:101-106).  Called once per frame per channel, frames in order. */
+ * through (fft.rs:101-106).  Called once per frame per channel, frames in order.
+ * Clock: the reference reads SystemTime before every frame (fft.rs:89-92) and polls for a new library before every
+ * frame (fft.rs:78-81).  Here a host `apply` gets the wall clock of its own call; a device `apply` gets ONE
+ * elapsed_ms per launch -- all frames of a batch (up to 1 GiB of spectra, or a whole fused launch) are computed at
+ * the same moment -- and new libraries are taken between batches.  A segment that starts mid-stream without
+ * d_tail_in re-analyses the frame before it, so `apply` sees that frame once more. */
 typedef int (*rcg_apply_fn)(size_t elapsed_ms, const float *in_re_im, size_t n_bins,
                             float *out_re_im);
 /* what receiving a Library on kernel_recv does (fft.rs:78-81) */
@@ -232,6 +262,8 @@ int rcg_host_free(void *ptr);
  * node bound to, or -1 when the box exposes no NUMA information (then nothing changes).  Optional: call it once
  * per rank before rcg_host_alloc / rcg_create on multi-socket, multi-GPU boxes. */
 int rcg_bind_host_thread(int device, int *numa_node);
+/* number of CUDA devices this library can run on (sm_100); 0 with RCG_OK when there is none */
+int rcg_device_count(int *n);
 /* FP32 FMA throughput of the current device, TFLOP/s: the measured compute-roofline denominator */
 int rcg_measure_fp32_peak(double *tflops, int reps);
 /* kernels launched by this engine so far */

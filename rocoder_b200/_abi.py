@@ -27,6 +27,9 @@ RCG_ERR_STATE = 10
 
 RCG_FLAG_RANDOM_SEED = 1
 RCG_FLAG_BYPASS_RESYNTH = 2
+RCG_FLAG_SHARD_HALO = 4
+RCG_FLAG_SHARD_ALWAYS = 8
+RCG_MAX_DEVICES = 16
 RCG_SEG_DEFER_FIRST = 1
 
 
@@ -47,6 +50,7 @@ class rcg_config(C.Structure):
         ("pitch_multiple", C.c_int32), ("buffer_dur_s", C.c_float), ("seed", C.c_uint64),
         ("device", C.c_int32), ("flags", C.c_uint32), ("max_lookahead_calls", C.c_uint32),
         ("first_channel", C.c_uint32),
+        ("n_devices", C.c_uint32), ("devices", C.c_int32 * RCG_MAX_DEVICES),
     ]
 
 
@@ -98,6 +102,7 @@ def lib() -> C.CDLL:
         "rcg_set_window": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
         "rcg_get_plan": (C.c_int, [C.c_void_p, P(rcg_plan_info)]),
         "rcg_process_all": (C.c_int, [C.c_void_p, P(C.c_void_p), C.c_uint64, P(C.c_void_p), C.c_uint64, P(C.c_uint64)]),
+        "rcg_last_partition": (C.c_int, [C.c_void_p, P(C.c_uint32), P(C.c_char_p), P(C.c_uint32)]),
         "rcg_process_segment": (C.c_int, [C.c_void_p, P(rcg_segment)]),
         "rcg_finish_boundary": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
         "rcg_synchronize": (C.c_int, [C.c_void_p]),
@@ -118,6 +123,7 @@ def lib() -> C.CDLL:
                                       C.c_uint64, C.c_void_p]),
         "rcg_fade_keyframes": (C.c_int, [C.c_float, C.c_uint32, C.c_uint64, P(C.c_uint64), P(C.c_uint64), P(C.c_uint64)]),
         "rcg_measure_fp32_peak": (C.c_int, [P(C.c_double), C.c_int]),
+        "rcg_device_count": (C.c_int, [P(C.c_int)]),
         "rcg_host_alloc": (C.c_int, [P(C.c_void_p), C.c_size_t]),
         "rcg_bind_host_thread": (C.c_int, [C.c_int, P(C.c_int)]),
         "rcg_host_free": (C.c_int, [C.c_void_p]),
@@ -142,7 +148,8 @@ def check(status: int) -> None:
 
 def make_config(channels: int, sample_rate: int, window_len: int = 16384, factor: float = 1.0,
                 amplitude: float = 1.0, pitch_multiple: int = 1, buffer_dur_s: float = 1.0, seed: int = 0,
-                device: int = 0, flags: int = 0, max_lookahead_calls: int = 0, first_channel: int = 0) -> rcg_config:
+                device: int = 0, flags: int = 0, max_lookahead_calls: int = 0, first_channel: int = 0,
+                devices=None) -> rcg_config:
     cfg = rcg_config()
     cfg.struct_size = C.sizeof(rcg_config)
     cfg.channels = channels
@@ -157,4 +164,12 @@ def make_config(channels: int, sample_rate: int, window_len: int = 16384, factor
     cfg.flags = flags
     cfg.max_lookahead_calls = max_lookahead_calls
     cfg.first_channel = first_channel
+    if devices is not None:   # several GPUs behind one engine (the same ordinal may repeat)
+        devices = [int(d) for d in devices]
+        if not 1 <= len(devices) <= RCG_MAX_DEVICES:
+            raise ValueError(f"1 to {RCG_MAX_DEVICES} devices")
+        cfg.n_devices = len(devices)
+        for i, d in enumerate(devices):
+            cfg.devices[i] = d
+        cfg.device = devices[0]
     return cfg

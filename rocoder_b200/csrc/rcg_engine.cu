@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -17,6 +18,7 @@
 #include <mutex>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rocoder_b200.h"
@@ -185,6 +187,8 @@ struct FreqKernel {
     cudaLibrary_t lib = nullptr;
     cudaKernel_t dev = nullptr;     // gather form: runs on the spectra in HBM between analysis and synthesis
     cudaKernel_t fused = nullptr;   // bin-local form: the whole stretch kernel with the user's apply compiled in
+    cudaLibrary_t twin_lib = nullptr;   // bin-local form again as a plain per-bin kernel over spectra in HBM (`dev` points
+                                        // into it): takes over mid-batch when the kernel above it on the stack fails
 };
 
 struct rcg_engine {
@@ -230,8 +234,22 @@ struct rcg_engine {
     // hotswapper.rs:14-33: watched source file, builds queued for the next batch
     std::unique_ptr<rcg::KernelWatcher> watcher;
     uint32_t swaps = 0;
+    // ---- several devices behind one engine (rcg_config.n_devices > 1) --------------------------------------
+    // The object the caller holds only routes: `shards` are complete single-device engines, one per listed device
+    // (all channels each, so any shard can take any channel range).  Exchange buffers of a shard that runs a
+    // time range: raw first half of its first block, the neighbour's carried half window, and the event that says
+    // its own last carried half window is final.
+    std::vector<rcg_engine*> shards;
+    float *d_head = nullptr, *d_prev_tail = nullptr;
+    cudaEvent_t tail_ready = nullptr;
+    const float* final_tail = nullptr;      // where the last launch of the current job left the carried half window
+    // how the last rcg_process_all was partitioned
+    uint32_t part_devices = 1, part_exchanges = 0;
+    const char* part_split = "none";
 };
 static int drain_watcher(rcg_engine* e, uint32_t* swapped);
+static uint64_t total_launches(const rcg_engine* e);
+static int install_everywhere(rcg_engine* e, const std::vector<char>& cubin, const std::vector<char>* twin);
 
 static int pick_run_len(uint64_t frames_per_channel, uint32_t channels, int slots) {
     // minimise waves * (frames per item + 1 halo frame)
@@ -248,14 +266,28 @@ static int pick_run_len(uint64_t frames_per_channel, uint32_t channels, int slot
     return best;
 }
 
-extern "C" int rcg_create(const rcg_config* cfg, rcg_engine** out) {
-    if (!cfg || !out) return fail(RCG_ERR_INVALID_ARG, "null argument");
+// rcg_config as ABI 1 laid it out (everything before n_devices): still accepted, means one device
+static constexpr size_t kConfigSizeV1 = offsetof(rcg_config, n_devices);
+
+static int create_group(const rcg_config& cfg, const rcg_plan_info& pl, rcg_engine** out);
+
+extern "C" int rcg_create(const rcg_config* cfg_in, rcg_engine** out) {
+    if (!cfg_in || !out) return fail(RCG_ERR_INVALID_ARG, "null argument");
     *out = nullptr;
-    if (cfg->struct_size != sizeof(rcg_config))
-        return fail(RCG_ERR_INVALID_ARG, "rcg_config.struct_size %u != %zu", cfg->struct_size, sizeof(rcg_config));
+    if (cfg_in->struct_size != sizeof(rcg_config) && cfg_in->struct_size != kConfigSizeV1)
+        return fail(RCG_ERR_INVALID_ARG, "rcg_config.struct_size %u: expected %zu (or %zu, ABI 1)", cfg_in->struct_size,
+                    sizeof(rcg_config), kConfigSizeV1);
+    rcg_config cfg_full;
+    memset(&cfg_full, 0, sizeof(cfg_full));
+    memcpy(&cfg_full, cfg_in, cfg_in->struct_size);
+    cfg_full.struct_size = sizeof(rcg_config);
+    const rcg_config* cfg = &cfg_full;
+    if (cfg->n_devices > RCG_MAX_DEVICES) return fail(RCG_ERR_INVALID_ARG, "n_devices %u > %d", cfg->n_devices, RCG_MAX_DEVICES);
     rcg_plan_info pl;
     int rc = rcg_plan(cfg, &pl);
     if (rc) return rc;
+    if (cfg->n_devices > 1) return create_group(cfg_full, pl, out);
+    if (cfg->n_devices == 1) cfg_full.device = cfg_full.devices[0];
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (ndev == 0) return fail(RCG_ERR_NO_DEVICE, "no CUDA device");
@@ -349,6 +381,9 @@ extern "C" int rcg_create(const rcg_config* cfg, rcg_engine** out) {
     TRY_E(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
     TRY_E(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) TRY_E(cudaMalloc(&e->d_tail_pp[i], (size_t)cfg->channels * H * sizeof(float)));
+    TRY_E(cudaMalloc(&e->d_head, (size_t)cfg->channels * H * sizeof(float)));
+    TRY_E(cudaMalloc(&e->d_prev_tail, (size_t)cfg->channels * H * sizeof(float)));
+    TRY_E(cudaEventCreateWithFlags(&e->tail_ready, cudaEventDisableTiming));
     e->ch.resize(cfg->channels);
     for (auto& c : e->ch)
         for (int i = 0; i < 2; i++) {
@@ -360,9 +395,54 @@ extern "C" int rcg_create(const rcg_config* cfg, rcg_engine** out) {
     return RCG_OK;
 }
 
+// n_devices > 1: one complete engine per listed device; the returned object routes
+static int create_group(const rcg_config& cfg, const rcg_plan_info& pl, rcg_engine** out) {
+    rcg_engine* g = new rcg_engine();
+    g->cfg = cfg;
+    g->plan = pl;
+    g->log2w = log2_exact(cfg.window_len);
+    g->device = cfg.devices[0];
+    g->seed = cfg.seed;
+    if (cfg.flags & RCG_FLAG_RANDOM_SEED) {   // one seed for every shard, or the shards would disagree
+        std::random_device rd;
+        g->seed = ((uint64_t)rd() << 32) ^ rd();
+    }
+    for (uint32_t i = 0; i < cfg.n_devices; i++) {
+        rcg_config c = cfg;
+        c.n_devices = 0;
+        c.device = cfg.devices[i];
+        c.seed = g->seed;
+        c.flags &= ~(uint32_t)RCG_FLAG_RANDOM_SEED;
+        rcg_engine* sh = nullptr;
+        const int rc = rcg_create(&c, &sh);
+        if (rc) { rcg_destroy(g); return rc; }
+        g->shards.push_back(sh);
+    }
+    // neighbours exchange the carried half window: direct peer access where the hardware offers it (NVLink on an
+    // HGX board); cudaMemcpyPeerAsync stages through the host otherwise
+    for (size_t i = 0; i + 1 < g->shards.size(); i++) {
+        const int a = g->shards[i]->device, b = g->shards[i + 1]->device;
+        if (a == b) continue;
+        int ok = 0;
+        if (cudaDeviceCanAccessPeer(&ok, b, a) == cudaSuccess && ok) {
+            cudaSetDevice(b);
+            if (cudaDeviceEnablePeerAccess(a, 0) != cudaSuccess) (void)cudaGetLastError();   // already enabled is fine
+        }
+        (void)cudaGetLastError();
+    }
+    *out = g;
+    return RCG_OK;
+}
+
 extern "C" void rcg_destroy(rcg_engine* e) {
     if (!e) return;
     e->watcher.reset();   // joins the polling thread
+    if (!e->shards.empty()) {
+        for (rcg_engine* sh : e->shards) rcg_destroy(sh);
+        for (void* l : e->libs) dlclose(l);
+        delete e;
+        return;
+    }
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->d2h) cudaStreamSynchronize(e->d2h);
@@ -373,7 +453,9 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     cudaFree(e->d_pair_cross); cudaFree(e->d_pair_even); cudaFree(e->d_pair_odd);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_tail_pp[0]); cudaFree(e->d_tail_pp[1]);
     cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_spec); cudaFree(e->d_spec2);
-    for (auto& k : e->kernels) if (k.lib) cudaLibraryUnload(k.lib);
+    for (auto& k : e->kernels) { if (k.lib) cudaLibraryUnload(k.lib); if (k.twin_lib) cudaLibraryUnload(k.twin_lib); }
+    cudaFree(e->d_head); cudaFree(e->d_prev_tail);
+    if (e->tail_ready) cudaEventDestroy(e->tail_ready);
     cudaFree(e->d_plug_tail[0]); cudaFree(e->d_plug_tail[1]);
     if (e->h_spec) cudaFreeHost(e->h_spec);
     if (e->h_sout) cudaFreeHost(e->h_sout);
@@ -391,12 +473,36 @@ extern "C" void rcg_destroy(rcg_engine* e) {
 extern "C" int rcg_set_window(rcg_engine* e, const float* window, size_t len) {
     if (!e || !window) return fail(RCG_ERR_INVALID_ARG, "null argument");
     if (len != e->cfg.window_len) return fail(RCG_ERR_INVALID_ARG, "window has %zu samples, engine window_len is %u", len, e->cfg.window_len);
-    if (e->launches > 0) return fail(RCG_ERR_STATE, "the window must be set before processing starts");
+    if (!e->shards.empty()) {
+        for (rcg_engine* sh : e->shards)
+            if (int rc = rcg_set_window(sh, window, len)) return rc;
+        return RCG_OK;
+    }
+    if (total_launches(e) > 0) return fail(RCG_ERR_STATE, "the window must be set before processing starts");
     CUDA_TRY(cudaSetDevice(e->device));
     std::vector<float> w(window, window + len), we = host_decimate2(w);
     CUDA_TRY(cudaMemcpy(e->d_window, w.data(), len * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(e->d_window_even, we.data(), we.size() * sizeof(float), cudaMemcpyHostToDevice));
     return RCG_OK;
+}
+
+static uint64_t total_launches(const rcg_engine* e) {
+    uint64_t n = e->launches;
+    for (const rcg_engine* sh : e->shards) n += sh->launches;
+    return n;
+}
+
+// the shard of a multi-device engine whose device owns the device pointer `p` (the engine itself when it has one device)
+static rcg_engine* shard_for_pointer(rcg_engine* e, const void* p) {
+    if (e->shards.empty()) return e;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeDevice) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    for (rcg_engine* sh : e->shards)
+        if (sh->device == at.device) return sh;
+    return nullptr;
 }
 
 extern "C" int rcg_get_plan(const rcg_engine* e, rcg_plan_info* out) {
@@ -406,11 +512,16 @@ extern "C" int rcg_get_plan(const rcg_engine* e, rcg_plan_info* out) {
 }
 extern "C" int rcg_launch_count(const rcg_engine* e, uint64_t* n) {
     if (!e || !n) return fail(RCG_ERR_INVALID_ARG, "null argument");
-    *n = e->launches;
+    *n = total_launches(e);
     return RCG_OK;
 }
 extern "C" int rcg_synchronize(rcg_engine* e) {
     if (!e) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (!e->shards.empty()) {
+        for (rcg_engine* sh : e->shards)
+            if (int rc = rcg_synchronize(sh)) return rc;
+        return RCG_OK;
+    }
     CUDA_TRY(cudaSetDevice(e->device));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->h2d));
@@ -446,9 +557,9 @@ static void fill_params(const rcg_engine* e, StretchParams& p) {
 // launch calls [first_call, first_call + n_calls) for `channels` rows
 struct SpectrumRef { cf* spectrum; long long frame0, frames; };
 
-static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream,
-                          int channel_offset = 0, const SpectrumRef* spec = nullptr, cudaKernel_t fused = nullptr) {
-    if (s.n_calls == 0) return RCG_OK;
+// Caller errors in a segment description, checked once before any kernel is tried: a bad argument must never be
+// mistaken for a failing frequency kernel (which is dropped for good, fft.rs:101-106).
+static int validate_segment(const rcg_engine* e, const rcg_segment& s, bool spectra_given) {
     auto misaligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) != 0; };
     // float2 stores: the carried / head buffers always; the output only where it is written
     // directly from the overlap-add phase (pitch 1, and pitch 2 on the half-rate path)
@@ -457,6 +568,18 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
         return fail(RCG_ERR_INVALID_ARG, "tail / head buffers must be 8-byte aligned");
     if (direct_out && (misaligned(s.d_out) || (s.out_stride & 1)))
         return fail(RCG_ERR_INVALID_ARG, "d_out must be 8-byte aligned and out_stride even for pitch multiples 1 and 2");
+    if ((s.flags & RCG_SEG_DEFER_FIRST) && !s.d_head_out) return fail(RCG_ERR_INVALID_ARG, "RCG_SEG_DEFER_FIRST needs d_head_out");
+    const long long frame_begin = (long long)(s.first_call * e->plan.frames_per_call);
+    const bool needs_halo = frame_begin > 0 && !s.d_tail_in && !(s.flags & RCG_SEG_DEFER_FIRST);
+    if (needs_halo && !spectra_given && s.in_origin > (frame_begin - 1) * (long long)e->plan.sample_step_len)
+        return fail(RCG_ERR_INVALID_ARG, "segment starts at frame %lld but its input starts past the halo frame", frame_begin);
+    return RCG_OK;
+}
+
+static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream,
+                          int channel_offset = 0, const SpectrumRef* spec = nullptr, cudaKernel_t fused = nullptr) {
+    if (s.n_calls == 0) return RCG_OK;
+    if (int rc = validate_segment(e, s, spec != nullptr)) return rc;
     StretchParams p;
     fill_params(e, p);
     if (spec) {
@@ -473,14 +596,7 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
     p.channels = channels;
     p.channel_offset = (int)e->cfg.first_channel + channel_offset;
     p.tail_in = s.d_tail_in; p.tail_out = s.d_tail_out; p.head_out = s.d_head_out;
-    if (s.flags & RCG_SEG_DEFER_FIRST) {
-        if (!s.d_head_out) return fail(RCG_ERR_INVALID_ARG, "RCG_SEG_DEFER_FIRST needs d_head_out");
-        p.flags |= kFlagDeferFirst;
-    }
-    const bool needs_halo = p.frame_begin > 0 && !s.d_tail_in && !(s.flags & RCG_SEG_DEFER_FIRST);
-    if (needs_halo && !spec && s.in_origin > (p.frame_begin - 1) * (long long)p.step)
-        return fail(RCG_ERR_INVALID_ARG, "segment starts at frame %lld but its input starts past the halo frame",
-                    p.frame_begin);
+    if (s.flags & RCG_SEG_DEFER_FIRST) p.flags |= kFlagDeferFirst;
     const uint64_t nframes = (uint64_t)(p.frame_end - p.frame_begin);
     const int max_grid = e->max_grid;
     const int slots = max_grid * e->geo.frames_per_cta;
@@ -509,25 +625,39 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
 }
 
 
+// drop the newest frequency kernel for good ("kernel panicked, retrying with last or noop.", fft.rs:101-106)
+static void pop_kernel(rcg_engine* e) {
+    FreqKernel& k = e->kernels.back();
+    if (k.lib) cudaLibraryUnload(k.lib);
+    if (k.twin_lib) cudaLibraryUnload(k.twin_lib);
+    e->kernels.pop_back();
+}
+
 // ---- frequency-kernel path (fft.rs:76-108) ---------------------------------------------------
-// apply the kernel stack to one frame's spectrum in place; mirrors the pop-and-retry of
-// fft.rs:101-106: a failing kernel is dropped for good, the previous one is tried, and with none
-// left the spectrum passes through unchanged.
-static void apply_kernels(rcg_engine* e, float* spectrum, size_t n_bins) {
-    while (!e->kernels.empty() && e->kernels.back().host) {
+// Host `apply` on one frame's spectrum, in place; mirrors the pop-and-retry of fft.rs:101-106: a failing kernel is
+// dropped for good and the previous one is tried.  Returns false when the frame is still unprocessed because the
+// kernel now on top is a device kernel (the caller continues on the device from this frame on); true otherwise
+// (applied, or no kernel left: the spectrum passes through unchanged).
+static bool apply_host_kernels(rcg_engine* e, float* spectrum, size_t n_bins) {
+    while (!e->kernels.empty()) {
+        if (!e->kernels.back().host) return false;
         const size_t ms = (size_t)std::chrono::duration_cast<std::chrono::milliseconds>(
                               std::chrono::system_clock::now().time_since_epoch()).count();  // fft.rs:89-92
         e->plug_tmp.resize(2 * n_bins);
         if (e->kernels.back().host(ms, spectrum, n_bins, e->plug_tmp.data()) == 0) {
             memcpy(spectrum, e->plug_tmp.data(), 2 * n_bins * sizeof(float));
-            return;
+            return true;
         }
-        e->kernels.pop_back();  // "kernel panicked, retrying with last or noop."
+        pop_kernel(e);  // "kernel panicked, retrying with last or noop."
     }
+    return true;
 }
 
-// calls [first_call, first_call + n_calls) with host frequency kernels: analysis kernel ->
-// spectra to the host -> apply() per frame in the reference's order -> back -> synthesis kernel
+// calls [first_call, first_call + n_calls) with frequency kernels that need the spectra in memory: analysis kernel
+// -> `apply` per frame (host kernels: over PCIe, in the reference's call order; device kernels: in HBM) -> synthesis
+// kernel.  The kernel on top of the stack can change in the middle of a batch (a host kernel fails and a device
+// kernel lies beneath it, or the other way round): the frames not yet processed then continue with the new top,
+// exactly where the reference's retry would (fft.rs:101-106).
 static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream,
                                int channel_offset) {
     const uint64_t k = e->plan.frames_per_call, W = e->plan.window_len, H = W / 2;
@@ -576,45 +706,96 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
         if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "analysis kernel launch failed: %s", cudaGetErrorString(ce));
         e->launches++;
         const size_t bytes = (size_t)channels * nframes * W * sizeof(cf);
+
+        // Frames of the batch in the reference's order (stretcher_processor.rs:62-70: call by call, channel by
+        // channel, frame by frame; a recomputed halo frame first).  next[c] = first frame index (relative to a0) of
+        // channel c that no kernel has processed yet; the spectra live in d_spec, and in h_spec while `on_host`.
+        std::vector<uint64_t> next((size_t)channels, 0);
+        bool on_host = false;
         cf* synth_src = e->d_spec;
-        bool on_device = false;
-        while (!e->kernels.empty() && e->kernels.back().dev) {
-            // device `apply`: the spectra never leave HBM -- analysis -> apply kernel -> synthesis
+        while (!e->kernels.empty()) {
+            bool all_done = true;
+            for (int c = 0; c < channels; c++) all_done = all_done && next[c] >= nframes;
+            if (all_done) break;
+            if (e->kernels.back().host) {
+                if (!on_host) {   // pinned staging only when spectra really visit the host
+                    if (e->h_spec_cap < need) {
+                        if (e->h_spec) cudaFreeHost(e->h_spec);
+                        e->h_spec = nullptr; e->h_spec_cap = 0;
+                        CUDA_TRY(cudaMallocHost(&e->h_spec, need * sizeof(cf)));
+                        e->h_spec_cap = need;
+                    }
+                    CUDA_TRY(cudaMemcpyAsync(e->h_spec, e->d_spec, bytes, cudaMemcpyDeviceToHost, stream));
+                    CUDA_TRY(cudaStreamSynchronize(stream));
+                    on_host = true;
+                }
+                // walk the reference order, skipping what is already done; stop when the top stops being a host kernel
+                bool handed_over = false;
+                const uint64_t lead = halo ? 1 : 0;   // frame 0 of the batch is the halo frame
+                for (uint64_t call = 0; call <= nb && !handed_over; call++) {   // call 0 = the halo frames, if any
+                    const uint64_t fb = call == 0 ? 0 : lead + (call - 1) * k, fe = call == 0 ? lead : lead + call * k;
+                    for (int c = 0; c < channels && !handed_over; c++)
+                        for (uint64_t fi = std::max(fb, next[c]); fi < fe; fi++) {
+                            if (!apply_host_kernels(e, reinterpret_cast<float*>(e->h_spec + ((size_t)c * nframes + fi) * W), W)) {
+                                handed_over = true;
+                                break;
+                            }
+                            next[c] = fi + 1;
+                        }
+                }
+                if (!handed_over)
+                    for (int c = 0; c < channels; c++) next[c] = nframes;
+                continue;
+            }
+            // device `apply` (the gather form, or the per-bin twin of a fused kernel): the spectra stay in HBM
+            if (on_host) {
+                CUDA_TRY(cudaMemcpyAsync(e->d_spec, e->h_spec, bytes, cudaMemcpyHostToDevice, stream));
+                on_host = false;
+            }
             const unsigned n_bins = (unsigned)W;
-            const unsigned long long n_fr = (unsigned long long)channels * nframes;
             const unsigned long long ms = (unsigned long long)std::chrono::duration_cast<std::chrono::milliseconds>(
                                               std::chrono::system_clock::now().time_since_epoch()).count();
-            const cf* in_p = e->d_spec;
-            cf* out_p = e->d_spec2;
-            void* args[] = {(void*)&in_p, (void*)&out_p, (void*)&n_bins, (void*)&n_fr, (void*)&ms};
-            const unsigned long long total = n_fr * n_bins;
-            const unsigned blocks = (unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)e->sm_count * 16);
-            cudaError_t le = cudaLaunchKernel((const void*)e->kernels.back().dev, dim3(blocks), dim3(256), args, 0, stream);
-            if (le == cudaSuccess) { e->launches++; synth_src = e->d_spec2; on_device = true; break; }
-            (void)cudaGetLastError();
-            cudaLibraryUnload(e->kernels.back().lib);
-            e->kernels.pop_back();   // unusable kernel: fall back to the previous one (fft.rs:101-106)
-        }
-        if (!on_device) {
-        if (e->h_spec_cap < need) {   // pinned staging only when spectra really visit the host
-            if (e->h_spec) cudaFreeHost(e->h_spec);
-            e->h_spec = nullptr; e->h_spec_cap = 0;
-            CUDA_TRY(cudaMallocHost(&e->h_spec, need * sizeof(cf)));
-            e->h_spec_cap = need;
-        }
-        CUDA_TRY(cudaMemcpyAsync(e->h_spec, e->d_spec, bytes, cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        // reference order (stretcher_processor.rs:62-70): call by call, channel by channel, frame by frame
-        if (halo)
-            for (int c = 0; c < channels; c++) apply_kernels(e, reinterpret_cast<float*>(e->h_spec + (size_t)c * nframes * W), W);
-        for (uint64_t call = c0; call < c0 + nb; call++)
-            for (int c = 0; c < channels; c++)
-                for (uint64_t r = 0; r < k; r++) {
-                    const size_t fi = (size_t)((long long)(call * k + r) - a0);
-                    apply_kernels(e, reinterpret_cast<float*>(e->h_spec + ((size_t)c * nframes + fi) * W), W);
+            bool failed = false;
+            bool untouched = true;
+            for (int c = 0; c < channels; c++) untouched = untouched && next[c] == 0;
+            if (untouched) {   // the usual case: one launch over the whole batch, synthesis reads its output buffer
+                const unsigned long long n_fr = (unsigned long long)channels * nframes;
+                const cf* in_p = e->d_spec;
+                cf* out_p = e->d_spec2;
+                void* args[] = {(void*)&in_p, (void*)&out_p, (void*)&n_bins, (void*)&n_fr, (void*)&ms};
+                const unsigned long long total = n_fr * n_bins;
+                const unsigned blocks = (unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)e->sm_count * 16);
+                if (cudaLaunchKernel((const void*)e->kernels.back().dev, dim3(blocks), dim3(256), args, 0, stream) == cudaSuccess) {
+                    e->launches++;
+                    synth_src = e->d_spec2;
+                    break;
                 }
-        CUDA_TRY(cudaMemcpyAsync(e->d_spec, e->h_spec, bytes, cudaMemcpyHostToDevice, stream));
+                failed = true;
+            }
+            for (int c = 0; c < channels && !failed; c++) {
+                if (next[c] >= nframes) continue;
+                const unsigned long long n_fr = nframes - next[c];
+                const cf* in_p = e->d_spec + ((size_t)c * nframes + next[c]) * W;
+                cf* out_p = e->d_spec2 + ((size_t)c * nframes + next[c]) * W;
+                void* args[] = {(void*)&in_p, (void*)&out_p, (void*)&n_bins, (void*)&n_fr, (void*)&ms};
+                const unsigned long long total = n_fr * n_bins;
+                const unsigned blocks = (unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)e->sm_count * 16);
+                if (cudaLaunchKernel((const void*)e->kernels.back().dev, dim3(blocks), dim3(256), args, 0, stream) != cudaSuccess) {
+                    failed = true;
+                    break;
+                }
+                e->launches++;
+                // (a gather kernel reads other bins of its frame: it must not write in place)
+                CUDA_TRY(cudaMemcpyAsync(e->d_spec + ((size_t)c * nframes + next[c]) * W, out_p, (size_t)total * sizeof(cf),
+                                         cudaMemcpyDeviceToDevice, stream));
+                next[c] = nframes;
+            }
+            if (failed) {
+                (void)cudaGetLastError();
+                pop_kernel(e);   // unusable kernel: fall back to the previous one (fft.rs:101-106)
+            }
         }
+        if (on_host) CUDA_TRY(cudaMemcpyAsync(e->d_spec, e->h_spec, bytes, cudaMemcpyHostToDevice, stream));
         rcg_segment b = s;
         b.first_call = c0; b.n_calls = nb;
         b.d_out = s.d_out + (c0 - s.first_call) * e->plan.out_len_per_call;
@@ -634,19 +815,29 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
 static int run_segment(rcg_engine* e, const rcg_segment& s, int channels, cudaStream_t stream, int channel_offset) {
     if (e->watcher)   // fft.rs:78-81: take what the hot-swapper has built, without blocking
         if (int rc = drain_watcher(e, nullptr)) return rc;
+    if (s.n_calls == 0) return RCG_OK;
+    if (int rc = validate_segment(e, s, false)) return rc;
     while (!e->kernels.empty() && !(e->cfg.flags & RCG_FLAG_BYPASS_RESYNTH)) {
         if (!e->kernels.back().fused) return run_segment_plugins(e, s, channels, stream, channel_offset);
         // newest kernel is bin-local: one fused launch, no spectra in memory
-        if (launch_segment(e, s, channels, stream, channel_offset, nullptr, e->kernels.back().fused) == RCG_OK) return RCG_OK;
+        const int rc = launch_segment(e, s, channels, stream, channel_offset, nullptr, e->kernels.back().fused);
+        if (rc == RCG_OK) return RCG_OK;
+        if (rc != RCG_ERR_CUDA) return rc;   // not the kernel's fault: keep it
         (void)cudaGetLastError();
-        cudaLibraryUnload(e->kernels.back().lib);
-        e->kernels.pop_back();   // unusable kernel: fall back to the previous one (fft.rs:101-106)
+        pop_kernel(e);   // unusable kernel: fall back to the previous one (fft.rs:101-106)
     }
     return launch_segment(e, s, channels, stream, channel_offset);
 }
 
 extern "C" int rcg_process_segment(rcg_engine* e, const rcg_segment* seg) {
     if (!e || !seg || !seg->d_in || !seg->d_out) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (!e->shards.empty()) {
+        if (e->watcher)
+            if (int rc = drain_watcher(e, nullptr)) return rc;
+        rcg_engine* sh = shard_for_pointer(e, seg->d_out);
+        if (!sh) return fail(RCG_ERR_INVALID_ARG, "d_out is not memory of a device this engine lists");
+        return rcg_process_segment(sh, seg);
+    }
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = seg->stream ? (cudaStream_t)seg->stream : e->stream;
     return run_segment(e, *seg, (int)e->cfg.channels, st, 0);
@@ -655,6 +846,11 @@ extern "C" int rcg_process_segment(rcg_engine* e, const rcg_segment* seg) {
 extern "C" int rcg_finish_boundary(rcg_engine* e, float* d_out, int64_t out_stride, uint64_t first_call,
                                    const float* d_head, const float* d_tail_prev, void* stream) {
     if (!e || !d_out || !d_head || !d_tail_prev) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (!e->shards.empty()) {
+        rcg_engine* sh = shard_for_pointer(e, d_out);
+        if (!sh) return fail(RCG_ERR_INVALID_ARG, "d_out is not memory of a device this engine lists");
+        return rcg_finish_boundary(sh, d_out, out_stride, first_call, d_head, d_tail_prev, stream);
+    }
     CUDA_TRY(cudaSetDevice(e->device));
     StretchParams p;
     fill_params(e, p);
@@ -680,17 +876,38 @@ static cudaEvent_t get_event(rcg_engine* e, size_t i) {
 }
 
 // -- batched, host buffers -----------------------------------------------------------------------
-extern "C" int rcg_process_all(rcg_engine* e, const float* const* in, uint64_t n_in, float* const* out,
-                               uint64_t out_cap, uint64_t* n_out) {
-    if (!e || !out || (!in && n_in)) return fail(RCG_ERR_INVALID_ARG, "null argument");
+// What one device does for its share of a job: channels [ch0, ch0 + nch) x calls [call0, call1).
+// Time shards (call0 > 0) get the half window carried into their first block from the neighbour device
+// (`prev`), or recompute the frame before it (RCG_FLAG_SHARD_HALO).
+struct TailSignal {   // "the event after my last launch has been recorded" (or: I failed), shard g -> shard g + 1
+    std::mutex m;
+    std::condition_variable cv;
+    int state = 0;    // 0 pending, 1 recorded, -1 failed
+    void set(int v) { { std::lock_guard<std::mutex> l(m); state = v; } cv.notify_all(); }
+    int wait() { std::unique_lock<std::mutex> l(m); cv.wait(l, [&] { return state != 0; }); return state; }
+};
+struct RangeJob {
+    uint32_t ch0 = 0, nch = 0;
+    uint64_t call0 = 0, call1 = 0;
+    rcg_engine* prev = nullptr;       // exchange: shard that owns the calls before call0
+    TailSignal* prev_signal = nullptr;
+    TailSignal* my_signal = nullptr;  // set when a later shard waits for this one's carried half window
+};
+
+static int process_range_impl(rcg_engine* e, const float* const* in, uint64_t n_in, float* const* out, const RangeJob& job) {
     CUDA_TRY(cudaSetDevice(e->device));
-    const uint32_t C = e->cfg.channels;
-    uint64_t calls, frames, out_len;
-    counts_for(e->plan, n_in, &calls, &frames, &out_len);
-    if (out_len > out_cap)
-        return fail(RCG_ERR_CAPACITY, "output needs %llu samples per channel, capacity %llu",
-                    (unsigned long long)out_len, (unsigned long long)out_cap);
-    const size_t in_stride = ((size_t)n_in + 3) & ~(size_t)3;
+    const uint32_t C = job.nch;
+    const uint64_t k = e->plan.frames_per_call, step = e->plan.sample_step_len, W = e->plan.window_len;
+    const uint64_t olen = e->plan.out_len_per_call, H = W / 2;
+    const uint64_t calls = job.call1 - job.call0;
+    if (calls == 0 || C == 0) return RCG_OK;
+    const bool exchange = job.call0 > 0 && job.prev != nullptr;
+    const bool halo = job.call0 > 0 && !exchange;
+    // device input = samples [s_lo, s_hi) of every channel of the range
+    const uint64_t s_lo = std::min<uint64_t>(n_in, (job.call0 * k - (halo ? 1 : 0)) * step);
+    const uint64_t s_hi = std::max(s_lo, std::min<uint64_t>(n_in, (job.call1 * k - 1) * step + W));
+    const uint64_t n_span = s_hi - s_lo, out_len = calls * olen;
+    const size_t in_stride = ((size_t)n_span + 3) & ~(size_t)3;
     const size_t out_stride = ((size_t)out_len + 3) & ~(size_t)3;
     if (e->d_in_cap < in_stride * C) {
         cudaFree(e->d_in); e->d_in = nullptr; e->d_in_cap = 0;
@@ -704,54 +921,177 @@ extern "C" int rcg_process_all(rcg_engine* e, const float* const* in, uint64_t n
     }
     // chunks: enough frames per chunk to keep every work lane busy for >= 16 frames,
     // at most 16 chunks, so that device->host copies of finished chunks overlap compute
-    const uint64_t k = e->plan.frames_per_call, step = e->plan.sample_step_len, W = e->plan.window_len;
     const uint64_t slots = (uint64_t)e->max_grid * e->geo.frames_per_cta;
     uint64_t min_calls = (slots * 16 + k * C - 1) / (k * C);
     uint64_t chunk_calls = std::max<uint64_t>(min_calls, (calls + 15) / 16);
     chunk_calls = std::max<uint64_t>(1, std::min(chunk_calls, calls));
-    uint64_t uploaded = 0;  // samples of every channel already on the device
+    uint64_t uploaded = 0;  // samples of the span already on the device
     size_t ev_i = 0;
     int pp = 0;
-    for (uint64_t c0 = 0; c0 < calls; c0 += chunk_calls) {
-        const uint64_t nc = std::min(chunk_calls, calls - c0);
+    for (uint64_t c0 = job.call0; c0 < job.call1; c0 += chunk_calls) {
+        const uint64_t nc = std::min(chunk_calls, job.call1 - c0);
+        const bool first = (c0 == job.call0), last = (c0 + nc == job.call1);
         // input this chunk reads: up to the end of its last frame
         const uint64_t need = std::min<uint64_t>(n_in, ((c0 + nc) * k - 1) * step + W);
-        if (need > uploaded) {
+        const uint64_t need_rel = need > s_lo ? need - s_lo : 0;
+        if (need_rel > uploaded) {
             for (uint32_t c = 0; c < C; c++)
-                CUDA_TRY(cudaMemcpyAsync(e->d_in + c * in_stride + uploaded, in[c] + uploaded,
-                                         (need - uploaded) * sizeof(float), cudaMemcpyHostToDevice, e->h2d));
-            uploaded = need;
+                CUDA_TRY(cudaMemcpyAsync(e->d_in + c * in_stride + uploaded, in[job.ch0 + c] + s_lo + uploaded,
+                                         (need_rel - uploaded) * sizeof(float), cudaMemcpyHostToDevice, e->h2d));
+            uploaded = need_rel;
             cudaEvent_t up = get_event(e, ev_i++);
             CUDA_TRY(cudaEventRecord(up, e->h2d));
             CUDA_TRY(cudaStreamWaitEvent(e->stream, up, 0));
         }
         rcg_segment s{};
-        s.d_in = e->d_in; s.in_stride = (int64_t)in_stride; s.in_origin = 0; s.in_valid = (int64_t)n_in;
-        s.d_out = e->d_out + c0 * e->plan.out_len_per_call; s.out_stride = (int64_t)out_stride;
+        s.d_in = e->d_in; s.in_stride = (int64_t)in_stride; s.in_origin = (int64_t)s_lo; s.in_valid = (int64_t)n_span;
+        s.d_out = e->d_out + (c0 - job.call0) * olen; s.out_stride = (int64_t)out_stride;
         s.first_call = c0; s.n_calls = nc;
-        s.d_tail_in = c0 ? e->d_tail_pp[pp] : nullptr;
+        s.d_tail_in = first ? nullptr : e->d_tail_pp[pp];
         s.d_tail_out = e->d_tail_pp[pp ^ 1];
+        if (first && exchange) { s.flags |= RCG_SEG_DEFER_FIRST; s.d_head_out = e->d_head; }
         pp ^= 1;
-        int rc = run_segment(e, s, (int)C, e->stream, 0);
+        int rc = run_segment(e, s, (int)C, e->stream, (int)job.ch0);
+        if (rc) return rc;
+        if (last) {
+            e->final_tail = s.d_tail_out;
+            if (job.my_signal) {
+                CUDA_TRY(cudaEventRecord(e->tail_ready, e->stream));
+                job.my_signal->set(1);
+            }
+        }
+        cudaEvent_t done = get_event(e, ev_i++);
+        CUDA_TRY(cudaEventRecord(done, e->stream));
+        CUDA_TRY(cudaStreamWaitEvent(e->d2h, done, 0));
+        // the deferred first block leaves later, once the neighbour's half window has been added
+        const uint64_t skip = (first && exchange) ? olen : 0;
+        const uint64_t o0 = (c0 - job.call0) * olen + skip, on = nc * olen - skip;
+        if (on)
+            for (uint32_t c = 0; c < C; c++)
+                CUDA_TRY(cudaMemcpyAsync(out[job.ch0 + c] + job.call0 * olen + o0, e->d_out + c * out_stride + o0,
+                                         on * sizeof(float), cudaMemcpyDeviceToHost, e->d2h));
+    }
+    if (exchange) {
+        // one exchange per boundary: the neighbour's last carried half window (C x W/2 floats), peer to peer
+        if (job.prev_signal->wait() < 0) return fail(RCG_ERR_STATE, "the device before this time shard failed");
+        CUDA_TRY(cudaStreamWaitEvent(e->stream, job.prev->tail_ready, 0));
+        CUDA_TRY(cudaMemcpyPeerAsync(e->d_prev_tail, e->device, job.prev->final_tail, job.prev->device,
+                                     (size_t)C * H * sizeof(float), e->stream));
+        int rc = rcg_finish_boundary(e, e->d_out, (int64_t)out_stride, job.call0, e->d_head, e->d_prev_tail, e->stream);
         if (rc) return rc;
         cudaEvent_t done = get_event(e, ev_i++);
         CUDA_TRY(cudaEventRecord(done, e->stream));
         CUDA_TRY(cudaStreamWaitEvent(e->d2h, done, 0));
-        const uint64_t o0 = c0 * e->plan.out_len_per_call, on = nc * e->plan.out_len_per_call;
         for (uint32_t c = 0; c < C; c++)
-            CUDA_TRY(cudaMemcpyAsync(out[c] + o0, e->d_out + c * out_stride + o0, on * sizeof(float),
+            CUDA_TRY(cudaMemcpyAsync(out[job.ch0 + c] + job.call0 * olen, e->d_out + c * out_stride, olen * sizeof(float),
                                      cudaMemcpyDeviceToHost, e->d2h));
     }
     CUDA_TRY(cudaStreamSynchronize(e->d2h));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return RCG_OK;
+}
+
+static int process_range(rcg_engine* e, const float* const* in, uint64_t n_in, float* const* out, const RangeJob& job) {
+    const int rc = process_range_impl(e, in, n_in, out, job);
+    if (rc && job.my_signal) job.my_signal->set(-1);   // never leave the next shard waiting
+    return rc;
+}
+
+// a host `apply` on top of the stack is called from one thread, in the reference's order: such jobs stay on one device
+static bool top_kernel_is_host(const rcg_engine* e) { return !e->kernels.empty() && e->kernels.back().host != nullptr; }
+
+static int process_all_group(rcg_engine* g, const float* const* in, uint64_t n_in, float* const* out, uint64_t calls,
+                             uint64_t out_len) {
+    if (g->watcher)   // fft.rs:78-81: take what the hot-swapper has built, for every shard, before the job starts
+        if (int rc = drain_watcher(g, nullptr)) return rc;
+    const uint32_t C = g->cfg.channels;
+    // a device must have something to amortise its launch, copies and thread on: >= 8 MB of samples in + out
+    const uint64_t bytes = (uint64_t)C * (n_in + out_len) * sizeof(float);
+    uint32_t G = (uint32_t)std::min<uint64_t>(g->shards.size(), std::max<uint64_t>(1, bytes >> 23));
+    if (g->cfg.flags & RCG_FLAG_SHARD_ALWAYS) G = (uint32_t)g->shards.size();
+    if (top_kernel_is_host(g->shards[0]) && !(g->cfg.flags & RCG_FLAG_BYPASS_RESYNTH)) G = 1;
+    std::vector<RangeJob> jobs;
+    std::vector<std::unique_ptr<TailSignal>> signals;
+    const char* split = "none";
+    if (G > 1 && C % G == 0) {            // by channel: no communication at all (main.rs:133-153)
+        split = "channel";
+        for (uint32_t i = 0; i < G; i++) {
+            RangeJob j;
+            j.ch0 = i * (C / G); j.nch = C / G; j.call0 = 0; j.call1 = calls;
+            jobs.push_back(j);
+        }
+    } else if (G > 1 && calls >= 2) {     // by time: contiguous call ranges of every channel
+        split = "time";
+        G = (uint32_t)std::min<uint64_t>(G, calls);
+        const bool exchange = !(g->cfg.flags & RCG_FLAG_SHARD_HALO);
+        for (uint32_t i = 0; i < G; i++) signals.emplace_back(new TailSignal());
+        for (uint32_t i = 0; i < G; i++) {
+            RangeJob j;
+            j.ch0 = 0; j.nch = C;
+            j.call0 = calls * i / G; j.call1 = calls * (i + 1) / G;
+            if (exchange && i > 0) { j.prev = g->shards[i - 1]; j.prev_signal = signals[i - 1].get(); }
+            if (exchange && i + 1 < G) j.my_signal = signals[i].get();
+            jobs.push_back(j);
+        }
+    } else {
+        RangeJob j;
+        j.ch0 = 0; j.nch = C; j.call0 = 0; j.call1 = calls;
+        jobs.push_back(j);
+    }
+    g->part_devices = (uint32_t)jobs.size();
+    g->part_split = jobs.size() > 1 ? split : "none";
+    g->part_exchanges = 0;
+    for (auto& j : jobs) if (j.prev) g->part_exchanges++;
+    std::vector<int> rcs(jobs.size(), RCG_OK);
+    std::vector<std::string> errs(jobs.size());
+    auto work = [&](size_t i) {
+        rcs[i] = process_range(g->shards[i], in, n_in, out, jobs[i]);
+        if (rcs[i]) errs[i] = g_err;   // g_err is thread-local: carry the message back to the caller's thread
+    };
+    std::vector<std::thread> threads;
+    for (size_t i = 1; i < jobs.size(); i++) threads.emplace_back(work, i);
+    work(0);
+    for (auto& t : threads) t.join();
+    for (size_t i = 0; i < jobs.size(); i++)
+        if (rcs[i]) return fail(rcs[i], "device %d: %s", g->shards[i]->device, errs[i].c_str());
+    return RCG_OK;
+}
+
+extern "C" int rcg_process_all(rcg_engine* e, const float* const* in, uint64_t n_in, float* const* out,
+                               uint64_t out_cap, uint64_t* n_out) {
+    if (!e || !out || (!in && n_in)) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    const uint32_t C = e->cfg.channels;
+    uint64_t calls, frames, out_len;
+    counts_for(e->plan, n_in, &calls, &frames, &out_len);
+    if (out_len > out_cap)
+        return fail(RCG_ERR_CAPACITY, "output needs %llu samples per channel, capacity %llu",
+                    (unsigned long long)out_len, (unsigned long long)out_cap);
+    int rc;
+    if (!e->shards.empty()) {
+        rc = process_all_group(e, in, n_in, out, calls, out_len);
+    } else {
+        RangeJob j;
+        j.ch0 = 0; j.nch = C; j.call0 = 0; j.call1 = calls;
+        rc = process_range(e, in, n_in, out, j);
+    }
+    if (rc) return rc;
     if (n_out)
         for (uint32_t c = 0; c < C; c++) n_out[c] = out_len;
+    return RCG_OK;
+}
+
+extern "C" int rcg_last_partition(const rcg_engine* e, uint32_t* devices_used, const char** split, uint32_t* exchanges) {
+    if (!e) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (devices_used) *devices_used = e->part_devices;
+    if (split) *split = e->part_split;
+    if (exchanges) *exchanges = e->part_exchanges;
     return RCG_OK;
 }
 
 // -- streaming: Stretcher::next_window ---------------------------------------------------------
 extern "C" int rcg_send(rcg_engine* e, uint32_t channel, const float* chunk, uint64_t n) {
     if (!e || channel >= e->cfg.channels || (!chunk && n)) return fail(RCG_ERR_INVALID_ARG, "bad channel or chunk");
+    if (!e->shards.empty()) return rcg_send(e->shards[channel % e->shards.size()], channel, chunk, n);
     ChannelState& c = e->ch[channel];
     if (c.closed) return fail(RCG_ERR_STATE, "channel %u input is closed", channel);
     c.input.insert(c.input.end(), chunk, chunk + n);
@@ -760,11 +1100,13 @@ extern "C" int rcg_send(rcg_engine* e, uint32_t channel, const float* chunk, uin
 }
 extern "C" int rcg_close_input(rcg_engine* e, uint32_t channel) {
     if (!e || channel >= e->cfg.channels) return fail(RCG_ERR_INVALID_ARG, "bad channel");
+    if (!e->shards.empty()) return rcg_close_input(e->shards[channel % e->shards.size()], channel);
     e->ch[channel].closed = true;
     return RCG_OK;
 }
 extern "C" int rcg_is_done(rcg_engine* e, uint32_t channel, int* done) {
     if (!e || channel >= e->cfg.channels || !done) return fail(RCG_ERR_INVALID_ARG, "bad channel");
+    if (!e->shards.empty()) return rcg_is_done(e->shards[channel % e->shards.size()], channel, done);
     *done = e->ch[channel].done ? 1 : 0;
     return RCG_OK;
 }
@@ -838,6 +1180,11 @@ static int stream_compute(rcg_engine* e, uint32_t channel) {
 
 extern "C" int rcg_next_window(rcg_engine* e, uint32_t channel, float* out, uint64_t cap, uint64_t* n_out) {
     if (!e || channel >= e->cfg.channels || !out) return fail(RCG_ERR_INVALID_ARG, "bad channel or buffer");
+    if (!e->shards.empty()) {   // every channel is an independent Stretcher (main.rs:133-153): device = channel mod n
+        if (e->watcher)
+            if (int rc = drain_watcher(e, nullptr)) return rc;
+        return rcg_next_window(e->shards[channel % e->shards.size()], channel, out, cap, n_out);
+    }
     if (cap < e->plan.out_len_per_call)
         return fail(RCG_ERR_CAPACITY, "window needs %llu samples", (unsigned long long)e->plan.out_len_per_call);
     CUDA_TRY(cudaSetDevice(e->device));
@@ -858,7 +1205,8 @@ extern "C" int rcg_next_window(rcg_engine* e, uint32_t channel, float* out, uint
 // With an even pitch multiple the fused path carries even samples only between launches; the
 // first kernel must therefore be pushed before any audio has been processed.
 static int check_kernel_push(rcg_engine* e) {
-    if (e->launches > 0 && !e->had_kernels && use_half_rate(e->cfg.pitch_multiple, 0u))
+    const bool had = e->shards.empty() ? e->had_kernels : e->shards[0]->had_kernels;
+    if (total_launches(e) > 0 && !had && use_half_rate(e->cfg.pitch_multiple, 0u))
         return fail(RCG_ERR_STATE, "with an even pitch multiple the first frequency kernel must be pushed before processing starts");
     return RCG_OK;
 }
@@ -866,6 +1214,11 @@ static int check_kernel_push(rcg_engine* e) {
 extern "C" int rcg_push_frequency_kernel(rcg_engine* e, rcg_apply_fn fn) {
     if (!e || !fn) return fail(RCG_ERR_INVALID_ARG, "null argument");
     if (int rc = check_kernel_push(e)) return rc;
+    if (!e->shards.empty()) {
+        for (rcg_engine* sh : e->shards)
+            if (int rc = rcg_push_frequency_kernel(sh, fn)) return rc;
+        return RCG_OK;
+    }
     FreqKernel k;
     k.host = fn;
     e->kernels.push_back(k);
@@ -882,7 +1235,12 @@ extern "C" int rcg_load_frequency_kernel(rcg_engine* e, const char* so_path) {
         dlclose(lib);
         return fail(RCG_ERR_PLUGIN, "%s has no `apply` symbol", so_path);
     }
-    e->libs.push_back(lib);
+    e->libs.push_back(lib);   // (a multi-device engine keeps the handle itself and hands `apply` to every shard)
+    if (!e->shards.empty()) {
+        for (rcg_engine* sh : e->shards)
+            if (int rc = rcg_push_frequency_kernel(sh, (rcg_apply_fn)sym)) return rc;
+        return RCG_OK;
+    }
     FreqKernel k;
     k.host = (rcg_apply_fn)sym;
     e->kernels.push_back(k);
@@ -931,16 +1289,29 @@ extern "C" __global__ void rcg_apply_kernel(const float2* in, float2* out, unsig
     }
 }
 )";
+// the bin-local form as a plain kernel over spectra in memory (same entry point and arguments as the gather form)
+const char* kLocalTwinWrapper = R"(
+extern "C" __global__ void rcg_apply_kernel(const float2* in, float2* out, unsigned n_bins,
+                                            unsigned long long n_frames, unsigned long long elapsed_ms) {
+    const unsigned long long total = n_frames * n_bins;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned b = (unsigned)(i % n_bins);
+        out[i] = apply((size_t)elapsed_ms, b, n_bins, in[i]);
+    }
+}
+)";
 }  // namespace
 
 // user source -> cubin for sm_100a; no CUDA context needed (runs on the watcher thread too)
-static bool compile_device_source(const std::string& user_src, std::vector<char>& cubin, std::string& log) {
+static bool compile_device_source(const std::string& user_src, std::vector<char>& cubin, std::string& log,
+                                  const char* wrapper = kDeviceWrapper) {
     static std::mutex load_mutex;
     {
         std::lock_guard<std::mutex> g(load_mutex);
         if (!g_nvrtc.load()) { log = std::string("libnvrtc could not be loaded: ") + (dlerror() ? dlerror() : ""); return false; }
     }
-    const std::string src = user_src + kDeviceWrapper;
+    const std::string src = user_src + wrapper;
     nvrtcProgram_t prog = nullptr;
     if (g_nvrtc.create(&prog, src.c_str(), "frequency_kernel.cu", 0, nullptr, nullptr) != 0) {
         log = "nvrtcCreateProgram failed";
@@ -980,18 +1351,20 @@ static int install_cubin(rcg_engine* e, const std::vector<char>& cubin) {
 extern "C" int rcg_push_device_frequency_kernel(rcg_engine* e, const char* cuda_source) {
     if (!e || !cuda_source) return fail(RCG_ERR_INVALID_ARG, "null argument");
     if (int rc = check_kernel_push(e)) return rc;
-    CUDA_TRY(cudaSetDevice(e->device));
     std::vector<char> cubin;
     std::string log;
     if (!compile_device_source(cuda_source, cubin, log))   // compile failure keeps the previous kernel (hotswapper.rs:36-42)
         return fail(RCG_ERR_PLUGIN, "device frequency kernel failed to compile: %.400s", log.c_str());
-    return install_cubin(e, cubin);
+    return install_everywhere(e, cubin, nullptr);
 }
 
 // ---- bin-local device kernels: NVRTC builds the whole stretch kernel around the user's apply ----------------
 #include "rcg_jit_sources.inc"
 
-static bool compile_fused_source(const std::string& user_src, int log2h, std::vector<char>& cubin, std::string& log) {
+static bool compile_fused_source(const std::string& user_src, int log2h, std::vector<char>& cubin, std::vector<char>& twin,
+                                 std::string& log) {
+    // the per-bin twin first (small): it takes over when the kernel above this one fails in the middle of a batch
+    if (!compile_device_source(user_src, twin, log, kLocalTwinWrapper)) return false;
     static std::mutex load_mutex;
     {
         std::lock_guard<std::mutex> g(load_mutex);
@@ -1022,29 +1395,43 @@ static bool compile_fused_source(const std::string& user_src, int log2h, std::ve
     return true;
 }
 
-static int install_fused_cubin(rcg_engine* e, const std::vector<char>& cubin) {
+static int install_fused_cubin(rcg_engine* e, const std::vector<char>& cubin, const std::vector<char>& twin) {
     FreqKernel k;
     CUDA_TRY(cudaLibraryLoadData(&k.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     cudaError_t ke = cudaLibraryGetKernel(&k.fused, k.lib, "rcg_jit_stretch");
     if (ke == cudaSuccess)
         ke = cudaFuncSetAttribute((const void*)k.fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->geo.smem_bytes);
+    if (ke == cudaSuccess) ke = cudaLibraryLoadData(&k.twin_lib, twin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (ke == cudaSuccess) ke = cudaLibraryGetKernel(&k.dev, k.twin_lib, "rcg_apply_kernel");
     if (ke != cudaSuccess) {
         (void)cudaGetLastError();
         cudaLibraryUnload(k.lib);
+        if (k.twin_lib) cudaLibraryUnload(k.twin_lib);
         return fail(RCG_ERR_PLUGIN, "fused frequency kernel could not be loaded: %s", cudaGetErrorString(ke));
     }
     e->kernels.push_back(k);
     return RCG_OK;
 }
 
+// load a compiled device kernel on the engine's device -- on every shard's device for a multi-device engine.
+// twin != nullptr: the bin-local form (cubin = the fused stretch kernel, *twin = its per-bin twin).
+static int install_everywhere(rcg_engine* e, const std::vector<char>& cubin, const std::vector<char>* twin) {
+    if (!e->shards.empty()) {
+        for (rcg_engine* sh : e->shards)
+            if (int rc = install_everywhere(sh, cubin, twin)) return rc;
+        return RCG_OK;
+    }
+    CUDA_TRY(cudaSetDevice(e->device));
+    return twin ? install_fused_cubin(e, cubin, *twin) : install_cubin(e, cubin);
+}
+
 extern "C" int rcg_push_local_device_frequency_kernel(rcg_engine* e, const char* cuda_source) {
     if (!e || !cuda_source) return fail(RCG_ERR_INVALID_ARG, "null argument");
-    CUDA_TRY(cudaSetDevice(e->device));
-    std::vector<char> cubin;
+    std::vector<char> cubin, twin;
     std::string log;
-    if (!compile_fused_source(cuda_source, e->log2w - 1, cubin, log))   // compile failure keeps the previous kernel
+    if (!compile_fused_source(cuda_source, e->log2w - 1, cubin, twin, log))   // compile failure keeps the previous kernel
         return fail(RCG_ERR_PLUGIN, "bin-local frequency kernel failed to compile: %.400s", log.c_str());
-    return install_fused_cubin(e, cubin);
+    return install_everywhere(e, cubin, &twin);
 }
 
 // ---- hot swap from a watched file (hotswapper.rs:14-33 + fft.rs:78-81) ------------------------------
@@ -1055,14 +1442,17 @@ static int drain_watcher(rcg_engine* e, uint32_t* swapped) {
     while (e->watcher->try_recv(b)) {
         if (b.host) {
             e->libs.push_back(b.dl);       // every library stays loaded (fft.rs:22)
-            FreqKernel k;
-            k.host = (rcg_apply_fn)b.host;
-            e->kernels.push_back(k);
-            e->had_kernels = true;
+            if (e->shards.empty()) {
+                FreqKernel k;
+                k.host = (rcg_apply_fn)b.host;
+                e->kernels.push_back(k);
+                e->had_kernels = true;
+            } else {
+                for (rcg_engine* sh : e->shards) rcg_push_frequency_kernel(sh, (rcg_apply_fn)b.host);
+            }
             n++;
         } else {
-            CUDA_TRY(cudaSetDevice(e->device));
-            const int rc = b.local ? install_fused_cubin(e, b.cubin) : install_cubin(e, b.cubin);
+            const int rc = install_everywhere(e, b.cubin, b.local ? &b.twin : nullptr);
             if (rc) status = rc; else n++;
         }
         b = rcg::BuiltKernel();
@@ -1080,10 +1470,11 @@ extern "C" int rcg_watch_frequency_kernel(rcg_engine* e, const char* path, uint3
         return fail(RCG_ERR_PLUGIN, "frequency kernel %s: want a .cu, .c, .cc, .cpp, .so or .rs file", path);
     // from here on this engine runs the full-rate path: a kernel may arrive between any two batches
     e->had_kernels = true;
+    for (rcg_engine* sh : e->shards) sh->had_kernels = true;
     const int log2h = e->log2w - 1;
     e->watcher.reset(new rcg::KernelWatcher(path, poll_ms,
-        [log2h](const std::string& src, bool local, std::vector<char>& cubin, std::string& log) {
-            return local ? compile_fused_source(src, log2h, cubin, log) : compile_device_source(src, cubin, log);
+        [log2h](const std::string& src, bool local, std::vector<char>& cubin, std::vector<char>& twin, std::string& log) {
+            return local ? compile_fused_source(src, log2h, cubin, twin, log) : compile_device_source(src, cubin, log);
         }));
     e->watcher->start();   // first build happens here, on the caller's thread (hotswapper.rs:17)
     return drain_watcher(e, nullptr);
@@ -1113,11 +1504,22 @@ extern "C" int rcg_watch_log(const rcg_engine* e, char* buf, size_t cap) {
 
 extern "C" int rcg_frequency_kernel_count(const rcg_engine* e, uint32_t* n) {
     if (!e || !n) return fail(RCG_ERR_INVALID_ARG, "null argument");
-    *n = (uint32_t)e->kernels.size();
+    *n = (uint32_t)(e->shards.empty() ? e->kernels.size() : e->shards[0]->kernels.size());
     return RCG_OK;
 }
 
 // -- helpers -------------------------------------------------------------------------------------
+extern "C" int rcg_device_count(int* n) {
+    if (!n) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    *n = 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { (void)cudaGetLastError(); return RCG_OK; }
+    for (int d = 0; d < ndev; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) (*n)++;
+    }
+    return RCG_OK;
+}
 extern "C" int rcg_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return fail(RCG_ERR_INVALID_ARG, "null argument");
     CUDA_TRY(cudaMallocHost(ptr, bytes ? bytes : 1));

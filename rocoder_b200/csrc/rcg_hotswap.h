@@ -50,12 +50,13 @@ struct BuiltKernel {
     void* dl = nullptr;           // dlopen handle (host kernels); owned by whoever pops it
     host_apply_fn host = nullptr;
     std::vector<char> cubin;      // device kernels
+    std::vector<char> twin;       // bin-local form only: the same `apply` as a plain per-bin kernel over spectra in memory
     bool local = false;           // device kernel of the bin-local form, fused into the stretch kernel
 };
 
 // source text -> cubin; returns false and fills `log` on a compile error
 // local: the bin-local form `float2 apply(size_t, unsigned bin, unsigned n_bins, float2 x)` (file *.local.cu)
-typedef std::function<bool(const std::string& src, bool local, std::vector<char>& cubin, std::string& log)> DeviceCompileFn;
+typedef std::function<bool(const std::string& src, bool local, std::vector<char>& cubin, std::vector<char>& twin, std::string& log)> DeviceCompileFn;
 
 class KernelWatcher {
   public:
@@ -256,7 +257,7 @@ class KernelWatcher {
                 if (!read_file(path_, src)) { log = "cannot read " + path_; return false; }
                 if (!dev_) { log = "no device compiler"; return false; }
                 b.local = is_local_device_source(path_);
-                return dev_(src, b.local, b.cubin, log);
+                return dev_(src, b.local, b.cubin, b.twin, log);
             }
             case kHostSource: {
                 const std::string so = temp_path(".so");   // tempfile::Builder::new().suffix(".so") (:58)

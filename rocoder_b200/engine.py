@@ -99,6 +99,13 @@ def bind_host_thread(device: int = 0) -> int:
     return node.value
 
 
+def device_count() -> int:
+    """CUDA devices the library can run on (sm_100)"""
+    n = C.c_int()
+    check(lib().rcg_device_count(C.byref(n)))
+    return n.value
+
+
 def measure_fp32_peak(reps: int = 5) -> float:
     v = C.c_double()
     check(lib().rcg_measure_fp32_peak(C.byref(v), reps))
@@ -130,14 +137,16 @@ class PinnedBuffer:
 
 
 class Engine:
-    """All channels of one stretch job on one GPU."""
+    """All channels of one stretch job on one GPU, or -- `devices=[0, 1, ...]` -- partitioned over several
+    (by channel when the channels divide evenly, else by time; rcg_config.n_devices)."""
 
     def __init__(self, channels: int, sample_rate: int, window_len: int = 16384, factor: float = 1.0,
                  amplitude: float = 1.0, pitch_multiple: int = 1, buffer_dur_s: float = 1.0, seed: int = 0,
-                 device: int = 0, flags: int = 0, max_lookahead_calls: int = 0, first_channel: int = 0):
+                 device: int = 0, flags: int = 0, max_lookahead_calls: int = 0, first_channel: int = 0,
+                 devices: Optional[Sequence[int]] = None):
         self._h = C.c_void_p()
         self.cfg = make_config(channels, sample_rate, window_len, factor, amplitude, pitch_multiple, buffer_dur_s,
-                               seed, device, flags, max_lookahead_calls, first_channel)
+                               seed, device, flags, max_lookahead_calls, first_channel, devices)
         check(lib().rcg_create(C.byref(self.cfg), C.byref(self._h)))
         p = rcg_plan_info()
         check(lib().rcg_get_plan(self._h, C.byref(p)))
@@ -183,6 +192,12 @@ class Engine:
         n_out = (C.c_uint64 * self.channels)()
         check(lib().rcg_process_all(self._h, ins, inp.shape[1], outs, out.shape[1], n_out))
         return int(n_out[0])
+
+    def last_partition(self) -> dict:
+        """how the last process_all was spread over the engine's devices"""
+        n, ex, split = C.c_uint32(), C.c_uint32(), C.c_char_p()
+        check(lib().rcg_last_partition(self._h, C.byref(n), C.byref(split), C.byref(ex)))
+        return {"devices_used": n.value, "split": split.value.decode(), "exchanges": ex.value}
 
     def process_all(self, inp: np.ndarray) -> np.ndarray:
         inp = np.ascontiguousarray(inp, dtype=np.float32)
@@ -298,5 +313,5 @@ class Engine:
         return n.value
 
 
-__all__ = ["Engine", "PinnedBuffer", "bind_host_thread", "fade_in_out", "fade_keyframes", "measure_fp32_peak", "RcgError", "WouldBlock", "hanning", "hanning_crossfade_compensation",
+__all__ = ["Engine", "PinnedBuffer", "bind_host_thread", "device_count", "fade_in_out", "fade_keyframes", "measure_fp32_peak", "RcgError", "WouldBlock", "hanning", "hanning_crossfade_compensation",
            "plan", "expected_counts", "channel_bound", "phase"]

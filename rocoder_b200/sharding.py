@@ -65,10 +65,15 @@ class TimeShardedStretch:
         return (self.c1 - self.c0) * self.plan["out_len_per_call"]
 
     def run(self, seg_in, in_origin: int, out, stream: Optional[int] = None) -> None:
-        """seg_in [channels, n] holds the channel samples from in_origin on; out [channels, out_len()]"""
+        """seg_in [channels, n] holds the channel samples from in_origin on; out [channels, out_len()].
+        `stream` is a cudaStream_t handle; None = torch's current stream, the one torch.distributed orders its
+        point-to-point operations against (the engine's private stream would let the send start before the
+        stretch kernel has written the carried half window)."""
         if not self.has_work:
             return
         dist = self.torch.distributed
+        if stream is None and self.head.is_cuda:
+            stream = self.torch.cuda.current_stream(self.head.device).cuda_stream
         defer = self.prev_rank is not None
         self.backend.process_segment(seg_in, seg_in.stride(0), in_origin, seg_in.shape[1], out, out.stride(0),
                                      self.c0, self.c1 - self.c0, tail_out=self.tail, head_out=self.head,

@@ -102,7 +102,7 @@ int main(int argc, char** argv) {
         const std::string src = dir + "/k.cu";
         write_file(src, "AAA");
         int calls = 0;
-        rcg::KernelWatcher w(src, 20, [&](const std::string& s, bool local, std::vector<char>& cubin, std::string& log) {
+        rcg::KernelWatcher w(src, 20, [&](const std::string& s, bool local, std::vector<char>& cubin, std::vector<char>&, std::string& log) {
             CHECK(!local);
             calls++;
             if (s == "bad") { log = "syntax error"; return false; }

@@ -304,3 +304,46 @@ def snr_db(ref: np.ndarray, test: np.ndarray) -> float:
     if num == 0.0:
         return float("-inf")
     return 10.0 * np.log10(num / den)
+
+
+def process_calls(x_span: np.ndarray, span_origin: int, factor: float, pitch: int, W: int, seed: int, channel: int,
+                  first_call: int, n_calls: int, precision: int = 64, amplitude: float = 1.0,
+                  bypass: bool = False) -> np.ndarray:
+    """Calls [first_call, first_call + n_calls) of ONE channel out of the middle of a long job, from the oracle.
+    x_span holds the channel's samples from span_origin on and must start at or before the first sample of call
+    first_call - 1: the stretcher is started one call early (phase counters set to that frame,
+    ro_stretcher_set_first_frame) so that the half window carried into call first_call is the real one, and the
+    extra call is discarded.  The input must reach the end of the last frame (no zero padding is wanted here)."""
+    L = oracle()
+    c = constants(factor, pitch, W, amplitude)
+    k, step, olen = c["frames_per_call"], c["sample_step_len"], c["out_len_per_call"]
+    lead = 1 if first_call > 0 else 0
+    start_call = first_call - lead
+    s_first = start_call * k * step
+    s_end = ((first_call + n_calls) * k - 1) * step + W
+    assert span_origin <= s_first and span_origin + x_span.size >= s_end, "span does not cover the calls"
+    w = hanning(W)
+    h = L.ro_stretcher_new(1, 48000, factor, amplitude, pitch, w.ctypes.data_as(PF), W, 1.0, precision)
+    assert h
+    try:
+        if bypass:
+            L.ro_stretcher_set_phase_bypass(h)
+        else:
+            L.ro_stretcher_set_phase_philox(h, seed, channel)
+        L.ro_stretcher_set_first_frame(h, start_call * k)
+        chunk = np.ascontiguousarray(x_span[s_first - span_origin:s_end - span_origin], np.float32)
+        L.ro_stretcher_send(h, chunk.ctypes.data_as(PF), chunk.size)
+        outs = []
+        m = C.c_size_t()
+        for _ in range(lead + n_calls):
+            if precision == 64:
+                o = np.zeros(olen, np.float64)
+                rc = L.ro_stretcher_next_window_f64(h, o.ctypes.data_as(PD), C.byref(m))
+            else:
+                o = np.zeros(olen, np.float32)
+                rc = L.ro_stretcher_next_window(h, o.ctypes.data_as(PF), C.byref(m))
+            assert rc == 0 and m.value == olen
+            outs.append(o)
+        return np.concatenate(outs[lead:])
+    finally:
+        L.ro_stretcher_free(h)

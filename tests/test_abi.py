@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported():
     L = C.CDLL(rb.LIB_PATH)
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
-    assert L.rcg_abi_version() == 1
+    assert L.rcg_abi_version() == 2
 
 
 def test_binding_covers_the_header():

@@ -149,24 +149,7 @@ def test_gpu_plugin_streaming_and_shared_object(tmp_path):
     assert np.abs(got - ref).max() <= 1e-4 and ol.snr_db(ref, got) > 100.0
 
 
-DEVICE_X2 = """
-__device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, const float2* spectrum) {
-    float2 v = spectrum[bin];
-    return make_float2(v.x * 2.0f, v.y * 2.0f);        // README.md:121-129
-}
-"""
-DEVICE_TILT = """
-float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, const float2* spectrum) {   // -default-device
-    float g = 0.25f + (float)bin / (float)n_bins;
-    float2 v = spectrum[bin];
-    return make_float2((v.x * 0.6f - v.y * 0.8f) * g, (v.x * 0.8f + v.y * 0.6f) * g);
-}
-"""
-DEVICE_LOWPASS = """
-__device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, const float2* spectrum) {
-    return bin < n_bins / 8 ? spectrum[bin] : make_float2(0.0f, 0.0f);
-}
-"""
+DEVICE_X2, DEVICE_TILT, DEVICE_LOWPASS = plugins.DEVICE_X2, plugins.DEVICE_TILT, plugins.DEVICE_LOWPASS
 
 
 @pytest.mark.gpu
@@ -200,22 +183,7 @@ def test_gpu_device_kernel_compile_error_keeps_previous():
     assert np.abs(got - ref).max() <= 1e-4
 
 
-LOCAL_X2 = """
-__device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, float2 x) {
-    return make_float2(x.x * 2.0f, x.y * 2.0f);        // README.md:121-129
-}
-"""
-LOCAL_TILT = """
-float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, float2 v) {   // -default-device
-    float g = 0.25f + (float)bin / (float)n_bins;
-    return make_float2((v.x * 0.6f - v.y * 0.8f) * g, (v.x * 0.8f + v.y * 0.6f) * g);
-}
-"""
-LOCAL_LOWPASS = """
-__device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, float2 x) {
-    return bin < n_bins / 8 ? x : make_float2(0.0f, 0.0f);
-}
-"""
+LOCAL_X2, LOCAL_TILT, LOCAL_LOWPASS = plugins.LOCAL_X2, plugins.LOCAL_TILT, plugins.LOCAL_LOWPASS
 
 
 @pytest.mark.gpu
@@ -289,3 +257,53 @@ def test_gpu_fused_local_kernel_streaming_equals_batch():
             for c in range(2):
                 outs[c].append(e.next_window(c))
     assert np.array_equal(np.stack([np.concatenate(o) for o in outs]), batch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("beneath", ["gather", "fused"])
+@pytest.mark.parametrize("good", [0, 7, 23])
+def test_gpu_mixed_stack_retries_with_the_kernel_beneath_mid_batch(beneath, good):
+    """fft.rs:101-106 on a mixed stack: a host kernel that panics in the middle of a batch is dropped and the SAME frame
+    is retried with the kernel beneath it -- here a device kernel (gather form, or a fused bin-local one through its
+    per-bin twin); frames already processed keep the host kernel's result.  The oracle runs the equivalent single
+    kernel 'half_gain for the first `good` frames in the reference's call order, tilt afterwards'."""
+    import rocoder_b200 as rb
+    n, f, p, W = 30000, 2.0, 1, 1024
+    x = _input(n)
+    ref = ol.process_all(x, f, p, W, seed=4, precision=64, plugin=plugins.GainThenTilt(good))
+    host = plugins.FailsAfter(good)
+    with rb.Engine(2, 48000, W, f, 1.0, p, seed=4) as e:
+        if beneath == "gather":
+            e.push_device_frequency_kernel(plugins.DEVICE_TILT)
+        else:
+            e.push_local_device_frequency_kernel(plugins.LOCAL_TILT)
+        from rocoder_b200 import _abi
+        cb = _abi.APPLY_FN(host)
+        e._keep.append(cb)     # the callback object must outlive the engine
+        _abi.check(_abi.lib().rcg_push_frequency_kernel(e._h, cb))
+        assert e.frequency_kernel_count() == 2
+        got = e.process_all(x)
+        assert e.frequency_kernel_count() == 1      # the host kernel is gone for good
+        again = e.process_all(x)                    # and the next job runs on the device kernel alone
+    assert host.calls == good + 1
+    assert np.abs(got - ref).max() <= 1e-4 and ol.snr_db(ref, got) > 100.0
+    tilt_only = ol.process_all(x, f, p, W, seed=4, precision=64, plugin=plugins.tilt)
+    assert np.abs(again - tilt_only).max() <= 1e-4 and ol.snr_db(tilt_only, again) > 100.0
+
+
+@pytest.mark.gpu
+def test_gpu_bad_segment_argument_does_not_drop_the_kernel():
+    """a caller error in a segment description is not a failing frequency kernel: the stack stays as it was"""
+    import torch
+    import rocoder_b200 as rb
+    x = torch.zeros((2, 20000), device="cuda")
+    out = torch.zeros((2, 50000), device="cuda")
+    with rb.Engine(2, 48000, 1024, 2.0, 1.0, 1, seed=4) as e:
+        e.push_local_device_frequency_kernel(plugins.LOCAL_X2)
+        with pytest.raises(rb.RcgError):   # output of a direct-store mode at an odd (4-byte aligned) offset
+            e.process_segment(x, x.stride(0), 0, 20000, out[:, 1:], out.stride(0), 0, 2,
+                              stream=torch.cuda.current_stream().cuda_stream)
+        with pytest.raises(rb.RcgError):   # deferred first block without a place for its head
+            e.process_segment(x, x.stride(0), 0, 20000, out, out.stride(0), 2, 2, defer_first=True,
+                              stream=torch.cuda.current_stream().cuda_stream)
+        assert e.frequency_kernel_count() == 1

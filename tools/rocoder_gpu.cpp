@@ -2,13 +2,16 @@
 // file-to-file path (main.rs:124-160, 190-204):  rocoder_gpu -i in.wav -o out.wav -f 8 -p 2 -w 16384
 // Recording (no -i) and live playback (no -o) belong to the reference's audio-device layer and are
 // not provided: both are reported as errors.  Extra flags: --seed N (phase seed; default: random,
-// like rand::thread_rng), --device N, --bench (print timing as JSON).
+// like rand::thread_rng), --device N or --device 0,1,... (the job is partitioned over every listed GPU: by channel
+// when the channels divide evenly, else by time with one carried-half-window exchange per boundary), --bench
+// (print timing as JSON).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <string>
+#include <vector>
 
 #include "../include/rocoder_b200.h"
 #include "../rocoder_b200/host/rocoder_audio.hpp"
@@ -29,7 +32,7 @@ struct Opt {                       // main.rs:27-122
     std::string output;            // -o, --output
     bool has_seed = false;
     uint64_t seed = 0;
-    int device = 0;
+    std::vector<int> devices{0};   // --device 0,1,...
     bool bench = false;
 };
 
@@ -50,7 +53,7 @@ static void usage() {
         "  -s, --start <dur>          Start time in input audio (hh:mm:ss.ss)\n"
         "  -d, --duration <dur>       Duration to use from input audio (hh:mm:ss.ss)\n"
         "  -o, --output <path>        Output .wav file path. Uses 32-bit float.\n"
-        "      --seed <n>  --device <n>  --bench\n", stderr);
+        "      --seed <n>  --device <n[,n...]>  --bench\n", stderr);
 }
 
 static bool parse(int argc, char** argv, Opt& o) {
@@ -77,7 +80,16 @@ static bool parse(int argc, char** argv, Opt& o) {
         else if (a == "-d" || a == "--duration") o.duration = val();
         else if (a == "-o" || a == "--output") o.output = val();
         else if (a == "--seed") { o.seed = std::stoull(val()); o.has_seed = true; }
-        else if (a == "--device") o.device = std::stoi(val());
+        else if (a == "--device") {
+            o.devices.clear();
+            std::string list = val();
+            for (size_t pos = 0; pos <= list.size();) {
+                const size_t comma = std::min(list.find(',', pos), list.size());
+                o.devices.push_back(std::stoi(list.substr(pos, comma - pos)));
+                pos = comma + 1;
+            }
+            if (o.devices.empty() || o.devices.size() > RCG_MAX_DEVICES) throw AudioError("--device: 1 to 16 ordinals");
+        }
         else if (a == "--bench") o.bench = true;
         else if (a == "-h" || a == "--help") { usage(); return false; }
         else throw AudioError("unknown argument " + a);
@@ -114,7 +126,9 @@ int main(int argc, char** argv) {
         cfg.pitch_multiple = opt.pitch_multiple;
         cfg.buffer_dur_s = (float)buffer_ms / 1000.0f;
         cfg.seed = opt.seed;
-        cfg.device = opt.device;
+        cfg.device = opt.devices[0];
+        cfg.n_devices = (uint32_t)opt.devices.size();
+        for (size_t i = 0; i < opt.devices.size(); i++) cfg.devices[i] = opt.devices[i];
         cfg.flags = opt.has_seed ? 0u : RCG_FLAG_RANDOM_SEED;
         rcg_engine* eng = nullptr;
         if (rcg_create(&cfg, &eng) != RCG_OK) throw AudioError(rcg_last_error());
@@ -142,13 +156,18 @@ int main(int argc, char** argv) {
         if (rcg_process_all(eng, in_ptrs.data(), n_in, out_ptrs.data(), out_len, n_out.data()) != RCG_OK)
             throw AudioError(rcg_last_error());
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        uint32_t used = 1, exchanges = 0;
+        const char* split = "none";
+        rcg_last_partition(eng, &used, &split, &exchanges);
         rcg_destroy(eng);
         write_wav_file(opt.output, out, audio.spec.sample_rate);   // handle_result, main.rs:195-204
         std::fprintf(stderr, "stretch process completed: %llu calls, %llu frames, %llu samples/channel in %.3f s\n",
                      (unsigned long long)calls, (unsigned long long)frames, (unsigned long long)out_len, secs);
         if (opt.bench)
-            std::printf("{\"calls\": %llu, \"frames\": %llu, \"out_samples_per_channel\": %llu, \"channels\": %u, \"seconds\": %.6f}\n",
-                        (unsigned long long)calls, (unsigned long long)frames, (unsigned long long)out_len, cfg.channels, secs);
+            std::printf("{\"calls\": %llu, \"frames\": %llu, \"out_samples_per_channel\": %llu, \"channels\": %u, \"seconds\": %.6f, "
+                        "\"devices_used\": %u, \"split\": \"%s\", \"exchanges\": %u}\n",
+                        (unsigned long long)calls, (unsigned long long)frames, (unsigned long long)out_len, cfg.channels, secs,
+                        used, split, exchanges);
         return 0;
     } catch (const std::exception& e) {
         std::fprintf(stderr, "rocoder_gpu: %s\n", e.what());
