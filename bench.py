@@ -14,7 +14,15 @@ One JSON line on stdout (rank 0).  `value` = device-resident throughput (input a
 output left in HBM); `e2e` = the same metric through rcg_process_all with pinned HOST buffers,
 copies inside the timed region; `roofline` = the stretch kernel's algorithmic HBM bytes per
 launch / its CUDA-event duration against the measured copy bandwidth; `cpu_baseline` = the
-oracle timed on this box's host cores on a bounded sample.
+oracle timed on this box's host cores on a bounded sample.  Also on the line:
+  boundary_check  N > 1: every rank > 0 recomputes its first call with the zero-communication halo path and
+                  compares it bit for bit with the block the NCCL exchange finished; a mismatch
+                  makes the run exit non-zero
+  host_link_gbs   copy-only benchmark (no engine): pinned host <-> device, all ranks at once -- the ceiling `e2e`
+                  is measured against
+  configs         BASELINE configs 4 (1 h stereo, -f 20 -p -3, STRONG scaling over the N GPUs by time) and 5 (8
+                  channels 96 kHz with the x2 frequency kernel, sharded by channel): device-resident with one rank
+                  per GPU, and end to end through ONE engine that lists all N devices (rcg_config.n_devices)
 """
 from __future__ import annotations
 
@@ -169,7 +177,7 @@ def cpu_leg(target_seconds: float, native: bool = True, replicas: bool = True):
     import ctypes as C
     import oracle_lib as ol
     from rocoder_b200 import build
-    from rocoder_b200.signals import noise_chirp
+    from rocoder_b200.signals import noise_chirp_span
 
     path = None
     if native:
@@ -180,7 +188,7 @@ def cpu_leg(target_seconds: float, native: bool = True, replicas: bool = True):
     L = ol.oracle(path) if path else ol.oracle()
     secs = 600   # the workload's own 10 minutes of channel 0; the sample is its first `calls` calls
     if "x" not in _CPU_CACHE:
-        _CPU_CACHE["x"] = noise_chirp(SAMPLE_RATE * secs, SAMPLE_RATE, 1, seed=0)[0]
+        _CPU_CACHE["x"] = noise_chirp_span(0, SAMPLE_RATE * secs, SAMPLE_RATE, 1, seed=0, total_seconds=float(secs))[0]
     x = _CPU_CACHE["x"]
     sink = np.zeros(WINDOW * 2, np.float32)
     n_out = C.c_size_t()
@@ -190,6 +198,33 @@ def cpu_leg(target_seconds: float, native: bool = True, replicas: bool = True):
         made = L.ro_bench_channel(x.ctypes.data_as(ol.PF), x.size, SAMPLE_RATE, FACTOR, 1.0, PITCH, WINDOW, SEED, 0,
                                   calls, sink.ctypes.data_as(ol.PF), C.byref(n_out))
         return time.perf_counter() - t0, made, n_out.value
+
+    # The oracle's own FFT is plain C; the reference's rustfft picks SIMD kernels at run time.  So the FFT of the
+    # timed run is handed to a SIMD library too (scipy's pocketfft, through ro_set_fft_hook_f32) and the faster of the
+    # two runs is the baseline; both are reported.
+    hook_cb = None
+    try:
+        import scipy.fft as sf
+        HOOK = C.CFUNCTYPE(None, ol.PF, C.c_size_t, C.c_int)
+
+        def _pocketfft(ptr, n, inverse):
+            a = np.ctypeslib.as_array(ptr, shape=(2 * n,)).view(np.complex64)
+            a[:] = sf.ifft(a, norm="forward") if inverse else sf.fft(a)
+        hook_cb = HOOK(_pocketfft)
+        L.ro_set_fft_hook_f32.argtypes = [HOOK]
+        L.ro_set_fft_hook_f32.restype = None
+    except Exception:
+        hook_cb = None
+    t_own, made_own, outs_own = run(40)
+    own_fft_value = outs_own / t_own / 1e6
+    pocket_value = None
+    if hook_cb is not None:
+        L.ro_set_fft_hook_f32(hook_cb)
+        t_p, made_p, outs_p = run(40)
+        pocket_value = outs_p / t_p / 1e6
+        if pocket_value <= own_fft_value:
+            L.ro_set_fft_hook_f32(C.cast(None, HOOK))   # the built-in transform is the faster one here
+    fft_used = "pocketfft (scipy.fft, SIMD)" if (pocket_value or 0) > own_fft_value else "oracle's own radix-4 Stockham"
 
     t, made, outs = run(40)  # probe
     per_call = t / max(made, 1)
@@ -202,8 +237,11 @@ def cpu_leg(target_seconds: float, native: bool = True, replicas: bool = True):
     # all cores, one independent replica each (ctypes drops the GIL): labelled separately -- the
     # reference itself drives every channel from ONE thread (stretcher_processor.rs:55-71)
     ncores = os.cpu_count() or 1
+    if hook_cb is not None:
+        L.ro_set_fft_hook_f32(C.cast(None, HOOK))   # (the replica threads below would serialise on the GIL in the hook)
+    fft_info = {"fft": fft_used, "value_own_fft_probe": own_fft_value, "value_pocketfft_probe": pocket_value}
     if not replicas:
-        return {"value": outs / t / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
+        return {"value": outs / t / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port", **fft_info,
                 "sample": f"first {made} calls of channel 0 of the workload, {t:.1f} s on 1 thread", "seconds": t}
     rep_calls = max(20, calls // 4)
     sinks = [np.zeros(WINDOW * 2, np.float32) for _ in range(ncores)]
@@ -221,11 +259,11 @@ def cpu_leg(target_seconds: float, native: bool = True, replicas: bool = True):
     t_rep = time.perf_counter() - t0
     replica_value = sum(o.value for o in outs_r) / t_rep / 1e6
     return {"value": outs / t / 1e6, "unit": "Msamples/s", "cores": 1,
-            "replica_value": replica_value, "replica_cores": ncores,
-            "kind": "port",
+            "replica_value": replica_value, "replica_cores": ncores, "replica_fft": "oracle's own radix-4 Stockham",
+            "kind": "port", **fft_info,
             "sample": f"first {made} calls ({made * 4} frames, {outs} output samples) of channel 0 of the workload, "
                       f"{t:.1f} s on 1 thread (the reference DSP loop is single-threaded); "
-                      f"oracle built {'-O3 -march=native' if path else '-O2'}",
+                      f"oracle built {'-O3 -march=native' if path else '-O2'}, FFT: {fft_used}",
             "seconds": t}
 
 
@@ -276,12 +314,209 @@ def ensure_built():
         time.sleep(1.0)
 
 
+
+def boundary_ok(torch, eng, job, d_out, n_total, total_s, dev, stream, channels=CHANNELS, sample_rate=SAMPLE_RATE,
+                first_channel=0):
+    """rank r > 0 recomputes its first call with the zero-communication variant (the frame before it is
+    recomputed from the input, no exchange) and compares it bit for bit with the block the exchange finished"""
+    from rocoder_b200.signals import noise_chirp_span_torch
+    if job.prev_rank is None or not job.has_work:
+        return True
+    pl = job.plan
+    k, step, W, olen = pl["frames_per_call"], pl["sample_step_len"], pl["window_len"], pl["out_len_per_call"]
+    h0 = (job.c0 * k - 1) * step
+    h1 = min(n_total, ((job.c0 + 1) * k - 1) * step + W)
+    seg = noise_chirp_span_torch(h0, h1, sample_rate, channels, seed=0, device=dev, total_seconds=total_s,
+                                 first_channel=first_channel)
+    tmp = torch.full((channels, olen + 2), float("nan"), dtype=torch.float32, device=dev)
+    eng.process_segment(seg, seg.stride(0), h0, seg.shape[1], tmp, tmp.stride(0), job.c0, 1, stream=stream)
+    torch.cuda.synchronize()
+    return bool(torch.equal(tmp[:, :olen], d_out[:, :olen]))
+
+
+def host_link(torch, dist, dev, world, mb=512, reps=4):
+    """Copy-only benchmark, no engine: pinned host <-> device on this rank's GPU while every other rank does the
+    same (barrier first).  GB/s per GPU: each direction alone, then both at once (what an end-to-end step does:
+    input up while output comes down)."""
+    n = mb * (1 << 20) // 4
+    h_up = torch.empty(n, dtype=torch.float32).pin_memory()
+    h_dn = torch.empty(n, dtype=torch.float32).pin_memory()
+    d_up = torch.empty(n, dtype=torch.float32, device=dev)
+    d_dn = torch.zeros(n, dtype=torch.float32, device=dev)
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(up, dn):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s_up):
+                    d_up.copy_(h_up, non_blocking=True)
+            if dn:
+                with torch.cuda.stream(s_dn):
+                    h_dn.copy_(d_dn, non_blocking=True)
+        torch.cuda.synchronize()
+        return reps * n * 4 / (time.perf_counter() - t0) / 1e9
+
+    run(True, True)
+    res = {"h2d": run(True, False), "d2h": run(False, True)}
+    both = run(True, True)
+    res["h2d_concurrent"] = res["d2h_concurrent"] = both
+    out = {"mb_per_copy": mb, "n_gpus": world}
+    for key, v in res.items():
+        t = torch.tensor([v, -v], dtype=torch.float64, device=dev)
+        if dist is not None:
+            tsum = t.clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out[key + "_aggregate"] = float(tsum[0])
+            out[key + "_per_gpu_min"] = float(-t[1])
+        else:
+            out[key + "_aggregate"] = v
+            out[key + "_per_gpu_min"] = v
+    return out
+
+
+LOCAL_X2 = """
+__device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, float2 x) {
+    return make_float2(x.x * 2.0f, x.y * 2.0f);        // README.md:121-129
+}
+"""
+
+
+def _timed(torch, dist, dev, run, reps=3):
+    """CUDA-event time of `run` on the current stream, max over ranks"""
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def _e2e_one_engine(torch, dist, rb, rank, world, make_engine, channels, n, sample_rate, total_s, dev, reps=2):
+    """end to end through ONE engine that lists all `world` devices (rcg_config.n_devices): rank 0 drives it with
+    pinned host buffers while the other ranks wait; returns (ms, partition, checksum) on rank 0"""
+    import psutil
+    from rocoder_b200.signals import noise_chirp_span_torch
+    res = None
+    if rank == 0:
+        eng = make_engine(list(range(world)))
+        out_len = eng.expected_counts(n)[2]
+        need = 4 * channels * (n + out_len)
+        if psutil.virtual_memory().available < 2 * need + (8 << 30):
+            res = {"skipped": f"host memory: {need / 1e9:.1f} GB of pinned buffers wanted"}
+        else:
+            hin, hout = rb.PinnedBuffer((channels, n)), rb.PinnedBuffer((channels, out_len))
+            piece = 1 << 26
+            for a in range(0, n, piece):   # synthesise on the device, stage down in pieces
+                b = min(a + piece, n)
+                hin.array[:, a:b] = noise_chirp_span_torch(a, b, sample_rate, channels, seed=0, device=dev,
+                                                           total_seconds=total_s).cpu().numpy()
+            eng.process_all_into(hin.array, hout.array)
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                eng.process_all_into(hin.array, hout.array)
+            ms = (time.perf_counter() - t0) * 1e3 / reps
+            part = eng.last_partition()
+            res = {"ms": ms, "out_Msamples_s": out_len * channels / ms / 1e3, "h2d_bytes": 4 * channels * n,
+                   "d2h_bytes": 4 * channels * out_len, "gbs": need / ms / 1e6, "partition": part,
+                   "checksum": float(np.abs(hout.array[:, ::65537]).sum())}
+            del hin, hout
+        eng.close()
+    if dist is not None:
+        dist.barrier()
+    return res
+
+
+def config4(torch, dist, rb, rank, world, local, dev, stream, args):
+    """BASELINE config 4: 1 h stereo 48 kHz, -f 20 -p -3 -w 16384: STRONG scaling, the calls of the hour split over the
+    ranks by time, carried half window exchanged once per step over NCCL"""
+    from rocoder_b200.sharding import TimeShardedStretch, input_span
+    from rocoder_b200.signals import noise_chirp_span_torch
+    ch, rate, secs, f, p, W = 2, 48000, 3600, 20.0, -3, 16384
+    n = rate * secs
+    eng = rb.Engine(ch, rate, W, f, 1.0, p, seed=SEED, device=local)
+    calls, frames, out_len = eng.expected_counts(n)
+    job = TimeShardedStretch(eng, eng.plan, ch, calls, rank, world, dev)
+    s0, s1 = input_span(eng.plan, job.c0, job.c1, n)
+    x = noise_chirp_span_torch(s0, s1, rate, ch, seed=0, device=dev, total_seconds=float(secs))
+    out = torch.empty((ch, job.out_len()), dtype=torch.float32, device=dev)
+    ms = _timed(torch, dist, dev, lambda: job.run(x, s0, out, stream=stream))
+    ok = boundary_ok(torch, eng, job, out, n, float(secs), dev, stream, ch, rate)
+    if dist is not None:
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item())
+    finite = bool(torch.isfinite(out[:, ::4099]).all())
+    del x, out, job
+    eng.close()
+    torch.cuda.empty_cache()
+    e2e = None
+    if not args.no_e2e_configs:
+        e2e = _e2e_one_engine(torch, dist, rb, rank, world,
+                              lambda devs: rb.Engine(ch, rate, W, f, 1.0, p, seed=SEED, devices=devs), ch, n, rate,
+                              float(secs), dev)
+    return {"workload": "config4: 1 h stereo 48 kHz, -f 20 -p -3 -w 16384", "scaling": "strong", "sharding": "time",
+            "n_gpus": world, "frames": frames * ch, "out_samples": out_len * ch, "device_ms": ms,
+            "device_Msamples_s": out_len * ch / ms / 1e3, "realtime_x": secs / (ms * 1e-3),
+            "hbm_GBs_algorithmic": 4.0 * ch * (n + out_len) / ms / 1e6,
+            "boundary_check": "n/a (one rank)" if world == 1 else ("bit-exact" if ok else "MISMATCH"), "finite": finite,
+            "e2e_one_engine": e2e}
+
+
+def config5(torch, dist, rb, rank, world, local, dev, stream, args):
+    """BASELINE config 5: 7.1 (8 channels) 96 kHz, 60 s, -f 2 with the amplitude-scale frequency kernel in its fused
+    bin-local form: the channels are independent Stretchers (main.rs:133-153), sharded by channel, no communication"""
+    from rocoder_b200.signals import noise_chirp_span_torch
+    ch_all, rate, secs, f, p, W = 8, 96000, 60, 2.0, 1, 16384
+    n = rate * secs
+    per = (ch_all + world - 1) // world
+    first = rank * per
+    ch = max(0, min(per, ch_all - first))
+    eng = rb.Engine(max(ch, 1), rate, W, f, 1.0, p, seed=SEED, device=local, first_channel=first)
+    eng.push_local_device_frequency_kernel(LOCAL_X2)
+    calls, frames, out_len = eng.expected_counts(n)
+    x = noise_chirp_span_torch(0, n, rate, max(ch, 1), seed=0, device=dev, total_seconds=float(secs), first_channel=first)
+    out = torch.empty((max(ch, 1), out_len), dtype=torch.float32, device=dev)
+    run = (lambda: eng.process_segment(x, x.stride(0), 0, n, out, out.stride(0), 0, calls, stream=stream)) if ch else (lambda: None)
+    ms = _timed(torch, dist, dev, run, reps=5)
+    finite = bool(torch.isfinite(out[:, ::4099]).all())
+    del x, out
+    eng.close()
+    torch.cuda.empty_cache()
+
+    def make(devs):
+        e = rb.Engine(ch_all, rate, W, f, 1.0, p, seed=SEED, devices=devs)
+        e.push_local_device_frequency_kernel(LOCAL_X2)
+        return e
+    e2e = None if args.no_e2e_configs else _e2e_one_engine(torch, dist, rb, rank, world, make, ch_all, n, rate, float(secs), dev, reps=3)
+    return {"workload": "config5: 8 channels 96 kHz 60 s, -f 2 -w 16384, x2 frequency kernel (fused bin-local form)",
+            "scaling": "strong", "sharding": "channel", "n_gpus": world, "frames": frames * ch_all,
+            "out_samples": out_len * ch_all, "device_ms": ms, "device_Msamples_s": out_len * ch_all / ms / 1e3,
+            "realtime_x": secs / (ms * 1e-3), "hbm_GBs_algorithmic": 4.0 * ch_all * (n + out_len) / ms / 1e6,
+            "finite": finite, "e2e_one_engine": e2e}
+
+
 def run_ours(args):
     ensure_built()
     import torch
     import rocoder_b200 as rb
     from rocoder_b200.sharding import TimeShardedStretch, input_span
-    from rocoder_b200.signals import noise_chirp
+    from rocoder_b200.signals import noise_chirp_span_torch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -305,10 +540,10 @@ def run_ours(args):
     total_calls = eng.expected_counts(n_total)[0]
     job = TimeShardedStretch(eng, plan, CHANNELS, total_calls, rank, world, dev)
     s0, s1 = input_span(plan, job.c0, job.c1, n_total)
-    # synthetic segment: each rank synthesises its own span (seeded by rank); what matters is shape
-    host_in = rb.PinnedBuffer((CHANNELS, s1 - s0))
-    host_in.array[:] = noise_chirp(s1 - s0, SAMPLE_RATE, CHANNELS, seed=rank)
-    d_in = torch.from_numpy(host_in.array).to(dev)
+    # synthetic job: ONE noise+chirp signal of world x 10 min; sample i is a pure function of i, so every rank
+    # synthesises its own span (and later the halo of the boundary check) on its device
+    total_s = float(SECONDS * world)
+    d_in = noise_chirp_span_torch(s0, s1, SAMPLE_RATE, CHANNELS, seed=0, device=dev, total_seconds=total_s)
     out_len = job.out_len()
     d_out = torch.empty((CHANNELS, out_len), dtype=torch.float32, device=dev)
     frames = (job.c1 - job.c0) * k
@@ -362,9 +597,20 @@ def run_ours(args):
     flops = frames * CHANNELS * (2 * 5 * WINDOW * 14 + 20 * WINDOW)
     fp32_peak = rb.measure_fp32_peak() if rank == 0 else None
 
+    # N > 1: the block the NCCL exchange finished == the same call recomputed with the halo frame, bit for bit
+    ok = boundary_ok(torch, eng, job, d_out, n_total, total_s, dev, stream)
+    if dist is not None:
+        t = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item())
+    boundary = "n/a (one rank)" if world == 1 else ("bit-exact" if ok else "MISMATCH")
+
+    link = host_link(torch, dist, dev, world)
+
     # end to end through the C ABI with pinned host buffers (rank-local 10 minutes)
     e2e_in = rb.PinnedBuffer((CHANNELS, N_IN))
-    e2e_in.array[:] = host_in.array[:, :N_IN] if host_in.array.shape[1] >= N_IN else noise_chirp(N_IN, SAMPLE_RATE, CHANNELS, seed=rank)
+    e2e_in.array[:] = noise_chirp_span_torch(rank * N_IN, (rank + 1) * N_IN, SAMPLE_RATE, CHANNELS, seed=0, device=dev,
+                                             total_seconds=total_s).cpu().numpy()
     e2e_len = eng.expected_counts(N_IN)[2]
     e2e_out = rb.PinnedBuffer((CHANNELS, e2e_len))
     eng2 = rb.Engine(CHANNELS, SAMPLE_RATE, WINDOW, FACTOR, 1.0, PITCH, seed=SEED, device=local)
@@ -382,6 +628,14 @@ def run_ours(args):
         e2e_ms = float(t.item())
     e2e_value = e2e_len * CHANNELS * world / (e2e_ms * 1e-3) / 1e6
     checksum = float(np.abs(e2e_out.array[:, ::4099]).sum())
+
+    del e2e_in, e2e_out, eng2
+    configs = None
+    if not args.no_configs:
+        del d_in, d_out, job
+        torch.cuda.empty_cache()
+        configs = {"config4": config4(torch, dist, rb, rank, world, local, dev, stream, args),
+                   "config5": config5(torch, dist, rb, rank, world, local, dev, stream, args)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -405,12 +659,22 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": 4 * CHANNELS * N_IN,
                     "d2h_bytes_per_step": 4 * CHANNELS * e2e_len, "ms_per_step": e2e_ms, "checksum": checksum,
-                    "host_numa_node_rank0": numa},
+                    "host_numa_node_rank0": numa,
+                    # output bytes per second per GPU against what a bare device-to-host copy loop reaches on this box
+                    # with every rank copying at once (host_link_gbs.d2h_per_gpu_min); a step moves 8x more down than up
+                    "d2h_gbs_per_gpu": 4 * CHANNELS * e2e_len / (e2e_ms * 1e-3) / 1e9,
+                    "link_frac": (4 * CHANNELS * e2e_len / (e2e_ms * 1e-3) / 1e9) / link["d2h_per_gpu_min"]
+                    if link.get("d2h_per_gpu_min") else None},
+            "boundary_check": boundary,
+            "host_link_gbs": link,
+            "configs": configs,
             "gpu_launches": int(launches),
             "clocks": clocks,
         }))
     if dist is not None:
         dist.destroy_process_group()
+    if boundary == "MISMATCH":
+        raise SystemExit("bench.py: the NCCL-finished boundary block differs from the halo recomputation")
 
 
 def main():
@@ -420,6 +684,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs object (BASELINE configs 4 and 5)")
+    ap.add_argument("--no-e2e-configs", action="store_true", help="configs: device-resident numbers only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -181,6 +181,8 @@ static double ro_hypot_f64(double a, double b) { return hypot(a, b); }
 #undef REAL
 #undef SUF
 
+void ro_set_fft_hook_f32(ro_fft_hook_f32 hook) { g_fft_hook_f32 = hook; }
+
 void ro_fft_f32(float *re_im, size_t n, int inverse) {
     fft_plan_f32 *p = fft_plan_new_f32(n);
     fft_exec_f32(p, (cpx_f32 *)re_im, inverse);

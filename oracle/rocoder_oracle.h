@@ -72,6 +72,10 @@ void ro_phase_fill(uint64_t seed, uint32_t channel, uint64_t frame, uint32_t win
  * Stockham radix-4/2; otherwise an O(n^2) DFT accumulated in double). */
 void ro_fft_f32(float *re_im, size_t n, int inverse);
 void ro_fft_f64(double *re_im, size_t n, int inverse);
+/* Timed CPU baseline only: route every f32 transform of this library through `hook` (NULL restores the built-in
+ * one).  bench.py passes scipy's pocketfft so that the baseline's FFT is a SIMD library like the reference's. */
+typedef void (*ro_fft_hook_f32)(float *re_im, size_t n, int inverse);
+void ro_set_fft_hook_f32(ro_fft_hook_f32 hook);
 
 /* ---- plugin ABI (C form of fft.rs:93 `apply`) ------------------------------------ *
  * in/out: n_bins interleaved (re, im) pairs.  Return 0 on success; non-zero stands for

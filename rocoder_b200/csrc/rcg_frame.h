@@ -162,25 +162,13 @@ RCG_HD cf ld_once(const cf* p) {
 }
 RCG_HD cf ld_pair(const float* p) { return *reinterpret_cast<const cf*>(p); }
 RCG_HD void st_pair(float* p, float a, float b) { *reinterpret_cast<cf*>(p) = make_cf(a, b); }
+RCG_HD void st_cf(float* p, cf v) { *reinterpret_cast<cf*>(p) = v; }
 
 // ---- twiddles -------------------------------------------------------------------------
-RCG_HD void cmul(float ar, float ai, float br, float bi, float& cr, float& ci) {
-    cr = ar * br - ai * bi;
-    ci = ar * bi + ai * br;
-}
-// x[j] *= w (CONJ: x[j] *= conj(w))
-template <bool CONJ>
-RCG_HD void tw_apply(float& xr, float& xi, float wr, float wi) {
-    float nr, ni;
-    if constexpr (CONJ) { nr = xr * wr + xi * wi; ni = xi * wr - xr * wi; }
-    else { nr = xr * wr - xi * wi; ni = xi * wr + xr * wi; }
-    xr = nr; xi = ni;
-}
-
 // Multiply element j (1 <= j < R) of a butterfly by w^(m*j) (or its conjugate), w = the pass's
 // principal root, using the table layout tw_scheme() selected.
 // the stored power-of-two exponents of the pow scheme, fetched ahead of the butterfly so that
-// their (L1 / L2) latency overlaps the shared-memory loads and the DFT
+// their (L1 / L2 / shared-memory) latency overlaps the data loads and the DFT
 struct TwPre { cf w1, w2, w4, w8; };
 template <int LOG2H, int PASS, int R, bool HR = false>
 RCG_HD TwPre tw_preload(const cf* tw, int m) {
@@ -196,58 +184,52 @@ RCG_HD TwPre tw_preload(const cf* tw, int m) {
     return p;
 }
 
+// Packed arithmetic (rcg_dft.h): a product with a twiddle whose rotated copy is at hand is two instructions.
 template <int LOG2H, int PASS, bool CONJ, int R, bool HR = false>
-RCG_HD void twiddle_butterfly(float (&xr)[R], float (&xi)[R], const cf* tw, int m, const TwPre& pre) {
+RCG_HD void twiddle_butterfly(cf (&x)[R], const cf* tw, int m, const TwPre& pre) {
     constexpr int SCHEME = tw_scheme(LOG2H, PASS, HR);
     constexpr int M = 1 << make_plan(LOG2H, HR).mlog2[PASS];
     if constexpr (SCHEME == kTwFull) {
 #pragma unroll
-        for (int j = 1; j < R; j++) {
-            const cf w = ld_tw<LOG2H>(tw + (j - 1) * M + m);
-            tw_apply<CONJ>(xr[j], xi[j], w.x, w.y);
-        }
+        for (int j = 1; j < R; j++) x[j] = tw_mul<CONJ>(x[j], make_tw(ld_tw<LOG2H>(tw + (j - 1) * M + m)));
     } else if constexpr (SCHEME == kTwTwoLevel) {
         static_assert(SCHEME != kTwTwoLevel || R == 2, "two-level tables serve radix-2 passes");
-        const cf a = ld_tw<LOG2H>(tw + (m >> 6)), b = ld_tw<LOG2H>(tw + M / 64 + (m & 63));
-        float wr, wi;
-        cmul(a.x, a.y, b.x, b.y, wr, wi);
-        tw_apply<CONJ>(xr[1], xi[1], wr, wi);
+        // w^m = A[m >> 6] B[m & 63]: the two factors are applied one after the other
+        const Tw a = make_tw(ld_tw<LOG2H>(tw + (m >> 6))), b = make_tw(ld_tw<LOG2H>(tw + M / 64 + (m & 63)));
+        x[1] = tw_mul<CONJ>(tw_mul<CONJ>(x[1], a), b);
     } else if constexpr (SCHEME == kTwPow) {
-        // stored: w1, w2, w4, w8; kept products: w3 = w1 w2, w12 = w8 w4; every other exponent is
-        // one product of two of those (depth <= 2 multiplications from correctly rounded tables)
-        const cf w1 = pre.w1, w2 = pre.w2;
-        tw_apply<CONJ>(xr[1], xi[1], w1.x, w1.y);
-        tw_apply<CONJ>(xr[2], xi[2], w2.x, w2.y);
-        float w3r, w3i;
-        cmul(w1.x, w1.y, w2.x, w2.y, w3r, w3i);
-        tw_apply<CONJ>(xr[3], xi[3], w3r, w3i);
+        // stored: w1, w2, w4, w8 (correctly rounded); kept products: w3 = w1 w2, w12 = w8 w4; an exponent with two
+        // set bits beyond those is two products applied in sequence (depth <= 2 multiplications either way)
+        const Tw t1 = make_tw(pre.w1), t2 = make_tw(pre.w2);
+        const Tw t3 = tw_product(t1, t2);
+        x[1] = tw_mul<CONJ>(x[1], t1);
+        x[2] = tw_mul<CONJ>(x[2], t2);
+        x[3] = tw_mul<CONJ>(x[3], t3);
         if constexpr (R >= 8) {
-            const cf w4 = pre.w4;
-            float tr, ti;
-            tw_apply<CONJ>(xr[4], xi[4], w4.x, w4.y);
-            cmul(w4.x, w4.y, w1.x, w1.y, tr, ti); tw_apply<CONJ>(xr[5], xi[5], tr, ti);
-            cmul(w4.x, w4.y, w2.x, w2.y, tr, ti); tw_apply<CONJ>(xr[6], xi[6], tr, ti);
-            cmul(w4.x, w4.y, w3r, w3i, tr, ti);   tw_apply<CONJ>(xr[7], xi[7], tr, ti);
+            const Tw t4 = make_tw(pre.w4);
+            x[4] = tw_mul<CONJ>(x[4], t4);
+            x[5] = tw_mul<CONJ>(tw_mul<CONJ>(x[5], t4), t1);
+            x[6] = tw_mul<CONJ>(tw_mul<CONJ>(x[6], t4), t2);
+            x[7] = tw_mul<CONJ>(tw_mul<CONJ>(x[7], t4), t3);
             if constexpr (R >= 16) {
-                const cf w8 = pre.w8;
-                tw_apply<CONJ>(xr[8], xi[8], w8.x, w8.y);
-                cmul(w8.x, w8.y, w1.x, w1.y, tr, ti); tw_apply<CONJ>(xr[9], xi[9], tr, ti);
-                cmul(w8.x, w8.y, w2.x, w2.y, tr, ti); tw_apply<CONJ>(xr[10], xi[10], tr, ti);
-                cmul(w8.x, w8.y, w3r, w3i, tr, ti);   tw_apply<CONJ>(xr[11], xi[11], tr, ti);
-                float w12r, w12i;
-                cmul(w8.x, w8.y, w4.x, w4.y, w12r, w12i);
-                tw_apply<CONJ>(xr[12], xi[12], w12r, w12i);
-                cmul(w12r, w12i, w1.x, w1.y, tr, ti); tw_apply<CONJ>(xr[13], xi[13], tr, ti);
-                cmul(w12r, w12i, w2.x, w2.y, tr, ti); tw_apply<CONJ>(xr[14], xi[14], tr, ti);
-                cmul(w12r, w12i, w3r, w3i, tr, ti);   tw_apply<CONJ>(xr[15], xi[15], tr, ti);
+                const Tw t8 = make_tw(pre.w8);
+                const Tw t12 = tw_product(t8, t4);
+                x[8] = tw_mul<CONJ>(x[8], t8);
+                x[9] = tw_mul<CONJ>(tw_mul<CONJ>(x[9], t8), t1);
+                x[10] = tw_mul<CONJ>(tw_mul<CONJ>(x[10], t8), t2);
+                x[11] = tw_mul<CONJ>(tw_mul<CONJ>(x[11], t8), t3);
+                x[12] = tw_mul<CONJ>(x[12], t12);
+                x[13] = tw_mul<CONJ>(tw_mul<CONJ>(x[13], t12), t1);
+                x[14] = tw_mul<CONJ>(tw_mul<CONJ>(x[14], t12), t2);
+                x[15] = tw_mul<CONJ>(tw_mul<CONJ>(x[15], t12), t3);
             }
         }
     }
 }
 
 template <int LOG2H, int PASS, bool CONJ, int R, bool HR = false>
-RCG_HD void twiddle_butterfly(float (&xr)[R], float (&xi)[R], const cf* tw, int m) {
-    twiddle_butterfly<LOG2H, PASS, CONJ, R, HR>(xr, xi, tw, m, tw_preload<LOG2H, PASS, R, HR>(tw, m));
+RCG_HD void twiddle_butterfly(cf (&x)[R], const cf* tw, int m) {
+    twiddle_butterfly<LOG2H, PASS, CONJ, R, HR>(x, tw, m, tw_preload<LOG2H, PASS, R, HR>(tw, m));
 }
 
 // shared-memory offset of butterfly input a relative to input 0: phys(base + a*M) - phys(base)
@@ -284,35 +266,33 @@ RCG_HD LoadCtx<LOG2H> make_load_ctx(const StretchParams& prm, int channel, long 
 // (ALIGNED: the whole frame lies inside the input and is 8-byte aligned -> branch-free float2 loads,
 // which lets the compiler batch the loads of several unrolled iterations)
 template <int LOG2H, int R, bool ALIGNED>
-RCG_HD void load_fetch(const LoadCtx<LOG2H>& c, const StretchParams& prm, int m, float (&xr)[R], float (&xi)[R]) {
+RCG_HD void load_fetch(const LoadCtx<LOG2H>& c, const StretchParams& prm, int m, cf (&x)[R]) {
     constexpr int M = 1 << make_plan(LOG2H).mlog2[0];
 #pragma unroll
     for (int a = 0; a < R; a++) {
         const int n = m + a * M;  // packed index: samples 2n, 2n+1
-        float x0, x1;
+        cf v;
         if constexpr (ALIGNED) {
-            const cf x = ld_stream2(c.in + c.base + 2 * n);
-            x0 = x.x; x1 = x.y;
+            v = ld_stream2(c.in + c.base + 2 * n);
         } else {
             const long long i0 = c.base + 2 * n;
-            x0 = (i0 >= 0 && i0 < prm.in_valid) ? ld_stream(c.in + i0) : 0.0f;
-            x1 = (i0 + 1 >= 0 && i0 + 1 < prm.in_valid) ? ld_stream(c.in + i0 + 1) : 0.0f;
+            v.x = (i0 >= 0 && i0 < prm.in_valid) ? ld_stream(c.in + i0) : 0.0f;
+            v.y = (i0 + 1 >= 0 && i0 + 1 < prm.in_valid) ? ld_stream(c.in + i0 + 1) : 0.0f;
         }
-        const cf w = ld_stream2(prm.window + 2 * n);
-        xr[a] = RCG_MUL(x0, w.x); xi[a] = RCG_MUL(x1, w.y);
+        x[a] = ex_mul(v, ld_stream2(prm.window + 2 * n));   // samples * window (fft.rs:51-55), rounded before any add
     }
 }
 // first DIF pass on the fetched values -> shared memory
 template <int LOG2H, int R, bool BYPASS = false>
-RCG_HD void load_finish(cf* S, const LoadCtx<LOG2H>& c, int m, float (&xr)[R], float (&xi)[R]) {
+RCG_HD void load_finish(cf* S, const LoadCtx<LOG2H>& c, int m, cf (&x)[R]) {
     constexpr int M = 1 << make_plan(LOG2H).mlog2[0];
     if constexpr (!BYPASS) {
-        Dft<R>::run(xr, xi);
-        twiddle_butterfly<LOG2H, 0, false, R>(xr, xi, c.tw, m);
+        Dft<R>::run(x);
+        twiddle_butterfly<LOG2H, 0, false, R>(x, c.tw, m);
     }
     cf* p = S + phys(m);
 #pragma unroll
-    for (int j = 0; j < R; j++) p[slot_off<M>(j)] = make_cf(xr[j], xi[j]);
+    for (int j = 0; j < R; j++) p[slot_off<M>(j)] = x[j];
 }
 
 template <int LOG2H>
@@ -322,22 +302,22 @@ RCG_HD void phase_load(cf* S, int t, const StretchParams& prm, int channel, long
     const LoadCtx<LOG2H> c = make_load_ctx<LOG2H>(prm, channel, frame);
     if (c.bypass) {
         for (int m = t; m < M; m += C::NT) {
-            float xr[R], xi[R];
-            load_fetch<LOG2H, R, false>(c, prm, m, xr, xi);
-            load_finish<LOG2H, R, true>(S, c, m, xr, xi);
+            cf x[R];
+            load_fetch<LOG2H, R, false>(c, prm, m, x);
+            load_finish<LOG2H, R, true>(S, c, m, x);
         }
     } else if (c.aligned) {
 RCG_UNROLL(RCG_LOAD_UNROLL)
         for (int m = t; m < M; m += C::NT) {
-            float xr[R], xi[R];
-            load_fetch<LOG2H, R, true>(c, prm, m, xr, xi);
-            load_finish<LOG2H, R>(S, c, m, xr, xi);
+            cf x[R];
+            load_fetch<LOG2H, R, true>(c, prm, m, x);
+            load_finish<LOG2H, R>(S, c, m, x);
         }
     } else {
         for (int m = t; m < M; m += C::NT) {
-            float xr[R], xi[R];
-            load_fetch<LOG2H, R, false>(c, prm, m, xr, xi);
-            load_finish<LOG2H, R>(S, c, m, xr, xi);
+            cf x[R];
+            load_fetch<LOG2H, R, false>(c, prm, m, x);
+            load_finish<LOG2H, R>(S, c, m, x);
         }
     }
 }
@@ -350,21 +330,18 @@ RCG_HD void fft_butterfly(cf* S, const cf* tw_all, int b) {
     const int m = b & (M - 1), blk = b >> ML;
     const TwPre pre = tw_preload<LOG2H, PASS, R>(tw, m);
     cf* p = S + phys((blk << (ML + RL)) + m);
-    float xr[R], xi[R];
+    cf x[R];
 #pragma unroll
-    for (int a = 0; a < R; a++) {
-        const cf v = p[slot_off<M>(a)];
-        xr[a] = v.x; xi[a] = v.y;
-    }
+    for (int a = 0; a < R; a++) x[a] = p[slot_off<M>(a)];
     if constexpr (INV) {
-        twiddle_butterfly<LOG2H, PASS, true, R>(xr, xi, tw, m, pre);  // conj twiddle on the inputs (DIT)
-        Dft<R>::run(xi, xr);
+        twiddle_butterfly<LOG2H, PASS, true, R>(x, tw, m, pre);  // conj twiddle on the inputs (DIT)
+        Dft<R, true>::run(x);
     } else {
-        Dft<R>::run(xr, xi);
-        twiddle_butterfly<LOG2H, PASS, false, R>(xr, xi, tw, m, pre);  // twiddle on the outputs (DIF)
+        Dft<R>::run(x);
+        twiddle_butterfly<LOG2H, PASS, false, R>(x, tw, m, pre);  // twiddle on the outputs (DIF)
     }
 #pragma unroll
-    for (int j = 0; j < R; j++) p[slot_off<M>(j)] = make_cf(xr[j], xi[j]);
+    for (int j = 0; j < R; j++) p[slot_off<M>(j)] = x[j];
 }
 
 template <int LOG2H, int PASS, bool INV>
@@ -421,43 +398,58 @@ RCG_HD float plugin_mag_raw(unsigned long long ms, uint32_t bin, uint32_t n_bins
 #define plugin_mag(prm, bin, n_bins, xr, xi) plugin_mag_raw((prm).elapsed_ms, (bin), (n_bins), (xr), (xi))
 #endif
 
+// (cos, sin) of the phase word u: e^{i phi}
+RCG_HD cf cis_phase(uint32_t u) {
+    float s, c;
+    sincos_phase(phase_from_u32(u), s, c);
+    return make_cf(c, s);
+}
+
 // One bin pair (kk, H-kk) of the half-size forward transform: real-FFT split -> magnitudes of
 // bins kk and H-kk -> the four random phases of bins {kk, W-kk, H-kk, H+kk} (one Philox block)
 // -> Hermitian fold.  Returns A = Y[kk] + conj(Y[H-kk]) and B = Y[kk] - conj(Y[H-kk]) where
 // Y[k] = |X[k]| (e^{i phi_k} + e^{-i phi_{W-k}}) / 2 is the Hermitian part of the reference's
 // W-bin spectrum (fft.rs:65-68): the real part of its inverse FFT is the inverse of Y.
+// t = exp(-2 pi i kk / W) with its rotated copy.  Packed arithmetic (rcg_dft.h): a conjugation or a rotation by
+// -+i is the (1, -1) / (-1, 1) factor or the swapped operand of the instruction that consumes the value.
 // kk = the pair's bin number, n_bins = W: only read when a bin-local frequency kernel is fused in (RCG_PLUGIN_LOCAL,
 // rcg_jit_entry.h): the magnitudes are then those of the kernel's output for the four bins.
-RCG_HD void pair_fold(cf za, cf zb, cf tw, const uint32_t (&u)[4], float& ar, float& ai, float& br, float& bi,
+RCG_HD void pair_fold(cf za, cf zb, const Tw& t, const uint32_t (&u)[4], cf& A, cf& B,
                       const StretchParams& prm, uint32_t kk, uint32_t n_bins) {
+    using SA = Ar<(RCG_PK_SPEC != 0)>;
+    const cf PM = make_cf(1.0f, -1.0f), MP = make_cf(-1.0f, 1.0f);
     // P = za + conj(zb), Q = za - conj(zb), U = -i t Q;  X[kk] = (P + U)/2, conj(X[H-kk]) = (P - U)/2
-    float pr = za.x + zb.x, pi = za.y - zb.y, qr = za.x - zb.x, qi = za.y + zb.y;
-    float tqr = tw.x * qr - tw.y * qi, tqi = tw.x * qi + tw.y * qr;
-    float ur = tqi, ui = -tqr;
-    float xkr = pr + ur, xki = pi + ui;   // halves folded into the 0.25 below
-    float xbr = pr - ur, xbi = pi - ui;
-    float s0, c0, s1, c1, s2, c2, s3, c3;
-    sincos_phase(phase_from_u32(u[0]), s0, c0);  // bin kk
-    sincos_phase(phase_from_u32(u[1]), s1, c1);  // bin W - kk
-    sincos_phase(phase_from_u32(u[2]), s2, c2);  // bin H - kk
-    sincos_phase(phase_from_u32(u[3]), s3, c3);  // bin H + kk
+    const cf P = SA::fma(zb, PM, za), Q = SA::fma(zb, MP, za);
+    const cf tq = tw_mul<false, (RCG_PK_SPEC != 0)>(Q, t);
+    const cf xk = SA::fma(pk_swap(tq), PM, P);   // halves folded into the 0.25 below
+    const cf xb = SA::fma(pk_swap(tq), MP, P);
+    const cf e0 = cis_phase(u[0]);  // bin kk
+    const cf e1 = cis_phase(u[1]);  // bin W - kk
+    const cf e2 = cis_phase(u[2]);  // bin H - kk
+    const cf e3 = cis_phase(u[3]);  // bin H + kk
 #if defined(RCG_PLUGIN_LOCAL)
     // X[kk] = (xk)/2, X[W-kk] = conj X[kk]; X[H-kk] = conj(xb)/2, X[H+kk] = conj X[H-kk]  (real input frame)
     const uint32_t hh = n_bins >> 1;
-    const float m0 = plugin_mag(prm, kk, n_bins, 0.5f * xkr, 0.5f * xki);
-    const float m1 = plugin_mag(prm, n_bins - kk, n_bins, 0.5f * xkr, -0.5f * xki);
-    const float m2 = plugin_mag(prm, hh - kk, n_bins, 0.5f * xbr, -0.5f * xbi);
-    const float m3 = plugin_mag(prm, hh + kk, n_bins, 0.5f * xbr, 0.5f * xbi);
-    float ykr = 0.5f * (m0 * c0 + m1 * c1), yki = 0.5f * (m0 * s0 - m1 * s1);
-    float ybr = 0.5f * (m2 * c2 + m3 * c3), ybi = 0.5f * (m2 * s2 - m3 * s3);
+    const float m0 = plugin_mag(prm, kk, n_bins, 0.5f * xk.x, 0.5f * xk.y);
+    const float m1 = plugin_mag(prm, n_bins - kk, n_bins, 0.5f * xk.x, -0.5f * xk.y);
+    const float m2 = plugin_mag(prm, hh - kk, n_bins, 0.5f * xb.x, -0.5f * xb.y);
+    const float m3 = plugin_mag(prm, hh + kk, n_bins, 0.5f * xb.x, 0.5f * xb.y);
+    // Y = (m e + m' conj(e')) / 2
+    const cf yk = SA::scale(SA::fma(SA::mul(e1, PM), pk_bcast(m1), SA::scale(e0, m0)), 0.5f);
+    const cf yb = SA::scale(SA::fma(SA::mul(e3, PM), pk_bcast(m3), SA::scale(e2, m2)), 0.5f);
 #else
     (void)prm; (void)kk; (void)n_bins;
-    float mk = fast_sqrt(xkr * xkr + xki * xki), mb = fast_sqrt(xbr * xbr + xbi * xbi);
-    float hk = 0.25f * mk, hb = 0.25f * mb;
-    float ykr = hk * (c0 + c1), yki = hk * (s0 - s1);
-    float ybr = hb * (c2 + c3), ybi = hb * (s2 - s3);
+    const float mk = fast_sqrt(xk.x * xk.x + xk.y * xk.y), mb = fast_sqrt(xb.x * xb.x + xb.y * xb.y);
+    const cf yk = SA::scale(SA::fma(e1, PM, e0), 0.25f * mk);   // |X[kk]| (e0 + conj(e1)) / 2
+    const cf yb = SA::scale(SA::fma(e3, PM, e2), 0.25f * mb);
 #endif
-    ar = ykr + ybr; ai = yki - ybi; br = ykr - ybr; bi = yki + ybi;
+    A = SA::fma(yb, PM, yk);   // yk + conj(yb)
+    B = SA::fma(yb, MP, yk);   // yk - conj(yb)
+}
+// i conj(t) * b for a twiddle t: the factor is swap(t.w), its rotated copy -swap(t.iw) -- both operand modifiers
+RCG_HD cf mul_i_conj(cf b, const Tw& t) {
+    using SA = Ar<(RCG_PK_SPEC != 0)>;
+    return SA::fma(pk_bcast(b.y), pk_neg(pk_swap(t.iw)), SA::mul(pk_bcast(b.x), pk_swap(t.w)));
 }
 
 // ---- SPECTRAL, half-rate synthesis (even pitch multiples) --------------------------------------
@@ -473,6 +465,7 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
     constexpr int Q = C::H / 2;
     const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
     const uint32_t chan = (uint32_t)(channel + prm.channel_offset);
+    const cf PM = make_cf(1.0f, -1.0f), MP = make_cf(-1.0f, 1.0f);
     for (int c = t; c < C::H / 4; c += C::NT) {
         uint32_t u[4];
         if (c == 0) {
@@ -505,9 +498,9 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
             const int ph = phys(bin_to_pos<LOG2H>(Q / 2));
             const cf za = S[ph], zb = S[phys(bin_to_pos<LOG2H>(C::H - Q / 2))];
             philox4x32_10((uint32_t)(Q / 2), f_lo, f_hi, chan, prm.keys, u);
-            float ar, ai, br, bi;
-            pair_fold(za, zb, make_cf(0.70710678118654752f, -0.70710678118654752f), u, ar, ai, br, bi, prm, (uint32_t)(Q / 2), (uint32_t)C::W);
-            S[ph] = make_cf(2.0f * ar, -2.0f * ai);
+            cf A, B;
+            pair_fold(za, zb, make_tw<(RCG_PK_SPEC != 0)>(make_cf(0.70710678118654752f, -0.70710678118654752f)), u, A, B, prm, (uint32_t)(Q / 2), (uint32_t)C::W);
+            S[ph] = make_cf(2.0f * A.x, -2.0f * A.y);
             continue;
         }
         // slot indices of bins k, H-k, Q-k, Q+k and k itself: frame-invariant, precomputed on the host
@@ -515,19 +508,23 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
         const int pa = (int)(qt.x & 0xFFFFu), pc = (int)(qt.y & 0xFFFFu);
         const cf za = S[pa], zb = S[qt.x >> 16];
         const cf zc = S[pc], zd = S[qt.y >> 16];
-        const cf tw = ld_cf(prm.spec_tw_hr + c);  // exp(-2 pi i k / W)
-        float ar, ai, er, ei, br, bi;
+        const Tw tw = make_tw<(RCG_PK_SPEC != 0)>(ld_cf(prm.spec_tw_hr + c));  // exp(-2 pi i k / W)
+        // exp(-2 pi i (Q-k)/W) = -i conj(tw) = -swap(tw); its rotated copy is swap(i tw): no instruction either
+        Tw tw_c;
+        tw_c.w = pk_neg(pk_swap(tw.w));
+        tw_c.iw = pk_swap(tw.iw);
+        cf E, F, unused;
         const uint32_t k = qt.z;
         philox4x32_10(k, f_lo, f_hi, chan, prm.keys, u);
-        pair_fold(za, zb, tw, u, ar, ai, br, bi, prm, k, (uint32_t)C::W);                              // E[k]
+        pair_fold(za, zb, tw, u, E, unused, prm, k, (uint32_t)C::W);                           // E[k]
         philox4x32_10((uint32_t)Q - k, f_lo, f_hi, chan, prm.keys, u);
-        pair_fold(zc, zd, make_cf(-tw.y, -tw.x), u, er, ei, br, bi, prm, (uint32_t)Q - k, (uint32_t)C::W);   // E[Q-k]; exp(-2 pi i (Q-k)/W) = -i conj(tw)
+        pair_fold(zc, zd, tw_c, u, F, unused, prm, (uint32_t)Q - k, (uint32_t)C::W);           // E[Q-k]
         // A2 = E[k] + conj(E[Q-k]), B2 = E[k] - conj(E[Q-k]), C2 = i conj(t2) B2, t2 = exp(-2 pi i k/H) = tw^2
-        const float a2r = ar + er, a2i = ai - ei, b2r = ar - er, b2i = ai + ei;
-        const float t2r = tw.x * tw.x - tw.y * tw.y, t2i = 2.0f * tw.x * tw.y;
-        const float cr = -(t2r * b2i - t2i * b2r), ci = t2r * b2r + t2i * b2i;
-        S[pa] = make_cf(a2r + cr, a2i + ci);       // Z''[k]
-        S[pc] = make_cf(a2r - cr, -(a2i - ci));    // Z''[Q-k] = conj(A2 - C2)
+        using SA = Ar<(RCG_PK_SPEC != 0)>;
+        const cf a2 = SA::fma(F, PM, E), b2 = SA::fma(F, MP, E);
+        const cf c2 = mul_i_conj(b2, make_tw<(RCG_PK_SPEC != 0)>(tw_mul<false, (RCG_PK_SPEC != 0)>(tw.w, tw)));
+        S[pa] = SA::add(a2, c2);                  // Z''[k]
+        S[pc] = SA::mul(SA::sub(a2, c2), PM);     // Z''[Q-k] = conj(A2 - C2)
     }
 }
 
@@ -577,14 +574,15 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
         const uint2 pt = ld_u2(prm.pair_tab + c);   // frame-invariant slot indices of bins k, H-k and k itself
         const int pa = (int)(pt.x & 0xFFFFu), pb = (int)(pt.x >> 16);
         const cf za = S[pa], zb = S[pb];
-        const cf tw = ld_cf(prm.spec_tw + c);  // exp(-2 pi i k / W)
+        const Tw tw = make_tw<(RCG_PK_SPEC != 0)>(ld_cf(prm.spec_tw + c));  // exp(-2 pi i k / W)
         philox4x32_10(pt.y * (uint32_t)KMUL, f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
         // A = Y[k] + conj(Y[H-k]), B = Y[k] - conj(Y[H-k]), Cc = i conj(t) B
-        float ar, ai, br, bi;
-        pair_fold(za, zb, tw, u, ar, ai, br, bi, prm, pt.y * (uint32_t)KMUL, (uint32_t)(C::W * KMUL));
-        float cr = -(tw.x * bi - tw.y * br), ci = tw.x * br + tw.y * bi;
-        S[pa] = make_cf(ar + cr, ai + ci);      // Z'[k]   = A + Cc
-        S[pb] = make_cf(ar - cr, -(ai - ci));   // Z'[H-k] = conj(A - Cc)
+        cf A, B;
+        pair_fold(za, zb, tw, u, A, B, prm, pt.y * (uint32_t)KMUL, (uint32_t)(C::W * KMUL));
+        const cf Cc = mul_i_conj(B, tw);
+        using SA = Ar<(RCG_PK_SPEC != 0)>;
+        S[pa] = SA::add(A, Cc);                              // Z'[k]   = A + Cc
+        S[pb] = SA::mul(SA::sub(A, Cc), make_cf(1.0f, -1.0f));  // Z'[H-k] = conj(A - Cc)
     }
 }
 
@@ -740,44 +738,42 @@ RCG_HD void phase_ola_impl(cf* S, int t, const StretchParams& prm, int channel, 
     constexpr int RL = make_plan(LOG2H).rlog2[0], R = 1 << RL, ML = make_plan(LOG2H).mlog2[0], M = 1 << ML;
     constexpr int RH = R / 2;
     constexpr bool bypass = BYPASS;
+    constexpr bool IO_PK = (RCG_PK_IO != 0);
     float* out = prm.out + (long long)channel * prm.out_stride;
     const cf* tw = prm.tw + tw_offset(LOG2H, 0);
 RCG_UNROLL(RCG_OLA_UNROLL)
     for (int m = t; m < M; m += C::NT) {
         cf* p = S + phys(m);
-        float xr[R], xi[R];
+        cf x[R];
 #pragma unroll
-        for (int a = 0; a < R; a++) {
-            const cf v = p[slot_off<M>(a)];
-            xr[a] = v.x; xi[a] = v.y;
-        }
+        for (int a = 0; a < R; a++) x[a] = p[slot_off<M>(a)];
         if constexpr (!bypass) {
-            twiddle_butterfly<LOG2H, 0, true, R>(xr, xi, tw, m);
-            Dft<R>::run(xi, xr);
+            twiddle_butterfly<LOG2H, 0, true, R>(x, tw, m);
+            Dft<R, true>::run(x);
         }
+        // the reference's operation order: (re / W) * w, then ((y + tail) * env) * amp; the multiply and the add
+        // around y are scalar so that nothing can fuse them (see ex_mul), the rest may be packed
 #pragma unroll
         for (int a = 0; a < RH; a++) {
             const int n = m + a * M;              // packed index inside the first half window
             const cf wa = ld_stream2(prm.window + 2 * n), wb = ld_stream2(prm.window + C::H + 2 * n);
-            float y0, y1, t0, t1;
+            cf y, tl;
             if constexpr (bypass) {
-                y0 = RCG_MUL(xr[a], wa.x); y1 = RCG_MUL(xi[a], wa.y);
-                t0 = RCG_MUL(xr[a + RH], wb.x); t1 = RCG_MUL(xi[a + RH], wb.y);
+                y = ex_mul(x[a], wa); tl = ex_mul(x[a + RH], wb);
             } else {
-                y0 = RCG_MUL(RCG_MUL(xr[a], prm.inv_w), wa.x); y1 = RCG_MUL(RCG_MUL(xi[a], prm.inv_w), wa.y);
-                t0 = RCG_MUL(RCG_MUL(xr[a + RH], prm.inv_w), wb.x); t1 = RCG_MUL(RCG_MUL(xi[a + RH], prm.inv_w), wb.y);
+                y = ex_mul(mul_chain<IO_PK>(x[a], pk_bcast(prm.inv_w)), wa);
+                tl = ex_mul(mul_chain<IO_PK>(x[a + RH], pk_bcast(prm.inv_w)), wb);
             }
             const cf old = ld_pair(tail + 2 * n);
-            st_pair(tail + 2 * n, t0, t1);
+            st_cf(tail + 2 * n, tl);
             const cf e = ld_stream2(prm.env + 2 * n);   // unconditional: keeps the loop body free of branches around loads
-            if (write_head) st_pair(prm.head_out + (long long)channel * C::H + 2 * n, y0, y1);
+            if (write_head) st_cf(prm.head_out + (long long)channel * C::H + 2 * n, y);
             if (emit) {
-                const float z0 = RCG_MUL(RCG_MUL(RCG_ADD(y0, old.x), e.x), prm.amp);
-                const float z1 = RCG_MUL(RCG_MUL(RCG_ADD(y1, old.y), e.y), prm.amp);
+                const cf z = mul_chain<IO_PK>(mul_chain<IO_PK>(ex_add(y, old), e), pk_bcast(prm.amp));
                 if (prm.pitch == 1) {
-                    st_pair(out + (frame * (long long)C::H + 2 * n - prm.out_origin), z0, z1);
+                    st_cf(out + (frame * (long long)C::H + 2 * n - prm.out_origin), z);
                 } else {
-                    p[slot_off<M>(a)] = make_cf(z0, z1);  // staged at packed index n for the resampling gather
+                    p[slot_off<M>(a)] = z;  // staged at packed index n for the resampling gather
                 }
             }
         }
@@ -806,16 +802,13 @@ RCG_HD void fft_butterfly_hr(cf* S, const cf* tw_all, int b) {
     if constexpr (M >= 128) m = (m & ~0x48) | ((m & 0x08) << 3) | ((m & 0x40) >> 3);
     const TwPre pre = tw_preload<LOG2H, PASS, R, true>(tw, m);
     cf* p = S + phys(expand_hr((blk << (ML + RL)) + m));
-    float xr[R], xi[R];
+    cf x[R];
 #pragma unroll
-    for (int a = 0; a < R; a++) {
-        const cf v = p[slot_off<STRIDE>(a)];
-        xr[a] = v.x; xi[a] = v.y;
-    }
-    twiddle_butterfly<LOG2H, PASS, true, R, true>(xr, xi, tw, m, pre);
-    Dft<R>::run(xi, xr);
+    for (int a = 0; a < R; a++) x[a] = p[slot_off<STRIDE>(a)];
+    twiddle_butterfly<LOG2H, PASS, true, R, true>(x, tw, m, pre);
+    Dft<R, true>::run(x);
 #pragma unroll
-    for (int j = 0; j < R; j++) p[slot_off<STRIDE>(j)] = make_cf(xr[j], xi[j]);
+    for (int j = 0; j < R; j++) p[slot_off<STRIDE>(j)] = x[j];
 }
 
 template <int LOG2H, int PASS>
@@ -863,6 +856,7 @@ RCG_HD void phase_ola_hr(cf* S, int t, const StretchParams& prm, int channel, lo
     constexpr int RL = P.rlog2[0], R = 1 << RL, ML = P.mlog2[0], M = 1 << ML;
     constexpr int RH = R / 2, Q = C::H / 2;
     constexpr int STRIDE = (M == 1) ? 1 : 2 * M;
+    constexpr bool IO_PK = (RCG_PK_IO != 0);
     float* out = prm.out + (long long)channel * prm.out_stride;
     if (prm.flags & kFlagBypass) {
         // test hook: y[n] = (s[n] w[n]) w[n]; the load phase left s[2n] w[2n] in S[phys(n)].x
@@ -884,31 +878,27 @@ RCG_HD void phase_ola_hr(cf* S, int t, const StretchParams& prm, int channel, lo
 RCG_UNROLL(RCG_OLA_UNROLL)
     for (int m = t; m < M; m += C::NT) {
         cf* p = S + phys(expand_hr(m));
-        float xr[R], xi[R];
+        cf x[R];
 #pragma unroll
-        for (int a = 0; a < R; a++) {
-            const cf v = p[slot_off<STRIDE>(a)];
-            xr[a] = v.x; xi[a] = v.y;
-        }
-        twiddle_butterfly<LOG2H, 0, true, R, true>(xr, xi, tw, m);
-        Dft<R>::run(xi, xr);
+        for (int a = 0; a < R; a++) x[a] = p[slot_off<STRIDE>(a)];
+        twiddle_butterfly<LOG2H, 0, true, R, true>(x, tw, m);
+        Dft<R, true>::run(x);
 #pragma unroll
         for (int a = 0; a < RH; a++) {
             const int n = m + a * M;   // packed index: even samples 2n, 2n+1 of the emitted half
             const cf wa = ld_stream2(prm.window_even + 2 * n), wb = ld_stream2(prm.window_even + Q + 2 * n);
-            const float y0 = RCG_MUL(RCG_MUL(xr[a], prm.inv_w), wa.x), y1 = RCG_MUL(RCG_MUL(xi[a], prm.inv_w), wa.y);
-            const float t0 = RCG_MUL(RCG_MUL(xr[a + RH], prm.inv_w), wb.x), t1 = RCG_MUL(RCG_MUL(xi[a + RH], prm.inv_w), wb.y);
+            const cf y = ex_mul(mul_chain<IO_PK>(x[a], pk_bcast(prm.inv_w)), wa);
+            const cf tl = ex_mul(mul_chain<IO_PK>(x[a + RH], pk_bcast(prm.inv_w)), wb);
             const cf old = ld_pair(tail + 2 * n);
-            st_pair(tail + 2 * n, t0, t1);
+            st_cf(tail + 2 * n, tl);
             const cf e = ld_stream2(prm.env_even + 2 * n);  // unconditional: no branches around loads
-            if (write_head) st_pair(prm.head_out + (long long)channel * C::H + 2 * n, y0, y1);
+            if (write_head) st_cf(prm.head_out + (long long)channel * C::H + 2 * n, y);
             if (emit) {
-                const float z0 = RCG_MUL(RCG_MUL(RCG_ADD(y0, old.x), e.x), prm.amp);
-                const float z1 = RCG_MUL(RCG_MUL(RCG_ADD(y1, old.y), e.y), prm.amp);
+                const cf z = mul_chain<IO_PK>(mul_chain<IO_PK>(ex_add(y, old), e), pk_bcast(prm.amp));
                 if (prm.pitch == 2) {
-                    st_pair(out + (frame * (long long)Q + 2 * n - prm.out_origin), z0, z1);
+                    st_cf(out + (frame * (long long)Q + 2 * n - prm.out_origin), z);
                 } else {
-                    p[slot_off<STRIDE>(a)] = make_cf(z0, z1);  // staged for the decimating gather
+                    p[slot_off<STRIDE>(a)] = z;  // staged for the decimating gather
                 }
             }
         }

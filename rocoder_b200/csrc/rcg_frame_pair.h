@@ -34,9 +34,7 @@ struct PairTables {
 
 RCG_HD cf pair_cross_tw(const cf* tab, int n) {
     const cf a = ld_cf(tab + (n >> 6)), b = ld_cf(tab + kPairHL / 64 + (n & 63));
-    cf w;
-    cmul(a.x, a.y, b.x, b.y, w.x, w.y);
-    return w;
+    return tw_mul<false>(a, make_tw(b));
 }
 
 // ---- LOAD + cross-CTA radix-2 DIF stage ---------------------------------------------------------
@@ -96,14 +94,15 @@ RCG_HD void pair_phase_spectral_odd(cf* S, int t, const StretchParams& prm, cons
         const int k = 2 * j + 1;
         const int pa = phys(pos), pb = phys(bin_to_pos<kPairLog2HL>(kPairHL - 1 - j));
         const cf za = S[pa], zb = S[pb];
-        const cf tw = ld_cf(pt.spec_tw_odd + c);
+        const Tw tw = make_tw<(RCG_PK_SPEC != 0)>(ld_cf(pt.spec_tw_odd + c));
         uint32_t u[4];
         philox4x32_10((uint32_t)k, f_lo, f_hi, chan, prm.keys, u);
-        float ar, ai, br, bi;
-        pair_fold(za, zb, tw, u, ar, ai, br, bi, prm, (uint32_t)k, (uint32_t)kPairW);
-        const float cr = -(tw.x * bi - tw.y * br), ci = tw.x * br + tw.y * bi;
-        S[pa] = make_cf(ar + cr, ai + ci);
-        S[pb] = make_cf(ar - cr, -(ai - ci));
+        cf A, B;
+        pair_fold(za, zb, tw, u, A, B, prm, (uint32_t)k, (uint32_t)kPairW);
+        const cf Cc = mul_i_conj(B, tw);
+        using SA = Ar<(RCG_PK_SPEC != 0)>;
+        S[pa] = SA::add(A, Cc);
+        S[pb] = SA::mul(SA::sub(A, Cc), make_cf(1.0f, -1.0f));
     }
 }
 

@@ -52,10 +52,10 @@ def _run_and_check(channels, rate, seconds, f, p, W, extra_slices=(), n_check=4,
             s1 = min(n, ((c0 + nc) * k - 1) * step + W)
             # (a) the same calls as their own segment: bit-identical
             seg = x[:, s0:s1].contiguous()
-            o = torch.full((channels, nc * olen + 1), float("nan"), device=dev)
-            o_view = o[:, (c0 * olen) % 2:][:, :nc * olen] if p in (1, 2) else o[:, 1:]   # direct-store modes need 8-byte alignment
-            if p in (1, 2):
-                o_view = o[:, :nc * olen]
+            o = torch.full((channels, nc * olen + 2), float("nan"), device=dev)
+            # pitch 1 / 2 store float2 straight from the overlap-add registers (8-byte aligned output, even stride); the
+            # resampled modes take any 4-byte aligned offset: give them an odd one
+            o_view = o[:, :nc * olen] if p in (1, 2) else o[:, 1:1 + nc * olen]
             e.process_segment(seg, seg.stride(0), s0, seg.shape[1], o_view, o.stride(0), c0, nc, stream=st)
             torch.cuda.synchronize()
             big = out[:, c0 * olen:(c0 + nc) * olen]
