@@ -95,8 +95,16 @@ extern "C" int rcg_plan(const rcg_config* cfg, rcg_plan_info* out) {
     if (p < -127 || p > 127) return fail(RCG_ERR_PITCH, "pitch_multiple outside the reference's i8 range");
     const uint32_t W = cfg->window_len;
     const int l2 = log2_exact(W);
-    if (l2 < 6 || l2 > 16)
-        return fail(RCG_ERR_WINDOW, "window_len %u: need a power of two in [64, 65536]", W);
+    if (l2 < 0) {
+        // not a power of two (README.md:100 allows any length): the chirp-z path, rcg_frame_bluestein.h
+        if (W & 1u)
+            return fail(RCG_ERR_WINDOW, "window_len %u is odd: the reference appends W - W/2 samples per frame while "
+                                        "advancing by W/2 (stretcher.rs:101-103); not supported", W);
+        if (W < 64 || W > 8192)
+            return fail(RCG_ERR_WINDOW, "window_len %u: windows that are not a power of two are supported from 64 to 8192", W);
+    } else if (l2 < 6 || l2 > 16) {
+        return fail(RCG_ERR_WINDOW, "window_len %u: need a power of two in [64, 65536] (or an even length in [64, 8192])", W);
+    }
     if (cfg->channels == 0) return fail(RCG_ERR_INVALID_ARG, "channels must be >= 1");
     const float abs_p = (float)(p < 0 ? -p : p);
     // stretcher.rs:42-46
@@ -206,6 +214,10 @@ struct rcg_engine {
     uint2* d_pair_tab = nullptr;
     uint4* d_quad_tab = nullptr;
     cf *d_tw = nullptr, *d_spec_tw = nullptr, *d_spec_tw_hr = nullptr;
+    bool bluestein = false;   // window_len is not a power of two: chirp-z path (rcg_frame_bluestein.h)
+    int bs_lm = 0;            // log2 of its convolution length
+    BluesteinTables bt{};
+    cf *d_bs_chirp = nullptr, *d_bs_filter = nullptr;
     bool pair = false;        // W = 65536: a frame across a 2-CTA cluster
     PairTables pt{};
     cf *d_pair_cross = nullptr, *d_pair_even = nullptr, *d_pair_odd = nullptr;
@@ -318,7 +330,13 @@ extern "C" int rcg_create(const rcg_config* cfg_in, rcg_engine** out) {
             return bail(fail(RCG_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)));        \
     } while (0)
     e->pair = (e->log2w == 16);
-    if (e->pair) {
+    e->bluestein = (e->log2w < 0);
+    if (e->bluestein) {
+        e->bs_lm = bluestein_log2m((int)cfg->window_len);
+        TRY_E(bluestein_geometry(e->bs_lm, (int)cfg->window_len, &e->geo));
+        if (e->geo.max_ctas_per_sm < 1) return bail(fail(RCG_ERR_CUDA, "chirp-z kernel does not fit on an SM"));
+        e->max_grid = e->sm_count * e->geo.max_ctas_per_sm;
+    } else if (e->pair) {
         TRY_E(pair_geometry(&e->geo));
         e->max_grid = e->sm_count / 2;   // clusters
     } else {
@@ -330,7 +348,7 @@ extern "C" int rcg_create(const rcg_config* cfg_in, rcg_engine** out) {
     std::vector<float> window(W), env(H);
     host_hanning(window.data(), W);           // main.rs:131
     host_crossfade_compensation(env.data(), H);  // stretcher.rs:56
-    const int plan_log2h = e->pair ? kPairLog2HL : e->log2w - 1;   // the in-CTA transform
+    const int plan_log2h = e->bluestein ? e->bs_lm : e->pair ? kPairLog2HL : e->log2w - 1;   // the in-CTA transform
     std::vector<cf> tw = host_pass_twiddles(plan_log2h), stw = host_spectral_twiddles(plan_log2h);
     std::vector<cf> stw_hr = host_spectral_twiddles_hr(plan_log2h);
     if (e->pair) {
@@ -342,6 +360,14 @@ extern "C" int rcg_create(const rcg_config* cfg_in, rcg_engine** out) {
         TRY_E(cudaMemcpy(e->d_pair_cross, cross.data(), cross.size() * sizeof(cf), cudaMemcpyHostToDevice));
         TRY_E(cudaMemcpy(e->d_pair_even, se.data(), se.size() * sizeof(cf), cudaMemcpyHostToDevice));
         TRY_E(cudaMemcpy(e->d_pair_odd, so.data(), so.size() * sizeof(cf), cudaMemcpyHostToDevice));
+    }
+    if (e->bluestein) {
+        std::vector<cf> chirp = host_bluestein_chirp((int)W), filt = host_bluestein_filter((int)W, e->bs_lm);
+        TRY_E(cudaMalloc(&e->d_bs_chirp, chirp.size() * sizeof(cf)));
+        TRY_E(cudaMalloc(&e->d_bs_filter, filt.size() * sizeof(cf)));
+        TRY_E(cudaMemcpy(e->d_bs_chirp, chirp.data(), chirp.size() * sizeof(cf), cudaMemcpyHostToDevice));
+        TRY_E(cudaMemcpy(e->d_bs_filter, filt.data(), filt.size() * sizeof(cf), cudaMemcpyHostToDevice));
+        e->bt = BluesteinTables{e->d_bs_chirp, e->d_bs_filter, (int)W};
     }
     std::vector<float> we = host_decimate2(window), ee = host_decimate2(env);
     {   // frame-invariant slot-index tables of the spectral steps
@@ -451,6 +477,7 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     cudaFree(e->d_window_even); cudaFree(e->d_env_even); cudaFree(e->d_spec_tw_hr); cudaFree(e->d_lerp_ratio);
     cudaFree(e->d_pair_tab); cudaFree(e->d_quad_tab);
     cudaFree(e->d_pair_cross); cudaFree(e->d_pair_even); cudaFree(e->d_pair_odd);
+    cudaFree(e->d_bs_chirp); cudaFree(e->d_bs_filter);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_tail_pp[0]); cudaFree(e->d_tail_pp[1]);
     cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_spec); cudaFree(e->d_spec2);
     for (auto& k : e->kernels) { if (k.lib) cudaLibraryUnload(k.lib); if (k.twin_lib) cudaLibraryUnload(k.twin_lib); }
@@ -534,7 +561,7 @@ extern "C" int rcg_synchronize(rcg_engine* e) {
 // keeps the full layout), so the carried half windows of fused and plugin launches are never mixed within one
 // engine state.
 static bool engine_half_rate(const rcg_engine* e) {
-    return use_half_rate(e->cfg.pitch_multiple, 0u) && !e->had_kernels && !e->pair;
+    return use_half_rate(e->cfg.pitch_multiple, 0u) && !e->had_kernels && !e->pair && !e->bluestein;
 }
 
 static void fill_params(const rcg_engine* e, StretchParams& p) {
@@ -563,7 +590,7 @@ static int validate_segment(const rcg_engine* e, const rcg_segment& s, bool spec
     auto misaligned = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 7u) != 0; };
     // float2 stores: the carried / head buffers always; the output only where it is written
     // directly from the overlap-add phase (pitch 1, and pitch 2 on the half-rate path)
-    const bool direct_out = e->cfg.pitch_multiple == 1 || (e->cfg.pitch_multiple == 2 && engine_half_rate(e));
+    const bool direct_out = !e->bluestein && (e->cfg.pitch_multiple == 1 || (e->cfg.pitch_multiple == 2 && engine_half_rate(e)));
     if (misaligned(s.d_tail_in) || misaligned(s.d_tail_out) || misaligned(s.d_head_out))
         return fail(RCG_ERR_INVALID_ARG, "tail / head buffers must be 8-byte aligned");
     if (direct_out && (misaligned(s.d_out) || (s.out_stride & 1)))
@@ -617,7 +644,9 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
              : e->pair  ? cudaLaunchKernel((const void*)fused, dim3(2 * grid), dim3(e->geo.threads), pair_args, e->geo.smem_bytes, stream)
                         : cudaLaunchKernel((const void*)fused, dim3(grid), dim3(e->geo.threads), args, e->geo.smem_bytes, stream);
     } else {
-        ce = e->pair ? launch_stretch_pair(p, e->pt, grid, stream) : launch_stretch(e->log2w, p, grid, stream);
+        ce = e->bluestein ? launch_bluestein(e->bs_lm, p, e->bt, grid, stream)
+             : e->pair    ? launch_stretch_pair(p, e->pt, grid, stream)
+                          : launch_stretch(e->log2w, p, grid, stream);
     }
     if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "stretch kernel launch failed: %s", cudaGetErrorString(ce));
     e->launches++;
@@ -859,8 +888,9 @@ extern "C" int rcg_finish_boundary(rcg_engine* e, float* d_out, int64_t out_stri
     p.frame_begin = (long long)(first_call * e->plan.frames_per_call);
     if (engine_half_rate(e)) p.flags |= kFlagHalfRate;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    cudaError_t ce = e->pair ? launch_boundary_pair(p, e->pt, d_head, d_tail_prev, st)
-                             : launch_boundary(e->log2w, p, d_head, d_tail_prev, st);
+    cudaError_t ce = e->bluestein ? launch_boundary_bluestein(e->bs_lm, p, e->bt, d_head, d_tail_prev, st)
+                     : e->pair    ? launch_boundary_pair(p, e->pt, d_head, d_tail_prev, st)
+                                  : launch_boundary(e->log2w, p, d_head, d_tail_prev, st);
     if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "boundary kernel launch failed: %s", cudaGetErrorString(ce));
     e->launches++;
     return RCG_OK;
@@ -1205,6 +1235,8 @@ extern "C" int rcg_next_window(rcg_engine* e, uint32_t channel, float* out, uint
 // With an even pitch multiple the fused path carries even samples only between launches; the
 // first kernel must therefore be pushed before any audio has been processed.
 static int check_kernel_push(rcg_engine* e) {
+    if (log2_exact(e->cfg.window_len) < 0)
+        return fail(RCG_ERR_STATE, "frequency kernels need a power-of-two window (window_len %u runs the chirp-z path)", e->cfg.window_len);
     const bool had = e->shards.empty() ? e->had_kernels : e->shards[0]->had_kernels;
     if (total_launches(e) > 0 && !had && use_half_rate(e->cfg.pitch_multiple, 0u))
         return fail(RCG_ERR_STATE, "with an even pitch multiple the first frequency kernel must be pushed before processing starts");
@@ -1427,6 +1459,8 @@ static int install_everywhere(rcg_engine* e, const std::vector<char>& cubin, con
 
 extern "C" int rcg_push_local_device_frequency_kernel(rcg_engine* e, const char* cuda_source) {
     if (!e || !cuda_source) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (log2_exact(e->cfg.window_len) < 0)
+        return fail(RCG_ERR_STATE, "frequency kernels need a power-of-two window (window_len %u runs the chirp-z path)", e->cfg.window_len);
     std::vector<char> cubin, twin;
     std::string log;
     if (!compile_fused_source(cuda_source, e->log2w - 1, cubin, twin, log))   // compile failure keeps the previous kernel

@@ -120,7 +120,6 @@ RCG_HD void bs_resynth(Exec& ex, cf* S, const StretchParams& prm, const Bluestei
             S[phys(k)] = v;
         }
     });
-    ex.par([&](int) {});   // (every thread read its own slots only; the barrier orders the padding writes)
     bs_convolve<LM>(ex, S, prm, bt, work);
     // y[n] = Re(conj(conj(c[n]) conv[n])) = Re(c[n] conj(conv[n])) = c.x conv.x + c.y conv.y; then / W * w[n]
     ex.par([&](int t) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "rcg_frame.h"
+#include "rcg_frame_bluestein.h"
 #include "rcg_frame_pair.h"
 
 namespace rcg {
@@ -31,5 +32,12 @@ cudaError_t launch_stretch_pair(const StretchParams& prm, const PairTables& pt, 
 cudaError_t launch_analysis_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream);
 cudaError_t launch_boundary_pair(const StretchParams& prm, const PairTables& pt, const float* head, const float* tail_prev,
                                  cudaStream_t stream);
+
+// windows that are not a power of two (rcg_frame_bluestein.h): lm = log2 of the convolution length, 7..14;
+// prm.tail_scratch must hold grid * W/2 floats
+cudaError_t bluestein_geometry(int lm, int W, LaunchGeometry* g);
+cudaError_t launch_bluestein(int lm, const StretchParams& prm, const BluesteinTables& bt, int grid, cudaStream_t stream);
+cudaError_t launch_boundary_bluestein(int lm, const StretchParams& prm, const BluesteinTables& bt, const float* head,
+                                      const float* tail_prev, cudaStream_t stream);
 
 }  // namespace rcg

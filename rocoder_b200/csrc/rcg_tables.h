@@ -127,6 +127,61 @@ inline std::vector<cf> host_pair_spectral_twiddles(int log2h, int odd) {
     return tw;
 }
 
+// ---- windows that are not a power of two: Bluestein's chirp tables (rcg_frame_bluestein.h) ----------------------
+// smallest LM with 2^LM >= 2W - 1
+inline int bluestein_log2m(int W) {
+    int lm = 0;
+    while ((1 << lm) < 2 * W - 1) lm++;
+    return lm;
+}
+// c[n] = exp(i pi n^2 / W): the exponent is reduced exactly (n^2 mod 2W) before it meets floating point
+inline std::vector<cf> host_bluestein_chirp(int W) {
+    std::vector<cf> c((size_t)W);
+    const double pi = 3.14159265358979323846264338327950288;
+    for (long long n = 0; n < W; n++) {
+        const long long r = (n * n) % (2LL * W);
+        const double a = pi * (double)r / (double)W;
+        c[(size_t)n] = make_cf((float)cos(a), (float)sin(a));
+    }
+    return c;
+}
+// FFT_M(b) / M with b[n] = b[M - n] = c[n] for n < W, in the position order the DIF passes of plan LM leave
+inline std::vector<cf> host_bluestein_filter(int W, int lm) {
+    const int M = 1 << lm;
+    const double pi = 3.14159265358979323846264338327950288;
+    std::vector<double> re((size_t)M, 0.0), im((size_t)M, 0.0);
+    for (long long n = 0; n < W; n++) {
+        const long long r = (n * n) % (2LL * W);
+        const double a = pi * (double)r / (double)W;
+        re[(size_t)n] = cos(a); im[(size_t)n] = sin(a);
+        if (n) { re[(size_t)(M - n)] = cos(a); im[(size_t)(M - n)] = sin(a); }
+    }
+    // in-place radix-2 decimation-in-time FFT in double (M <= 16384: a table built once per engine)
+    for (int i = 1, j = 0; i < M; i++) {
+        int bit = M >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) { std::swap(re[(size_t)i], re[(size_t)j]); std::swap(im[(size_t)i], im[(size_t)j]); }
+    }
+    for (int len = 2; len <= M; len <<= 1) {
+        for (int i = 0; i < M; i += len)
+            for (int k = 0; k < len / 2; k++) {
+                const double a = -2.0 * pi * (double)k / (double)len, wr = cos(a), wi = sin(a);
+                const size_t u = (size_t)(i + k), v = (size_t)(i + k + len / 2);
+                const double tr = re[v] * wr - im[v] * wi, ti = re[v] * wi + im[v] * wr;
+                re[v] = re[u] - tr; im[v] = im[u] - ti;
+                re[u] += tr; im[u] += ti;
+            }
+    }
+    const PlanDesc d = make_plan(lm);
+    std::vector<cf> f((size_t)M);
+    for (int pos = 0; pos < M; pos++) {
+        const int k = rt_pos_to_bin(d, pos);
+        f[(size_t)pos] = make_cf((float)(re[(size_t)k] / M), (float)(im[(size_t)k] / M));
+    }
+    return f;
+}
+
 // frame-invariant index tables of the spectral steps: padded shared-memory slot indices of the bins
 // a pair / quad thread touches, and the pair's bin number
 inline std::vector<uint2> host_pair_table(int log2h) {

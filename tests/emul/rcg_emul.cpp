@@ -23,6 +23,7 @@ static inline float2 apply(size_t, unsigned bin, unsigned n_bins, float2 v) {
 
 #include "../../rocoder_b200/csrc/rcg_frame.h"
 #include "../../rocoder_b200/csrc/rcg_frame_pair.h"
+#include "../../rocoder_b200/csrc/rcg_frame_bluestein.h"
 #include "../../rocoder_b200/csrc/rcg_tables.h"
 
 using namespace rcg;
@@ -167,7 +168,80 @@ static int emul_boundary(StretchParams prm, const float* head, const float* tail
     return 0;
 }
 
+// windows that are not a power of two: the chirp-z path (rcg_frame_bluestein.h), one CTA's threads phase by phase
+template <int LM>
+static int emul_run_bluestein(StretchParams prm, int W) {
+    using C = FrameCfg<LM>;
+    const int H = W / 2;
+    std::vector<float> window(W), env(H);
+    host_hanning(window.data(), W);
+    host_crossfade_compensation(env.data(), H);
+    std::vector<cf> tw = host_pass_twiddles(LM), chirp = host_bluestein_chirp(W), filt = host_bluestein_filter(W, LM);
+    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data();
+    std::vector<float> lr = lerp_table(prm.pitch);
+    prm.lerp_ratio = lr.data();
+    BluesteinTables bt{chirp.data(), filt.data(), W};
+    std::vector<cf> S(C::SMEM_CF);
+    std::vector<float> zbuf(H), tail(H);
+    HostExec ex{C::NT};
+    const int items = prm.channels * prm.n_runs;
+    for (int item = 0; item < items; item++) run_work_item_bluestein<LM>(ex, S.data(), zbuf.data(), prm, bt, item, tail.data(), true);
+    return 0;
+}
+template <int LM>
+static int emul_boundary_bluestein(StretchParams prm, int W, const float* head, const float* tail_prev) {
+    using C = FrameCfg<LM>;
+    const int H = W / 2;
+    std::vector<float> env(H), zbuf(H);
+    host_crossfade_compensation(env.data(), H);
+    prm.env = env.data();
+    std::vector<float> lr = lerp_table(prm.pitch);
+    prm.lerp_ratio = lr.data();
+    BluesteinTables bt{nullptr, nullptr, W};
+    HostExec ex{C::NT};
+    for (int c = 0; c < prm.channels; c++) run_boundary_bluestein<LM>(ex, zbuf.data(), prm, bt, c, head, tail_prev);
+    return 0;
+}
+
 extern "C" {
+
+// the same entry points for a window that is not a power of two (W even, 64..8192)
+int rcg_emul_stretch_any(int W, const float* in, long long in_stride, long long in_origin, long long in_valid, float* out,
+                         long long out_stride, long long out_origin, long long frame_begin, long long frame_end, int run_len,
+                         int channels, int step, int pitch, int samples_needed, float amp, unsigned long long seed,
+                         unsigned flags, int first_channel, const float* tail_in, float* tail_out, float* head_out) {
+    StretchParams p;
+    memset(&p, 0, sizeof(p));
+    p.in = in; p.in_stride = in_stride; p.in_origin = in_origin; p.in_valid = in_valid;
+    p.out = out; p.out_stride = out_stride; p.out_origin = out_origin;
+    p.frame_begin = frame_begin; p.frame_end = frame_end; p.run_len = run_len;
+    long long nf = frame_end - frame_begin;
+    p.n_runs = nf > 0 ? (int)((nf + run_len - 1) / run_len) : 0;
+    p.channels = channels; p.channel_offset = first_channel; p.step = step; p.pitch = pitch; p.samples_needed = samples_needed;
+    p.amp = amp; p.flags = flags;
+    p.keys = make_philox_keys(seed);
+    p.tail_in = tail_in; p.tail_out = tail_out; p.head_out = head_out;
+    switch (bluestein_log2m(W)) {
+#define CASE(L) case L: return emul_run_bluestein<L>(p, W);
+        CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+#undef CASE
+    }
+    return -1;
+}
+int rcg_emul_boundary_any(int W, float* out, long long out_stride, long long out_origin, long long frame_begin, int channels,
+                          int pitch, int samples_needed, float amp, const float* head, const float* tail_prev) {
+    StretchParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = out; p.out_stride = out_stride; p.out_origin = out_origin;
+    p.frame_begin = frame_begin; p.channels = channels; p.pitch = pitch;
+    p.samples_needed = samples_needed; p.amp = amp;
+    switch (bluestein_log2m(W)) {
+#define CASE(L) case L: return emul_boundary_bluestein<L>(p, W, head, tail_prev);
+        CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14)
+#undef CASE
+    }
+    return -1;
+}
 
 // force the full-rate synthesis path even for even pitch multiples (A/B checks)
 void rcg_emul_disable_half_rate(int v) { g_disable_half_rate = v; }

@@ -216,6 +216,8 @@ def _declare_emulator(E):
                                    C.c_int, C.c_float, C.c_ulonglong, C.c_uint, C.c_int, PF, PF, PF]
     E.rcg_emul_boundary.argtypes = [C.c_int, PF, C.c_longlong, C.c_longlong, C.c_longlong, C.c_int, C.c_int,
                                     C.c_int, C.c_float, PF, PF]
+    E.rcg_emul_stretch_any.argtypes = E.rcg_emul_stretch.argtypes
+    E.rcg_emul_boundary_any.argtypes = E.rcg_emul_boundary.argtypes
     E.rcg_emul_stretch_plugin.argtypes = [C.c_int, PF, C.c_longlong, C.c_longlong, PF, C.c_longlong,
                                           C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                           C.c_ulonglong, APPLY_FN]
@@ -252,8 +254,10 @@ def emul_segment(x: np.ndarray, in_origin: int, out: np.ndarray, factor: float, 
     k, olen = c["frames_per_call"], c["out_len_per_call"]
     ch, n = x.shape
     flags = (1 if bypass else 0) | (2 if defer_first else 0)
-    rc = (lib or emulator()).rcg_emul_stretch(
-        int(np.log2(W)), _pf(x), x.strides[0] // 4, in_origin, n, _pf(out), out.strides[0] // 4,
+    pow2 = W & (W - 1) == 0
+    E = lib or emulator()
+    rc = (E.rcg_emul_stretch if pow2 else E.rcg_emul_stretch_any)(
+        int(np.log2(W)) if pow2 else W, _pf(x), x.strides[0] // 4, in_origin, n, _pf(out), out.strides[0] // 4,
         first_call * olen, first_call * k, (first_call + n_calls) * k, run_len, ch, c["sample_step_len"], pitch,
         c["samples_needed_per_window"], c["corrected_amp_factor"], seed, flags, first_channel, _pf(tail_in),
         _pf(tail_out), _pf(head_out))
@@ -263,7 +267,9 @@ def emul_segment(x: np.ndarray, in_origin: int, out: np.ndarray, factor: float, 
 def emul_boundary(out: np.ndarray, factor: float, pitch: int, W: int, first_call: int, head: np.ndarray,
                   tail_prev: np.ndarray, amplitude: float = 1.0):
     c = constants(factor, pitch, W, amplitude)
-    rc = emulator().rcg_emul_boundary(int(np.log2(W)), _pf(out), out.strides[0] // 4,
+    pow2 = W & (W - 1) == 0
+    rc = (emulator().rcg_emul_boundary if pow2 else emulator().rcg_emul_boundary_any)(
+        int(np.log2(W)) if pow2 else W, _pf(out), out.strides[0] // 4,
                                       first_call * c["out_len_per_call"], first_call * c["frames_per_call"],
                                       out.shape[0], pitch, c["samples_needed_per_window"],
                                       c["corrected_amp_factor"], _pf(head), _pf(tail_prev))
