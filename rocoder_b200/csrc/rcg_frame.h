@@ -934,20 +934,31 @@ RCG_HD void phase_resample(const cf* S, int t, const StretchParams& prm, int cha
             out[o - prm.out_origin] = frame_value(S, i);
         }
     } else if (p < -1) {
-        // resample_slower (resampler.rs:20-35): out[i*q + j] = z[i] + (z[i+1] - z[i]) * (j / q).
-        // (i, j) advance by (NT / q, NT % q) per iteration: no integer division in the loop; the
-        // q ratios j/q come from a host-computed table (same IEEE division as the reference).
+        // resample_slower (resampler.rs:20-35): out[i*q + j] = z[i] + (z[i+1] - z[i]) * (j / q), i < S - 1.
+        // Consecutive threads write consecutive outputs (whole sectors per warp store; a thread per input interval
+        // writing its q outputs was measured 32 % slower on config 4: partial-sector stores).  The threads used are
+        // a multiple of q, so that a thread's j -- and its ratio j/q, from a host-computed table (same IEEE division
+        // as the reference) -- never changes and i advances by a constant: no division, no branch in the loop.
         const int q = -p;
         const int n = (prm.samples_needed - 1) * q;
         float* dst = out + (frame * (long long)n - prm.out_origin);
-        const int di = C::NT / q, dj = C::NT - di * q;
-        int i = t / q, j = t - i * q;
-        for (int tt = t; tt < n; tt += C::NT) {
-            const float cur = frame_value(S, i), nxt = frame_value(S, i + 1);
-            const float ratio = prm.lerp_ratio[j];
-            dst[tt] = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), ratio));
-            i += di; j += dj;
-            if (j >= q) { j -= q; i++; }
+        const int nt_q = (C::NT / q) * q;
+        if (nt_q > 0) {
+            if (t < nt_q) {
+                const int di = nt_q / q;
+                int i = t / q;
+                const float ratio = prm.lerp_ratio[t - i * q];
+                for (int tt = t; tt < n; tt += nt_q, i += di) {
+                    const float cur = frame_value(S, i), nxt = frame_value(S, i + 1);
+                    dst[tt] = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), ratio));
+                }
+            }
+        } else {   // more steps per interval than threads in the lane (tiny windows with a large |p|)
+            for (int tt = t; tt < n; tt += C::NT) {
+                const int i = tt / q, j = tt - i * q;
+                const float cur = frame_value(S, i), nxt = frame_value(S, i + 1);
+                dst[tt] = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), prm.lerp_ratio[j]));
+            }
         }
     }
 }

@@ -68,10 +68,13 @@ constexpr int min_ctas() { return (LOG2H >= 14 || FrameCfg<LOG2H>::TW_SMEM) ? 1 
 // every mode.
 //   0  generic (bypass hook, anything else)     1  pitch 2 on the half-rate path (the headline `-p 2`)
 //   2  pitch 1, full rate                       3  any other pitch, full rate
+//   4  pitch -2                                 5  pitch -3 (BASELINE config 4): the lerp walk's strides are constants
 RCG_HD constexpr int stretch_mode_of(int pitch, uint32_t flags) {
     const uint32_t fl = flags & ~(uint32_t)kFlagDeferFirst;
     if (fl == kFlagHalfRate && pitch == 2) return 1;
     if (fl == 0u && pitch == 1) return 2;
+    if (fl == 0u && pitch == -2) return 4;
+    if (fl == 0u && pitch == -3) return 5;
     if (fl == 0u) return 3;
     return 0;
 }
@@ -81,6 +84,8 @@ __device__ __forceinline__ StretchParams with_mode_constants(const StretchParams
     if constexpr (MODE == 1) { p.pitch = 2; p.flags = (in.flags & kFlagDeferFirst) | kFlagHalfRate; }
     if constexpr (MODE == 2) { p.pitch = 1; p.flags = in.flags & kFlagDeferFirst; }
     if constexpr (MODE == 3) { p.flags = in.flags & kFlagDeferFirst; }
+    if constexpr (MODE == 4) { p.pitch = -2; p.flags = in.flags & kFlagDeferFirst; }
+    if constexpr (MODE == 5) { p.pitch = -3; p.flags = in.flags & kFlagDeferFirst; }
     return p;
 }
 

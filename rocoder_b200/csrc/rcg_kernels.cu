@@ -81,6 +81,7 @@ cudaError_t geometry_t(LaunchGeometry* g) {
     cudaError_t e = cudaSuccess;
     const void* kernels[] = {(const void*)stretch_kernel<LOG2H, false, 0>, (const void*)stretch_kernel<LOG2H, false, 1>,
                              (const void*)stretch_kernel<LOG2H, false, 2>, (const void*)stretch_kernel<LOG2H, false, 3>,
+                             (const void*)stretch_kernel<LOG2H, false, 4>, (const void*)stretch_kernel<LOG2H, false, 5>,
                              (const void*)stretch_kernel<LOG2H, true, 0>};
     for (const void* k : kernels) {
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
@@ -112,6 +113,8 @@ cudaError_t launch_t(const StretchParams& prm, int grid, cudaStream_t stream) {
             case 1: stretch_kernel<LOG2H, false, 1><<<grid, block, smem, stream>>>(prm, n_items); break;
             case 2: stretch_kernel<LOG2H, false, 2><<<grid, block, smem, stream>>>(prm, n_items); break;
             case 3: stretch_kernel<LOG2H, false, 3><<<grid, block, smem, stream>>>(prm, n_items); break;
+            case 4: stretch_kernel<LOG2H, false, 4><<<grid, block, smem, stream>>>(prm, n_items); break;
+            case 5: stretch_kernel<LOG2H, false, 5><<<grid, block, smem, stream>>>(prm, n_items); break;
             default: stretch_kernel<LOG2H, false, 0><<<grid, block, smem, stream>>>(prm, n_items); break;
         }
     }
