@@ -179,74 +179,91 @@ RCG_HD void pair_phase_spectral_in_odd(cf* S, int t, const StretchParams& prm, c
 }
 
 // ---- cross-CTA radix-2 DIT stage + overlap-add -------------------------------------------------------
-// CTA 0: first half window: /W * window, + carried half, * envelope * amp, emit (pitch 1) or stage
-// in global memory for the resampling gather.  CTA 1: second half window -> carried buffer.
-RCG_HD void pair_phase_ola(const cf* S, const cf* peer, int r, int t, const StretchParams& prm, const PairTables& pt,
-                           int channel, long long frame, const float* tail_old, float* tail_new, float* stage,
-                           bool emit, bool write_head) {
+// After the local inverses CTA 0 holds u[n], CTA 1 holds v[n], n < HL; the last DIT stage is
+//     first half window [n] = u[n] + conj(w^n) v[n]      second half window [n] = u[n] - conj(w^n) v[n].
+// CTA r finishes BOTH half windows for the packed indices n in [r HL/2, (r+1) HL/2): it needs its own buffer and only
+// half of the peer's.  That half is PUSHED: before the phase each CTA writes the part of its buffer the peer needs
+// into the peer's landing zone (distributed shared memory, posted stores; one cluster barrier makes them visible),
+// so no remote load sits on the critical path, and the carried half window of an index range is read and written
+// by the same CTA -- it never crosses the pair.
+constexpr int kPairNR = kPairHL / 2;                       // packed indices per CTA in this phase
+constexpr int kPairLandCf = kPairNR + (kPairNR >> 4);      // landing zone: the padded slots of kPairNR elements
+
+// copy the padded slots of the packed indices the peer will finish into the peer's landing zone
+RCG_HD void pair_phase_push(const cf* S, cf* peer_land, int r, int t) {
+    using C = FrameCfg<kPairLog2HL>;
+    // CTA 0 gives [NR, HL) to CTA 1, CTA 1 gives [0, NR) to CTA 0; NR is a multiple of 16, so the padded slots of a
+    // range are contiguous and phys(n) - phys(base) = phys(n - base)
+    const cf* src = S + phys((1 - r) * kPairNR);
+    for (int i = t; i < kPairLandCf; i += C::NT) peer_land[i] = src[i];
+}
+
+// first half window: /W * window, + carried half, * envelope * amp, emit (pitch 1) or stage in global memory for the
+// resampling gather; second half window -> carried buffer (same index, same thread: in place)
+RCG_HD void pair_phase_ola(const cf* S, const cf* land, int r, int t, const StretchParams& prm, const PairTables& pt,
+                           int channel, long long frame, float* tail, float* stage, bool emit, bool write_head) {
     using C = FrameCfg<kPairLog2HL>;
     const bool bypass = prm.flags & kFlagBypass;
     float* out = prm.out + (long long)channel * prm.out_stride;
     const float scale = bypass ? 1.0f : prm.inv_w;
 RCG_UNROLL(RCG_PAIR_OLA_UNROLL)
-    for (int n = t; n < kPairHL; n += C::NT) {
-        float zr, zi;
+    for (int i = t; i < kPairNR; i += C::NT) {
+        const int n = r * kPairNR + i;
+        const cf own = S[phys(n)], got = land[phys(i)];
+        const cf u = r == 0 ? own : got;      // CTA 0's buffer
+        const cf v = r == 0 ? got : own;      // CTA 1's buffer
+        cf za, zb;                            // first / second half window, before scaling
         if (bypass) {
-            const cf own = S[phys(n)];
-            zr = own.x; zi = own.y;
+            za = u; zb = v;                   // the load phase left the two half windows in the two buffers
         } else {
-            const cf u = r == 0 ? S[phys(n)] : peer[phys(n)];
-            const cf v = r == 0 ? peer[phys(n)] : S[phys(n)];
             const cf w = pair_cross_tw(pt.cross_tw, n);  // conj(w) v
             const float pr = v.x * w.x + v.y * w.y, pi = v.y * w.x - v.x * w.y;
-            zr = r == 0 ? u.x + pr : u.x - pr;
-            zi = r == 0 ? u.y + pi : u.y - pi;
+            za = make_cf(u.x + pr, u.y + pi);
+            zb = make_cf(u.x - pr, u.y - pi);
         }
-        if (r == 0) {
-            const cf wa = ld_stream2(prm.window + 2 * n);
-            const float y0 = RCG_MUL(RCG_MUL(zr, scale), wa.x), y1 = RCG_MUL(RCG_MUL(zi, scale), wa.y);
-            const cf old = ld_pair(tail_old + 2 * n);      // unconditional: no branches around loads
-            const cf e = ld_stream2(prm.env + 2 * n);
-            if (write_head) st_pair(prm.head_out + (long long)channel * kPairH + 2 * n, y0, y1);
-            if (emit) {
-                const float z0 = RCG_MUL(RCG_MUL(RCG_ADD(y0, old.x), e.x), prm.amp);
-                const float z1 = RCG_MUL(RCG_MUL(RCG_ADD(y1, old.y), e.y), prm.amp);
-                if (prm.pitch == 1) st_pair(out + (frame * (long long)kPairH + 2 * n - prm.out_origin), z0, z1);
-                else st_pair(stage + 2 * n, z0, z1);
-            }
-        } else {
-            const cf wb = ld_stream2(prm.window + kPairH + 2 * n);
-            st_pair(tail_new + 2 * n, RCG_MUL(RCG_MUL(zr, scale), wb.x), RCG_MUL(RCG_MUL(zi, scale), wb.y));
+        const cf wa = ld_stream2(prm.window + 2 * n), wb = ld_stream2(prm.window + kPairH + 2 * n);
+        const float y0 = RCG_MUL(RCG_MUL(za.x, scale), wa.x), y1 = RCG_MUL(RCG_MUL(za.y, scale), wa.y);
+        const cf old = ld_pair(tail + 2 * n);      // unconditional: no branches around loads
+        st_pair(tail + 2 * n, RCG_MUL(RCG_MUL(zb.x, scale), wb.x), RCG_MUL(RCG_MUL(zb.y, scale), wb.y));
+        const cf e = ld_stream2(prm.env + 2 * n);
+        if (write_head) st_pair(prm.head_out + (long long)channel * kPairH + 2 * n, y0, y1);
+        if (emit) {
+            const float z0 = RCG_MUL(RCG_MUL(RCG_ADD(y0, old.x), e.x), prm.amp);
+            const float z1 = RCG_MUL(RCG_MUL(RCG_ADD(y1, old.y), e.y), prm.amp);
+            if (prm.pitch == 1) st_pair(out + (frame * (long long)kPairH + 2 * n - prm.out_origin), z0, z1);
+            else st_pair(stage + 2 * n, z0, z1);
         }
     }
 }
 
-// resample from the staged half window in global memory (CTA 0 only)
-RCG_HD void pair_phase_resample(const float* stage, int t, const StretchParams& prm, int channel, long long frame) {
-    using C = FrameCfg<kPairLog2HL>;
+// resample from the staged half window in global memory: thread tg of nthr (both CTAs of the pair share the block)
+RCG_HD void pair_phase_resample(const float* stage, int tg, int nthr, const StretchParams& prm, int channel, long long frame) {
     float* out = prm.out + (long long)channel * prm.out_stride;
     const int p = prm.pitch;
     if (p > 1) {
         const long long g0 = frame * (long long)kPairH;
         const long long o_begin = (g0 + p - 1) / p, o_end = (g0 + kPairH + p - 1) / p;
-        for (long long o = o_begin + t; o < o_end; o += C::NT) out[o - prm.out_origin] = stage[(int)(o * p - g0)];
+        for (long long o = o_begin + tg; o < o_end; o += nthr) out[o - prm.out_origin] = stage[(int)(o * p - g0)];
     } else if (p < -1) {
         const int q = -p;
         const int n = (prm.samples_needed - 1) * q;
         float* dst = out + (frame * (long long)n - prm.out_origin);
-        const int di = C::NT / q, dj = C::NT - di * q;
-        int i = t / q, j = t - i * q;
-        for (int tt = t; tt < n; tt += C::NT) {
-            const float cur = stage[i], nxt = stage[i + 1];
-            dst[tt] = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), prm.lerp_ratio[j]));
-            i += di; j += dj;
-            if (j >= q) { j -= q; i++; }
+        const int nt_q = (nthr / q) * q;   // a multiple of q threads: a thread's j and ratio never change (see phase_resample)
+        if (tg < nt_q) {
+            const int di = nt_q / q;
+            int i = tg / q;
+            const float ratio = prm.lerp_ratio[tg - i * q];
+            for (int tt = tg; tt < n; tt += nt_q, i += di) {
+                const float cur = stage[i], nxt = stage[i + 1];
+                dst[tt] = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), ratio));
+            }
         }
     }
 }
 
 // Exec for the pair: par(f) runs f(r, t) for every thread of both CTAs, then a CTA barrier;
-// par_cluster(f) ends in a cluster barrier (release/acquire) instead.  bufs[r] is CTA r's buffer.
+// par_cluster(f) ends in a cluster barrier (release/acquire) instead; cluster_arrive() / cluster_wait() are the two
+// halves of one more cluster barrier, issued apart.  bufs[r] is CTA r's buffer.
 // passes FIRST..LAST of the local transform one by one (each ends in a CTA barrier)
 template <int PASS, int LAST, bool INV, class Exec>
 RCG_HD void pair_fft_range(Exec& ex, cf* const (&bufs)[2], const StretchParams& prm, bool work) {
@@ -265,9 +282,13 @@ RCG_HD void pair_fft_all(Exec& ex, cf* const (&bufs)[2], const StretchParams& pr
     if constexpr (INV) pair_fft_range<NP - 3, 0, true>(ex, bufs, prm, work);
 }
 
+// bufs[r] = CTA r's transform buffer, land[r] = CTA r's landing zone (land[r ^ 1] is written through distributed
+// shared memory).  Cluster barriers of one frame: wait (the peer is done with its landing zone) -> push ->
+// arrive + wait (landing zones complete) -> overlap-add -> arrive; the arrive / wait pair around the push is split,
+// so it costs nothing unless the peer really is a whole phase behind.
 template <class Exec>
-RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], const StretchParams& prm, const PairTables& pt,
-                               int item, float* scratch, bool active) {
+RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], cf* const (&land)[2], const StretchParams& prm,
+                               const PairTables& pt, int item, float* scratch, bool active) {
     using C = FrameCfg<kPairLog2HL>;
     const int channel = active ? item / prm.n_runs : 0;
     const int run = active ? item - channel * prm.n_runs : 0;
@@ -280,16 +301,15 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], const StretchPara
     const bool halo = active && f0 > 0 && !defer && !have_tail_in;
     const bool bypass = prm.flags & kFlagBypass;
     const bool spectrum_in = prm.flags & kFlagSpectrumIn;
-    float* tails[2] = {scratch, scratch + kPairH};
-    float* stage = scratch + 2 * kPairH;
-    // carried half window for the first iteration lives in tails[0]
-    ex.par_cluster([&](int r, int t) {
-        if (!active || r != 1) return;
+    float* tail = scratch;                 // [H]: carried half window; CTA r owns the samples of its index range
+    float* stage = scratch + 2 * kPairH;   // [H]: finished half window for the resampling gather
+    ex.par([&](int r, int t) {
+        if (!active) return;
         const float* src = have_tail_in ? prm.tail_in + (long long)channel * kPairH : nullptr;
-        for (int i = t; i < kPairH; i += C::NT) tails[0][i] = src ? src[i] : 0.0f;
+        for (int i = 2 * r * kPairNR + t; i < 2 * (r + 1) * kPairNR; i += C::NT) tail[i] = src ? src[i] : 0.0f;
     });
+    ex.cluster_arrive();   // pairs with the first frame's wait
     const int n_iter = prm.run_len + 1;
-    int cnt = 0;  // frames done so far: the carried half window is in tails[cnt & 1]
     for (int it = 0; it < n_iter; it++) {
         const long long f = f0 - 1 + it;
         const bool is_halo = (it == 0);
@@ -326,21 +346,26 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], const StretchPara
             pair_fft_all<true>(ex, bufs, prm, work);
         }
         }
-        ex.cluster_sync();   // both halves of the inverse are complete
-        ex.par_cluster([&](int r, int t) {   // ends in a cluster barrier: peers are done reading, tails are visible
-            if (work) pair_phase_ola(bufs[r], bufs[r ^ 1], r, t, prm, pt, channel, f, tails[cnt & 1], tails[(cnt & 1) ^ 1],
-                                     stage, emit, head);
-        });
-        if (work) cnt++;
-        if (prm.pitch != 1)
-            ex.par([&](int r, int t) { if (emit && r == 0) pair_phase_resample(stage, t, prm, channel, f); });
+        ex.cluster_wait();   // the peer has finished reading its landing zone (previous frame)
+        ex.par_cluster([&](int r, int t) { if (work) pair_phase_push(bufs[r], land[r ^ 1], r, t); });   // + barrier: zones complete
+        auto ola = [&](int r, int t) {
+            if (work) pair_phase_ola(bufs[r], land[r], r, t, prm, pt, channel, f, tail, stage, emit, head);
+        };
+        if (prm.pitch != 1) {
+            ex.par_cluster(ola);   // the staged half window crosses the pair through global memory
+            ex.par([&](int r, int t) { if (emit) pair_phase_resample(stage, r * C::NT + t, 2 * C::NT, prm, channel, f); });
+            // (the stage is written again only after the next frame's wait below has seen the peer's arrive)
+        } else {
+            ex.par(ola);
+        }
+        ex.cluster_arrive();   // done with my landing zone
     }
+    ex.cluster_wait();
     if (prm.tail_out != nullptr) {
         ex.par([&](int r, int t) {
-            if (!active || f1 != prm.frame_end || r != 1) return;
-            const float* last = tails[cnt & 1];
+            if (!active || f1 != prm.frame_end) return;
             float* dst = prm.tail_out + (long long)channel * kPairH;
-            for (int i = t; i < kPairH; i += C::NT) dst[i] = last[i];
+            for (int i = 2 * r * kPairNR + t; i < 2 * (r + 1) * kPairNR; i += C::NT) dst[i] = tail[i];
         });
     }
 }
@@ -387,7 +412,7 @@ RCG_HD void run_boundary_pair(ExecCta& ex, const StretchParams& prm, int channel
             else stage[i] = z;
         }
     });
-    if (prm.pitch != 1) ex.par([&](int t) { pair_phase_resample(stage, t, prm, channel, frame); });
+    if (prm.pitch != 1) ex.par([&](int t) { pair_phase_resample(stage, t, C::NT, prm, channel, frame); });
 }
 
 }  // namespace rcg

@@ -47,20 +47,25 @@ struct PairDeviceExec {
         cluster_barrier();
     }
     __device__ __forceinline__ void cluster_sync() { cluster_barrier(); }
+    // the two halves of one barrier, issued apart: whatever lies between them overlaps the peer's progress
+    __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+    __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 };
 
 __device__ __forceinline__ void stretch_pair_body(const StretchParams& prm, const PairTables& pt, int n_items,
                                                   unsigned char* smem_raw) {
     const int r = (int)cluster_cta_rank();
     cf* S = reinterpret_cast<cf*>(smem_raw);
-    cf* bufs[2];
-    bufs[r] = S;
-    bufs[r ^ 1] = cluster_map_shared(S, (unsigned)(r ^ 1));   // the peer's half, read through DSMEM
+    cf* zone = S + FrameCfg<kPairLog2HL>::SMEM_CF;             // landing zone behind the transform buffer
+    cf* bufs[2] = {S, S};                                      // only bufs[r] is touched: transforms are local
+    cf* land[2];
+    land[r] = zone;
+    land[r ^ 1] = cluster_map_shared(zone, (unsigned)(r ^ 1));   // the peer's zone, written through DSMEM
     PairDeviceExec ex{r, (int)threadIdx.x};
     const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
     float* scratch = pt.scratch + (long long)cid * 3 * kPairH;
-    for (int item = cid; item < n_items; item += ncl) run_work_item_pair(ex, bufs, prm, pt, item, scratch, true);
-    cluster_barrier();  // no CTA may exit while its peer can still read its shared memory
+    for (int item = cid; item < n_items; item += ncl) run_work_item_pair(ex, bufs, land, prm, pt, item, scratch, true);
+    cluster_barrier();  // no CTA may exit while its peer can still write into its shared memory
 }
 
 }  // namespace rcg

@@ -115,6 +115,8 @@ struct PairHostExec {
     template <class F>
     void par_cluster(F f) { par(f); }
     void cluster_sync() {}
+    void cluster_arrive() {}
+    void cluster_wait() {}
 };
 
 static int emul_run_pair(StretchParams prm) {
@@ -134,9 +136,11 @@ static int emul_run_pair(StretchParams prm) {
     PairTables pt{cross.data(), se.data(), so.data(), scratch.data()};
     std::vector<cf> S0(C::SMEM_CF), S1(C::SMEM_CF);
     cf* bufs[2] = {S0.data(), S1.data()};
+    std::vector<cf> L0(kPairLandCf), L1(kPairLandCf);
+    cf* land[2] = {L0.data(), L1.data()};
     PairHostExec ex{C::NT};
     const int items = prm.channels * prm.n_runs;
-    for (int item = 0; item < items; item++) run_work_item_pair(ex, bufs, prm, pt, item, scratch.data(), true);
+    for (int item = 0; item < items; item++) run_work_item_pair(ex, bufs, land, prm, pt, item, scratch.data(), true);
     return 0;
 }
 
@@ -358,7 +362,9 @@ static int emul_plugin_pair(StretchParams prm, apply_fn fn) {
             if (fn && fn(1234, x, kPairW, tmp.data()) == 0) memcpy(x, tmp.data(), sizeof(float) * 2 * kPairW);
         }
     prm.flags |= kFlagSpectrumIn;
-    for (int item = 0; item < items; item++) run_work_item_pair(ex, bufs, prm, pt, item, scratch.data(), true);
+    std::vector<cf> L0(kPairLandCf), L1(kPairLandCf);
+    cf* land[2] = {L0.data(), L1.data()};
+    for (int item = 0; item < items; item++) run_work_item_pair(ex, bufs, land, prm, pt, item, scratch.data(), true);
     return 0;
 }
 
