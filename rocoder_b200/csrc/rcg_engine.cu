@@ -566,7 +566,7 @@ static bool engine_half_rate(const rcg_engine* e) {
 
 static void fill_params(const rcg_engine* e, StretchParams& p) {
     memset(&p, 0, sizeof(p));
-    p.window = e->d_window; p.env = e->d_env; p.tw = e->d_tw; p.spec_tw = e->d_spec_tw;
+    p.window = e->d_window; p.env = e->d_env; p.tw = e->d_tw; p.tw0 = e->d_tw; p.spec_tw = e->d_spec_tw;
     p.spec_tw_hr = e->d_spec_tw_hr; p.window_even = e->d_window_even; p.env_even = e->d_env_even;
     p.lerp_ratio = e->d_lerp_ratio;
     p.pair_tab = e->d_pair_tab; p.quad_tab = e->d_quad_tab;

@@ -58,6 +58,7 @@ struct StretchParams {
     const float* window;    // [W]   windows::hanning (host-computed, windows.rs:4-9)
     const float* env;       // [H]   crossfade::hanning_crossfade_compensation (crossfade.rs:4-10)
     const cf* tw;           // packed per-pass twiddles
+    const cf* tw0;          // the table of pass 0 (== tw unless a kernel moved the other passes' tables, see rcg_pair_body.h)
     const cf* spec_tw;      // [H/2] exp(-2 pi i k/W) in the spectral step's pair order
     const cf* spec_tw_hr;   // [H/4] the same in the half-rate quad order
     const float* window_even;  // [H]   window[2i]   (half-rate synthesis)
@@ -132,7 +133,9 @@ RCG_HD cf ld_cf(const cf* p) {
 // pass twiddles: read-only global tables, or the CTA's shared-memory copy (FrameCfg::TW_SMEM)
 template <int LOG2H>
 RCG_HD cf ld_tw(const cf* p) {
-    if constexpr (FrameCfg<LOG2H>::TW_SMEM) return *p;
+    // LOG2H == 14: the W = 65536 pair kernel keeps the tables of passes >= 1 in shared memory, the W = 32768 kernel
+    // in global memory: a generic load serves both
+    if constexpr (FrameCfg<LOG2H>::TW_SMEM || LOG2H == 14) return *p;
     else return ld_cf(p);
 }
 RCG_HD uint4 ld_u4(const uint4* p) {

@@ -32,8 +32,8 @@ struct PairTables {
     float* scratch;          // per cluster: tail[2][H] then stage[H]
 };
 
-RCG_HD cf pair_cross_tw(const cf* tab, int n) {
-    const cf a = ld_cf(tab + (n >> 6)), b = ld_cf(tab + kPairHL / 64 + (n & 63));
+RCG_HD cf pair_cross_tw(const cf* tab, int n) {   // tab: global memory, or the CTA's shared-memory copy
+    const cf a = tab[n >> 6], b = tab[kPairHL / 64 + (n & 63)];
     return tw_mul<false>(a, make_tw(b));
 }
 
@@ -206,9 +206,14 @@ RCG_HD void pair_phase_ola(const cf* S, const cf* land, int r, int t, const Stre
     const bool bypass = prm.flags & kFlagBypass;
     float* out = prm.out + (long long)channel * prm.out_stride;
     const float scale = bypass ? 1.0f : prm.inv_w;
+    // the carried half window is read and written in place by the same thread; the next iteration's value is
+    // fetched before this iteration's store so that the load does not wait behind it
+    cf old_next = ld_pair(tail + 2 * (r * kPairNR + t));
 RCG_UNROLL(RCG_PAIR_OLA_UNROLL)
     for (int i = t; i < kPairNR; i += C::NT) {
         const int n = r * kPairNR + i;
+        const cf old = old_next;
+        if (i + C::NT < kPairNR) old_next = ld_pair(tail + 2 * (n + C::NT));
         const cf own = S[phys(n)], got = land[phys(i)];
         const cf u = r == 0 ? own : got;      // CTA 0's buffer
         const cf v = r == 0 ? got : own;      // CTA 1's buffer
@@ -223,7 +228,6 @@ RCG_UNROLL(RCG_PAIR_OLA_UNROLL)
         }
         const cf wa = ld_stream2(prm.window + 2 * n), wb = ld_stream2(prm.window + kPairH + 2 * n);
         const float y0 = RCG_MUL(RCG_MUL(za.x, scale), wa.x), y1 = RCG_MUL(RCG_MUL(za.y, scale), wa.y);
-        const cf old = ld_pair(tail + 2 * n);      // unconditional: no branches around loads
         st_pair(tail + 2 * n, RCG_MUL(RCG_MUL(zb.x, scale), wb.x), RCG_MUL(RCG_MUL(zb.y, scale), wb.y));
         const cf e = ld_stream2(prm.env + 2 * n);
         if (write_head) st_pair(prm.head_out + (long long)channel * kPairH + 2 * n, y0, y1);
@@ -268,7 +272,7 @@ RCG_HD void pair_phase_resample(const float* stage, int tg, int nthr, const Stre
 template <int PASS, int LAST, bool INV, class Exec>
 RCG_HD void pair_fft_range(Exec& ex, cf* const (&bufs)[2], const StretchParams& prm, bool work) {
     if constexpr (INV ? PASS >= LAST : PASS <= LAST) {
-        ex.par([&](int r, int t) { if (work) phase_fft_pass<kPairLog2HL, PASS, INV>(bufs[r], t, prm.tw); });
+        ex.par([&](int r, int t) { if (work) phase_fft_pass<kPairLog2HL, PASS, INV>(bufs[r], t, PASS == 0 ? prm.tw0 : prm.tw); });
         pair_fft_range<INV ? PASS - 1 : PASS + 1, LAST, INV>(ex, bufs, prm, work);
     }
 }

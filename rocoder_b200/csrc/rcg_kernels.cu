@@ -183,7 +183,7 @@ cudaError_t pair_geometry(LaunchGeometry* g) {
     using C = FrameCfg<kPairLog2HL>;
     g->threads = C::NT;
     g->frames_per_cta = 1;
-    g->smem_bytes = (size_t)(C::SMEM_CF + kPairLandCf) * sizeof(cf);   // transform buffer + landing zone
+    g->smem_bytes = kPairSmemBytes;   // transform buffer + landing zone + small twiddle tables
     g->max_ctas_per_sm = 1;
     cudaError_t e = cudaFuncSetAttribute(analysis_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g->smem_bytes);
     if (e != cudaSuccess) return e;
@@ -193,14 +193,14 @@ cudaError_t launch_analysis_pair(const StretchParams& prm, const PairTables& pt,
     using C = FrameCfg<kPairLog2HL>;
     const int n_items = prm.channels * prm.n_runs;
     if (n_items <= 0) return cudaSuccess;
-    analysis_pair_kernel<<<2 * n_clusters, C::NT, (size_t)(C::SMEM_CF + kPairLandCf) * sizeof(cf), stream>>>(prm, pt, n_items);
+    analysis_pair_kernel<<<2 * n_clusters, C::NT, kPairSmemBytes, stream>>>(prm, pt, n_items);
     return cudaGetLastError();
 }
 cudaError_t launch_stretch_pair(const StretchParams& prm, const PairTables& pt, int n_clusters, cudaStream_t stream) {
     using C = FrameCfg<kPairLog2HL>;
     const int n_items = prm.channels * prm.n_runs;
     if (n_items <= 0) return cudaSuccess;
-    stretch_pair_kernel<<<2 * n_clusters, C::NT, (size_t)(C::SMEM_CF + kPairLandCf) * sizeof(cf), stream>>>(prm, pt, n_items);
+    stretch_pair_kernel<<<2 * n_clusters, C::NT, kPairSmemBytes, stream>>>(prm, pt, n_items);
     return cudaGetLastError();
 }
 cudaError_t launch_boundary_pair(const StretchParams& prm, const PairTables& pt, const float* head, const float* tail_prev,

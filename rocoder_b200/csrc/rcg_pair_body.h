@@ -52,11 +52,30 @@ struct PairDeviceExec {
     __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 };
 
-__device__ __forceinline__ void stretch_pair_body(const StretchParams& prm, const PairTables& pt, int n_items,
+// Shared memory of a CTA of the pair: transform buffer, landing zone, and the small twiddle tables -- those of the
+// local passes >= 1 (1264 values) and the two-level table of the cross stage (320): the CTA holds one frame with 16
+// warps, so every table load that goes to L2 is a bubble nothing hides (ncu: 10 % of the stall samples before).
+// Pass 0's table (8192 values, read once per element, unit stride) stays in global memory.
+constexpr int kPairTwSmemFirst = tw_offset(kPairLog2HL, 1);
+constexpr int kPairTwSmemCf = tw_offset(kPairLog2HL, make_plan(kPairLog2HL).npasses) - kPairTwSmemFirst;
+constexpr size_t kPairSmemBytes =
+    (size_t)(FrameCfg<kPairLog2HL>::SMEM_CF + kPairLandCf + kPairTwSmemCf + kPairTwLen) * sizeof(cf);
+
+__device__ __forceinline__ void stretch_pair_body(const StretchParams& prm_in, const PairTables& pt_in, int n_items,
                                                   unsigned char* smem_raw) {
     const int r = (int)cluster_cta_rank();
     cf* S = reinterpret_cast<cf*>(smem_raw);
     cf* zone = S + FrameCfg<kPairLog2HL>::SMEM_CF;             // landing zone behind the transform buffer
+    cf* tw_s = zone + kPairLandCf;
+    cf* cross_s = tw_s + kPairTwSmemCf;
+    for (int i = threadIdx.x; i < kPairTwSmemCf; i += blockDim.x) tw_s[i] = __ldg(prm_in.tw + kPairTwSmemFirst + i);
+    for (int i = threadIdx.x; i < kPairTwLen; i += blockDim.x) cross_s[i] = __ldg(pt_in.cross_tw + i);
+    __syncthreads();
+    StretchParams prm = prm_in;
+    prm.tw0 = prm_in.tw;
+    prm.tw = tw_s - kPairTwSmemFirst;     // only passes >= 1 index it (pair_fft_range hands pass 0 prm.tw0)
+    PairTables pt = pt_in;
+    pt.cross_tw = cross_s;
     cf* bufs[2] = {S, S};                                      // only bufs[r] is touched: transforms are local
     cf* land[2];
     land[r] = zone;

@@ -73,7 +73,7 @@ static int emul_run(StretchParams prm) {
     std::vector<cf> tw = host_pass_twiddles(LOG2H), stw = host_spectral_twiddles(LOG2H);
     std::vector<cf> stw_hr = host_spectral_twiddles_hr(LOG2H);
     std::vector<float> we = host_decimate2(window), ee = host_decimate2(env);
-    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.spec_tw = stw.data();
+    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.tw0 = tw.data(); prm.spec_tw = stw.data();
     prm.spec_tw_hr = stw_hr.data(); prm.window_even = we.data(); prm.env_even = ee.data();
     std::vector<float> lr = lerp_table(prm.pitch);
     prm.lerp_ratio = lr.data();
@@ -127,7 +127,7 @@ static int emul_run_pair(StretchParams prm) {
     std::vector<cf> tw = host_pass_twiddles(kPairLog2HL);
     std::vector<cf> cross = host_pair_cross_twiddles(kPairLog2HL + 1);
     std::vector<cf> se = host_pair_spectral_twiddles(kPairLog2HL + 1, 0), so = host_pair_spectral_twiddles(kPairLog2HL + 1, 1);
-    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data();
+    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.tw0 = tw.data();
     std::vector<float> lr = lerp_table(prm.pitch);
     prm.lerp_ratio = lr.data();
     std::vector<uint2> ptab = host_pair_table(kPairLog2HL);
@@ -181,7 +181,7 @@ static int emul_run_bluestein(StretchParams prm, int W) {
     host_hanning(window.data(), W);
     host_crossfade_compensation(env.data(), H);
     std::vector<cf> tw = host_pass_twiddles(LM), chirp = host_bluestein_chirp(W), filt = host_bluestein_filter(W, LM);
-    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data();
+    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.tw0 = tw.data();
     std::vector<float> lr = lerp_table(prm.pitch);
     prm.lerp_ratio = lr.data();
     BluesteinTables bt{chirp.data(), filt.data(), W};
@@ -308,7 +308,7 @@ static int emul_plugin(StretchParams prm, apply_fn fn) {
     host_hanning(window.data(), W);
     host_crossfade_compensation(env.data(), H);
     std::vector<cf> tw = host_pass_twiddles(LOG2H), stw = host_spectral_twiddles(LOG2H);
-    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.spec_tw = stw.data();
+    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.tw0 = tw.data(); prm.spec_tw = stw.data();
     std::vector<float> lr = lerp_table(prm.pitch);
     prm.lerp_ratio = lr.data();
     std::vector<uint2> ptab = host_pair_table(LOG2H);
@@ -340,7 +340,7 @@ static int emul_plugin_pair(StretchParams prm, apply_fn fn) {
     std::vector<cf> tw = host_pass_twiddles(kPairLog2HL);
     std::vector<cf> cross = host_pair_cross_twiddles(kPairLog2HL + 1);
     std::vector<cf> se = host_pair_spectral_twiddles(kPairLog2HL + 1, 0), so = host_pair_spectral_twiddles(kPairLog2HL + 1, 1);
-    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data();
+    prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.tw0 = tw.data();
     std::vector<float> lr = lerp_table(prm.pitch);
     prm.lerp_ratio = lr.data();
     std::vector<uint2> ptab = host_pair_table(kPairLog2HL);
