@@ -103,3 +103,27 @@ def test_cli_frequency_kernel_source(tmp_path):
     got, _ = _read_wav_f32(tmp_path / "out.wav")
     ref = ol.process_all(x, 2.0, 1, 1024, seed=5, precision=64, plugin=plugins.amplitude_x2)
     assert np.abs(got - ref).max() <= 1e-4 and ol.snr_db(ref, got) > 100.0
+
+
+@pytest.mark.gpu
+def test_cli_device_list_partitions_the_job(tmp_path):
+    """`--device 0,0,...`: one process, every listed device takes its share (rcg_config.n_devices); the file written
+    is bit-identical to the single-device run.  (The same ordinal twice shares that GPU: enough to run on any box.)"""
+    from rocoder_b200 import build
+    import json
+    exe = build.build_cli()
+    rate, n = 48000, 48000 * 30                     # 30 s stereo: big enough for the engine to use both devices
+    rng = np.random.default_rng(3)
+    x = ((rng.random((2, n), dtype=np.float32) * 2 - 1) * 0.5).astype(np.float32)
+    _write_wav(tmp_path / "in.wav", x, rate, 32.5)
+    outs = []
+    for devs, want in (("0", (1, "none", 0)), ("0,0", (2, "channel", 0)), ("0,0,0", (3, "time", 2))):
+        r = subprocess.run([exe, "-i", str(tmp_path / "in.wav"), "-o", str(tmp_path / f"out_{len(outs)}.wav"), "-f", "4", "-p", "-2",
+                            "-w", "4096", "--seed", "9", "--device", devs, "--bench"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        info = json.loads(r.stdout.strip().splitlines()[-1])
+        assert (info["devices_used"], info["split"], info["exchanges"]) == want
+        outs.append(_read_wav_f32(tmp_path / f"out_{len(outs)}.wav")[0])
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    r = subprocess.run([exe, "-i", str(tmp_path / "in.wav"), "-o", str(tmp_path / "o.wav"), "--device", "0,99"], capture_output=True, text=True)
+    assert r.returncode == 1 and "device" in r.stderr
