@@ -2,7 +2,9 @@
 """Randomised parity sweep of the CUDA path against the oracle: random window, factor, pitch multiple, input
 length and channel count inside the reference's valid domain (1 <= step <= W, p not in {0, -1}).
 Index path bit-exact (bypass mode), PCM within the north-star tolerance of the fp64 arbiter, batch == streaming,
-batch == time-sharded segments (halo recompute / tail chaining / deferred boundary) at random cut points.
+batch == time-sharded segments (halo recompute / tail chaining / deferred boundary) at random cut points,
+batch == the same job partitioned over a device list behind one engine (exchange and halo variants); one window in
+five is an even length that is not a power of two (chirp-z path).
 usage: python scripts/fuzz_parity.py [n_cases] [seed]"""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -15,9 +17,14 @@ n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 bad = []
 done = 0
-n_stream = n_segments = 0
+n_stream = n_segments = n_devices = n_anyw = 0
 while done < n_cases:
     W = int(2 ** rng.integers(6, 17))
+    if rng.random() < 0.2:
+        W = 2 * int(rng.integers(32, 700))      # even, usually not a power of two; small enough for the oracle's O(n^2) DFT
+        if W & (W - 1) == 0:
+            W += 2
+        n_anyw += 1
     p = int(rng.choice([1, 1, 2, 2, 3, 4, 5, 6, 8, -2, -2, -3, -3, -4, -5, -7]))
     f = float(np.float32(rng.choice([0.5, 0.75, 1.0, 1.0, 1.5, 2.0, 2.5, 3.0, 4.0, 8.0, 20.0, rng.uniform(0.5, 12.0)])))
     try:
@@ -28,7 +35,7 @@ while done < n_cases:
     if not (1 <= step <= W):
         continue
     ch = int(rng.choice([1, 2, 2, 3, 8]))
-    frames_target = int(rng.integers(1, 40 if W >= 16384 else 120))
+    frames_target = int(rng.integers(1, 40 if W >= 16384 else (30 if W & (W - 1) else 120)))
     n = int(rng.integers(0, W + frames_target * step + 1))
     if n * c["pitch_shifted_factor"] * ch > 6e6:     # keep the oracle in seconds
         continue
@@ -93,8 +100,17 @@ while done < n_cases:
                     e.finish_boundary(out[:, c0 * olen:], out.stride(0), c0, heads[i], tails[i - 1], stream=st_)
                 torch.cuda.synchronize(); res.append(out.cpu().numpy())
             ok_g = all(np.array_equal(r, got) for r in res)
-        if not (ok_b and ok_p and ok_s and ok_g):
-            bad.append(dict(tag, index_exact=bool(ok_b), pcm_ok=bool(ok_p), stream_ok=bool(ok_s), segments_ok=bool(ok_g), max_abs=err))
+        ok_d = True
+        if done % 5 == 0 and n > 0:      # one engine, several devices (the same GPU listed repeatedly): bit-identical
+            n_devices += 1
+            devs = [0] * int(rng.integers(2, 6))
+            fl = rb.RCG_FLAG_SHARD_ALWAYS | (rb.RCG_FLAG_SHARD_HALO if rng.random() < 0.5 else 0)
+            with rb.Engine(ch, 48000, W, f, 1.0, p, seed=seed, devices=devs, flags=fl) as e:
+                many = e.process_all(x)
+            ok_d = many.shape == got.shape and np.array_equal(many, got)
+        if not (ok_b and ok_p and ok_s and ok_g and ok_d):
+            bad.append(dict(tag, index_exact=bool(ok_b), pcm_ok=bool(ok_p), stream_ok=bool(ok_s), segments_ok=bool(ok_g),
+                            devices_ok=bool(ok_d), max_abs=err))
             print("FAIL", json.dumps(bad[-1]), flush=True)
     except Exception as ex:   # noqa
         bad.append(dict(tag, error=repr(ex)[:300]))
@@ -102,5 +118,6 @@ while done < n_cases:
     done += 1
     if done % 20 == 0:
         print(f"{done} cases, {len(bad)} failures", flush=True)
-print(json.dumps({"cases": done, "streaming_checks": n_stream, "segment_checks": n_segments, "failures": len(bad), "failed": bad[:20]}))
+print(json.dumps({"cases": done, "streaming_checks": n_stream, "segment_checks": n_segments, "device_list_checks": n_devices,
+                  "non_power_of_two_windows": n_anyw, "failures": len(bad), "failed": bad[:20]}))
 sys.exit(1 if bad else 0)
