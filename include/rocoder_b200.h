@@ -52,6 +52,10 @@ typedef enum rcg_status {
                                       receiving the carried half window from the neighbour device: zero communication,
                                       bit-identical output; the check of the exchange path (see n_devices) */
 #define RCG_FLAG_SHARD_ALWAYS 8u   /* use every listed device even for jobs too small to gain from it (tests) */
+#define RCG_FLAG_FRAME_CLOCK 16u   /* device frequency kernels get a per-frame elapsed_ms: the clock base (wall clock at the
+                                      engine's first processing call, or rcg_set_clock_base) plus the frame's position in
+                                      output time -- what the reference's per-frame clock (fft.rs:89-92) reads in a run
+                                      paced by playback.  Without the flag: one wall-clock value per launch. */
 
 /* Arguments of Stretcher::new (stretcher.rs:30-39) plus the phase seed and the device(s).
  * The Hann window of main.rs:131 is built internally from window_len.
@@ -203,7 +207,7 @@ int rcg_is_done(rcg_engine *e, uint32_t channel, int *done);
  * Clock: the reference reads SystemTime before every frame (fft.rs:89-92) and polls for a new library before every
  * frame (fft.rs:78-81).  Here a host `apply` gets the wall clock of its own call; a device `apply` gets ONE
  * elapsed_ms per launch -- all frames of a batch (up to 1 GiB of spectra, or a whole fused launch) are computed at
- * the same moment -- and new libraries are taken between batches.  A segment that starts mid-stream without
+ * the same moment -- unless RCG_FLAG_FRAME_CLOCK asks for a per-frame clock; new libraries are taken between batches.  A segment that starts mid-stream without
  * d_tail_in re-analyses the frame before it, so `apply` sees that frame once more. */
 typedef int (*rcg_apply_fn)(size_t elapsed_ms, const float *in_re_im, size_t n_bins,
                             float *out_re_im);
@@ -227,6 +231,9 @@ int rcg_push_device_frequency_kernel(rcg_engine *e, const char *cuda_source);
  * without a kernel.  Same stack / fall-back rules as the other forms. */
 int rcg_push_local_device_frequency_kernel(rcg_engine *e, const char *cuda_source);
 int rcg_frequency_kernel_count(const rcg_engine *e, uint32_t *n);
+/* RCG_FLAG_FRAME_CLOCK: elapsed_ms of frame 0 (instead of the wall clock at the first processing call): makes a
+ * render with a time-dependent device kernel reproducible */
+int rcg_set_clock_base(rcg_engine *e, uint64_t base_ms);
 /* hotswapper::hotswap(path) (hotswapper.rs:14-33, called from ReFFT::new, fft.rs:31-35): build `path` now on
  * the calling thread, then poll it every poll_ms (0 = the reference's 100 ms, hotswapper.rs:12) on a background
  * thread and build it again whenever it is modified.  Each successful build is queued and becomes the newest

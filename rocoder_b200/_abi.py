@@ -29,6 +29,7 @@ RCG_FLAG_RANDOM_SEED = 1
 RCG_FLAG_BYPASS_RESYNTH = 2
 RCG_FLAG_SHARD_HALO = 4
 RCG_FLAG_SHARD_ALWAYS = 8
+RCG_FLAG_FRAME_CLOCK = 16
 RCG_MAX_DEVICES = 16
 RCG_SEG_DEFER_FIRST = 1
 
@@ -115,6 +116,7 @@ def lib() -> C.CDLL:
         "rcg_push_device_frequency_kernel": (C.c_int, [C.c_void_p, C.c_char_p]),
         "rcg_push_local_device_frequency_kernel": (C.c_int, [C.c_void_p, C.c_char_p]),
         "rcg_frequency_kernel_count": (C.c_int, [C.c_void_p, P(C.c_uint32)]),
+        "rcg_set_clock_base": (C.c_int, [C.c_void_p, C.c_uint64]),
         "rcg_watch_frequency_kernel": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32]),
         "rcg_poll_frequency_kernels": (C.c_int, [C.c_void_p, P(C.c_uint32)]),
         "rcg_watch_stats": (C.c_int, [C.c_void_p, P(C.c_uint32), P(C.c_uint32), P(C.c_uint32)]),

@@ -255,6 +255,9 @@ struct rcg_engine {
     float *d_head = nullptr, *d_prev_tail = nullptr;
     cudaEvent_t tail_ready = nullptr;
     const float* final_tail = nullptr;      // where the last launch of the current job left the carried half window
+    // RCG_FLAG_FRAME_CLOCK: elapsed_ms of frame 0 (0 = not fixed yet: the wall clock at the first processing call)
+    uint64_t clock_base = 0;
+    bool clock_base_set = false;
     // how the last rcg_process_all was partitioned
     uint32_t part_devices = 1, part_exchanges = 0;
     const char* part_split = "none";
@@ -581,6 +584,21 @@ static void fill_params(const rcg_engine* e, StretchParams& p) {
     p.keys = e->keys;
 }
 
+static unsigned long long wall_clock_ms() {
+    return (unsigned long long)std::chrono::duration_cast<std::chrono::milliseconds>(
+               std::chrono::system_clock::now().time_since_epoch()).count();   // fft.rs:89-92
+}
+// the clock a device frequency kernel sees: {base, num, den} with elapsed_ms(frame) = base + frame * num / den.
+// Default: the wall clock of this launch for every frame.  RCG_FLAG_FRAME_CLOCK: base = the engine's clock base,
+// advancing by one frame's share of output time, 1000 * out_len_per_call / (frames_per_call * sample_rate) ms.
+struct KernelClock { unsigned long long base, num, den; };
+static KernelClock kernel_clock(rcg_engine* e) {
+    if (!(e->cfg.flags & RCG_FLAG_FRAME_CLOCK)) return KernelClock{wall_clock_ms(), 0ull, 1ull};
+    if (!e->clock_base_set) { e->clock_base = wall_clock_ms(); e->clock_base_set = true; }
+    return KernelClock{e->clock_base, 1000ull * e->plan.out_len_per_call,
+                       std::max<unsigned long long>(1ull, e->plan.frames_per_call * (unsigned long long)e->cfg.sample_rate)};
+}
+
 // launch calls [first_call, first_call + n_calls) for `channels` rows
 struct SpectrumRef { cf* spectrum; long long frame0, frames; };
 
@@ -635,8 +653,8 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
     const int grid = (int)std::min<long long>(items, max_grid);
     cudaError_t ce;
     if (fused) {   // the stretch kernel NVRTC built around a bin-local frequency kernel (same geometry as the fused one)
-        p.elapsed_ms = (unsigned long long)std::chrono::duration_cast<std::chrono::milliseconds>(
-                           std::chrono::system_clock::now().time_since_epoch()).count();   // fft.rs:89-92
+        const KernelClock kc = kernel_clock(e);
+        p.elapsed_ms = kc.base; p.clock_num = kc.num; p.clock_den = kc.den;
         int n_items = (int)items;
         void* args[] = {(void*)&p, (void*)&n_items};
         void* pair_args[] = {(void*)&p, (void*)&e->pt, (void*)&n_items};   // W = 65536: `grid` counts 2-CTA clusters
@@ -782,8 +800,8 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
                 on_host = false;
             }
             const unsigned n_bins = (unsigned)W;
-            const unsigned long long ms = (unsigned long long)std::chrono::duration_cast<std::chrono::milliseconds>(
-                                              std::chrono::system_clock::now().time_since_epoch()).count();
+            const KernelClock kc = kernel_clock(e);
+            const unsigned long long ms = kc.base, ck_num = kc.num, ck_den = kc.den, fpc = nframes;
             bool failed = false;
             bool untouched = true;
             for (int c = 0; c < channels; c++) untouched = untouched && next[c] == 0;
@@ -791,7 +809,9 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
                 const unsigned long long n_fr = (unsigned long long)channels * nframes;
                 const cf* in_p = e->d_spec;
                 cf* out_p = e->d_spec2;
-                void* args[] = {(void*)&in_p, (void*)&out_p, (void*)&n_bins, (void*)&n_fr, (void*)&ms};
+                const unsigned long long fr0 = (unsigned long long)a0;   // frame of spectrum 0 of every channel
+                void* args[] = {(void*)&in_p, (void*)&out_p, (void*)&n_bins, (void*)&n_fr, (void*)&ms, (void*)&fr0, (void*)&fpc,
+                                (void*)&ck_num, (void*)&ck_den};
                 const unsigned long long total = n_fr * n_bins;
                 const unsigned blocks = (unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)e->sm_count * 16);
                 if (cudaLaunchKernel((const void*)e->kernels.back().dev, dim3(blocks), dim3(256), args, 0, stream) == cudaSuccess) {
@@ -806,7 +826,9 @@ static int run_segment_plugins(rcg_engine* e, const rcg_segment& s, int channels
                 const unsigned long long n_fr = nframes - next[c];
                 const cf* in_p = e->d_spec + ((size_t)c * nframes + next[c]) * W;
                 cf* out_p = e->d_spec2 + ((size_t)c * nframes + next[c]) * W;
-                void* args[] = {(void*)&in_p, (void*)&out_p, (void*)&n_bins, (void*)&n_fr, (void*)&ms};
+                const unsigned long long fr0 = (unsigned long long)a0 + next[c];   // one channel's remaining frames
+                void* args[] = {(void*)&in_p, (void*)&out_p, (void*)&n_bins, (void*)&n_fr, (void*)&ms, (void*)&fr0, (void*)&n_fr,
+                                (void*)&ck_num, (void*)&ck_den};
                 const unsigned long long total = n_fr * n_bins;
                 const unsigned blocks = (unsigned)std::min<unsigned long long>((total + 255) / 256, (unsigned long long)e->sm_count * 16);
                 if (cudaLaunchKernel((const void*)e->kernels.back().dev, dim3(blocks), dim3(256), args, 0, stream) != cudaSuccess) {
@@ -1034,6 +1056,7 @@ static int process_all_group(rcg_engine* g, const float* const* in, uint64_t n_i
                              uint64_t out_len) {
     if (g->watcher)   // fft.rs:78-81: take what the hot-swapper has built, for every shard, before the job starts
         if (int rc = drain_watcher(g, nullptr)) return rc;
+    if ((g->cfg.flags & RCG_FLAG_FRAME_CLOCK) && !g->clock_base_set) rcg_set_clock_base(g, wall_clock_ms());   // one base for every shard
     const uint32_t C = g->cfg.channels;
     // a device must have something to amortise its launch, copies and thread on: >= 8 MB of samples in + out
     const uint64_t bytes = (uint64_t)C * (n_in + out_len) * sizeof(float);
@@ -1310,26 +1333,35 @@ struct Nvrtc {
 } g_nvrtc;
 
 const char* kDeviceWrapper = R"(
+// spectra [channel][frame][bin]; spectrum f of the buffer is frame frame0 + f % frames_per_channel of its channel,
+// and that frame's clock is elapsed_ms + frame * clock_num / clock_den (clock_num = 0: one clock for the launch)
 extern "C" __global__ void rcg_apply_kernel(const float2* in, float2* out, unsigned n_bins,
-                                            unsigned long long n_frames, unsigned long long elapsed_ms) {
+                                            unsigned long long n_frames, unsigned long long elapsed_ms,
+                                            unsigned long long frame0, unsigned long long frames_per_channel,
+                                            unsigned long long clock_num, unsigned long long clock_den) {
     const unsigned long long total = n_frames * n_bins;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long f = i / n_bins;
         const unsigned b = (unsigned)(i - f * n_bins);
-        out[i] = apply((size_t)elapsed_ms, b, n_bins, in + f * n_bins);
+        const unsigned long long ms = elapsed_ms + (clock_num ? (frame0 + f % frames_per_channel) * clock_num / clock_den : 0ull);
+        out[i] = apply((size_t)ms, b, n_bins, in + f * n_bins);
     }
 }
 )";
 // the bin-local form as a plain kernel over spectra in memory (same entry point and arguments as the gather form)
 const char* kLocalTwinWrapper = R"(
 extern "C" __global__ void rcg_apply_kernel(const float2* in, float2* out, unsigned n_bins,
-                                            unsigned long long n_frames, unsigned long long elapsed_ms) {
+                                            unsigned long long n_frames, unsigned long long elapsed_ms,
+                                            unsigned long long frame0, unsigned long long frames_per_channel,
+                                            unsigned long long clock_num, unsigned long long clock_den) {
     const unsigned long long total = n_frames * n_bins;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned b = (unsigned)(i % n_bins);
-        out[i] = apply((size_t)elapsed_ms, b, n_bins, in[i]);
+        const unsigned long long f = i / n_bins;
+        const unsigned b = (unsigned)(i - f * n_bins);
+        const unsigned long long ms = elapsed_ms + (clock_num ? (frame0 + f % frames_per_channel) * clock_num / clock_den : 0ull);
+        out[i] = apply((size_t)ms, b, n_bins, in[i]);
     }
 }
 )";
@@ -1533,6 +1565,14 @@ extern "C" int rcg_watch_log(const rcg_engine* e, char* buf, size_t cap) {
     if (!e || !buf || !cap) return fail(RCG_ERR_INVALID_ARG, "null argument");
     const std::string log = e->watcher ? e->watcher->last_log() : std::string();
     snprintf(buf, cap, "%s", log.c_str());
+    return RCG_OK;
+}
+
+extern "C" int rcg_set_clock_base(rcg_engine* e, uint64_t base_ms) {
+    if (!e) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    e->clock_base = base_ms;
+    e->clock_base_set = true;
+    for (rcg_engine* sh : e->shards) { sh->clock_base = base_ms; sh->clock_base_set = true; }
     return RCG_OK;
 }
 

@@ -87,7 +87,10 @@ struct StretchParams {
     cf* spectrum;
     long long spec_frame0;
     long long spec_frames;  // frames per channel in the buffer
-    unsigned long long elapsed_ms;  // what a fused bin-local frequency kernel receives (fft.rs:89-92)
+    unsigned long long elapsed_ms;  // what a fused bin-local frequency kernel receives (fft.rs:89-92): the clock of
+                                    // the launch, or -- RCG_FLAG_FRAME_CLOCK -- of frame 0 of the stream, to which
+    unsigned long long clock_num;   // frame * clock_num / clock_den milliseconds are added (0 / 1: one clock per launch)
+    unsigned long long clock_den;
     PhiloxKeys keys;
 };
 
@@ -398,8 +401,15 @@ RCG_HD float plugin_mag_raw(unsigned long long ms, uint32_t bin, uint32_t n_bins
     const float2 p = apply((size_t)ms, (unsigned)bin, (unsigned)n_bins, make_float2(xr, xi));
     return fast_sqrt(p.x * p.x + p.y * p.y);
 }
-#define plugin_mag(prm, bin, n_bins, xr, xi) plugin_mag_raw((prm).elapsed_ms, (bin), (n_bins), (xr), (xi))
+// `frame_ms` = the clock of the frame being processed, a local of the calling phase (frame_clock below)
+#define plugin_mag(prm, bin, n_bins, xr, xi) plugin_mag_raw(frame_ms, (bin), (n_bins), (xr), (xi))
 #endif
+// elapsed_ms a frequency kernel sees for `frame`: the reference reads the wall clock before every frame
+// (fft.rs:89-92); a launch computes thousands of frames at the same moment, so the per-frame clock is the frame's
+// position in output time (what a run paced by playback would read), when the engine was asked for one
+RCG_HD unsigned long long frame_clock(const StretchParams& prm, long long frame) {
+    return prm.elapsed_ms + (prm.clock_num ? (unsigned long long)frame * prm.clock_num / prm.clock_den : 0ull);
+}
 
 // (cos, sin) of the phase word u: e^{i phi}
 RCG_HD cf cis_phase(uint32_t u) {
@@ -418,7 +428,7 @@ RCG_HD cf cis_phase(uint32_t u) {
 // kk = the pair's bin number, n_bins = W: only read when a bin-local frequency kernel is fused in (RCG_PLUGIN_LOCAL,
 // rcg_jit_entry.h): the magnitudes are then those of the kernel's output for the four bins.
 RCG_HD void pair_fold(cf za, cf zb, const Tw& t, const uint32_t (&u)[4], cf& A, cf& B,
-                      const StretchParams& prm, uint32_t kk, uint32_t n_bins) {
+                      const StretchParams& prm, uint32_t kk, uint32_t n_bins, unsigned long long frame_ms) {
     using SA = Ar<(RCG_PK_SPEC != 0)>;
     const cf PM = make_cf(1.0f, -1.0f), MP = make_cf(-1.0f, 1.0f);
     // P = za + conj(zb), Q = za - conj(zb), U = -i t Q;  X[kk] = (P + U)/2, conj(X[H-kk]) = (P - U)/2
@@ -441,7 +451,7 @@ RCG_HD void pair_fold(cf za, cf zb, const Tw& t, const uint32_t (&u)[4], cf& A, 
     const cf yk = SA::scale(SA::fma(SA::mul(e1, PM), pk_bcast(m1), SA::scale(e0, m0)), 0.5f);
     const cf yb = SA::scale(SA::fma(SA::mul(e3, PM), pk_bcast(m3), SA::scale(e2, m2)), 0.5f);
 #else
-    (void)prm; (void)kk; (void)n_bins;
+    (void)prm; (void)kk; (void)n_bins; (void)frame_ms;
     const float mk = fast_sqrt(xk.x * xk.x + xk.y * xk.y), mb = fast_sqrt(xb.x * xb.x + xb.y * xb.y);
     const cf yk = SA::scale(SA::fma(e1, PM, e0), 0.25f * mk);   // |X[kk]| (e0 + conj(e1)) / 2
     const cf yb = SA::scale(SA::fma(e3, PM, e2), 0.25f * mb);
@@ -469,6 +479,8 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
     const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
     const uint32_t chan = (uint32_t)(channel + prm.channel_offset);
     const cf PM = make_cf(1.0f, -1.0f), MP = make_cf(-1.0f, 1.0f);
+    const unsigned long long frame_ms = frame_clock(prm, frame);
+    (void)frame_ms;
     for (int c = t; c < C::H / 4; c += C::NT) {
         uint32_t u[4];
         if (c == 0) {
@@ -502,7 +514,7 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
             const cf za = S[ph], zb = S[phys(bin_to_pos<LOG2H>(C::H - Q / 2))];
             philox4x32_10((uint32_t)(Q / 2), f_lo, f_hi, chan, prm.keys, u);
             cf A, B;
-            pair_fold(za, zb, make_tw<(RCG_PK_SPEC != 0)>(make_cf(0.70710678118654752f, -0.70710678118654752f)), u, A, B, prm, (uint32_t)(Q / 2), (uint32_t)C::W);
+            pair_fold(za, zb, make_tw<(RCG_PK_SPEC != 0)>(make_cf(0.70710678118654752f, -0.70710678118654752f)), u, A, B, prm, (uint32_t)(Q / 2), (uint32_t)C::W, frame_ms);
             S[ph] = make_cf(2.0f * A.x, -2.0f * A.y);
             continue;
         }
@@ -519,9 +531,9 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
         cf E, F, unused;
         const uint32_t k = qt.z;
         philox4x32_10(k, f_lo, f_hi, chan, prm.keys, u);
-        pair_fold(za, zb, tw, u, E, unused, prm, k, (uint32_t)C::W);                           // E[k]
+        pair_fold(za, zb, tw, u, E, unused, prm, k, (uint32_t)C::W, frame_ms);                           // E[k]
         philox4x32_10((uint32_t)Q - k, f_lo, f_hi, chan, prm.keys, u);
-        pair_fold(zc, zd, tw_c, u, F, unused, prm, (uint32_t)Q - k, (uint32_t)C::W);           // E[Q-k]
+        pair_fold(zc, zd, tw_c, u, F, unused, prm, (uint32_t)Q - k, (uint32_t)C::W, frame_ms);           // E[Q-k]
         // A2 = E[k] + conj(E[Q-k]), B2 = E[k] - conj(E[Q-k]), C2 = i conj(t2) B2, t2 = exp(-2 pi i k/H) = tw^2
         using SA = Ar<(RCG_PK_SPEC != 0)>;
         const cf a2 = SA::fma(F, PM, E), b2 = SA::fma(F, MP, E);
@@ -540,6 +552,8 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
     using C = FrameCfg<LOG2H>;
     static_assert(C::RLAST == 16, "the spectral slot order assumes a radix-16 last pass");
     const uint32_t f_lo = (uint32_t)(unsigned long long)frame, f_hi = (uint32_t)((unsigned long long)frame >> 32);
+    const unsigned long long frame_ms = frame_clock(prm, frame);
+    (void)frame_ms;
     for (int c = t; c < C::H / 2; c += C::NT) {
         uint32_t u[4];
         if (c == 0) {
@@ -581,7 +595,7 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
         philox4x32_10(pt.y * (uint32_t)KMUL, f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
         // A = Y[k] + conj(Y[H-k]), B = Y[k] - conj(Y[H-k]), Cc = i conj(t) B
         cf A, B;
-        pair_fold(za, zb, tw, u, A, B, prm, pt.y * (uint32_t)KMUL, (uint32_t)(C::W * KMUL));
+        pair_fold(za, zb, tw, u, A, B, prm, pt.y * (uint32_t)KMUL, (uint32_t)(C::W * KMUL), frame_ms);
         const cf Cc = mul_i_conj(B, tw);
         using SA = Ar<(RCG_PK_SPEC != 0)>;
         S[pa] = SA::add(A, Cc);                              // Z'[k]   = A + Cc

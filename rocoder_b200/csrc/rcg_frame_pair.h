@@ -98,7 +98,7 @@ RCG_HD void pair_phase_spectral_odd(cf* S, int t, const StretchParams& prm, cons
         uint32_t u[4];
         philox4x32_10((uint32_t)k, f_lo, f_hi, chan, prm.keys, u);
         cf A, B;
-        pair_fold(za, zb, tw, u, A, B, prm, (uint32_t)k, (uint32_t)kPairW);
+        pair_fold(za, zb, tw, u, A, B, prm, (uint32_t)k, (uint32_t)kPairW, frame_clock(prm, frame));
         const cf Cc = mul_i_conj(B, tw);
         using SA = Ar<(RCG_PK_SPEC != 0)>;
         S[pa] = SA::add(A, Cc);

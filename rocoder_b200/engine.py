@@ -302,6 +302,10 @@ class Engine:
         check(lib().rcg_watch_log(self._h, buf, len(buf)))
         return buf.value.decode(errors="replace")
 
+    def set_clock_base(self, base_ms: int) -> None:
+        """RCG_FLAG_FRAME_CLOCK: elapsed_ms of frame 0 (default: the wall clock at the first processing call)"""
+        check(lib().rcg_set_clock_base(self._h, base_ms))
+
     def frequency_kernel_count(self) -> int:
         n = C.c_uint32()
         check(lib().rcg_frequency_kernel_count(self._h, C.byref(n)))

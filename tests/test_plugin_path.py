@@ -307,3 +307,64 @@ def test_gpu_bad_segment_argument_does_not_drop_the_kernel():
             e.process_segment(x, x.stride(0), 0, 20000, out, out.stride(0), 2, 2, defer_first=True,
                               stream=torch.cuda.current_stream().cuda_stream)
         assert e.frequency_kernel_count() == 1
+
+
+GATE_LOCAL = """
+__device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, float2 x) {
+    return elapsed_ms >= GATE_MS ? x : make_float2(0.0f, 0.0f);     // silence until the clock reaches GATE_MS
+}
+"""
+GATE_GATHER = """
+__device__ float2 apply(size_t elapsed_ms, unsigned bin, unsigned n_bins, const float2* spectrum) {
+    return elapsed_ms >= GATE_MS ? spectrum[bin] : make_float2(0.0f, 0.0f);
+}
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("form", ["fused", "gather"])
+@pytest.mark.parametrize("f,p,W", [(2.0, 1, 1024), (4.0, 2, 4096)])
+def test_gpu_frame_clock_for_device_kernels(form, f, p, W):
+    """RCG_FLAG_FRAME_CLOCK: a device `apply` sees elapsed_ms advance frame by frame (the reference reads the clock
+    before every frame, fft.rs:89-92) -- clock base + the frame's position in output time.  A kernel that gates on the
+    clock silences exactly the frames before the gate and leaves the others as the identity kernel leaves them, in
+    every batch / launch split (one shot, streaming, three devices)."""
+    import rocoder_b200 as rb
+    n, rate, base = 60000, 48000, 5_000_000
+    x = _input(n)
+    with rb.Engine(2, rate, W, f, 1.0, p, seed=4) as e:
+        plan = e.plan
+        calls, frames, out_len = e.expected_counts(n)
+    k, olen, H = plan["frames_per_call"], plan["out_len_per_call"], W // 2
+    gate_frame = frames // 2 + 1
+    num, den = 1000 * olen, k * rate
+    gate_ms = base + gate_frame * num // den
+    while (gate_frame - 1) * num // den == gate_frame * num // den:     # the gate must fall between two distinct clock values
+        gate_frame += 1
+        gate_ms = base + gate_frame * num // den
+    src = ("#define GATE_MS %dull\n" % gate_ms) + (GATE_LOCAL if form == "fused" else GATE_GATHER)
+    ident = "#define GATE_MS 0ull\n" + (GATE_LOCAL if form == "fused" else GATE_GATHER)
+    push = "push_local_device_frequency_kernel" if form == "fused" else "push_device_frequency_kernel"
+
+    def run(source, **kw):
+        with rb.Engine(2, rate, W, f, 1.0, p, seed=4, flags=rb.RCG_FLAG_FRAME_CLOCK | kw.pop("flags", 0), **kw) as e:
+            e.set_clock_base(base)
+            getattr(e, push)(source)
+            return e.process_all(x)
+    open_ = run(ident)
+    gated = run(src)
+    # output block m mixes frames m and m-1: blocks before the gate frame are silent, blocks after it untouched
+    per_block = olen / k                     # output samples per frame block (exact for the pitches used here)
+    lo, hi = int((gate_frame - 1) * per_block), int((gate_frame + 1) * per_block)
+    assert not gated[:, :lo].any() and open_[:, :lo].any()
+    assert np.array_equal(gated[:, hi:], open_[:, hi:]) and gated[:, hi:].any()
+    # the clock belongs to the frame, not to the launch: other splits of the same job give the same samples
+    assert np.array_equal(run(src, devices=[0, 0, 0], flags=rb.RCG_FLAG_SHARD_ALWAYS), gated)
+    with rb.Engine(1, rate, W, f, 1.0, p, seed=4, flags=rb.RCG_FLAG_FRAME_CLOCK, max_lookahead_calls=3) as e:
+        e.set_clock_base(base)
+        getattr(e, push)(src)
+        e.send(0, x[0]); e.close_input(0)
+        wins = []
+        while not e.is_done(0):
+            wins.append(e.next_window(0))
+    assert np.array_equal(np.concatenate(wins), gated[0])
