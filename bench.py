@@ -515,6 +515,18 @@ def config5(torch, dist, rb, rank, world, local, dev, stream, args):
             "finite": finite, "e2e_one_engine": e2e}
 
 
+def build_info():
+    """what produced the library this run loaded: compiled here, or reused from the tree (rocoder_b200/build.py)"""
+    from rocoder_b200 import build
+    try:
+        d = json.load(open(build.BUILD_INFO))
+    except Exception:
+        d = {"mode": "unknown"}
+    d["library"] = os.path.relpath(build.LIB, ROOT)
+    d["library_mtime"] = time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime(os.path.getmtime(build.LIB))) if os.path.exists(build.LIB) else None
+    return d
+
+
 def run_ours(args):
     ensure_built()
     import torch
@@ -674,6 +686,7 @@ def run_ours(args):
             "configs": configs,
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "build": build_info(),
         }))
     if dist is not None:
         dist.destroy_process_group()
