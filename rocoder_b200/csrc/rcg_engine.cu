@@ -956,7 +956,9 @@ static int process_range_impl(rcg_engine* e, const float* const* in, uint64_t n_
     const bool exchange = job.call0 > 0 && job.prev != nullptr;
     const bool halo = job.call0 > 0 && !exchange;
     // device input = samples [s_lo, s_hi) of every channel of the range
-    const uint64_t s_lo = std::min<uint64_t>(n_in, (job.call0 * k - (halo ? 1 : 0)) * step);
+    // (rounded down to a multiple of 4 samples: frames keep the 8-byte alignment they have in the whole input, and
+    // with it the branch-free float2 load path)
+    const uint64_t s_lo = std::min<uint64_t>(n_in, (job.call0 * k - (halo ? 1 : 0)) * step) & ~(uint64_t)3;
     const uint64_t s_hi = std::max(s_lo, std::min<uint64_t>(n_in, (job.call1 * k - 1) * step + W));
     const uint64_t n_span = s_hi - s_lo, out_len = calls * olen;
     const size_t in_stride = ((size_t)n_span + 3) & ~(size_t)3;
