@@ -1425,10 +1425,19 @@ extern "C" int rcg_push_device_frequency_kernel(rcg_engine* e, const char* cuda_
 }
 
 // ---- bin-local device kernels: NVRTC builds the whole stretch kernel around the user's apply ----------------
+// The scalar configuration a fused kernel may assume at compile time.  Even positive pitch multiples run the half-rate
+// path only until a kernel that needs spectra in memory is installed, so their mode can change: generic build.
+static int fused_kernel_mode(const rcg_config& cfg) {
+    if (cfg.flags & RCG_FLAG_BYPASS_RESYNTH) return 0;
+    if (use_half_rate(cfg.pitch_multiple, 0u)) return 0;
+    return stretch_mode_of(cfg.pitch_multiple, 0u);
+}
+
 #include "rcg_jit_sources.inc"
 
-static bool compile_fused_source(const std::string& user_src, int log2h, std::vector<char>& cubin, std::vector<char>& twin,
-                                 std::string& log) {
+// mode: the launch configuration to fold in as constants (rcg_jit_entry.h), 0 = none
+static bool compile_fused_source(const std::string& user_src, int log2h, int mode, std::vector<char>& cubin,
+                                 std::vector<char>& twin, std::string& log) {
     // the per-bin twin first (small): it takes over when the kernel above this one fails in the middle of a batch
     if (!compile_device_source(user_src, twin, log, kLocalTwinWrapper)) return false;
     static std::mutex load_mutex;
@@ -1436,7 +1445,8 @@ static bool compile_fused_source(const std::string& user_src, int log2h, std::ve
         std::lock_guard<std::mutex> g(load_mutex);
         if (!g_nvrtc.load()) { log = "libnvrtc could not be loaded"; return false; }
     }
-    const std::string src = user_src + "\n#define RCG_JIT_LOG2H " + std::to_string(log2h) + "\n#include \"rcg_jit_entry.h\"\n";
+    const std::string src = user_src + "\n#define RCG_JIT_LOG2H " + std::to_string(log2h) + "\n#define RCG_JIT_MODE " +
+                            std::to_string(mode) + "\n#include \"rcg_jit_entry.h\"\n";
     const int n_headers = (int)(sizeof(kJitHeaderNames) / sizeof(kJitHeaderNames[0]));
     nvrtcProgram_t prog = nullptr;
     if (g_nvrtc.create(&prog, src.c_str(), "fused_frequency_kernel.cu", n_headers, kJitHeaderSources, kJitHeaderNames) != 0) {
@@ -1497,7 +1507,7 @@ extern "C" int rcg_push_local_device_frequency_kernel(rcg_engine* e, const char*
         return fail(RCG_ERR_STATE, "frequency kernels need a power-of-two window (window_len %u runs the chirp-z path)", e->cfg.window_len);
     std::vector<char> cubin, twin;
     std::string log;
-    if (!compile_fused_source(cuda_source, e->log2w - 1, cubin, twin, log))   // compile failure keeps the previous kernel
+    if (!compile_fused_source(cuda_source, e->log2w - 1, fused_kernel_mode(e->cfg), cubin, twin, log))   // compile failure keeps the previous kernel
         return fail(RCG_ERR_PLUGIN, "bin-local frequency kernel failed to compile: %.400s", log.c_str());
     return install_everywhere(e, cubin, &twin);
 }
@@ -1539,10 +1549,10 @@ extern "C" int rcg_watch_frequency_kernel(rcg_engine* e, const char* path, uint3
     // from here on this engine runs the full-rate path: a kernel may arrive between any two batches
     e->had_kernels = true;
     for (rcg_engine* sh : e->shards) sh->had_kernels = true;
-    const int log2h = e->log2w - 1;
+    const int log2h = e->log2w - 1, mode = fused_kernel_mode(e->cfg);
     e->watcher.reset(new rcg::KernelWatcher(path, poll_ms,
-        [log2h](const std::string& src, bool local, std::vector<char>& cubin, std::vector<char>& twin, std::string& log) {
-            return local ? compile_fused_source(src, log2h, cubin, twin, log) : compile_device_source(src, cubin, log);
+        [log2h, mode](const std::string& src, bool local, std::vector<char>& cubin, std::vector<char>& twin, std::string& log) {
+            return local ? compile_fused_source(src, log2h, mode, cubin, twin, log) : compile_device_source(src, cubin, log);
         }));
     e->watcher->start();   // first build happens here, on the caller's thread (hotswapper.rs:17)
     return drain_watcher(e, nullptr);

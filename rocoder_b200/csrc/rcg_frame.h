@@ -44,6 +44,17 @@ RCG_HD bool use_half_rate(int pitch, uint32_t flags) {
     return pitch > 0 && (pitch & 1) == 0 && !(flags & kFlagSpectrumIn);
 }
 
+// which compile-time specialisation of the stretch kernel serves a launch (rcg_kernel_body.h: MODE)
+RCG_HD constexpr int stretch_mode_of(int pitch, uint32_t flags) {
+    const uint32_t fl = flags & ~(uint32_t)kFlagDeferFirst;
+    if (fl == kFlagHalfRate && pitch == 2) return 1;
+    if (fl == 0u && pitch == 1) return 2;
+    if (fl == 0u && pitch == -2) return 4;
+    if (fl == 0u && pitch == -3) return 5;
+    if (fl == 0u) return 3;
+    return 0;
+}
+
 // Everything one launch needs.  Global indices (samples, frames, output positions) are
 // absolute within the channel so that segments of a long input computed by different
 // launches / GPUs produce identical values.

@@ -69,15 +69,7 @@ constexpr int min_ctas() { return (LOG2H >= 14 || FrameCfg<LOG2H>::TW_SMEM) ? 1 
 //   0  generic (bypass hook, anything else)     1  pitch 2 on the half-rate path (the headline `-p 2`)
 //   2  pitch 1, full rate                       3  any other pitch, full rate
 //   4  pitch -2                                 5  pitch -3 (BASELINE config 4): the lerp walk's strides are constants
-RCG_HD constexpr int stretch_mode_of(int pitch, uint32_t flags) {
-    const uint32_t fl = flags & ~(uint32_t)kFlagDeferFirst;
-    if (fl == kFlagHalfRate && pitch == 2) return 1;
-    if (fl == 0u && pitch == 1) return 2;
-    if (fl == 0u && pitch == -2) return 4;
-    if (fl == 0u && pitch == -3) return 5;
-    if (fl == 0u) return 3;
-    return 0;
-}
+// (stretch_mode_of, the rule that picks MODE from pitch and flags: rcg_frame.h, shared with the host)
 template <int MODE>
 __device__ __forceinline__ StretchParams with_mode_constants(const StretchParams& in) {
     StretchParams p = in;

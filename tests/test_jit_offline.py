@@ -42,13 +42,15 @@ def test_embedded_headers_equal_the_sources():
         assert text == open(os.path.join(CSRC, name)).read(), name
 
 
-@pytest.mark.parametrize("log2h", [5, 8, 11, 13, 14, 15])
-def test_fused_translation_unit_compiles_with_nvrtc(log2h):
+@pytest.mark.parametrize("log2h,mode", [(5, 0), (8, 2), (11, 5), (13, 0), (13, 2), (13, 4), (14, 3), (15, 0), (15, 2)])
+def test_fused_translation_unit_compiles_with_nvrtc(log2h, mode):
+    """every window size, generic and with the launch configuration folded in (RCG_JIT_MODE: pitch 1 / other /
+    -2 / -3, what rcg_engine.cu's fused_kernel_mode passes for odd and negative pitch multiples)"""
     nv = _nvrtc()
     hdr = _embedded_headers()
     names = (C.c_char_p * len(hdr))(*[n.encode() for n in hdr])
     srcs = (C.c_char_p * len(hdr))(*[t.encode() for t in hdr.values()])
-    src = (USER + f"\n#define RCG_JIT_LOG2H {log2h}\n#include \"rcg_jit_entry.h\"\n").encode()
+    src = (USER + f"\n#define RCG_JIT_LOG2H {log2h}\n#define RCG_JIT_MODE {mode}\n#include \"rcg_jit_entry.h\"\n").encode()
     prog = C.c_void_p()
     assert nv.nvrtcCreateProgram(C.byref(prog), src, b"fused_frequency_kernel.cu", len(hdr), srcs, names) == 0
     opts = (C.c_char_p * 3)(b"--gpu-architecture=sm_100a", b"--std=c++17", b"-default-device")
