@@ -680,6 +680,17 @@ static void pop_kernel(rcg_engine* e) {
     e->kernels.pop_back();
 }
 
+// A kernel that failed was dropped for good by the shard that met it; every shard of a multi-device engine carries
+// the same stack, pushed in the same order, so after a job all of them drop down to the shortest one left.
+static void equalise_kernel_stacks(rcg_engine* g) {
+    size_t depth = SIZE_MAX;
+    for (rcg_engine* sh : g->shards) depth = std::min(depth, sh->kernels.size());
+    for (rcg_engine* sh : g->shards) {
+        if (sh->kernels.size() > depth) cudaSetDevice(sh->device);
+        while (sh->kernels.size() > depth) pop_kernel(sh);
+    }
+}
+
 // ---- frequency-kernel path (fft.rs:76-108) ---------------------------------------------------
 // Host `apply` on one frame's spectrum, in place; mirrors the pop-and-retry of fft.rs:101-106: a failing kernel is
 // dropped for good and the previous one is tried.  Returns false when the frame is still unprocessed because the
@@ -887,7 +898,9 @@ extern "C" int rcg_process_segment(rcg_engine* e, const rcg_segment* seg) {
             if (int rc = drain_watcher(e, nullptr)) return rc;
         rcg_engine* sh = shard_for_pointer(e, seg->d_out);
         if (!sh) return fail(RCG_ERR_INVALID_ARG, "d_out is not memory of a device this engine lists");
-        return rcg_process_segment(sh, seg);
+        const int rc = rcg_process_segment(sh, seg);
+        equalise_kernel_stacks(e);
+        return rc;
     }
     CUDA_TRY(cudaSetDevice(e->device));
     cudaStream_t st = seg->stream ? (cudaStream_t)seg->stream : e->stream;
@@ -1107,6 +1120,7 @@ static int process_all_group(rcg_engine* g, const float* const* in, uint64_t n_i
     for (size_t i = 1; i < jobs.size(); i++) threads.emplace_back(work, i);
     work(0);
     for (auto& t : threads) t.join();
+    equalise_kernel_stacks(g);
     for (size_t i = 0; i < jobs.size(); i++)
         if (rcs[i]) return fail(rcs[i], "device %d: %s", g->shards[i]->device, errs[i].c_str());
     return RCG_OK;
@@ -1238,7 +1252,9 @@ extern "C" int rcg_next_window(rcg_engine* e, uint32_t channel, float* out, uint
     if (!e->shards.empty()) {   // every channel is an independent Stretcher (main.rs:133-153): device = channel mod n
         if (e->watcher)
             if (int rc = drain_watcher(e, nullptr)) return rc;
-        return rcg_next_window(e->shards[channel % e->shards.size()], channel, out, cap, n_out);
+        const int rc = rcg_next_window(e->shards[channel % e->shards.size()], channel, out, cap, n_out);
+        equalise_kernel_stacks(e);
+        return rc;
     }
     if (cap < e->plan.out_len_per_call)
         return fail(RCG_ERR_CAPACITY, "window needs %llu samples", (unsigned long long)e->plan.out_len_per_call);

@@ -104,3 +104,28 @@ def test_group_streaming_plugins_and_host_rule():
     ref = ol.process_all(x[:, :40000], f, p, W, seed=9, precision=64, plugin=plugins.half_gain)
     assert len(calls) == ol.expected_counts(40000, f, p, W)[1] * 4
     assert np.abs(got - ref).max() <= 1e-4
+
+
+@pytest.mark.gpu
+def test_group_kernel_stacks_stay_equal_after_a_failing_host_kernel():
+    """a host kernel that panics is dropped by the one shard that ran it (host kernels keep a job on the first
+    device); the other shards must drop it too, or the next multi-device job would mix two different stacks"""
+    n, f, p, W = 200000, 2.0, 1, 2048
+    x = _input(n, channels=2, seed=8)
+    with rb.Engine(2, 48000, W, f, 1.0, p, seed=9) as e:
+        e.push_device_frequency_kernel(plugins.DEVICE_TILT)
+        want = e.process_all(x)
+    with rb.Engine(2, 48000, W, f, 1.0, p, seed=9, devices=[0, 0, 0], flags=rb.RCG_FLAG_SHARD_ALWAYS) as g:
+        g.push_device_frequency_kernel(plugins.DEVICE_TILT)
+        calls = []
+
+        def bad(ms, spec):
+            calls.append(1)
+            raise RuntimeError("panic")
+        g.push_frequency_kernel(bad)
+        first = g.process_all(x)                       # host kernel on top: one device; it fails on its first frame
+        assert g.last_partition()["devices_used"] == 1 and len(calls) == 1
+        assert g.frequency_kernel_count() == 1
+        second = g.process_all(x)                      # now the device kernel is on top everywhere: all three devices
+        assert g.last_partition()["devices_used"] == 3 and len(calls) == 1
+    assert np.array_equal(first, want) and np.array_equal(second, want)
