@@ -185,18 +185,17 @@ RCG_HD void pair_phase_spectral_in_odd(cf* S, int t, const StretchParams& prm, c
 // half of the peer's.  That half is PUSHED: before the phase each CTA writes the part of its buffer the peer needs
 // into the peer's landing zone (distributed shared memory, posted stores; one cluster barrier makes them visible),
 // so no remote load sits on the critical path, and the carried half window of an index range is read and written
-// by the same CTA -- it never crosses the pair.
+// by the same CTA -- it never crosses the pair.  The push is one bulk asynchronous copy per CTA (cp.async.bulk
+// shared::cta -> shared::cluster, issued by one thread, completion counted in bytes on an mbarrier in the receiving
+// CTA): no thread moves data, and nobody waits for more than its own landing zone.
 constexpr int kPairNR = kPairHL / 2;                       // packed indices per CTA in this phase
 constexpr int kPairLandCf = kPairNR + (kPairNR >> 4);      // landing zone: the padded slots of kPairNR elements
 
-// copy the padded slots of the packed indices the peer will finish into the peer's landing zone
-RCG_HD void pair_phase_push(const cf* S, cf* peer_land, int r, int t) {
-    using C = FrameCfg<kPairLog2HL>;
-    // CTA 0 gives [NR, HL) to CTA 1, CTA 1 gives [0, NR) to CTA 0; NR is a multiple of 16, so the padded slots of a
-    // range are contiguous and phys(n) - phys(base) = phys(n - base)
-    const cf* src = S + phys((1 - r) * kPairNR);
-    for (int i = t; i < kPairLandCf; i += C::NT) peer_land[i] = src[i];
-}
+// What CTA r hands to its peer: the padded slots of the packed indices the peer will finish.  CTA 0 gives [NR, HL) to
+// CTA 1, CTA 1 gives [0, NR) to CTA 0; NR is a multiple of 16, so the padded slots of a range are contiguous
+// (phys(n) - phys(base) = phys(n - base)): ONE contiguous block of kPairLandCf values, which the device moves with a
+// single bulk asynchronous copy into the peer's shared memory (Exec::exchange, rcg_pair_body.h).
+RCG_HD const cf* pair_push_source(const cf* S, int r) { return S + phys((1 - r) * kPairNR); }
 
 // first half window: /W * window, + carried half, * envelope * amp, emit (pitch 1) or stage in global memory for the
 // resampling gather; second half window -> carried buffer (same index, same thread: in place)
@@ -286,10 +285,11 @@ RCG_HD void pair_fft_all(Exec& ex, cf* const (&bufs)[2], const StretchParams& pr
     if constexpr (INV) pair_fft_range<NP - 3, 0, true>(ex, bufs, prm, work);
 }
 
-// bufs[r] = CTA r's transform buffer, land[r] = CTA r's landing zone (land[r ^ 1] is written through distributed
-// shared memory).  Cluster barriers of one frame: wait (the peer is done with its landing zone) -> push ->
-// arrive + wait (landing zones complete) -> overlap-add -> arrive; the arrive / wait pair around the push is split,
-// so it costs nothing unless the peer really is a whole phase behind.
+// bufs[r] = CTA r's transform buffer, land[r] = CTA r's landing zone.  One cluster barrier per frame, issued in two
+// halves: `arrive` after the overlap-add (I am done with my landing zone, and -- my zone was complete -- the copy out
+// of the PEER's buffer has been consumed), `wait` at the top of the next frame (so the peer's zone is free for my next
+// push and my own buffer, the source of my last push, may be overwritten).  The exchange itself synchronises on the
+// receiving CTA's mbarrier only.
 template <class Exec>
 RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], cf* const (&land)[2], const StretchParams& prm,
                                const PairTables& pt, int item, float* scratch, bool active) {
@@ -315,6 +315,7 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], cf* const (&land)
     ex.cluster_arrive();   // pairs with the first frame's wait
     const int n_iter = prm.run_len + 1;
     for (int it = 0; it < n_iter; it++) {
+        ex.cluster_wait();   // the peer is through with the previous frame: its zone is free, my buffer has been read
         const long long f = f0 - 1 + it;
         const bool is_halo = (it == 0);
         const bool work = active && (is_halo ? halo : f < f1);
@@ -350,8 +351,7 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], cf* const (&land)
             pair_fft_all<true>(ex, bufs, prm, work);
         }
         }
-        ex.cluster_wait();   // the peer has finished reading its landing zone (previous frame)
-        ex.par_cluster([&](int r, int t) { if (work) pair_phase_push(bufs[r], land[r ^ 1], r, t); });   // + barrier: zones complete
+        if (work) ex.exchange(bufs, land, kPairLandCf);   // each CTA's share of the other buffer lands in its zone
         auto ola = [&](int r, int t) {
             if (work) pair_phase_ola(bufs[r], land[r], r, t, prm, pt, channel, f, tail, stage, emit, head);
         };

@@ -25,8 +25,44 @@ __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// 32-bit shared-window address of a shared-memory object of this CTA / of the same object in CTA `rank`
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned cluster_addr(unsigned cta_addr, unsigned rank) {
+    unsigned out;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(cta_addr), "r"(rank));
+    return out;
+}
+
 struct PairDeviceExec {
     int r, t;
+    unsigned mbar = 0;         // this CTA's mbarrier: counts the bytes the peer's bulk copy delivers into my zone
+    unsigned peer_mbar = 0;    // the peer's, as a shared::cluster address
+    unsigned peer_zone = 0;    // the peer's landing zone, shared::cluster address
+    unsigned parity = 0;
+    // Both CTAs hand each other kPairLandCf values: one thread arms its own mbarrier with the byte count it expects
+    // and starts ONE bulk asynchronous copy (TMA engine: no thread moves data) from its transform buffer into the
+    // peer's landing zone; the copy signals the peer's mbarrier as the bytes arrive.  Everybody then waits for the
+    // bytes of its own zone only.
+    __device__ __forceinline__ void exchange(cf* const (&bufs)[2], cf* const (&)[2], int n_cf) {
+        const unsigned bytes = (unsigned)n_cf * (unsigned)sizeof(cf);
+        // the passes wrote the buffer through the generic proxy; the copy reads it through the async proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (t == 0) {
+            const unsigned src = smem_addr(pair_push_source(bufs[r], r));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(peer_zone), "r"(src), "r"(bytes), "r"(peer_mbar) : "memory");
+        }
+        asm volatile(
+            "{\n\t.reg .pred p;\n"
+            "RCG_MBAR_WAIT:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra RCG_MBAR_DONE;\n\t"
+            "bra RCG_MBAR_WAIT;\n"
+            "RCG_MBAR_DONE:\n\t}" ::"r"(mbar), "r"(parity) : "memory");
+        parity ^= 1u;
+    }
     template <class F>
     __device__ __forceinline__ void par(F f) {
         f(r, t);
@@ -59,7 +95,7 @@ struct PairDeviceExec {
 constexpr int kPairTwSmemFirst = tw_offset(kPairLog2HL, 1);
 constexpr int kPairTwSmemCf = tw_offset(kPairLog2HL, make_plan(kPairLog2HL).npasses) - kPairTwSmemFirst;
 constexpr size_t kPairSmemBytes =
-    (size_t)(FrameCfg<kPairLog2HL>::SMEM_CF + kPairLandCf + kPairTwSmemCf + kPairTwLen) * sizeof(cf);
+    (size_t)(FrameCfg<kPairLog2HL>::SMEM_CF + kPairLandCf + kPairTwSmemCf + kPairTwLen) * sizeof(cf) + 16;   // + mbarrier
 
 __device__ __forceinline__ void stretch_pair_body(const StretchParams& prm_in, const PairTables& pt_in, int n_items,
                                                   unsigned char* smem_raw) {
@@ -77,10 +113,17 @@ __device__ __forceinline__ void stretch_pair_body(const StretchParams& prm_in, c
     PairTables pt = pt_in;
     pt.cross_tw = cross_s;
     cf* bufs[2] = {S, S};                                      // only bufs[r] is touched: transforms are local
-    cf* land[2];
-    land[r] = zone;
-    land[r ^ 1] = cluster_map_shared(zone, (unsigned)(r ^ 1));   // the peer's zone, written through DSMEM
+    cf* land[2] = {zone, zone};                                // only land[r] is read; the peer's zone is written by the copy
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(cross_s + kPairTwLen);
     PairDeviceExec ex{r, (int)threadIdx.x};
+    ex.mbar = smem_addr(mbar);
+    ex.peer_mbar = cluster_addr(ex.mbar, (unsigned)(r ^ 1));
+    ex.peer_zone = cluster_addr(smem_addr(zone), (unsigned)(r ^ 1));
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ex.mbar) : "memory");   // one arrival per phase: my own expect_tx
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster_barrier();   // both mbarriers exist before either CTA can be sent bytes
     const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
     float* scratch = pt.scratch + (long long)cid * 3 * kPairH;
     for (int item = cid; item < n_items; item += ncl) run_work_item_pair(ex, bufs, land, prm, pt, item, scratch, true);

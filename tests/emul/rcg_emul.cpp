@@ -117,6 +117,10 @@ struct PairHostExec {
     void cluster_sync() {}
     void cluster_arrive() {}
     void cluster_wait() {}
+    // what the device does with one bulk copy per CTA: each CTA's share of its buffer lands in the other's zone
+    void exchange(cf* const (&bufs)[2], cf* const (&land)[2], int n_cf) {
+        for (int r = 0; r < 2; r++) memcpy(land[r ^ 1], pair_push_source(bufs[r], r), sizeof(cf) * (size_t)n_cf);
+    }
 };
 
 static int emul_run_pair(StretchParams prm) {
