@@ -33,9 +33,10 @@ typedef enum rcg_status {
     RCG_OK = 0,
     RCG_ERR_INVALID_ARG = 1,
     RCG_ERR_PITCH = 2,       /* pitch_multiple 0 (assert, stretcher.rs:40), -1 (panic, resampler.rs:11), or outside i8 */
-    RCG_ERR_WINDOW = 3,      /* window_len: powers of two from 64 to 65536 (the fast kernels) and any other EVEN length from 64 to
-                                8192 (README.md:100 allows any length; chirp-z path, ~10x slower per sample) are supported;
-                                odd lengths are not (stretcher.rs:101-103 drifts by one sample per frame for them) */
+    RCG_ERR_WINDOW = 3,      /* window_len: every EVEN length from 64 to 1048576 is supported (README.md:100 allows any length):
+                                powers of two up to 65536 on the fast in-SM kernels, other lengths up to 8192 on the in-SM
+                                chirp-z kernels (~10x slower per sample), everything longer on chirp-z convolutions through
+                                HBM; odd lengths are not (stretcher.rs:101-103 drifts by one sample per frame for them) */
     RCG_ERR_STEP = 4,        /* sample_step_len outside 1..=W: the reference underflows usize at stretcher.rs:105-106 */
     RCG_ERR_CUDA = 5,
     RCG_ERR_NO_DEVICE = 6,

@@ -97,19 +97,18 @@ def phase_from_u32(u: np.ndarray) -> np.ndarray:
 
 
 def phases_for_frame(seed: int, channel: int, frame: int, window_len: int) -> np.ndarray:
+    """which Philox block / word serves a bin: the rule of rocoder_oracle.c ro_phase_slot, for every even W
+    (H = W/2 may be odd: the quadruple {k, W-k, H-k, H+k} then has no self-paired middle)"""
     W, H = window_len, window_len // 2
     Q = H // 2
-    pair = np.arange(Q + 1, dtype=np.uint32)
-    o = philox4x32_10(pair, np.uint32(frame & 0xFFFFFFFF), np.uint32(frame >> 32),
+    b = np.arange(W)
+    pair = np.where(b <= Q, b, np.where(b <= H, H - b, np.where(b < H + Q, b - H, W - b)))
+    word = np.where(b <= Q, 0, np.where(b <= H, 2, np.where(b < H + Q, 3, 1)))
+    blocks = np.arange(int(pair.max()) + 1, dtype=np.uint32)
+    o = philox4x32_10(blocks, np.uint32(frame & 0xFFFFFFFF), np.uint32(frame >> 32),
                       np.uint32(channel), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    ph = [phase_from_u32(x) for x in o]
-    out = np.zeros(W, dtype=F32)
-    out[0:Q + 1] = ph[0]                    # word 0 -> bin pair
-    out[H] = ph[2][0]                       # pair 0, word 2 -> bin H
-    out[W - pair[1:]] = ph[1][1:]           # word 1 -> bin W - pair
-    out[H - pair[1:Q]] = ph[2][1:Q]         # word 2 -> bin H - pair
-    out[H + pair[1:Q]] = ph[3][1:Q]         # word 3 -> bin H + pair
-    return out
+    ph = np.stack([phase_from_u32(x) for x in o])
+    return ph[word, pair].astype(F32)
 
 
 # ---- ReFFT (fft.rs:42-74) -------------------------------------------------------------

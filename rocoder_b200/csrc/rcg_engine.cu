@@ -81,6 +81,22 @@ static uint64_t resample_len(uint64_t n, int p) {
     return n ? (n - 1) * (uint64_t)(-p) : 0;
 }
 
+// longest window: the HBM-resident chirp-z path convolves at length 2^21 >= 2W - 1 (rcg_big.h)
+static constexpr uint32_t kMaxWindow = 1u << (kBigMaxLog2M - 1);
+
+// FFT_M of the chirp filter / M in the position order the forward passes of the HBM path leave (rcg_big.h)
+static std::vector<cf> host_big_filter(int W, int lm) {
+    std::vector<double> re, im;
+    host_bluestein_filter_spectrum(W, lm, re, im);
+    const size_t M = (size_t)1 << lm;
+    std::vector<cf> f(M);
+    for (size_t pos = 0; pos < M; pos++) {
+        const size_t k = (size_t)big_pos_to_bin(lm, (long long)pos);
+        f[pos] = make_cf((float)(re[k] / (double)M), (float)(im[k] / (double)M));
+    }
+    return f;
+}
+
 static int log2_exact(uint32_t w) {
     int l = 0;
     while ((1u << l) < w) l++;
@@ -96,14 +112,15 @@ extern "C" int rcg_plan(const rcg_config* cfg, rcg_plan_info* out) {
     const uint32_t W = cfg->window_len;
     const int l2 = log2_exact(W);
     if (l2 < 0) {
-        // not a power of two (README.md:100 allows any length): the chirp-z path, rcg_frame_bluestein.h
+        // not a power of two (README.md:100 allows any length): the chirp-z paths -- in one SM up to 8192
+        // (rcg_frame_bluestein.h), through HBM above that (rcg_big.h)
         if (W & 1u)
             return fail(RCG_ERR_WINDOW, "window_len %u is odd: the reference appends W - W/2 samples per frame while "
                                         "advancing by W/2 (stretcher.rs:101-103); not supported", W);
-        if (W < 64 || W > 8192)
-            return fail(RCG_ERR_WINDOW, "window_len %u: windows that are not a power of two are supported from 64 to 8192", W);
-    } else if (l2 < 6 || l2 > 16) {
-        return fail(RCG_ERR_WINDOW, "window_len %u: need a power of two in [64, 65536] (or an even length in [64, 8192])", W);
+        if (W < 64 || W > kMaxWindow)
+            return fail(RCG_ERR_WINDOW, "window_len %u: even window lengths from 64 to %u are supported", W, kMaxWindow);
+    } else if (l2 < 6 || W > kMaxWindow) {
+        return fail(RCG_ERR_WINDOW, "window_len %u: need an even length in [64, %u]", W, kMaxWindow);
     }
     if (cfg->channels == 0) return fail(RCG_ERR_INVALID_ARG, "channels must be >= 1");
     const float abs_p = (float)(p < 0 ? -p : p);
@@ -218,6 +235,10 @@ struct rcg_engine {
     int bs_lm = 0;            // log2 of its convolution length
     BluesteinTables bt{};
     cf *d_bs_chirp = nullptr, *d_bs_filter = nullptr;
+    bool big = false;         // window too long for an SM (pair): chirp-z convolutions through HBM (rcg_big.h)
+    BigTables bgt{};
+    cf* d_big_work = nullptr;
+    float *d_big_ybuf = nullptr, *d_big_carry = nullptr;
     bool pair = false;        // W = 65536: a frame across a 2-CTA cluster
     PairTables pt{};
     cf *d_pair_cross = nullptr, *d_pair_even = nullptr, *d_pair_odd = nullptr;
@@ -333,8 +354,13 @@ extern "C" int rcg_create(const rcg_config* cfg_in, rcg_engine** out) {
             return bail(fail(RCG_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)));        \
     } while (0)
     e->pair = (e->log2w == 16);
-    e->bluestein = (e->log2w < 0);
-    if (e->bluestein) {
+    e->big = (e->log2w < 0 && cfg->window_len > 8192) || e->log2w > 16;
+    e->bluestein = (e->log2w < 0) || e->big;
+    if (e->big) {
+        e->bs_lm = bluestein_log2m((int)cfg->window_len);
+        e->geo = LaunchGeometry{256, 1, 0, 1};
+        e->max_grid = e->sm_count;
+    } else if (e->bluestein) {
         e->bs_lm = bluestein_log2m((int)cfg->window_len);
         TRY_E(bluestein_geometry(e->bs_lm, (int)cfg->window_len, &e->geo));
         if (e->geo.max_ctas_per_sm < 1) return bail(fail(RCG_ERR_CUDA, "chirp-z kernel does not fit on an SM"));
@@ -351,7 +377,8 @@ extern "C" int rcg_create(const rcg_config* cfg_in, rcg_engine** out) {
     std::vector<float> window(W), env(H);
     host_hanning(window.data(), W);           // main.rs:131
     host_crossfade_compensation(env.data(), H);  // stretcher.rs:56
-    const int plan_log2h = e->bluestein ? e->bs_lm : e->pair ? kPairLog2HL : e->log2w - 1;   // the in-CTA transform
+    // the in-CTA transform (the HBM path has none: its tables of this kind are dummies)
+    const int plan_log2h = e->big ? 6 : e->bluestein ? e->bs_lm : e->pair ? kPairLog2HL : e->log2w - 1;
     std::vector<cf> tw = host_pass_twiddles(plan_log2h), stw = host_spectral_twiddles(plan_log2h);
     std::vector<cf> stw_hr = host_spectral_twiddles_hr(plan_log2h);
     if (e->pair) {
@@ -364,7 +391,23 @@ extern "C" int rcg_create(const rcg_config* cfg_in, rcg_engine** out) {
         TRY_E(cudaMemcpy(e->d_pair_even, se.data(), se.size() * sizeof(cf), cudaMemcpyHostToDevice));
         TRY_E(cudaMemcpy(e->d_pair_odd, so.data(), so.size() * sizeof(cf), cudaMemcpyHostToDevice));
     }
-    if (e->bluestein) {
+    if (e->big) {
+        std::vector<cf> chirp = host_bluestein_chirp((int)W), filt = host_big_filter((int)W, e->bs_lm);
+        TRY_E(cudaMalloc(&e->d_bs_chirp, chirp.size() * sizeof(cf)));
+        TRY_E(cudaMalloc(&e->d_bs_filter, filt.size() * sizeof(cf)));
+        TRY_E(cudaMemcpy(e->d_bs_chirp, chirp.data(), chirp.size() * sizeof(cf), cudaMemcpyHostToDevice));
+        TRY_E(cudaMemcpy(e->d_bs_filter, filt.data(), filt.size() * sizeof(cf), cudaMemcpyHostToDevice));
+        // frames per batch: 256 MB of convolution workspace
+        const int batch = (int)std::max<long long>(1, (1LL << 25) >> e->bs_lm);
+        TRY_E(cudaMalloc(&e->d_big_work, ((size_t)batch << e->bs_lm) * sizeof(cf)));
+        TRY_E(cudaMalloc(&e->d_big_ybuf, (size_t)batch * W * sizeof(float)));
+        TRY_E(cudaMalloc(&e->d_big_carry, (size_t)cfg->channels * H * sizeof(float)));
+        e->bgt = BigTables{};
+        e->bgt.chirp = e->d_bs_chirp; e->bgt.filter = e->d_bs_filter; e->bgt.work = e->d_big_work;
+        e->bgt.ybuf = e->d_big_ybuf; e->bgt.carry = e->d_big_carry;
+        e->bgt.w = (int)W; e->bgt.lm = e->bs_lm; e->bgt.batch = batch;
+        e->bgt.n_top = big_top_plan(e->bs_lm, e->bgt.top_rlog2);
+    } else if (e->bluestein) {
         std::vector<cf> chirp = host_bluestein_chirp((int)W), filt = host_bluestein_filter((int)W, e->bs_lm);
         TRY_E(cudaMalloc(&e->d_bs_chirp, chirp.size() * sizeof(cf)));
         TRY_E(cudaMalloc(&e->d_bs_filter, filt.size() * sizeof(cf)));
@@ -481,6 +524,7 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     cudaFree(e->d_pair_tab); cudaFree(e->d_quad_tab);
     cudaFree(e->d_pair_cross); cudaFree(e->d_pair_even); cudaFree(e->d_pair_odd);
     cudaFree(e->d_bs_chirp); cudaFree(e->d_bs_filter);
+    cudaFree(e->d_big_work); cudaFree(e->d_big_ybuf); cudaFree(e->d_big_carry);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_tail_pp[0]); cudaFree(e->d_tail_pp[1]);
     cudaFree(e->d_sin); cudaFree(e->d_sout); cudaFree(e->d_spec); cudaFree(e->d_spec2);
     for (auto& k : e->kernels) { if (k.lib) cudaLibraryUnload(k.lib); if (k.twin_lib) cudaLibraryUnload(k.twin_lib); }
@@ -662,7 +706,8 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
              : e->pair  ? cudaLaunchKernel((const void*)fused, dim3(2 * grid), dim3(e->geo.threads), pair_args, e->geo.smem_bytes, stream)
                         : cudaLaunchKernel((const void*)fused, dim3(grid), dim3(e->geo.threads), args, e->geo.smem_bytes, stream);
     } else {
-        ce = e->bluestein ? launch_bluestein(e->bs_lm, p, e->bt, grid, stream)
+        ce = e->big         ? launch_big(p, e->bgt, stream)
+             : e->bluestein ? launch_bluestein(e->bs_lm, p, e->bt, grid, stream)
              : e->pair    ? launch_stretch_pair(p, e->pt, grid, stream)
                           : launch_stretch(e->log2w, p, grid, stream);
     }
@@ -923,9 +968,10 @@ extern "C" int rcg_finish_boundary(rcg_engine* e, float* d_out, int64_t out_stri
     p.frame_begin = (long long)(first_call * e->plan.frames_per_call);
     if (engine_half_rate(e)) p.flags |= kFlagHalfRate;
     cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
-    cudaError_t ce = e->bluestein ? launch_boundary_bluestein(e->bs_lm, p, e->bt, d_head, d_tail_prev, st)
-                     : e->pair    ? launch_boundary_pair(p, e->pt, d_head, d_tail_prev, st)
-                                  : launch_boundary(e->log2w, p, d_head, d_tail_prev, st);
+    cudaError_t ce = e->big         ? launch_boundary_big(p, e->bgt, d_head, d_tail_prev, st)
+                     : e->bluestein ? launch_boundary_bluestein(e->bs_lm, p, e->bt, d_head, d_tail_prev, st)
+                     : e->pair      ? launch_boundary_pair(p, e->pt, d_head, d_tail_prev, st)
+                                    : launch_boundary(e->log2w, p, d_head, d_tail_prev, st);
     if (ce != cudaSuccess) return fail(RCG_ERR_CUDA, "boundary kernel launch failed: %s", cudaGetErrorString(ce));
     e->launches++;
     return RCG_OK;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "rcg_frame.h"
+#include "rcg_big.h"
 #include "rcg_frame_bluestein.h"
 #include "rcg_frame_pair.h"
 

@@ -41,8 +41,13 @@ RCG_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
 
 // rand 0.8.5 gen_range(0.0..PI) on f32 (fft.rs:13: the constant named TWO_PI is PI):
 // ((u >> 9) * 2^-23) * PI + 0.0
+// The scaling by 2^-23 is exact, so one product with the constant 2^-23 * PI (itself exact) rounds to the same value.
 RCG_HD float phase_from_u32(uint32_t u) {
+#if defined(RCG_PHASE_TWO_PRODUCTS)
     return (float)(u >> 9) * 1.1920928955078125e-07f * 3.14159274101257324f;
+#else
+    return (float)(u >> 9) * (1.1920928955078125e-07f * 3.14159274101257324f);
+#endif
 }
 
 }  // namespace rcg

@@ -145,34 +145,46 @@ inline std::vector<cf> host_bluestein_chirp(int W) {
     }
     return c;
 }
-// FFT_M(b) / M with b[n] = b[M - n] = c[n] for n < W, in the position order the DIF passes of plan LM leave
-inline std::vector<cf> host_bluestein_filter(int W, int lm) {
-    const int M = 1 << lm;
+// FFT_M(b) with b[n] = b[M - n] = c[n] for n < W (0 elsewhere), natural bin order, in double
+inline void host_bluestein_filter_spectrum(int W, int lm, std::vector<double>& re, std::vector<double>& im) {
+    const size_t M = (size_t)1 << lm;
     const double pi = 3.14159265358979323846264338327950288;
-    std::vector<double> re((size_t)M, 0.0), im((size_t)M, 0.0);
+    re.assign(M, 0.0); im.assign(M, 0.0);
     for (long long n = 0; n < W; n++) {
         const long long r = (n * n) % (2LL * W);
         const double a = pi * (double)r / (double)W;
         re[(size_t)n] = cos(a); im[(size_t)n] = sin(a);
-        if (n) { re[(size_t)(M - n)] = cos(a); im[(size_t)(M - n)] = sin(a); }
+        if (n) { re[M - (size_t)n] = cos(a); im[M - (size_t)n] = sin(a); }
     }
-    // in-place radix-2 decimation-in-time FFT in double (M <= 16384: a table built once per engine)
-    for (int i = 1, j = 0; i < M; i++) {
-        int bit = M >> 1;
+    // in-place radix-2 decimation-in-time FFT in double (a table built once per engine)
+    for (size_t i = 1, j = 0; i < M; i++) {
+        size_t bit = M >> 1;
         for (; j & bit; bit >>= 1) j ^= bit;
         j ^= bit;
-        if (i < j) { std::swap(re[(size_t)i], re[(size_t)j]); std::swap(im[(size_t)i], im[(size_t)j]); }
+        if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
     }
-    for (int len = 2; len <= M; len <<= 1) {
-        for (int i = 0; i < M; i += len)
-            for (int k = 0; k < len / 2; k++) {
-                const double a = -2.0 * pi * (double)k / (double)len, wr = cos(a), wi = sin(a);
-                const size_t u = (size_t)(i + k), v = (size_t)(i + k + len / 2);
-                const double tr = re[v] * wr - im[v] * wi, ti = re[v] * wi + im[v] * wr;
+    std::vector<double> wr(M / 2), wi(M / 2);
+    for (size_t k = 0; k < M / 2; k++) {
+        const double a = -2.0 * pi * (double)k / (double)M;
+        wr[k] = cos(a); wi[k] = sin(a);
+    }
+    for (size_t len = 2; len <= M; len <<= 1) {
+        const size_t stride = M / len;
+        for (size_t i = 0; i < M; i += len)
+            for (size_t k = 0; k < len / 2; k++) {
+                const double cr = wr[k * stride], ci = wi[k * stride];
+                const size_t u = i + k, v = i + k + len / 2;
+                const double tr = re[v] * cr - im[v] * ci, ti = re[v] * ci + im[v] * cr;
                 re[v] = re[u] - tr; im[v] = im[u] - ti;
                 re[u] += tr; im[u] += ti;
             }
     }
+}
+// ... / M, in the position order the DIF passes of plan LM leave (in-SM chirp-z kernels, rcg_frame_bluestein.h)
+inline std::vector<cf> host_bluestein_filter(int W, int lm) {
+    const int M = 1 << lm;
+    std::vector<double> re, im;
+    host_bluestein_filter_spectrum(W, lm, re, im);
     const PlanDesc d = make_plan(lm);
     std::vector<cf> f((size_t)M);
     for (int pos = 0; pos < M; pos++) {

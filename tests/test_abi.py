@@ -56,7 +56,7 @@ def test_invalid_arguments_return_error_codes_not_panics():
         with pytest.raises(rb.RcgError) as ei:
             rb.plan(1.0, p, 1024)
         assert ei.value.status == status
-    for W in (1001, 10000, 63, 32, 3, 0, 65536 * 2):   # odd, too long for the chirp-z path, too short, too long
+    for W in (1001, 10001, 63, 32, 3, 0, 2 ** 20 + 2, 2 ** 21):   # odd, too short, too long
         with pytest.raises(rb.RcgError) as ei:
             rb.plan(1.0, 1, W)
         assert ei.value.status == _abi.RCG_ERR_WINDOW
