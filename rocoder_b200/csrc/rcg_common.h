@@ -126,15 +126,70 @@ RCG_HD constexpr int threads_per_frame(int log2h) {
     if (nt < 1) nt = 1;
     return nt;
 }
-// W = 16384: three frame lanes share one CTA per SM and ONE copy of the pass twiddle tables in shared memory
-// (3 x 69.6 KB + 17 KB = 226 KB of the 227 KB an SM offers).  With three 1-lane CTAs per SM instead, the
-// carve-out leaves 28 KB of L1 and every twiddle load is an L2 round trip (ncu: 19 % L1 hit rate).
-RCG_HD constexpr bool tw_in_smem(int log2h) { return log2h == 13; }
+// W = 16384: three frame lanes (768 threads) share one CTA per SM: 3 x 69.6 KB of the 227 KB an SM offers.  (With three
+// 1-lane CTAs per SM instead, the carve-out leaves 28 KB of L1 and every twiddle load is an L2 round trip -- ncu: 19 %
+// L1 hit rate.)  Where the pass twiddles of that CTA live:
+//   tw_in_tmem  in Tensor Memory, one row per thread (below) -- the default
+//   tw_in_smem  one copy of the packed tables behind the frame buffers (+17 KB: 226 KB), -DRCG_TW_TMEM=0
+#ifndef RCG_TW_TMEM
+#define RCG_TW_TMEM 1
+#endif
+RCG_HD constexpr bool three_lanes(int log2h) { return log2h == 13; }
+RCG_HD constexpr bool tw_in_tmem(int log2h) { return RCG_TW_TMEM != 0 && three_lanes(log2h); }
+RCG_HD constexpr bool tw_in_smem(int log2h) { return three_lanes(log2h) && !tw_in_tmem(log2h); }
 RCG_HD constexpr int frames_per_cta(int log2h) {
-    if (tw_in_smem(log2h)) return 3;
+    if (three_lanes(log2h)) return 3;
     int nt = threads_per_frame(log2h);
     int f = 256 / nt;
     return f < 1 ? 1 : f;
+}
+
+// ---- pass twiddles in Tensor Memory (tw_in_tmem) ------------------------------------------------------------
+// A thread's butterflies see the same twiddles in every frame: butterfly b = t + NT i of a pass has m = b mod M, so
+// with M <= NT the thread needs ONE set w^(m j), j < R, for good, and with M > NT (the radix-2 passes fused into the
+// load / overlap-add phases) M / NT sets of one value.  Blackwell's Tensor Memory (256 KB per SM: 128 rows x 512
+// 32-bit columns, otherwise idle in a kernel without tensor-core work) gives warp w the rows 32 (w mod 4) .. + 31 --
+// one row per thread, shared by the warps that are equal mod 4 -- and tcgen05.ld moves 8 columns = 4 twiddles of a
+// row into registers per instruction, on a datapath of its own.  So every thread keeps its twiddles in its row
+// (176 columns at W = 16384; the two warps of a frame lane that share a row take columns 0.. and 256.., the three
+// frame lanes of a CTA read the same ones) and no twiddle load touches the shared-memory pipe, which the butterfly
+// data keep 55 % busy: a quarter of that pipe's wavefronts were twiddle loads.  Full tables for every pass also drop
+// the products the packed tables needed (w^5 = w^4 w^1 ..., two-level radix-2 twiddles).
+// Row layout: [full plan: pass 0 | pass 1 | ...][half-rate plan: pass 0 | ...]; a set of a radix-R pass is 2 R
+// columns (twiddle j at columns 2j, 2j+1; j = 0 unused), of a radix-2 pass 2 columns.
+RCG_HD constexpr int tmem_set_cols(int log2h, int pass, bool hr) {
+    const PlanDesc d = make_plan(log2h, hr);
+    if (d.mlog2[pass] == 0) return 0;
+    return d.rlog2[pass] == 1 ? 2 : 2 << d.rlog2[pass];
+}
+RCG_HD constexpr int tmem_sets(int log2h, int pass, bool hr) {
+    const PlanDesc d = make_plan(log2h, hr);
+    const int M = 1 << d.mlog2[pass], NT = threads_per_frame(log2h);
+    return M > NT ? M / NT : 1;
+}
+RCG_HD constexpr int tmem_col_offset(int log2h, int pass, bool hr) {
+    int off = 0;
+    const int np = make_plan(log2h).npasses;
+    if (hr) for (int p = 0; p < np; p++) off += tmem_sets(log2h, p, false) * tmem_set_cols(log2h, p, false);
+    for (int p = 0; p < pass; p++) off += tmem_sets(log2h, p, hr) * tmem_set_cols(log2h, p, hr);
+    return off;
+}
+RCG_HD constexpr int tmem_total_cols(int log2h) { return tmem_col_offset(log2h, make_plan(log2h).npasses, true); }
+// long-stride passes of the half-rate plan deal butterflies to lanes with bits 3 and 6 of m swapped (rcg_frame.h)
+RCG_HD constexpr int hr_lane_swizzle(int m) { return (m & ~0x48) | ((m & 0x08) << 3) | ((m & 0x40) >> 3); }
+// which m the butterflies of thread t see in set `set` of a pass, and a thread (row) that sees a given m
+RCG_HD constexpr int tmem_m_of_thread(int log2h, int pass, bool hr, int t, int set) {
+    const PlanDesc d = make_plan(log2h, hr);
+    const int M = 1 << d.mlog2[pass], NT = threads_per_frame(log2h);
+    if (M > NT) return t + NT * set;
+    const int m = t & (M - 1);
+    return (hr && M >= 128) ? hr_lane_swizzle(m) : m;
+}
+RCG_HD constexpr int tmem_row_of_m(int log2h, int pass, bool hr, int m) {
+    const PlanDesc d = make_plan(log2h, hr);
+    const int M = 1 << d.mlog2[pass], NT = threads_per_frame(log2h);
+    if (M >= NT) return m & (NT - 1);
+    return (hr && M >= 128) ? hr_lane_swizzle(m) : m;
 }
 
 // ---- twiddle tables --------------------------------------------------------------------

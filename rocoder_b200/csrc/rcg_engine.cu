@@ -231,6 +231,7 @@ struct rcg_engine {
     uint2* d_pair_tab = nullptr;
     uint4* d_quad_tab = nullptr;
     cf *d_tw = nullptr, *d_spec_tw = nullptr, *d_spec_tw_hr = nullptr;
+    float* d_tw_image = nullptr;   // pass twiddles as Tensor Memory rows (tw_in_tmem, rcg_common.h)
     bool bluestein = false;   // window_len is not a power of two: chirp-z path (rcg_frame_bluestein.h)
     int bs_lm = 0;            // log2 of its convolution length
     BluesteinTables bt{};
@@ -431,6 +432,11 @@ extern "C" int rcg_create(const rcg_config* cfg_in, rcg_engine** out) {
         TRY_E(cudaMalloc(&e->d_lerp_ratio, ratio.size() * sizeof(float)));
         TRY_E(cudaMemcpy(e->d_lerp_ratio, ratio.data(), ratio.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
+    if (!e->bluestein && !e->pair && tw_in_tmem(plan_log2h)) {
+        std::vector<float> img = host_tmem_image(plan_log2h);
+        TRY_E(cudaMalloc(&e->d_tw_image, img.size() * sizeof(float)));
+        TRY_E(cudaMemcpy(e->d_tw_image, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     TRY_E(cudaMalloc(&e->d_window_even, we.size() * sizeof(float)));
     TRY_E(cudaMalloc(&e->d_env_even, ee.size() * sizeof(float)));
     TRY_E(cudaMalloc(&e->d_spec_tw_hr, stw_hr.size() * sizeof(cf)));
@@ -521,7 +527,7 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     if (e->h2d) cudaStreamSynchronize(e->h2d);
     cudaFree(e->d_window); cudaFree(e->d_env); cudaFree(e->d_tw); cudaFree(e->d_spec_tw); cudaFree(e->d_scratch);
     cudaFree(e->d_window_even); cudaFree(e->d_env_even); cudaFree(e->d_spec_tw_hr); cudaFree(e->d_lerp_ratio);
-    cudaFree(e->d_pair_tab); cudaFree(e->d_quad_tab);
+    cudaFree(e->d_pair_tab); cudaFree(e->d_quad_tab); cudaFree(e->d_tw_image);
     cudaFree(e->d_pair_cross); cudaFree(e->d_pair_even); cudaFree(e->d_pair_odd);
     cudaFree(e->d_bs_chirp); cudaFree(e->d_bs_filter);
     cudaFree(e->d_big_work); cudaFree(e->d_big_ybuf); cudaFree(e->d_big_carry);
@@ -614,6 +620,7 @@ static bool engine_half_rate(const rcg_engine* e) {
 static void fill_params(const rcg_engine* e, StretchParams& p) {
     memset(&p, 0, sizeof(p));
     p.window = e->d_window; p.env = e->d_env; p.tw = e->d_tw; p.tw0 = e->d_tw; p.spec_tw = e->d_spec_tw;
+    p.tw_image = e->d_tw_image;
     p.spec_tw_hr = e->d_spec_tw_hr; p.window_even = e->d_window_even; p.env_even = e->d_env_even;
     p.lerp_ratio = e->d_lerp_ratio;
     p.pair_tab = e->d_pair_tab; p.quad_tab = e->d_quad_tab;

@@ -70,6 +70,8 @@ struct StretchParams {
     const float* env;       // [H]   crossfade::hanning_crossfade_compensation (crossfade.rs:4-10)
     const cf* tw;           // packed per-pass twiddles
     const cf* tw0;          // the table of pass 0 (== tw unless a kernel moved the other passes' tables, see rcg_pair_body.h)
+    const float* tw_image;  // [tmem_total_cols][NT] what the threads' Tensor Memory rows are filled from (tw_in_tmem, rcg_common.h)
+    uint32_t tmem_addr;     // tw_in_tmem: Tensor Memory address of this thread's row / column half; set by the kernel prologue
     const cf* spec_tw;      // [H/2] exp(-2 pi i k/W) in the spectral step's pair order
     const cf* spec_tw_hr;   // [H/4] the same in the half-rate quad order
     const float* window_even;  // [H]   window[2i]   (half-rate synthesis)
@@ -115,6 +117,7 @@ struct FrameCfg {
     static constexpr int SMEM_CF = padded_len(H);  // per frame lane
     static constexpr int RLAST = 1 << make_plan(LOG2H).rlog2[NP - 1];
     static constexpr bool TW_SMEM = tw_in_smem(LOG2H);   // prm.tw of the kernels points into shared memory
+    static constexpr bool TW_TMEM = tw_in_tmem(LOG2H);   // pass twiddles come from the thread's Tensor Memory row
     static constexpr int TW_CF = tw_total(LOG2H);
 };
 
@@ -181,15 +184,57 @@ RCG_HD cf ld_pair(const float* p) { return *reinterpret_cast<const cf*>(p); }
 RCG_HD void st_pair(float* p, float a, float b) { *reinterpret_cast<cf*>(p) = make_cf(a, b); }
 RCG_HD void st_cf(float* p, cf v) { *reinterpret_cast<cf*>(p) = v; }
 
+// ---- where a pass finds its twiddles -----------------------------------------------------------------------
+// The packed per-pass tables (global or shared memory), and -- kernels with FrameCfg::TW_TMEM -- the thread's Tensor
+// Memory row.  Code that passes a bare table pointer (CTA-pair and chirp-z kernels) gets the tables.
+struct TwSrc {
+    const cf* tw;
+    uint32_t tmem;        // device: row / column-half base of this thread
+    const float* image;   // host execution (tests/emul) reads the image the rows are filled from
+    RCG_HD TwSrc(const cf* p) : tw(p), tmem(0u), image(nullptr) {}
+    RCG_HD TwSrc(const cf* p, uint32_t a, const float* im) : tw(p), tmem(a), image(im) {}
+};
+RCG_HD TwSrc tw_src(const StretchParams& prm) { return TwSrc(prm.tw, prm.tmem_addr, prm.tw_image); }
+
+// N = 2 or 8 consecutive columns of the set the butterfly with index m reads, starting at column `col` of the set
+template <int LOG2H, int PASS, bool HR, int N>
+RCG_HD void tw_fetch(const TwSrc& s, int m, int col, float (&v)[N]) {
+    static_assert(N == 2 || N == 8, "tcgen05.ld shapes used here");
+    constexpr int OFF = tmem_col_offset(LOG2H, PASS, HR), SC = tmem_set_cols(LOG2H, PASS, HR);
+    constexpr int NT = threads_per_frame(LOG2H), M = 1 << make_plan(LOG2H, HR).mlog2[PASS];
+    const int set = (M > NT) ? m / NT : 0;
+#if defined(__CUDA_ARCH__)
+    const uint32_t a = s.tmem + (uint32_t)(OFF + set * SC + col);
+    uint32_t r[N];
+    // the registers are written asynchronously: nothing may read them before tcgen05.wait::ld, which is why the
+    // wait sits in the same statement
+    if constexpr (N == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(a));
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;"
+                     : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+    }
+#pragma unroll
+    for (int q = 0; q < N; q++) v[q] = __uint_as_float(r[q]);
+#else
+    const int row = tmem_row_of_m(LOG2H, PASS, HR, m);
+    for (int q = 0; q < N; q++) v[q] = s.image[(size_t)(OFF + set * SC + col + q) * NT + row];
+#endif
+}
+
 // ---- twiddles -------------------------------------------------------------------------
 // Multiply element j (1 <= j < R) of a butterfly by w^(m*j) (or its conjugate), w = the pass's
 // principal root, using the table layout tw_scheme() selected.
 // the stored power-of-two exponents of the pow scheme, fetched ahead of the butterfly so that
 // their (L1 / L2 / shared-memory) latency overlaps the data loads and the DFT
 struct TwPre { cf w1, w2, w4, w8; };
-template <int LOG2H, int PASS, int R, bool HR = false>
+template <int LOG2H, int PASS, int R, bool HR = false, bool TM = false>
 RCG_HD TwPre tw_preload(const cf* tw, int m) {
-    constexpr int SCHEME = tw_scheme(LOG2H, PASS, HR);
+    constexpr int SCHEME = TM ? (int)kTwNone : tw_scheme(LOG2H, PASS, HR);
     constexpr int M = 1 << make_plan(LOG2H, HR).mlog2[PASS];
     TwPre p;
     p.w1 = p.w2 = p.w4 = p.w8 = make_cf(1.0f, 0.0f);
@@ -202,11 +247,30 @@ RCG_HD TwPre tw_preload(const cf* tw, int m) {
 }
 
 // Packed arithmetic (rcg_dft.h): a product with a twiddle whose rotated copy is at hand is two instructions.
-template <int LOG2H, int PASS, bool CONJ, int R, bool HR = false>
-RCG_HD void twiddle_butterfly(cf (&x)[R], const cf* tw, int m, const TwPre& pre) {
+template <int LOG2H, int PASS, bool CONJ, int R, bool HR = false, bool TM = false>
+RCG_HD void twiddle_butterfly(cf (&x)[R], const TwSrc& src, int m, const TwPre& pre) {
     constexpr int SCHEME = tw_scheme(LOG2H, PASS, HR);
     constexpr int M = 1 << make_plan(LOG2H, HR).mlog2[PASS];
-    if constexpr (SCHEME == kTwFull) {
+    const cf* tw = src.tw + tw_offset(LOG2H, PASS, HR);
+    if constexpr (TM && SCHEME != kTwNone) {
+        // every w^(m j) straight from the thread's Tensor Memory row, four at a time
+        if constexpr (R == 2) {
+            float v[2];
+            tw_fetch<LOG2H, PASS, HR, 2>(src, m, 0, v);
+            x[1] = tw_mul<CONJ>(x[1], make_tw(make_cf(v[0], v[1])));
+        } else {
+#pragma unroll
+            for (int c = 0; c < R / 4; c++) {
+                float v[8];
+                tw_fetch<LOG2H, PASS, HR, 8>(src, m, 8 * c, v);
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int j = 4 * c + q;
+                    if (j >= 1) x[j] = tw_mul<CONJ>(x[j], make_tw(make_cf(v[2 * q], v[2 * q + 1])));
+                }
+            }
+        }
+    } else if constexpr (SCHEME == kTwFull) {
 #pragma unroll
         for (int j = 1; j < R; j++) x[j] = tw_mul<CONJ>(x[j], make_tw(ld_tw<LOG2H>(tw + (j - 1) * M + m)));
     } else if constexpr (SCHEME == kTwTwoLevel) {
@@ -244,9 +308,9 @@ RCG_HD void twiddle_butterfly(cf (&x)[R], const cf* tw, int m, const TwPre& pre)
     }
 }
 
-template <int LOG2H, int PASS, bool CONJ, int R, bool HR = false>
-RCG_HD void twiddle_butterfly(cf (&x)[R], const cf* tw, int m) {
-    twiddle_butterfly<LOG2H, PASS, CONJ, R, HR>(x, tw, m, tw_preload<LOG2H, PASS, R, HR>(tw, m));
+template <int LOG2H, int PASS, bool CONJ, int R, bool HR = false, bool TM = false>
+RCG_HD void twiddle_butterfly(cf (&x)[R], const TwSrc& src, int m) {
+    twiddle_butterfly<LOG2H, PASS, CONJ, R, HR, TM>(x, src, m, tw_preload<LOG2H, PASS, R, HR, TM>(src.tw + tw_offset(LOG2H, PASS, HR), m));
 }
 
 // shared-memory offset of butterfly input a relative to input 0: phys(base + a*M) - phys(base)
@@ -265,7 +329,8 @@ struct LoadCtx {
     const float* in;   // channel row
     long long base;    // local index of the frame's first sample
     bool bypass, aligned;
-    const cf* tw;
+    TwSrc tw;
+    RCG_HD LoadCtx() : tw(nullptr) {}
 };
 template <int LOG2H>
 RCG_HD LoadCtx<LOG2H> make_load_ctx(const StretchParams& prm, int channel, long long frame) {
@@ -276,7 +341,7 @@ RCG_HD LoadCtx<LOG2H> make_load_ctx(const StretchParams& prm, int channel, long 
     c.bypass = prm.flags & kFlagBypass;
     const bool interior = c.base >= 0 && c.base + C::W <= prm.in_valid;
     c.aligned = interior && ((reinterpret_cast<unsigned long long>(c.in + c.base) & 7ull) == 0);
-    c.tw = prm.tw + tw_offset(LOG2H, 0);
+    c.tw = tw_src(prm);
     return c;
 }
 // global loads of butterfly m of pass 0 (packed samples n = m + a*M) times the window
@@ -305,7 +370,7 @@ RCG_HD void load_finish(cf* S, const LoadCtx<LOG2H>& c, int m, cf (&x)[R]) {
     constexpr int M = 1 << make_plan(LOG2H).mlog2[0];
     if constexpr (!BYPASS) {
         Dft<R>::run(x);
-        twiddle_butterfly<LOG2H, 0, false, R>(x, c.tw, m);
+        twiddle_butterfly<LOG2H, 0, false, R, false, FrameCfg<LOG2H>::TW_TMEM>(x, c.tw, m);
     }
     cf* p = S + phys(m);
 #pragma unroll
@@ -340,39 +405,38 @@ RCG_UNROLL(RCG_LOAD_UNROLL)
 }
 
 // ---- one in-place butterfly of pass PASS >= 1 (pass 0 is fused into load / overlap-add) ---------
-template <int LOG2H, int PASS, bool INV>
-RCG_HD void fft_butterfly(cf* S, const cf* tw_all, int b) {
+template <int LOG2H, int PASS, bool INV, bool TM = FrameCfg<LOG2H>::TW_TMEM>
+RCG_HD void fft_butterfly(cf* S, const TwSrc& tw, int b) {
     constexpr int RL = make_plan(LOG2H).rlog2[PASS], R = 1 << RL, ML = make_plan(LOG2H).mlog2[PASS], M = 1 << ML;
-    const cf* tw = tw_all + tw_offset(LOG2H, PASS);
     const int m = b & (M - 1), blk = b >> ML;
-    const TwPre pre = tw_preload<LOG2H, PASS, R>(tw, m);
+    const TwPre pre = tw_preload<LOG2H, PASS, R, false, TM>(tw.tw + tw_offset(LOG2H, PASS), m);
     cf* p = S + phys((blk << (ML + RL)) + m);
     cf x[R];
 #pragma unroll
     for (int a = 0; a < R; a++) x[a] = p[slot_off<M>(a)];
     if constexpr (INV) {
-        twiddle_butterfly<LOG2H, PASS, true, R>(x, tw, m, pre);  // conj twiddle on the inputs (DIT)
+        twiddle_butterfly<LOG2H, PASS, true, R, false, TM>(x, tw, m, pre);  // conj twiddle on the inputs (DIT)
         Dft<R, true>::run(x);
     } else {
         Dft<R>::run(x);
-        twiddle_butterfly<LOG2H, PASS, false, R>(x, tw, m, pre);  // twiddle on the outputs (DIF)
+        twiddle_butterfly<LOG2H, PASS, false, R, false, TM>(x, tw, m, pre);  // twiddle on the outputs (DIF)
     }
 #pragma unroll
     for (int j = 0; j < R; j++) p[slot_off<M>(j)] = x[j];
 }
 
-template <int LOG2H, int PASS, bool INV>
-RCG_HD void phase_fft_pass(cf* S, int t, const cf* tw_all) {
+template <int LOG2H, int PASS, bool INV, bool TM = FrameCfg<LOG2H>::TW_TMEM>
+RCG_HD void phase_fft_pass(cf* S, int t, const TwSrc& tw_all) {
     using C = FrameCfg<LOG2H>;
     constexpr int NB = C::H >> make_plan(LOG2H).rlog2[PASS];
-    for (int b = t; b < NB; b += C::NT) fft_butterfly<LOG2H, PASS, INV>(S, tw_all, b);
+    for (int b = t; b < NB; b += C::NT) fft_butterfly<LOG2H, PASS, INV, TM>(S, tw_all, b);
 }
 
 // The last two passes (strides 16 and 1) of a warp's butterflies b .. b+31 touch the same 512
 // elements, so they run as consecutive steps of ONE phase separated by __syncwarp only:
 // step 2i and 2i+1 = the two passes for butterfly index t + NT*i.
 template <int LOG2H, bool INV>
-RCG_HD void fft_tail_step(cf* S, int t, int step, const cf* tw_all) {
+RCG_HD void fft_tail_step(cf* S, int t, int step, const TwSrc& tw_all) {
     using C = FrameCfg<LOG2H>;
     constexpr int NB = C::H / 16;
     static_assert(make_plan(LOG2H).rlog2[C::NP - 1] == 4 && make_plan(LOG2H).rlog2[C::NP - 2] == 4, "radix-16 tail");
@@ -768,7 +832,7 @@ RCG_HD void phase_ola_impl(cf* S, int t, const StretchParams& prm, int channel, 
     constexpr bool bypass = BYPASS;
     constexpr bool IO_PK = (RCG_PK_IO != 0);
     float* out = prm.out + (long long)channel * prm.out_stride;
-    const cf* tw = prm.tw + tw_offset(LOG2H, 0);
+    const TwSrc tw = tw_src(prm);
 RCG_UNROLL(RCG_OLA_UNROLL)
     for (int m = t; m < M; m += C::NT) {
         cf* p = S + phys(m);
@@ -776,7 +840,7 @@ RCG_UNROLL(RCG_OLA_UNROLL)
 #pragma unroll
         for (int a = 0; a < R; a++) x[a] = p[slot_off<M>(a)];
         if constexpr (!bypass) {
-            twiddle_butterfly<LOG2H, 0, true, R>(x, tw, m);
+            twiddle_butterfly<LOG2H, 0, true, R, false, C::TW_TMEM>(x, tw, m);
             Dft<R, true>::run(x);
         }
         // the reference's operation order: (re / W) * w, then ((y + tail) * env) * amp; the multiply and the add
@@ -819,28 +883,28 @@ RCG_HD void phase_ola(cf* S, int t, const StretchParams& prm, int channel, long 
 // stride pass the butterflies are dealt to lanes with bits 3 and 6 of m swapped, so that the two
 // 8-slot rows a 16-lane half warp touches are 8 rows apart (disjoint bank pairs).
 template <int LOG2H, int PASS>
-RCG_HD void fft_butterfly_hr(cf* S, const cf* tw_all, int b) {
+RCG_HD void fft_butterfly_hr(cf* S, const TwSrc& tw, int b) {
     constexpr PlanDesc P = make_plan(LOG2H, true);
     constexpr int RL = P.rlog2[PASS], R = 1 << RL, ML = P.mlog2[PASS], M = 1 << ML;
     constexpr int STRIDE = (M == 1) ? 1 : 2 * M;   // physical stride between butterfly inputs
     static_assert(M == 1 || M >= 8, "hr pass strides are 1 or multiples of 8");
-    const cf* tw = tw_all + tw_offset(LOG2H, PASS, true);
+    constexpr bool TM = FrameCfg<LOG2H>::TW_TMEM;
     int m = b & (M - 1);
     const int blk = b >> ML;
-    if constexpr (M >= 128) m = (m & ~0x48) | ((m & 0x08) << 3) | ((m & 0x40) >> 3);
-    const TwPre pre = tw_preload<LOG2H, PASS, R, true>(tw, m);
+    if constexpr (M >= 128) m = hr_lane_swizzle(m);
+    const TwPre pre = tw_preload<LOG2H, PASS, R, true, TM>(tw.tw + tw_offset(LOG2H, PASS, true), m);
     cf* p = S + phys(expand_hr((blk << (ML + RL)) + m));
     cf x[R];
 #pragma unroll
     for (int a = 0; a < R; a++) x[a] = p[slot_off<STRIDE>(a)];
-    twiddle_butterfly<LOG2H, PASS, true, R, true>(x, tw, m, pre);
+    twiddle_butterfly<LOG2H, PASS, true, R, true, TM>(x, tw, m, pre);
     Dft<R, true>::run(x);
 #pragma unroll
     for (int j = 0; j < R; j++) p[slot_off<STRIDE>(j)] = x[j];
 }
 
 template <int LOG2H, int PASS>
-RCG_HD void phase_fft_pass_hr(cf* S, int t, const cf* tw_all) {
+RCG_HD void phase_fft_pass_hr(cf* S, int t, const TwSrc& tw_all) {
     using C = FrameCfg<LOG2H>;
     constexpr int NB = (C::H / 2) >> make_plan(LOG2H, true).rlog2[PASS];
     for (int b = t; b < NB; b += C::NT) fft_butterfly_hr<LOG2H, PASS>(S, tw_all, b);
@@ -850,7 +914,7 @@ RCG_HD void phase_fft_pass_hr(cf* S, int t, const cf* tw_all) {
 // of 16 rows.  A warp's 32 radix-16 butterflies (index 32w'..32w'+31) cover rows 64w'..64w'+63,
 // so step 2i = those 64 radix-8 butterflies (two per lane), step 2i+1 = the radix-16 ones.
 template <int LOG2H>
-RCG_HD void fft_tail_step_hr(cf* S, int t, int step, const cf* tw_all) {
+RCG_HD void fft_tail_step_hr(cf* S, int t, int step, const TwSrc& tw_all) {
     using C = FrameCfg<LOG2H>;
     constexpr int NB_PREV = (C::H / 2) / 16, NB_LAST = (C::H / 2) / 8;
     const int b = t + C::NT * (step >> 1);
@@ -902,14 +966,14 @@ RCG_HD void phase_ola_hr(cf* S, int t, const StretchParams& prm, int channel, lo
         }
         return;
     }
-    const cf* tw = prm.tw + tw_offset(LOG2H, 0, true);
+    const TwSrc tw = tw_src(prm);
 RCG_UNROLL(RCG_OLA_UNROLL)
     for (int m = t; m < M; m += C::NT) {
         cf* p = S + phys(expand_hr(m));
         cf x[R];
 #pragma unroll
         for (int a = 0; a < R; a++) x[a] = p[slot_off<STRIDE>(a)];
-        twiddle_butterfly<LOG2H, 0, true, R, true>(x, tw, m);
+        twiddle_butterfly<LOG2H, 0, true, R, true, C::TW_TMEM>(x, tw, m);
         Dft<R, true>::run(x);
 #pragma unroll
         for (int a = 0; a < RH; a++) {
@@ -997,14 +1061,14 @@ RCG_HD void phase_resample(const cf* S, int t, const StretchParams& prm, int cha
 template <int LOG2H, bool INV, int PASS, int LAST, class Exec>
 RCG_HD void fft_range(Exec& ex, cf* S, const StretchParams& prm, bool work) {   // passes PASS..LAST one by one
     if constexpr (INV ? PASS >= LAST : PASS <= LAST) {
-        ex.par([&](int t) { if (work) phase_fft_pass<LOG2H, PASS, INV>(S, t, prm.tw); });
+        ex.par([&](int t) { if (work) phase_fft_pass<LOG2H, PASS, INV>(S, t, tw_src(prm)); });
         fft_range<LOG2H, INV, INV ? PASS - 1 : PASS + 1, LAST>(ex, S, prm, work);
     }
 }
 template <int LOG2H, int PASS, int LAST, class Exec>
 RCG_HD void fft_range_hr(Exec& ex, cf* S, const StretchParams& prm, bool work) {
     if constexpr (PASS >= LAST) {
-        ex.par([&](int t) { if (work) phase_fft_pass_hr<LOG2H, PASS>(S, t, prm.tw); });
+        ex.par([&](int t) { if (work) phase_fft_pass_hr<LOG2H, PASS>(S, t, tw_src(prm)); });
         fft_range_hr<LOG2H, PASS - 1, LAST>(ex, S, prm, work);
     }
 }
@@ -1015,7 +1079,7 @@ RCG_HD void fft_all(Exec& ex, cf* S, const StretchParams& prm, bool work) {
     using C = FrameCfg<LOG2H>;
     if constexpr (C::NP >= 3) {
         if constexpr (!INV) fft_range<LOG2H, false, 1, C::NP - 3>(ex, S, prm, work);
-        ex.par_steps(fft_tail_steps<LOG2H>(), [&](int step, int t) { if (work) fft_tail_step<LOG2H, INV>(S, t, step, prm.tw); });
+        ex.par_steps(fft_tail_steps<LOG2H>(), [&](int step, int t) { if (work) fft_tail_step<LOG2H, INV>(S, t, step, tw_src(prm)); });
         if constexpr (INV) fft_range<LOG2H, true, C::NP - 3, 1>(ex, S, prm, work);
     } else {
         fft_range<LOG2H, INV, INV ? C::NP - 1 : 1, INV ? 1 : C::NP - 1>(ex, S, prm, work);
@@ -1026,7 +1090,7 @@ template <int LOG2H, class Exec>
 RCG_HD void fft_inv_hr(Exec& ex, cf* S, const StretchParams& prm, bool work) {
     using C = FrameCfg<LOG2H>;
     if constexpr (C::NP >= 3) {
-        ex.par_steps(fft_tail_steps_hr<LOG2H>(), [&](int step, int t) { if (work) fft_tail_step_hr<LOG2H>(S, t, step, prm.tw); });
+        ex.par_steps(fft_tail_steps_hr<LOG2H>(), [&](int step, int t) { if (work) fft_tail_step_hr<LOG2H>(S, t, step, tw_src(prm)); });
         fft_range_hr<LOG2H, C::NP - 3, 1>(ex, S, prm, work);
     } else {
         fft_range_hr<LOG2H, C::NP - 1, 1>(ex, S, prm, work);

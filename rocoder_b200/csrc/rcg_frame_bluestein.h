@@ -41,7 +41,7 @@ template <int LM, bool INV, int PASS, class Exec>
 RCG_HD void bs_fft(Exec& ex, cf* S, const StretchParams& prm, bool work) {
     constexpr int NP = FrameCfg<LM>::NP;
     if constexpr (PASS >= 0 && PASS < NP) {
-        ex.par([&](int t) { if (work) phase_fft_pass<LM, PASS, INV>(S, t, prm.tw); });
+        ex.par([&](int t) { if (work) phase_fft_pass<LM, PASS, INV, false>(S, t, prm.tw); });
         bs_fft<LM, INV, INV ? PASS - 1 : PASS + 1>(ex, S, prm, work);
     }
 }

@@ -30,10 +30,15 @@ __launch_bounds__(rcg::FrameCfg<RCG_JIT_LOG2H>::NT * rcg::FrameCfg<RCG_JIT_LOG2H
 rcg_jit_stretch(const __grid_constant__ rcg::StretchParams prm_in, int n_items) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const rcg::StretchParams prm = rcg::with_mode_constants<RCG_JIT_MODE>(prm_in);
-    if constexpr (rcg::FrameCfg<RCG_JIT_LOG2H>::TW_SMEM)
+    if constexpr (rcg::FrameCfg<RCG_JIT_LOG2H>::TW_TMEM) {
+        rcg::stretch_body<RCG_JIT_LOG2H, false>(rcg::with_tmem_twiddles<RCG_JIT_LOG2H>(prm, rcg::tmem_slot<RCG_JIT_LOG2H>(smem_raw)),
+                                                n_items, smem_raw);
+        rcg::release_tmem_twiddles<RCG_JIT_LOG2H>(rcg::tmem_slot<RCG_JIT_LOG2H>(smem_raw));
+    } else if constexpr (rcg::FrameCfg<RCG_JIT_LOG2H>::TW_SMEM) {
         rcg::stretch_body<RCG_JIT_LOG2H, false>(rcg::with_smem_twiddles<RCG_JIT_LOG2H>(prm, reinterpret_cast<cf*>(smem_raw)),
                                                 n_items, smem_raw);
-    else
+    } else {
         rcg::stretch_body<RCG_JIT_LOG2H, false>(prm, n_items, smem_raw);
+    }
 }
 #endif

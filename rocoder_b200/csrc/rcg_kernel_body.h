@@ -54,13 +54,70 @@ __device__ __forceinline__ StretchParams with_smem_twiddles(const StretchParams&
     }
     return p;
 }
+
+// FrameCfg::TW_TMEM (rcg_common.h): the CTA takes all 512 columns of the SM's Tensor Memory (it is alone on the SM:
+// the frame buffers fill the shared memory), the threads of frame lane 0 copy their rows from the image in global
+// memory (176 columns x 256 threads, once per launch), and every thread remembers where its row starts: rows
+// 32 (warp mod 4) .., columns 0.. for the first four warps of a frame lane and 256.. for the other four.
+constexpr uint32_t kTmemCols = 512;
+template <int LOG2H>
+__device__ __forceinline__ StretchParams with_tmem_twiddles(const StretchParams& prm, uint32_t* slot) {
+    using C = FrameCfg<LOG2H>;
+    StretchParams p = prm;
+    if constexpr (C::TW_TMEM) {
+        constexpr int NCOL = tmem_total_cols(LOG2H);
+        static_assert(NCOL % 8 == 0 && NCOL <= 256, "two column halves of 256");
+        if (threadIdx.x < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(slot)), "n"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int t = (int)(threadIdx.x % C::NT), wl = t / 32;
+        const uint32_t mine = *slot + ((uint32_t)(32 * (wl % 4)) << 16) + (wl >= 4 ? 256u : 0u);
+        if (threadIdx.x < C::NT) {
+            for (int c = 0; c < NCOL; c += 8) {
+                uint32_t r[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) r[q] = __float_as_uint(__ldg(prm.tw_image + (size_t)(c + q) * C::NT + t));
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                             ::"r"(mine + (uint32_t)c), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),
+                               "r"(r[6]), "r"(r[7]) : "memory");
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        p.tmem_addr = mine;
+    }
+    return p;
+}
+// ... and hands the columns back before it exits
+template <int LOG2H>
+__device__ __forceinline__ void release_tmem_twiddles(const uint32_t* slot) {
+    if constexpr (FrameCfg<LOG2H>::TW_TMEM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x < 32)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*slot), "n"(kTmemCols) : "memory");
+    }
+}
+// the word behind the frame buffers (and the shared-memory tables, where there are any) that receives the allocation
+template <int LOG2H>
+__device__ __forceinline__ uint32_t* tmem_slot(unsigned char* smem_raw) {
+    using C = FrameCfg<LOG2H>;
+    return reinterpret_cast<uint32_t*>(reinterpret_cast<cf*>(smem_raw) + (size_t)C::FPC * C::SMEM_CF + (C::TW_SMEM ? C::TW_CF : 0));
+}
 template <int LOG2H>
 constexpr size_t kernel_smem_bytes() {
     using C = FrameCfg<LOG2H>;
-    return ((size_t)C::FPC * C::SMEM_CF + (C::TW_SMEM ? C::TW_CF : 0)) * sizeof(cf);
+    return ((size_t)C::FPC * C::SMEM_CF + (C::TW_SMEM ? C::TW_CF : 0)) * sizeof(cf) + (C::TW_TMEM ? 16 : 0);
 }
 template <int LOG2H>
-constexpr int min_ctas() { return (LOG2H >= 14 || FrameCfg<LOG2H>::TW_SMEM) ? 1 : 3; }
+constexpr int min_ctas() { return (LOG2H >= 14 || three_lanes(LOG2H)) ? 1 : 3; }
 
 // MODE: the launch's scalar configuration as compile-time constants.  The frame code reads pitch and flags in
 // many places (which synthesis path, where the overlap-add phase stores, whether a resample phase exists); with

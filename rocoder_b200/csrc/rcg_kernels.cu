@@ -26,14 +26,18 @@ template <int LOG2H, bool SPEC_IN = false, int MODE = 0>
 __global__ void __launch_bounds__(FrameCfg<LOG2H>::NT * FrameCfg<LOG2H>::FPC, min_ctas<LOG2H>())
 stretch_kernel(const __grid_constant__ StretchParams prm_in, int n_items) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    if constexpr (MODE == 0 && !FrameCfg<LOG2H>::TW_SMEM) {
+    if constexpr (MODE == 0 && !FrameCfg<LOG2H>::TW_SMEM && !FrameCfg<LOG2H>::TW_TMEM) {
         stretch_body<LOG2H, SPEC_IN>(prm_in, n_items, smem_raw);
     } else {
         const StretchParams prm = with_mode_constants<MODE>(prm_in);
-        if constexpr (FrameCfg<LOG2H>::TW_SMEM)
+        if constexpr (FrameCfg<LOG2H>::TW_TMEM) {
+            stretch_body<LOG2H, SPEC_IN>(with_tmem_twiddles<LOG2H>(prm, tmem_slot<LOG2H>(smem_raw)), n_items, smem_raw);
+            release_tmem_twiddles<LOG2H>(tmem_slot<LOG2H>(smem_raw));
+        } else if constexpr (FrameCfg<LOG2H>::TW_SMEM) {
             stretch_body<LOG2H, SPEC_IN>(with_smem_twiddles<LOG2H>(prm, reinterpret_cast<cf*>(smem_raw)), n_items, smem_raw);
-        else
+        } else {
             stretch_body<LOG2H, SPEC_IN>(prm, n_items, smem_raw);
+        }
     }
 }
 
@@ -57,10 +61,14 @@ template <int LOG2H>
 __global__ void __launch_bounds__(FrameCfg<LOG2H>::NT * FrameCfg<LOG2H>::FPC, min_ctas<LOG2H>())
 analysis_kernel(const __grid_constant__ StretchParams prm, int n_items) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    if constexpr (FrameCfg<LOG2H>::TW_SMEM)
+    if constexpr (FrameCfg<LOG2H>::TW_TMEM) {
+        analysis_body<LOG2H>(with_tmem_twiddles<LOG2H>(prm, tmem_slot<LOG2H>(smem_raw)), n_items, smem_raw);
+        release_tmem_twiddles<LOG2H>(tmem_slot<LOG2H>(smem_raw));
+    } else if constexpr (FrameCfg<LOG2H>::TW_SMEM) {
         analysis_body<LOG2H>(with_smem_twiddles<LOG2H>(prm, reinterpret_cast<cf*>(smem_raw)), n_items, smem_raw);
-    else
+    } else {
         analysis_body<LOG2H>(prm, n_items, smem_raw);
+    }
 }
 
 template <int LOG2H>

@@ -127,6 +127,32 @@ inline std::vector<cf> host_pair_spectral_twiddles(int log2h, int odd) {
     return tw;
 }
 
+// ---- pass twiddles as Tensor Memory rows (tw_in_tmem, rcg_common.h): image[column][thread] ------------------------
+inline std::vector<float> host_tmem_image(int log2h) {
+    const int NT = threads_per_frame(log2h), ncol = tmem_total_cols(log2h);
+    std::vector<float> img((size_t)ncol * NT, 0.0f);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int hr = 0; hr < 2; hr++) {
+        const PlanDesc d = make_plan(log2h, hr != 0);
+        for (int p = 0; p < d.npasses; p++) {
+            const int R = 1 << d.rlog2[p], sc = tmem_set_cols(log2h, p, hr != 0), off = tmem_col_offset(log2h, p, hr != 0);
+            if (sc == 0) continue;
+            const double n = (double)R * (double)(1 << d.mlog2[p]);
+            for (int t = 0; t < NT; t++)
+                for (int set = 0; set < tmem_sets(log2h, p, hr != 0); set++) {
+                    const int m = tmem_m_of_thread(log2h, p, hr != 0, t, set);
+                    for (int j = (R == 2 ? 1 : 0); j < R; j++) {
+                        const double a = -two_pi * (double)m * (double)j / n;
+                        const int col = off + set * sc + (R == 2 ? 0 : 2 * j);
+                        img[(size_t)col * NT + t] = (float)cos(a);
+                        img[(size_t)(col + 1) * NT + t] = (float)sin(a);
+                    }
+                }
+        }
+    }
+    return img;
+}
+
 // ---- windows that are not a power of two: Bluestein's chirp tables (rcg_frame_bluestein.h) ----------------------
 // smallest LM with 2^LM >= 2W - 1
 inline int bluestein_log2m(int W) {

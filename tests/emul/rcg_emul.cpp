@@ -75,6 +75,8 @@ static int emul_run(StretchParams prm) {
     std::vector<float> we = host_decimate2(window), ee = host_decimate2(env);
     prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.tw0 = tw.data(); prm.spec_tw = stw.data();
     prm.spec_tw_hr = stw_hr.data(); prm.window_even = we.data(); prm.env_even = ee.data();
+    std::vector<float> twi;   // the Tensor Memory rows of the device kernel, read straight from their image here
+    if (C::TW_TMEM) { twi = host_tmem_image(LOG2H); prm.tw_image = twi.data(); }
     std::vector<float> lr = lerp_table(prm.pitch);
     prm.lerp_ratio = lr.data();
     std::vector<uint2> ptab = host_pair_table(LOG2H);
@@ -313,6 +315,8 @@ static int emul_plugin(StretchParams prm, apply_fn fn) {
     host_crossfade_compensation(env.data(), H);
     std::vector<cf> tw = host_pass_twiddles(LOG2H), stw = host_spectral_twiddles(LOG2H);
     prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.tw0 = tw.data(); prm.spec_tw = stw.data();
+    std::vector<float> twi;
+    if (C::TW_TMEM) { twi = host_tmem_image(LOG2H); prm.tw_image = twi.data(); }
     std::vector<float> lr = lerp_table(prm.pitch);
     prm.lerp_ratio = lr.data();
     std::vector<uint2> ptab = host_pair_table(LOG2H);
