@@ -10,6 +10,7 @@ typedef long long int64_t;
 #else
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 #endif
 
 #if defined(__CUDACC__)
@@ -135,7 +136,14 @@ RCG_HD constexpr int threads_per_frame(int log2h) {
 #define RCG_TW_TMEM 1
 #endif
 RCG_HD constexpr bool three_lanes(int log2h) { return log2h == 13; }
-RCG_HD constexpr bool tw_in_tmem(int log2h) { return RCG_TW_TMEM != 0 && three_lanes(log2h); }
+// log2h = 14 (the W = 32768 kernel and the CTA pair of W = 65536): 512 threads, four warps per Tensor Memory row, 128
+// columns each -- exactly the full plan's twiddles; the half-rate plan (W = 32768 only) keeps its packed tables
+#ifndef RCG_TW_TMEM_512
+#define RCG_TW_TMEM_512 1
+#endif
+RCG_HD constexpr bool tw_in_tmem(int log2h, bool hr = false) {
+    return RCG_TW_TMEM != 0 && (log2h == 13 || (RCG_TW_TMEM_512 != 0 && log2h == 14 && !hr));
+}
 RCG_HD constexpr bool tw_in_smem(int log2h) { return three_lanes(log2h) && !tw_in_tmem(log2h); }
 RCG_HD constexpr int frames_per_cta(int log2h) {
     if (three_lanes(log2h)) return 3;
@@ -152,7 +160,7 @@ RCG_HD constexpr int frames_per_cta(int log2h) {
 // one row per thread, shared by the warps that are equal mod 4 -- and tcgen05.ld moves 8 columns = 4 twiddles of a
 // row into registers per instruction, on a datapath of its own.  So every thread keeps its twiddles in its row
 // (176 columns at W = 16384; the two warps of a frame lane that share a row take columns 0.. and 256.., the three
-// frame lanes of a CTA read the same ones) and no twiddle load touches the shared-memory pipe, which the butterfly
+// frame lanes of a CTA read the same ones; 128 columns x four warps per row at 512 threads per frame) and no twiddle load touches the shared-memory pipe, which the butterfly
 // data keep 55 % busy: a quarter of that pipe's wavefronts were twiddle loads.  Full tables for every pass also drop
 // the products the packed tables needed (w^5 = w^4 w^1 ..., two-level radix-2 twiddles).
 // Row layout: [full plan: pass 0 | pass 1 | ...][half-rate plan: pass 0 | ...]; a set of a radix-R pass is 2 R
@@ -174,7 +182,21 @@ RCG_HD constexpr int tmem_col_offset(int log2h, int pass, bool hr) {
     for (int p = 0; p < pass; p++) off += tmem_sets(log2h, p, hr) * tmem_set_cols(log2h, p, hr);
     return off;
 }
-RCG_HD constexpr int tmem_total_cols(int log2h) { return tmem_col_offset(log2h, make_plan(log2h).npasses, true); }
+RCG_HD constexpr int tmem_total_cols(int log2h) {
+    return tw_in_tmem(log2h, true) ? tmem_col_offset(log2h, make_plan(log2h).npasses, true)
+                                   : tmem_col_offset(log2h, make_plan(log2h).npasses, false);
+}
+// W = 16384 also keeps the frame-invariant table entries of the spectral step in the row, behind the twiddles: 64
+// columns -- 8 quads x {slots k | H-k, slots Q-k | Q+k, k, twiddle, -} on the half-rate path, 16 pairs x {slots, k,
+// twiddle} on the full-rate one (two images; a launch takes the one of its path).  The table loads from global
+// memory were the head of a load -> address -> shared-memory load chain in every iteration of the step.
+RCG_HD constexpr bool spectral_in_tmem(int log2h) { return tw_in_tmem(log2h) && log2h == 13; }
+RCG_HD constexpr int tmem_spectral_offset(int log2h) { return tmem_total_cols(log2h); }
+RCG_HD constexpr int tmem_spectral_cols(int log2h) { return spectral_in_tmem(log2h) ? 64 : 0; }
+RCG_HD constexpr int tmem_image_cols(int log2h) { return tmem_total_cols(log2h) + tmem_spectral_cols(log2h); }
+// the warps of a frame lane that share a row (equal mod 4) take one column group each
+RCG_HD constexpr int tmem_groups(int log2h) { return threads_per_frame(log2h) > 128 ? threads_per_frame(log2h) / 128 : 1; }
+RCG_HD constexpr int tmem_group_cols(int log2h) { return 512 / tmem_groups(log2h); }
 // long-stride passes of the half-rate plan deal butterflies to lanes with bits 3 and 6 of m swapped (rcg_frame.h)
 RCG_HD constexpr int hr_lane_swizzle(int m) { return (m & ~0x48) | ((m & 0x08) << 3) | ((m & 0x40) >> 3); }
 // which m the butterflies of thread t see in set `set` of a pass, and a thread (row) that sees a given m

@@ -231,7 +231,9 @@ struct rcg_engine {
     uint2* d_pair_tab = nullptr;
     uint4* d_quad_tab = nullptr;
     cf *d_tw = nullptr, *d_spec_tw = nullptr, *d_spec_tw_hr = nullptr;
-    float* d_tw_image = nullptr;   // pass twiddles as Tensor Memory rows (tw_in_tmem, rcg_common.h)
+    // pass twiddles (and, W = 16384, the spectral step's table entries) as Tensor Memory rows (rcg_common.h): the image
+    // of the full-rate path and, where it differs (spectral_in_tmem), the one of the half-rate path
+    float *d_tw_image = nullptr, *d_tw_image_hr = nullptr;
     bool bluestein = false;   // window_len is not a power of two: chirp-z path (rcg_frame_bluestein.h)
     int bs_lm = 0;            // log2 of its convolution length
     BluesteinTables bt{};
@@ -432,10 +434,15 @@ extern "C" int rcg_create(const rcg_config* cfg_in, rcg_engine** out) {
         TRY_E(cudaMalloc(&e->d_lerp_ratio, ratio.size() * sizeof(float)));
         TRY_E(cudaMemcpy(e->d_lerp_ratio, ratio.data(), ratio.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
-    if (!e->bluestein && !e->pair && tw_in_tmem(plan_log2h)) {
+    if (!e->bluestein && tw_in_tmem(plan_log2h)) {
         std::vector<float> img = host_tmem_image(plan_log2h);
         TRY_E(cudaMalloc(&e->d_tw_image, img.size() * sizeof(float)));
         TRY_E(cudaMemcpy(e->d_tw_image, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+        if (spectral_in_tmem(plan_log2h)) {
+            img = host_tmem_image(plan_log2h, true);
+            TRY_E(cudaMalloc(&e->d_tw_image_hr, img.size() * sizeof(float)));
+            TRY_E(cudaMemcpy(e->d_tw_image_hr, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
     }
     TRY_E(cudaMalloc(&e->d_window_even, we.size() * sizeof(float)));
     TRY_E(cudaMalloc(&e->d_env_even, ee.size() * sizeof(float)));
@@ -527,7 +534,7 @@ extern "C" void rcg_destroy(rcg_engine* e) {
     if (e->h2d) cudaStreamSynchronize(e->h2d);
     cudaFree(e->d_window); cudaFree(e->d_env); cudaFree(e->d_tw); cudaFree(e->d_spec_tw); cudaFree(e->d_scratch);
     cudaFree(e->d_window_even); cudaFree(e->d_env_even); cudaFree(e->d_spec_tw_hr); cudaFree(e->d_lerp_ratio);
-    cudaFree(e->d_pair_tab); cudaFree(e->d_quad_tab); cudaFree(e->d_tw_image);
+    cudaFree(e->d_pair_tab); cudaFree(e->d_quad_tab); cudaFree(e->d_tw_image); cudaFree(e->d_tw_image_hr);
     cudaFree(e->d_pair_cross); cudaFree(e->d_pair_even); cudaFree(e->d_pair_odd);
     cudaFree(e->d_bs_chirp); cudaFree(e->d_bs_filter);
     cudaFree(e->d_big_work); cudaFree(e->d_big_ybuf); cudaFree(e->d_big_carry);
@@ -682,7 +689,10 @@ static int launch_segment(rcg_engine* e, const rcg_segment& s, int channels, cud
         p.flags |= kFlagSpectrumIn;
         p.spectrum = spec->spectrum; p.spec_frame0 = spec->frame0; p.spec_frames = spec->frames;
     }
-    if (engine_half_rate(e)) p.flags |= kFlagHalfRate;
+    if (engine_half_rate(e)) {
+        p.flags |= kFlagHalfRate;
+        if (e->d_tw_image_hr) p.tw_image = e->d_tw_image_hr;
+    }
     const uint64_t k = e->plan.frames_per_call;
     p.in = s.d_in; p.in_stride = s.in_stride; p.in_origin = s.in_origin; p.in_valid = s.in_valid;
     p.out = s.d_out; p.out_stride = s.out_stride;

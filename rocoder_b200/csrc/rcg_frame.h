@@ -118,6 +118,7 @@ struct FrameCfg {
     static constexpr int RLAST = 1 << make_plan(LOG2H).rlog2[NP - 1];
     static constexpr bool TW_SMEM = tw_in_smem(LOG2H);   // prm.tw of the kernels points into shared memory
     static constexpr bool TW_TMEM = tw_in_tmem(LOG2H);   // pass twiddles come from the thread's Tensor Memory row
+    static constexpr bool TW_TMEM_HR = tw_in_tmem(LOG2H, true);   // ... those of the half-rate plan too
     static constexpr int TW_CF = tw_total(LOG2H);
 };
 
@@ -196,7 +197,11 @@ struct TwSrc {
 };
 RCG_HD TwSrc tw_src(const StretchParams& prm) { return TwSrc(prm.tw, prm.tmem_addr, prm.tw_image); }
 
-// N = 2 or 8 consecutive columns of the set the butterfly with index m reads, starting at column `col` of the set
+// N = 2 or 8 consecutive columns of the set the butterfly with index m reads, starting at column `col` of the set.
+// tcgen05.ld writes the registers asynchronously and nothing may read them before tcgen05.wait::ld, which is why the
+// wait sits in the same statement.  (Issuing the next four twiddles before multiplying by the last four -- load and
+// wait as separate statements, the registers passed through the wait as in/out operands -- was measured 3 % SLOWER on
+// config 2: 6.11 vs 5.93 ms, profiles/r3d_tmem_pipelined_variants.jsonl.  The load's latency is 12 cycles.)
 template <int LOG2H, int PASS, bool HR, int N>
 RCG_HD void tw_fetch(const TwSrc& s, int m, int col, float (&v)[N]) {
     static_assert(N == 2 || N == 8, "tcgen05.ld shapes used here");
@@ -206,8 +211,6 @@ RCG_HD void tw_fetch(const TwSrc& s, int m, int col, float (&v)[N]) {
 #if defined(__CUDA_ARCH__)
     const uint32_t a = s.tmem + (uint32_t)(OFF + set * SC + col);
     uint32_t r[N];
-    // the registers are written asynchronously: nothing may read them before tcgen05.wait::ld, which is why the
-    // wait sits in the same statement
     if constexpr (N == 8) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
                      "tcgen05.wait::ld.sync.aligned;"
@@ -223,6 +226,35 @@ RCG_HD void tw_fetch(const TwSrc& s, int m, int col, float (&v)[N]) {
 #else
     const int row = tmem_row_of_m(LOG2H, PASS, HR, m);
     for (int q = 0; q < N; q++) v[q] = s.image[(size_t)(OFF + set * SC + col + q) * NT + row];
+#endif
+}
+
+// N = 4 or 8 columns of the thread's row starting at absolute column `col`; host execution: row `row` of the image
+template <int LOG2H, int N>
+RCG_HD void row_fetch(const TwSrc& s, int row, int col, uint32_t (&r)[N]) {
+    static_assert(N == 4 || N == 8, "tcgen05.ld shapes used here");
+#if defined(__CUDA_ARCH__)
+    (void)row;
+    const uint32_t a = s.tmem + (uint32_t)col;
+    if constexpr (N == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(a));
+    } else {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+    }
+#else
+    for (int q = 0; q < N; q++) memcpy(&r[q], &s.image[(size_t)(col + q) * threads_per_frame(LOG2H) + row], sizeof(float));
+#endif
+}
+RCG_HD float bits_to_float(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, sizeof(f)); return f;
 #endif
 }
 
@@ -557,6 +589,16 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
     const unsigned long long frame_ms = frame_clock(prm, frame);
     (void)frame_ms;
     for (int c = t; c < C::H / 4; c += C::NT) {
+        // table entries of this iteration from the Tensor Memory row: the load is warp-collective (.sync.aligned), so it
+        // sits ahead of the c == 0 branch that thread 0 takes alone
+        uint4 qt;
+        cf qtw;
+        if constexpr (spectral_in_tmem(LOG2H)) {   // {qt.x, qt.y, qt.z, tw.x, tw.y, -, -, -} of iteration c / NT
+            uint32_t r[8];
+            row_fetch<LOG2H, 8>(tw_src(prm), c % C::NT, tmem_spectral_offset(LOG2H) + 8 * (c / C::NT), r);
+            qt.x = r[0]; qt.y = r[1]; qt.z = r[2]; qt.w = 0u;
+            qtw = make_cf(bits_to_float(r[3]), bits_to_float(r[4]));
+        }
         uint32_t u[4];
         if (c == 0) {
             // E[0] = Y[0] + Y[H] (both real), E[Q] = 2 Re Y[Q]
@@ -594,11 +636,14 @@ RCG_HD void phase_spectral_hr(cf* S, int t, const StretchParams& prm, int channe
             continue;
         }
         // slot indices of bins k, H-k, Q-k, Q+k and k itself: frame-invariant, precomputed on the host
-        const uint4 qt = ld_u4(prm.quad_tab + c);
+        if constexpr (!spectral_in_tmem(LOG2H)) {
+            qt = ld_u4(prm.quad_tab + c);
+            qtw = ld_cf(prm.spec_tw_hr + c);
+        }
         const int pa = (int)(qt.x & 0xFFFFu), pc = (int)(qt.y & 0xFFFFu);
         const cf za = S[pa], zb = S[qt.x >> 16];
         const cf zc = S[pc], zd = S[qt.y >> 16];
-        const Tw tw = make_tw<(RCG_PK_SPEC != 0)>(ld_cf(prm.spec_tw_hr + c));  // exp(-2 pi i k / W)
+        const Tw tw = make_tw<(RCG_PK_SPEC != 0)>(qtw);  // exp(-2 pi i k / W)
         // exp(-2 pi i (Q-k)/W) = -i conj(tw) = -swap(tw); its rotated copy is swap(i tw): no instruction either
         Tw tw_c;
         tw_c.w = pk_neg(pk_swap(tw.w));
@@ -630,6 +675,14 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
     const unsigned long long frame_ms = frame_clock(prm, frame);
     (void)frame_ms;
     for (int c = t; c < C::H / 2; c += C::NT) {
+        uint2 pt;
+        cf ptw;
+        if constexpr (spectral_in_tmem(LOG2H) && KMUL == 1) {   // {pt.x, pt.y, tw.x, tw.y} of iteration c / NT; ahead of the branch
+            uint32_t r[4];
+            row_fetch<LOG2H, 4>(tw_src(prm), c % C::NT, tmem_spectral_offset(LOG2H) + 4 * (c / C::NT), r);
+            pt.x = r[0]; pt.y = r[1];
+            ptw = make_cf(bits_to_float(r[2]), bits_to_float(r[3]));
+        }
         uint32_t u[4];
         if (c == 0) {
             // k = 0: bins 0 and H are real: X[0] = a + b, X[H] = a - b
@@ -663,10 +716,13 @@ RCG_HD void phase_spectral(cf* S, int t, const StretchParams& prm, int channel, 
 #endif
             continue;
         }
-        const uint2 pt = ld_u2(prm.pair_tab + c);   // frame-invariant slot indices of bins k, H-k and k itself
+        if constexpr (!(spectral_in_tmem(LOG2H) && KMUL == 1)) {
+            pt = ld_u2(prm.pair_tab + c);   // frame-invariant slot indices of bins k, H-k and k itself
+            ptw = ld_cf(prm.spec_tw + c);
+        }
         const int pa = (int)(pt.x & 0xFFFFu), pb = (int)(pt.x >> 16);
         const cf za = S[pa], zb = S[pb];
-        const Tw tw = make_tw<(RCG_PK_SPEC != 0)>(ld_cf(prm.spec_tw + c));  // exp(-2 pi i k / W)
+        const Tw tw = make_tw<(RCG_PK_SPEC != 0)>(ptw);  // exp(-2 pi i k / W)
         philox4x32_10(pt.y * (uint32_t)KMUL, f_lo, f_hi, (uint32_t)(channel + prm.channel_offset), prm.keys, u);
         // A = Y[k] + conj(Y[H-k]), B = Y[k] - conj(Y[H-k]), Cc = i conj(t) B
         cf A, B;
@@ -888,7 +944,7 @@ RCG_HD void fft_butterfly_hr(cf* S, const TwSrc& tw, int b) {
     constexpr int RL = P.rlog2[PASS], R = 1 << RL, ML = P.mlog2[PASS], M = 1 << ML;
     constexpr int STRIDE = (M == 1) ? 1 : 2 * M;   // physical stride between butterfly inputs
     static_assert(M == 1 || M >= 8, "hr pass strides are 1 or multiples of 8");
-    constexpr bool TM = FrameCfg<LOG2H>::TW_TMEM;
+    constexpr bool TM = FrameCfg<LOG2H>::TW_TMEM_HR;
     int m = b & (M - 1);
     const int blk = b >> ML;
     if constexpr (M >= 128) m = hr_lane_swizzle(m);
@@ -973,7 +1029,7 @@ RCG_UNROLL(RCG_OLA_UNROLL)
         cf x[R];
 #pragma unroll
         for (int a = 0; a < R; a++) x[a] = p[slot_off<STRIDE>(a)];
-        twiddle_butterfly<LOG2H, 0, true, R, true, C::TW_TMEM>(x, tw, m);
+        twiddle_butterfly<LOG2H, 0, true, R, true, C::TW_TMEM_HR>(x, tw, m);
         Dft<R, true>::run(x);
 #pragma unroll
         for (int a = 0; a < RH; a++) {

@@ -271,7 +271,11 @@ RCG_HD void pair_phase_resample(const float* stage, int tg, int nthr, const Stre
 template <int PASS, int LAST, bool INV, class Exec>
 RCG_HD void pair_fft_range(Exec& ex, cf* const (&bufs)[2], const StretchParams& prm, bool work) {
     if constexpr (INV ? PASS >= LAST : PASS <= LAST) {
-        ex.par([&](int r, int t) { if (work) phase_fft_pass<kPairLog2HL, PASS, INV>(bufs[r], t, PASS == 0 ? prm.tw0 : prm.tw); });
+        ex.par([&](int r, int t) {
+            if (!work) return;
+            if constexpr (FrameCfg<kPairLog2HL>::TW_TMEM) phase_fft_pass<kPairLog2HL, PASS, INV>(bufs[r], t, tw_src(prm));
+            else phase_fft_pass<kPairLog2HL, PASS, INV>(bufs[r], t, PASS == 0 ? prm.tw0 : prm.tw);
+        });
         pair_fft_range<INV ? PASS - 1 : PASS + 1, LAST, INV>(ex, bufs, prm, work);
     }
 }
@@ -281,7 +285,7 @@ RCG_HD void pair_fft_all(Exec& ex, cf* const (&bufs)[2], const StretchParams& pr
     constexpr int NP = FrameCfg<kPairLog2HL>::NP;
     if constexpr (!INV) pair_fft_range<0, NP - 3, false>(ex, bufs, prm, work);
     ex.par_steps(fft_tail_steps<kPairLog2HL>(),
-                 [&](int step, int r, int t) { if (work) fft_tail_step<kPairLog2HL, INV>(bufs[r], t, step, prm.tw); });
+                 [&](int step, int r, int t) { if (work) fft_tail_step<kPairLog2HL, INV>(bufs[r], t, step, tw_src(prm)); });
     if constexpr (INV) pair_fft_range<NP - 3, 0, true>(ex, bufs, prm, work);
 }
 

@@ -58,15 +58,15 @@ __device__ __forceinline__ StretchParams with_smem_twiddles(const StretchParams&
 // FrameCfg::TW_TMEM (rcg_common.h): the CTA takes all 512 columns of the SM's Tensor Memory (it is alone on the SM:
 // the frame buffers fill the shared memory), the threads of frame lane 0 copy their rows from the image in global
 // memory (176 columns x 256 threads, once per launch), and every thread remembers where its row starts: rows
-// 32 (warp mod 4) .., columns 0.. for the first four warps of a frame lane and 256.. for the other four.
+// 32 (warp mod 4) .., columns 0.. for the first four warps of a frame lane, the next column group for the next four.
 constexpr uint32_t kTmemCols = 512;
 template <int LOG2H>
 __device__ __forceinline__ StretchParams with_tmem_twiddles(const StretchParams& prm, uint32_t* slot) {
     using C = FrameCfg<LOG2H>;
     StretchParams p = prm;
     if constexpr (C::TW_TMEM) {
-        constexpr int NCOL = tmem_total_cols(LOG2H);
-        static_assert(NCOL % 8 == 0 && NCOL <= 256, "two column halves of 256");
+        constexpr int NCOL = tmem_image_cols(LOG2H);
+        static_assert(NCOL % 8 == 0 && NCOL <= tmem_group_cols(LOG2H), "a column group per warp that shares the row");
         if (threadIdx.x < 32) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                          ::"r"((uint32_t)__cvta_generic_to_shared(slot)), "n"(kTmemCols) : "memory");
@@ -76,7 +76,7 @@ __device__ __forceinline__ StretchParams with_tmem_twiddles(const StretchParams&
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int t = (int)(threadIdx.x % C::NT), wl = t / 32;
-        const uint32_t mine = *slot + ((uint32_t)(32 * (wl % 4)) << 16) + (wl >= 4 ? 256u : 0u);
+        const uint32_t mine = *slot + ((uint32_t)(32 * (wl % 4)) << 16) + (uint32_t)((wl / 4) * tmem_group_cols(LOG2H));
         if (threadIdx.x < C::NT) {
             for (int c = 0; c < NCOL; c += 8) {
                 uint32_t r[8];

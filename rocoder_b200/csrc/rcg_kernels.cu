@@ -169,14 +169,17 @@ stretch_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_cons
 
 // frequency-kernel path at W = 65536, analysis half: each CTA of the pair writes the bins of its parity
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(FrameCfg<kPairLog2HL>::NT, 1)
-analysis_pair_kernel(const __grid_constant__ StretchParams prm, const __grid_constant__ PairTables pt, int n_items) {
+analysis_pair_kernel(const __grid_constant__ StretchParams prm_in, const __grid_constant__ PairTables pt, int n_items) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int r = (int)cluster_cta_rank();
     cf* S = reinterpret_cast<cf*>(smem_raw);
     cf* bufs[2] = {S, S};   // only bufs[r] is touched: no data crosses the pair in this kernel
     PairDeviceExec ex{r, (int)threadIdx.x};
+    uint32_t* tm_slot = reinterpret_cast<uint32_t*>(smem_raw + kPairSmemBytes - 16);
+    const StretchParams prm = with_tmem_twiddles<kPairLog2HL>(prm_in, tm_slot);
     const int cid = blockIdx.x / 2, ncl = gridDim.x / 2;
     for (int item = cid; item < n_items; item += ncl) run_analysis_item_pair(ex, bufs, prm, pt, item, true);
+    release_tmem_twiddles<kPairLog2HL>(tm_slot);
 }
 
 __global__ void __launch_bounds__(FrameCfg<kPairLog2HL>::NT)

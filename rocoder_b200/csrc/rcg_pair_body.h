@@ -4,6 +4,7 @@
 // (NVRTC sees no toolkit headers).  Device code only.
 #pragma once
 #include "rcg_frame_pair.h"
+#include "rcg_kernel_body.h"
 
 namespace rcg {
 
@@ -95,7 +96,8 @@ struct PairDeviceExec {
 constexpr int kPairTwSmemFirst = tw_offset(kPairLog2HL, 1);
 constexpr int kPairTwSmemCf = tw_offset(kPairLog2HL, make_plan(kPairLog2HL).npasses) - kPairTwSmemFirst;
 constexpr size_t kPairSmemBytes =
-    (size_t)(FrameCfg<kPairLog2HL>::SMEM_CF + kPairLandCf + kPairTwSmemCf + kPairTwLen) * sizeof(cf) + 16;   // + mbarrier
+    (size_t)(FrameCfg<kPairLog2HL>::SMEM_CF + kPairLandCf + kPairTwSmemCf + kPairTwLen) * sizeof(cf) + 16    // + mbarrier
+    + (FrameCfg<kPairLog2HL>::TW_TMEM ? 16 : 0);                                                              // + Tensor Memory slot
 
 __device__ __forceinline__ void stretch_pair_body(const StretchParams& prm_in, const PairTables& pt_in, int n_items,
                                                   unsigned char* smem_raw) {
@@ -104,10 +106,13 @@ __device__ __forceinline__ void stretch_pair_body(const StretchParams& prm_in, c
     cf* zone = S + FrameCfg<kPairLog2HL>::SMEM_CF;             // landing zone behind the transform buffer
     cf* tw_s = zone + kPairLandCf;
     cf* cross_s = tw_s + kPairTwSmemCf;
-    for (int i = threadIdx.x; i < kPairTwSmemCf; i += blockDim.x) tw_s[i] = __ldg(prm_in.tw + kPairTwSmemFirst + i);
+    if constexpr (!FrameCfg<kPairLog2HL>::TW_TMEM)
+        for (int i = threadIdx.x; i < kPairTwSmemCf; i += blockDim.x) tw_s[i] = __ldg(prm_in.tw + kPairTwSmemFirst + i);
     for (int i = threadIdx.x; i < kPairTwLen; i += blockDim.x) cross_s[i] = __ldg(pt_in.cross_tw + i);
     __syncthreads();
-    StretchParams prm = prm_in;
+    // the pass twiddles of the local transform: each thread's Tensor Memory row (rcg_common.h), or the tables above
+    uint32_t* tm_slot = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(cross_s + kPairTwLen) + 16);
+    StretchParams prm = with_tmem_twiddles<kPairLog2HL>(prm_in, tm_slot);
     prm.tw0 = prm_in.tw;
     prm.tw = tw_s - kPairTwSmemFirst;     // only passes >= 1 index it (pair_fft_range hands pass 0 prm.tw0)
     PairTables pt = pt_in;
@@ -128,6 +133,7 @@ __device__ __forceinline__ void stretch_pair_body(const StretchParams& prm_in, c
     float* scratch = pt.scratch + (long long)cid * 3 * kPairH;
     for (int item = cid; item < n_items; item += ncl) run_work_item_pair(ex, bufs, land, prm, pt, item, scratch, true);
     cluster_barrier();  // no CTA may exit while its peer can still write into its shared memory
+    release_tmem_twiddles<kPairLog2HL>(tm_slot);
 }
 
 }  // namespace rcg

@@ -6,6 +6,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "rcg_common.h"
@@ -127,32 +128,6 @@ inline std::vector<cf> host_pair_spectral_twiddles(int log2h, int odd) {
     return tw;
 }
 
-// ---- pass twiddles as Tensor Memory rows (tw_in_tmem, rcg_common.h): image[column][thread] ------------------------
-inline std::vector<float> host_tmem_image(int log2h) {
-    const int NT = threads_per_frame(log2h), ncol = tmem_total_cols(log2h);
-    std::vector<float> img((size_t)ncol * NT, 0.0f);
-    const double two_pi = 6.283185307179586476925286766559;
-    for (int hr = 0; hr < 2; hr++) {
-        const PlanDesc d = make_plan(log2h, hr != 0);
-        for (int p = 0; p < d.npasses; p++) {
-            const int R = 1 << d.rlog2[p], sc = tmem_set_cols(log2h, p, hr != 0), off = tmem_col_offset(log2h, p, hr != 0);
-            if (sc == 0) continue;
-            const double n = (double)R * (double)(1 << d.mlog2[p]);
-            for (int t = 0; t < NT; t++)
-                for (int set = 0; set < tmem_sets(log2h, p, hr != 0); set++) {
-                    const int m = tmem_m_of_thread(log2h, p, hr != 0, t, set);
-                    for (int j = (R == 2 ? 1 : 0); j < R; j++) {
-                        const double a = -two_pi * (double)m * (double)j / n;
-                        const int col = off + set * sc + (R == 2 ? 0 : 2 * j);
-                        img[(size_t)col * NT + t] = (float)cos(a);
-                        img[(size_t)(col + 1) * NT + t] = (float)sin(a);
-                    }
-                }
-        }
-    }
-    return img;
-}
-
 // ---- windows that are not a power of two: Bluestein's chirp tables (rcg_frame_bluestein.h) ----------------------
 // smallest LM with 2^LM >= 2W - 1
 inline int bluestein_log2m(int W) {
@@ -248,6 +223,57 @@ inline std::vector<uint4> host_quad_table(int log2h) {
         tab[c].w = 0;
     }
     return tab;
+}
+
+// ---- pass twiddles as Tensor Memory rows (tw_in_tmem, rcg_common.h): image[column][thread] ------------------------
+// half_rate: which spectral-step table entries follow the twiddles (spectral_in_tmem): the quads of the half-rate path
+// or the pairs of the full-rate one
+inline std::vector<float> host_tmem_image(int log2h, bool half_rate = false) {
+    const int NT = threads_per_frame(log2h), ncol = tmem_image_cols(log2h);
+    std::vector<float> img((size_t)ncol * NT, 0.0f);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int hr = 0; hr < 2; hr++) {
+        if (!tw_in_tmem(log2h, hr != 0)) continue;
+        const PlanDesc d = make_plan(log2h, hr != 0);
+        for (int p = 0; p < d.npasses; p++) {
+            const int R = 1 << d.rlog2[p], sc = tmem_set_cols(log2h, p, hr != 0), off = tmem_col_offset(log2h, p, hr != 0);
+            if (sc == 0) continue;
+            const double n = (double)R * (double)(1 << d.mlog2[p]);
+            for (int t = 0; t < NT; t++)
+                for (int set = 0; set < tmem_sets(log2h, p, hr != 0); set++) {
+                    const int m = tmem_m_of_thread(log2h, p, hr != 0, t, set);
+                    for (int j = (R == 2 ? 1 : 0); j < R; j++) {
+                        const double a = -two_pi * (double)m * (double)j / n;
+                        const int col = off + set * sc + (R == 2 ? 0 : 2 * j);
+                        img[(size_t)col * NT + t] = (float)cos(a);
+                        img[(size_t)(col + 1) * NT + t] = (float)sin(a);
+                    }
+                }
+        }
+    }
+    if (spectral_in_tmem(log2h)) {
+        auto put = [&](int col, int t, uint32_t bits) { memcpy(&img[(size_t)col * NT + t], &bits, sizeof(float)); };
+        auto putf = [&](int col, int t, float f) { img[(size_t)col * NT + t] = f; };
+        const int off = tmem_spectral_offset(log2h), H = 1 << log2h;
+        if (half_rate) {
+            const std::vector<uint4> qt = host_quad_table(log2h);
+            const std::vector<cf> tw = host_spectral_twiddles_hr(log2h);
+            for (int c = 0; c < H / 4; c++) {
+                const int t = c % NT, col = off + 8 * (c / NT);
+                put(col, t, qt[c].x); put(col + 1, t, qt[c].y); put(col + 2, t, qt[c].z);
+                putf(col + 3, t, tw[c].x); putf(col + 4, t, tw[c].y);
+            }
+        } else {
+            const std::vector<uint2> pt = host_pair_table(log2h);
+            const std::vector<cf> tw = host_spectral_twiddles(log2h);
+            for (int c = 0; c < H / 2; c++) {
+                const int t = c % NT, col = off + 4 * (c / NT);
+                put(col, t, pt[c].x); put(col + 1, t, pt[c].y);
+                putf(col + 2, t, tw[c].x); putf(col + 3, t, tw[c].y);
+            }
+        }
+    }
+    return img;
 }
 
 // even samples of a table (half-rate synthesis reads window[2i], env[2i])

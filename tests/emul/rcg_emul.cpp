@@ -76,13 +76,13 @@ static int emul_run(StretchParams prm) {
     prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.tw0 = tw.data(); prm.spec_tw = stw.data();
     prm.spec_tw_hr = stw_hr.data(); prm.window_even = we.data(); prm.env_even = ee.data();
     std::vector<float> twi;   // the Tensor Memory rows of the device kernel, read straight from their image here
-    if (C::TW_TMEM) { twi = host_tmem_image(LOG2H); prm.tw_image = twi.data(); }
     std::vector<float> lr = lerp_table(prm.pitch);
     prm.lerp_ratio = lr.data();
     std::vector<uint2> ptab = host_pair_table(LOG2H);
     std::vector<uint4> qtab = host_quad_table(LOG2H);
     prm.pair_tab = ptab.data(); prm.quad_tab = qtab.data();
     if (use_half_rate(prm.pitch, prm.flags) && !g_disable_half_rate) prm.flags |= kFlagHalfRate;
+    if (C::TW_TMEM) { twi = host_tmem_image(LOG2H, (prm.flags & kFlagHalfRate) != 0); prm.tw_image = twi.data(); }
     std::vector<cf> S(C::SMEM_CF);
     std::vector<float> tail(H);
     HostExec ex{C::NT};
@@ -131,6 +131,8 @@ static int emul_run_pair(StretchParams prm) {
     host_hanning(window.data(), kPairW);
     host_crossfade_compensation(env.data(), kPairH);
     std::vector<cf> tw = host_pass_twiddles(kPairLog2HL);
+    std::vector<float> twi;   // the Tensor Memory rows of the device kernel, read straight from their image here
+    if (FrameCfg<kPairLog2HL>::TW_TMEM) { twi = host_tmem_image(kPairLog2HL); prm.tw_image = twi.data(); }
     std::vector<cf> cross = host_pair_cross_twiddles(kPairLog2HL + 1);
     std::vector<cf> se = host_pair_spectral_twiddles(kPairLog2HL + 1, 0), so = host_pair_spectral_twiddles(kPairLog2HL + 1, 1);
     prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.tw0 = tw.data();
@@ -346,6 +348,8 @@ static int emul_plugin_pair(StretchParams prm, apply_fn fn) {
     host_hanning(window.data(), kPairW);
     host_crossfade_compensation(env.data(), kPairH);
     std::vector<cf> tw = host_pass_twiddles(kPairLog2HL);
+    std::vector<float> twi;   // the Tensor Memory rows of the device kernel, read straight from their image here
+    if (FrameCfg<kPairLog2HL>::TW_TMEM) { twi = host_tmem_image(kPairLog2HL); prm.tw_image = twi.data(); }
     std::vector<cf> cross = host_pair_cross_twiddles(kPairLog2HL + 1);
     std::vector<cf> se = host_pair_spectral_twiddles(kPairLog2HL + 1, 0), so = host_pair_spectral_twiddles(kPairLog2HL + 1, 1);
     prm.window = window.data(); prm.env = env.data(); prm.tw = tw.data(); prm.tw0 = tw.data();
