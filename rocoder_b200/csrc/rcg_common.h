@@ -138,12 +138,25 @@ RCG_HD constexpr int threads_per_frame(int log2h) {
 RCG_HD constexpr bool three_lanes(int log2h) { return log2h == 13; }
 // log2h = 14 (the W = 32768 kernel and the CTA pair of W = 65536): 512 threads, four warps per Tensor Memory row, 128
 // columns each -- exactly the full plan's twiddles; the half-rate plan (W = 32768 only) keeps its packed tables
+// log2h = 9 .. 11 (W = 1024 .. 4096; one to four warps per frame lane, several lanes and at least three CTAs per SM):
+// a row serves thread t = row mod NT of every lane; 128 columns per CTA hold the full plan's twiddles and the spectral
+// step's table entries (below).  log2h = 12 (256 threads, two warps per row, three CTAs per SM): 2 x 64 columns, the
+// full plan's twiddles.  The half-rate plan keeps its packed tables at all of these sizes (at log2h = 9 its radix-16
+// pass has 16 butterflies for a 32-thread lane, and the Tensor Memory load is warp-collective).
 #ifndef RCG_TW_TMEM_512
 #define RCG_TW_TMEM_512 1
 #endif
+#ifndef RCG_TW_TMEM_SMALL
+#define RCG_TW_TMEM_SMALL 1
+#endif
 RCG_HD constexpr bool tw_in_tmem(int log2h, bool hr = false) {
-    return RCG_TW_TMEM != 0 && (log2h == 13 || (RCG_TW_TMEM_512 != 0 && log2h == 14 && !hr));
+    if (RCG_TW_TMEM == 0) return false;
+    if (log2h == 13) return true;
+    if (log2h == 14) return RCG_TW_TMEM_512 != 0 && !hr;
+    return RCG_TW_TMEM_SMALL != 0 && log2h >= 9 && log2h <= 12 && !hr;
 }
+// Tensor Memory columns a CTA takes (a power of two; every CTA that can share an SM must get its share of the 512)
+RCG_HD constexpr int tmem_alloc_cols(int log2h) { return log2h >= 13 ? 512 : 128; }
 RCG_HD constexpr bool tw_in_smem(int log2h) { return three_lanes(log2h) && !tw_in_tmem(log2h); }
 RCG_HD constexpr int frames_per_cta(int log2h) {
     if (three_lanes(log2h)) return 3;
@@ -186,17 +199,20 @@ RCG_HD constexpr int tmem_total_cols(int log2h) {
     return tw_in_tmem(log2h, true) ? tmem_col_offset(log2h, make_plan(log2h).npasses, true)
                                    : tmem_col_offset(log2h, make_plan(log2h).npasses, false);
 }
-// W = 16384 also keeps the frame-invariant table entries of the spectral step in the row, behind the twiddles: 64
-// columns -- 8 quads x {slots k | H-k, slots Q-k | Q+k, k, twiddle, -} on the half-rate path, 16 pairs x {slots, k,
-// twiddle} on the full-rate one (two images; a launch takes the one of its path).  The table loads from global
-// memory were the head of a load -> address -> shared-memory load chain in every iteration of the step.
-RCG_HD constexpr bool spectral_in_tmem(int log2h) { return tw_in_tmem(log2h) && log2h == 13; }
+// W = 1024 .. 4096 and 16384 also keep the frame-invariant table entries of the spectral step in the row, behind the
+// twiddles: per iteration of the step {slots k | H-k, slots Q-k | Q+k, k, twiddle, -} (8 columns) on the half-rate
+// path, {slots, k, twiddle} (4 columns) on the full-rate one -- 64 columns at W = 16384, 32 below (two images; a
+// launch takes the one of its path).  The table loads from global memory were the head of a load -> address ->
+// shared-memory load chain in every iteration of the step: config 3 at W = 16384 2.07 -> 1.84 ms.
+RCG_HD constexpr bool spectral_in_tmem(int log2h) { return tw_in_tmem(log2h) && (log2h == 13 || (log2h >= 9 && log2h <= 11)); }
 RCG_HD constexpr int tmem_spectral_offset(int log2h) { return tmem_total_cols(log2h); }
-RCG_HD constexpr int tmem_spectral_cols(int log2h) { return spectral_in_tmem(log2h) ? 64 : 0; }
+RCG_HD constexpr int tmem_spectral_cols(int log2h) {
+    return spectral_in_tmem(log2h) ? 4 * ((1 << log2h) / 2 / threads_per_frame(log2h)) : 0;
+}
 RCG_HD constexpr int tmem_image_cols(int log2h) { return tmem_total_cols(log2h) + tmem_spectral_cols(log2h); }
 // the warps of a frame lane that share a row (equal mod 4) take one column group each
 RCG_HD constexpr int tmem_groups(int log2h) { return threads_per_frame(log2h) > 128 ? threads_per_frame(log2h) / 128 : 1; }
-RCG_HD constexpr int tmem_group_cols(int log2h) { return 512 / tmem_groups(log2h); }
+RCG_HD constexpr int tmem_group_cols(int log2h) { return tmem_alloc_cols(log2h) / tmem_groups(log2h); }
 // long-stride passes of the half-rate plan deal butterflies to lanes with bits 3 and 6 of m swapped (rcg_frame.h)
 RCG_HD constexpr int hr_lane_swizzle(int m) { return (m & ~0x48) | ((m & 0x08) << 3) | ((m & 0x40) >> 3); }
 // which m the butterflies of thread t see in set `set` of a pass, and a thread (row) that sees a given m
@@ -205,13 +221,13 @@ RCG_HD constexpr int tmem_m_of_thread(int log2h, int pass, bool hr, int t, int s
     const int M = 1 << d.mlog2[pass], NT = threads_per_frame(log2h);
     if (M > NT) return t + NT * set;
     const int m = t & (M - 1);
-    return (hr && M >= 128) ? hr_lane_swizzle(m) : m;
+    return (hr && pass >= 1 && M >= 128) ? hr_lane_swizzle(m) : m;   // pass 0 is fused into the overlap-add: no swizzle
 }
 RCG_HD constexpr int tmem_row_of_m(int log2h, int pass, bool hr, int m) {
     const PlanDesc d = make_plan(log2h, hr);
     const int M = 1 << d.mlog2[pass], NT = threads_per_frame(log2h);
     if (M >= NT) return m & (NT - 1);
-    return (hr && M >= 128) ? hr_lane_swizzle(m) : m;
+    return (hr && pass >= 1 && M >= 128) ? hr_lane_swizzle(m) : m;
 }
 
 // ---- twiddle tables --------------------------------------------------------------------

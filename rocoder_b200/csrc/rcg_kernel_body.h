@@ -55,29 +55,32 @@ __device__ __forceinline__ StretchParams with_smem_twiddles(const StretchParams&
     return p;
 }
 
-// FrameCfg::TW_TMEM (rcg_common.h): the CTA takes all 512 columns of the SM's Tensor Memory (it is alone on the SM:
-// the frame buffers fill the shared memory), the threads of frame lane 0 copy their rows from the image in global
-// memory (176 columns x 256 threads, once per launch), and every thread remembers where its row starts: rows
-// 32 (warp mod 4) .., columns 0.. for the first four warps of a frame lane, the next column group for the next four.
-constexpr uint32_t kTmemCols = 512;
+// FrameCfg::TW_TMEM (rcg_common.h): the CTA takes its share of the SM's Tensor Memory columns (all 512 where it is
+// alone on the SM because the frame buffers fill the shared memory, 128 where three or four CTAs share one), the
+// first threads copy the rows from the image in global memory (once per launch), and every thread remembers where
+// its row starts: rows 32 (warp mod 4) .., columns 0.. for the first four warps of a frame lane, the next column
+// group for the next four.
 template <int LOG2H>
 __device__ __forceinline__ StretchParams with_tmem_twiddles(const StretchParams& prm, uint32_t* slot) {
     using C = FrameCfg<LOG2H>;
     StretchParams p = prm;
     if constexpr (C::TW_TMEM) {
-        constexpr int NCOL = tmem_image_cols(LOG2H);
+        constexpr int NCOL = tmem_image_cols(LOG2H), ALLOC = tmem_alloc_cols(LOG2H);
         static_assert(NCOL % 8 == 0 && NCOL <= tmem_group_cols(LOG2H), "a column group per warp that shares the row");
+        static_assert(C::NT >= 32, "a row serves one thread of a frame lane");
         if (threadIdx.x < 32) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                         ::"r"((uint32_t)__cvta_generic_to_shared(slot)), "n"(kTmemCols) : "memory");
+                         ::"r"((uint32_t)__cvta_generic_to_shared(slot)), "n"(ALLOC) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int t = (int)(threadIdx.x % C::NT), wl = t / 32;
-        const uint32_t mine = *slot + ((uint32_t)(32 * (wl % 4)) << 16) + (uint32_t)((wl / 4) * tmem_group_cols(LOG2H));
-        if (threadIdx.x < C::NT) {
+        // hardware rows of this warp: 32 (warp mod 4) ..; frame lanes narrower than four warps repeat every NT rows
+        const int warp = (int)(threadIdx.x / 32), t = (int)(threadIdx.x % C::NT);
+        const int group = C::NT > 128 ? (t / 32) / 4 : 0;
+        const uint32_t mine = *slot + ((uint32_t)(32 * (warp % 4)) << 16) + (uint32_t)(group * tmem_group_cols(LOG2H));
+        if (threadIdx.x < (C::NT > 128 ? C::NT : 128)) {   // every row of every group once
             for (int c = 0; c < NCOL; c += 8) {
                 uint32_t r[8];
 #pragma unroll
@@ -102,7 +105,7 @@ __device__ __forceinline__ void release_tmem_twiddles(const uint32_t* slot) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (threadIdx.x < 32)
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*slot), "n"(kTmemCols) : "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*slot), "n"(tmem_alloc_cols(LOG2H)) : "memory");
     }
 }
 // the word behind the frame buffers (and the shared-memory tables, where there are any) that receives the allocation
