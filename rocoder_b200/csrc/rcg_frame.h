@@ -12,6 +12,12 @@
 #include "rcg_philox.h"
 
 // unroll factors of the load and overlap-add loops (measured: 1..8 within 1 % of each other)
+// columns per Tensor Memory load of a radix-8 / 16 butterfly's twiddles: 16 (8 twiddles) from W = 4096 up, 8 below
+// (measured, profiles/r3j_*, r3k_*: -1.5 % at W = 16384 / 8192, -2 % at 32768, +1.3 % at 1024); -DRCG_TMEM_CHUNK=8|16
+// forces one value for every window
+#ifndef RCG_TMEM_CHUNK
+#define RCG_TMEM_CHUNK 0
+#endif
 #define RCG_LOAD_UNROLL 4
 #define RCG_OLA_UNROLL 2
 #define RCG_PRAGMA(x) _Pragma(#x)
@@ -204,14 +210,20 @@ RCG_HD TwSrc tw_src(const StretchParams& prm) { return TwSrc(prm.tw, prm.tmem_ad
 // config 2: 6.11 vs 5.93 ms, profiles/r3d_tmem_pipelined_variants.jsonl.  The load's latency is 12 cycles.)
 template <int LOG2H, int PASS, bool HR, int N>
 RCG_HD void tw_fetch(const TwSrc& s, int m, int col, float (&v)[N]) {
-    static_assert(N == 2 || N == 8, "tcgen05.ld shapes used here");
+    static_assert(N == 2 || N == 8 || N == 16, "tcgen05.ld shapes used here");
     constexpr int OFF = tmem_col_offset(LOG2H, PASS, HR), SC = tmem_set_cols(LOG2H, PASS, HR);
     constexpr int NT = threads_per_frame(LOG2H), M = 1 << make_plan(LOG2H, HR).mlog2[PASS];
     const int set = (M > NT) ? m / NT : 0;
 #if defined(__CUDA_ARCH__)
     const uint32_t a = s.tmem + (uint32_t)(OFF + set * SC + col);
     uint32_t r[N];
-    if constexpr (N == 8) {
+    if constexpr (N == 16) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(a));
+    } else if constexpr (N == 8) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
                      "tcgen05.wait::ld.sync.aligned;"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -291,13 +303,16 @@ RCG_HD void twiddle_butterfly(cf (&x)[R], const TwSrc& src, int m, const TwPre& 
             tw_fetch<LOG2H, PASS, HR, 2>(src, m, 0, v);
             x[1] = tw_mul<CONJ>(x[1], make_tw(make_cf(v[0], v[1])));
         } else {
+            // twiddles per load: 4 (8 columns), or 8 where the butterfly has that many
+            constexpr int CHUNK = RCG_TMEM_CHUNK != 0 ? RCG_TMEM_CHUNK : (LOG2H >= 11 ? 16 : 8);
+            constexpr int NCOLS = (CHUNK == 16 && R >= 8) ? 16 : 8, NTW = NCOLS / 2;
 #pragma unroll
-            for (int c = 0; c < R / 4; c++) {
-                float v[8];
-                tw_fetch<LOG2H, PASS, HR, 8>(src, m, 8 * c, v);
+            for (int c = 0; c < R / NTW; c++) {
+                float v[NCOLS];
+                tw_fetch<LOG2H, PASS, HR, NCOLS>(src, m, NCOLS * c, v);
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int j = 4 * c + q;
+                for (int q = 0; q < NTW; q++) {
+                    const int j = NTW * c + q;
                     if (j >= 1) x[j] = tw_mul<CONJ>(x[j], make_tw(make_cf(v[2 * q], v[2 * q + 1])));
                 }
             }

@@ -12,6 +12,8 @@
 // One source, several translation units so that the window sizes compile in parallel (rocoder_b200/build.py):
 //   -DRCG_TU_LOG2H=L   the kernels and launchers of W = 2^(L+1), L = 5..14
 //   (nothing)          the W = 65536 CTA-pair kernels and the dispatch by window size
+#include <algorithm>
+
 #include "rcg_kernels.h"
 
 #include "rcg_frame_pair.h"
@@ -103,6 +105,23 @@ cudaError_t geometry_t(LaunchGeometry* g) {
     if (e != cudaSuccess) return e;
     int n = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, stretch_kernel<LOG2H, false, 0>, g->threads, g->smem_bytes);
+    if (e == cudaSuccess && C::TW_TMEM && tmem_alloc_cols(LOG2H) < 512) {
+        // A kernel that allocates Tensor Memory is reported as one CTA per SM (ncu: grid 148 instead of 444) although
+        // each CTA takes 128 of the 512 columns: count by registers and shared memory, capped by the columns.
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, stretch_kernel<LOG2H, false, 0>);
+        if (e != cudaSuccess) return e;
+        cudaDeviceProp prop;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        e = cudaGetDeviceProperties(&prop, dev);
+        if (e != cudaSuccess) return e;
+        const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * g->threads;
+        const int by_regs = regs_per_cta > 0 ? prop.regsPerMultiprocessor / regs_per_cta : 1;
+        const int by_smem = (int)(prop.sharedMemPerMultiprocessor / (g->smem_bytes + fa.sharedSizeBytes + prop.reservedSharedMemPerBlock));
+        const int by_threads = prop.maxThreadsPerMultiProcessor / g->threads;
+        n = std::max(n, std::min(std::min(by_regs, by_smem), std::min(by_threads, 512 / tmem_alloc_cols(LOG2H))));
+    }
     g->max_ctas_per_sm = n;
     return e;
 }
