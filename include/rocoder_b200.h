@@ -278,6 +278,11 @@ int rcg_device_count(int *n);
 int rcg_measure_fp32_peak(double *tflops, int reps);
 /* kernels launched by this engine so far */
 int rcg_launch_count(const rcg_engine *e, uint64_t *n);
+/* how the engine's persistent stretch kernel is launched on its (first) device: threads per CTA, frame lanes per CTA,
+ * dynamic shared memory per CTA, CTAs resident per SM and the largest grid (SMs x CTAs per SM).  Diagnostic: no
+ * reference counterpart; tests pin the occupancy of the Tensor Memory kernels with it. */
+int rcg_launch_geometry(const rcg_engine *e, uint32_t *threads, uint32_t *lanes_per_cta, uint64_t *smem_bytes,
+                        uint32_t *ctas_per_sm, uint32_t *max_grid);
 
 #ifdef __cplusplus
 }

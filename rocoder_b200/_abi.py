@@ -130,6 +130,7 @@ def lib() -> C.CDLL:
         "rcg_bind_host_thread": (C.c_int, [C.c_int, P(C.c_int)]),
         "rcg_host_free": (C.c_int, [C.c_void_p]),
         "rcg_launch_count": (C.c_int, [C.c_void_p, P(C.c_uint64)]),
+        "rcg_launch_geometry": (C.c_int, [C.c_void_p, P(C.c_uint32), P(C.c_uint32), P(C.c_uint64), P(C.c_uint32), P(C.c_uint32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

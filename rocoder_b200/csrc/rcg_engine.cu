@@ -602,6 +602,17 @@ extern "C" int rcg_launch_count(const rcg_engine* e, uint64_t* n) {
     *n = total_launches(e);
     return RCG_OK;
 }
+extern "C" int rcg_launch_geometry(const rcg_engine* e, uint32_t* threads, uint32_t* lanes_per_cta, uint64_t* smem_bytes,
+                                   uint32_t* ctas_per_sm, uint32_t* max_grid) {
+    if (!e) return fail(RCG_ERR_INVALID_ARG, "null argument");
+    if (!e->shards.empty()) e = e->shards[0];
+    if (threads) *threads = (uint32_t)e->geo.threads;
+    if (lanes_per_cta) *lanes_per_cta = (uint32_t)e->geo.frames_per_cta;
+    if (smem_bytes) *smem_bytes = (uint64_t)e->geo.smem_bytes;
+    if (ctas_per_sm) *ctas_per_sm = (uint32_t)e->geo.max_ctas_per_sm;
+    if (max_grid) *max_grid = (uint32_t)e->max_grid;
+    return RCG_OK;
+}
 extern "C" int rcg_synchronize(rcg_engine* e) {
     if (!e) return fail(RCG_ERR_INVALID_ARG, "null argument");
     if (!e->shards.empty()) {

@@ -316,6 +316,13 @@ class Engine:
         check(lib().rcg_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def launch_geometry(self) -> dict:
+        """threads / frame lanes / shared memory per CTA, CTAs per SM and the largest grid of the stretch kernel"""
+        t, l, c, g = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+        sm = C.c_uint64()
+        check(lib().rcg_launch_geometry(self._h, C.byref(t), C.byref(l), C.byref(sm), C.byref(c), C.byref(g)))
+        return {"threads": t.value, "lanes_per_cta": l.value, "smem_bytes": sm.value, "ctas_per_sm": c.value, "max_grid": g.value}
+
 
 __all__ = ["Engine", "PinnedBuffer", "bind_host_thread", "device_count", "fade_in_out", "fade_keyframes", "measure_fp32_peak", "RcgError", "WouldBlock", "hanning", "hanning_crossfade_compensation",
            "plan", "expected_counts", "channel_bound", "phase"]

@@ -31,4 +31,4 @@ for i in range(a.reps + 3):
 ms = statistics.median(ts)
 print(json.dumps({"tag": a.tag, "lib": os.environ.get("RCG_LIB", "default"), "W": a.window, "f": a.factor, "p": a.pitch,
                   "frames": frames * a.channels, "kernel_ms": ms, "min_ms": min(ts), "out_Msamples_s": out_len * a.channels / ms / 1e3,
-                  "us_per_frame_per_sm": ms * 1e3 * 148 / (frames * a.channels), "checksum": float(d_out[:, ::4099].abs().sum())}))
+                  "us_per_frame_per_sm": ms * 1e3 * 148 / (frames * a.channels), "checksum": float(d_out[:, ::4099].abs().sum()), "geometry": e.launch_geometry()}))
