@@ -264,6 +264,20 @@ RCG_HD void pair_phase_resample(const float* stage, int tg, int nthr, const Stre
     }
 }
 
+// CTA r's entry of a per-CTA pointer pair.  On the device both entries are the CTA's own buffer (the host emulator
+// runs the two CTAs of a pair with two buffers), and the index must be a constant there: indexed by the runtime rank
+// the array lives in local memory, the pointer comes back without its address space, and every shared-memory access
+// of the kernel turns into a generic load / store on the long scoreboard (SASS before: 180 LD + 189 ST against 44 LDS
+// + 9 STS, 32 bytes of stack; ncu: long scoreboard 3.25 warps per issue cycle, lg_throttle in the butterflies).
+RCG_HD cf* pair_buf(cf* const (&b)[2], int r) {
+#if defined(__CUDA_ARCH__)
+    (void)r;
+    return b[0];
+#else
+    return b[r];
+#endif
+}
+
 // Exec for the pair: par(f) runs f(r, t) for every thread of both CTAs, then a CTA barrier;
 // par_cluster(f) ends in a cluster barrier (release/acquire) instead; cluster_arrive() / cluster_wait() are the two
 // halves of one more cluster barrier, issued apart.  bufs[r] is CTA r's buffer.
@@ -273,8 +287,8 @@ RCG_HD void pair_fft_range(Exec& ex, cf* const (&bufs)[2], const StretchParams& 
     if constexpr (INV ? PASS >= LAST : PASS <= LAST) {
         ex.par([&](int r, int t) {
             if (!work) return;
-            if constexpr (FrameCfg<kPairLog2HL>::TW_TMEM) phase_fft_pass<kPairLog2HL, PASS, INV>(bufs[r], t, tw_src(prm));
-            else phase_fft_pass<kPairLog2HL, PASS, INV>(bufs[r], t, PASS == 0 ? prm.tw0 : prm.tw);
+            if constexpr (FrameCfg<kPairLog2HL>::TW_TMEM) phase_fft_pass<kPairLog2HL, PASS, INV>(pair_buf(bufs, r), t, tw_src(prm));
+            else phase_fft_pass<kPairLog2HL, PASS, INV>(pair_buf(bufs, r), t, PASS == 0 ? prm.tw0 : prm.tw);
         });
         pair_fft_range<INV ? PASS - 1 : PASS + 1, LAST, INV>(ex, bufs, prm, work);
     }
@@ -285,7 +299,7 @@ RCG_HD void pair_fft_all(Exec& ex, cf* const (&bufs)[2], const StretchParams& pr
     constexpr int NP = FrameCfg<kPairLog2HL>::NP;
     if constexpr (!INV) pair_fft_range<0, NP - 3, false>(ex, bufs, prm, work);
     ex.par_steps(fft_tail_steps<kPairLog2HL>(),
-                 [&](int step, int r, int t) { if (work) fft_tail_step<kPairLog2HL, INV>(bufs[r], t, step, tw_src(prm)); });
+                 [&](int step, int r, int t) { if (work) fft_tail_step<kPairLog2HL, INV>(pair_buf(bufs, r), t, step, tw_src(prm)); });
     if constexpr (INV) pair_fft_range<NP - 3, 0, true>(ex, bufs, prm, work);
 }
 
@@ -326,7 +340,7 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], cf* const (&land)
         const bool head = work && defer && f == f0;
         const bool emit = work && !is_halo && !head;
         if (spectrum_in) {
-            ex.par([&](int r, int t) { if (work) pair_phase_mags_copyin(bufs[r], r, t, prm, channel, f); });
+            ex.par([&](int r, int t) { if (work) pair_phase_mags_copyin(pair_buf(bufs, r), r, t, prm, channel, f); });
             ex.par([&](int r, int t) {
                 if (!work) return;
                 if (r == 0) {
@@ -339,7 +353,7 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], cf* const (&land)
             });
             pair_fft_all<true>(ex, bufs, prm, work);
         } else {
-        ex.par([&](int r, int t) { if (work) pair_phase_load(bufs[r], r, t, prm, pt, channel, f); });
+        ex.par([&](int r, int t) { if (work) pair_phase_load(pair_buf(bufs, r), r, t, prm, pt, channel, f); });
         if (!bypass) {
             pair_fft_all<false>(ex, bufs, prm, work);
             ex.par([&](int r, int t) {
@@ -357,7 +371,7 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], cf* const (&land)
         }
         if (work) ex.exchange(bufs, land, kPairLandCf);   // each CTA's share of the other buffer lands in its zone
         auto ola = [&](int r, int t) {
-            if (work) pair_phase_ola(bufs[r], land[r], r, t, prm, pt, channel, f, tail, stage, emit, head);
+            if (work) pair_phase_ola(pair_buf(bufs, r), pair_buf(land, r), r, t, prm, pt, channel, f, tail, stage, emit, head);
         };
         if (prm.pitch != 1) {
             ex.par_cluster(ola);   // the staged half window crosses the pair through global memory
@@ -388,7 +402,7 @@ RCG_HD void run_analysis_item_pair(Exec& ex, cf* const (&bufs)[2], const Stretch
     for (int it = 0; it < prm.run_len; it++) {
         const long long f = f0 + it;
         const bool work = active && f < prm.frame_end;
-        ex.par([&](int r, int t) { if (work) pair_phase_load(bufs[r], r, t, prm, pt, channel, f); });
+        ex.par([&](int r, int t) { if (work) pair_phase_load(pair_buf(bufs, r), r, t, prm, pt, channel, f); });
         pair_fft_all<false>(ex, bufs, prm, work);
         ex.par([&](int r, int t) {
             if (!work) return;
@@ -400,7 +414,7 @@ RCG_HD void run_analysis_item_pair(Exec& ex, cf* const (&bufs)[2], const Stretch
                 pair_phase_spectrum_split_odd(bufs[1], t, pt);
             }
         });
-        ex.par([&](int r, int t) { if (work) pair_phase_spectrum_copyout(bufs[r], r, t, prm, channel, f); });
+        ex.par([&](int r, int t) { if (work) pair_phase_spectrum_copyout(pair_buf(bufs, r), r, t, prm, channel, f); });
     }
 }
 

@@ -50,7 +50,7 @@ struct PairDeviceExec {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         if (t == 0) {
-            const unsigned src = smem_addr(pair_push_source(bufs[r], r));
+            const unsigned src = smem_addr(pair_push_source(pair_buf(bufs, r), r));
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(peer_zone), "r"(src), "r"(bytes), "r"(peer_mbar) : "memory");
