@@ -14,8 +14,12 @@
 
 // unroll factors of the two phases that wait on global / distributed-shared loads (512 threads per CTA, one
 // CTA per SM: 128 registers per thread are available)
+#ifndef RCG_PAIR_LOAD_UNROLL
 #define RCG_PAIR_LOAD_UNROLL 4
+#endif
+#ifndef RCG_PAIR_OLA_UNROLL
 #define RCG_PAIR_OLA_UNROLL 2
+#endif
 
 namespace rcg {
 
