@@ -14,11 +14,17 @@
 
 // unroll factors of the two phases that wait on global / distributed-shared loads (512 threads per CTA, one
 // CTA per SM: 128 registers per thread are available)
+// (measured after the kernel's shared-memory accesses became LDS / STS, profiles/r3p_*, r3r_*: load 2 / overlap-add 8
+// is 7 % faster than the 4 / 2 of before; load 1, 3, 4, 8 and overlap-add 1, 2, 4 are all slower)
 #ifndef RCG_PAIR_LOAD_UNROLL
-#define RCG_PAIR_LOAD_UNROLL 4
+#define RCG_PAIR_LOAD_UNROLL 2
 #endif
 #ifndef RCG_PAIR_OLA_UNROLL
-#define RCG_PAIR_OLA_UNROLL 2
+#define RCG_PAIR_OLA_UNROLL 8
+#endif
+// 1: the stretch path reads a frame once per pair (pair_phase_load_split); 0: every CTA reads the whole frame
+#ifndef RCG_PAIR_SPLIT_LOAD
+#define RCG_PAIR_SPLIT_LOAD 1
 #endif
 
 namespace rcg {
@@ -282,6 +288,60 @@ RCG_HD cf* pair_buf(cf* const (&b)[2], int r) {
 #endif
 }
 
+// The same stage with the frame read ONCE per pair (the stretch path; the analysis path above reads it twice and never
+// synchronises the pair): CTA r loads the packed indices n in [r NR, (r+1) NR) of both half windows, forms BOTH outputs
+// of the stage, keeps its own and stores the peer's straight into the peer's transform buffer at the same slot
+// (Exec::store_peer: a posted distributed-shared-memory store on the device).  The cluster barrier that ends the phase
+// makes those stores visible.  Half the bytes per CTA (the phase ran at ~47 of the ~64 bytes per clock an SM gets from
+// L2: 15 % of the frame time), and the twiddle products of the stage are shared between the CTAs instead of all
+// falling on CTA 1.  Same operations on the same operands as pair_phase_load_impl: bit-identical results.
+template <bool FAST, class Exec>
+RCG_HD void pair_phase_load_split_impl(Exec& ex, cf* const (&bufs)[2], int r, int t, const StretchParams& prm,
+                                       const PairTables& pt, const float* in, long long base, bool bypass) {
+    using C = FrameCfg<kPairLog2HL>;
+    cf* S = pair_buf(bufs, r);
+    auto sample = [&](long long i) { return (i >= 0 && i < prm.in_valid) ? ld_stream(in + i) : 0.0f; };
+RCG_UNROLL(RCG_PAIR_LOAD_UNROLL)
+    for (int i = t; i < kPairNR; i += C::NT) {
+        const int n = r * kPairNR + i;
+        const cf wa = ld_stream2(prm.window + 2 * n), wb = ld_stream2(prm.window + kPairH + 2 * n);
+        cf xa, xb;
+        if constexpr (FAST) {
+            xa = ld_stream2(in + base + 2 * n);
+            xb = ld_stream2(in + base + kPairH + 2 * n);
+        } else {
+            xa = make_cf(sample(base + 2 * n), sample(base + 2 * n + 1));
+            xb = make_cf(sample(base + kPairH + 2 * n), sample(base + kPairH + 2 * n + 1));
+        }
+        const float a0 = RCG_MUL(xa.x, wa.x), a1 = RCG_MUL(xa.y, wa.y);
+        const float b0 = RCG_MUL(xb.x, wb.x), b1 = RCG_MUL(xb.y, wb.y);
+        cf v0, v1;   // CTA 0's / CTA 1's value
+        if (bypass) {
+            v0 = make_cf(a0, a1);
+            v1 = make_cf(b0, b1);
+        } else {
+            v0 = make_cf(a0 + b0, a1 + b1);
+            const cf w = pair_cross_tw(pt.cross_tw, n);
+            const float dr = a0 - b0, di = a1 - b1;
+            v1 = make_cf(dr * w.x - di * w.y, di * w.x + dr * w.y);
+        }
+        const int slot = phys(n);
+        S[slot] = r == 0 ? v0 : v1;
+        ex.store_peer(bufs, r, slot, r == 0 ? v1 : v0);
+    }
+}
+template <class Exec>
+RCG_HD void pair_phase_load_split(Exec& ex, cf* const (&bufs)[2], int r, int t, const StretchParams& prm,
+                                  const PairTables& pt, int channel, long long frame) {
+    const float* in = prm.in + (long long)channel * prm.in_stride;
+    const long long base = frame * (long long)prm.step - prm.in_origin;
+    const bool bypass = prm.flags & kFlagBypass;
+    const bool fast = base >= 0 && base + kPairW <= prm.in_valid &&
+                      (reinterpret_cast<unsigned long long>(in + base) & 7ull) == 0;
+    if (fast) pair_phase_load_split_impl<true>(ex, bufs, r, t, prm, pt, in, base, bypass);
+    else pair_phase_load_split_impl<false>(ex, bufs, r, t, prm, pt, in, base, bypass);
+}
+
 // Exec for the pair: par(f) runs f(r, t) for every thread of both CTAs, then a CTA barrier;
 // par_cluster(f) ends in a cluster barrier (release/acquire) instead; cluster_arrive() / cluster_wait() are the two
 // halves of one more cluster barrier, issued apart.  bufs[r] is CTA r's buffer.
@@ -357,7 +417,12 @@ RCG_HD void run_work_item_pair(Exec& ex, cf* const (&bufs)[2], cf* const (&land)
             });
             pair_fft_all<true>(ex, bufs, prm, work);
         } else {
+        // (the wait above: the peer has finished the last frame's overlap-add, so its buffer may be written)
+#if RCG_PAIR_SPLIT_LOAD
+        ex.par_pair([&](int r, int t) { if (work) pair_phase_load_split(ex, bufs, r, t, prm, pt, channel, f); });
+#else
         ex.par([&](int r, int t) { if (work) pair_phase_load(pair_buf(bufs, r), r, t, prm, pt, channel, f); });
+#endif
         if (!bypass) {
             pair_fft_all<false>(ex, bufs, prm, work);
             ex.par([&](int r, int t) {

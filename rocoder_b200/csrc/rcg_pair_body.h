@@ -39,6 +39,7 @@ struct PairDeviceExec {
     unsigned mbar = 0;         // this CTA's mbarrier: counts the bytes the peer's bulk copy delivers into my zone
     unsigned peer_mbar = 0;    // the peer's, as a shared::cluster address
     unsigned peer_zone = 0;    // the peer's landing zone, shared::cluster address
+    unsigned peer_buf = 0;     // the peer's transform buffer, shared::cluster address
     unsigned parity = 0;
     // Both CTAs hand each other kPairLandCf values: one thread arms its own mbarrier with the byte count it expects
     // and starts ONE bulk asynchronous copy (TMA engine: no thread moves data) from its transform buffer into the
@@ -76,6 +77,18 @@ struct PairDeviceExec {
             __syncwarp();
         }
         __syncthreads();
+    }
+    // a phase whose threads also store into the peer's buffer (store_peer): the cluster barrier (release / acquire at
+    // cluster scope) orders those stores before anything either CTA does next
+    template <class F>
+    __device__ __forceinline__ void par_pair(F f) {
+        f(r, t);
+        cluster_barrier();
+    }
+    // v into slot `slot` of the peer CTA's transform buffer (posted store through distributed shared memory)
+    __device__ __forceinline__ void store_peer(cf* const (&)[2], int, int slot, cf v) {
+        asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(peer_buf + (unsigned)slot * (unsigned)sizeof(cf)),
+                     "f"(v.x), "f"(v.y) : "memory");
     }
     template <class F>
     __device__ __forceinline__ void par_cluster(F f) {
@@ -124,6 +137,7 @@ __device__ __forceinline__ void stretch_pair_body(const StretchParams& prm_in, c
     ex.mbar = smem_addr(mbar);
     ex.peer_mbar = cluster_addr(ex.mbar, (unsigned)(r ^ 1));
     ex.peer_zone = cluster_addr(smem_addr(zone), (unsigned)(r ^ 1));
+    ex.peer_buf = cluster_addr(smem_addr(S), (unsigned)(r ^ 1));
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ex.mbar) : "memory");   // one arrival per phase: my own expect_tx
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -116,6 +116,9 @@ struct PairHostExec {
     }
     template <class F>
     void par_cluster(F f) { par(f); }
+    template <class F>
+    void par_pair(F f) { par(f); }
+    void store_peer(cf* const (&bufs)[2], int r, int slot, cf v) { bufs[r ^ 1][slot] = v; }
     void cluster_sync() {}
     void cluster_arrive() {}
     void cluster_wait() {}
