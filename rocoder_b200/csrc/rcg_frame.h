@@ -20,6 +20,14 @@
 #endif
 #define RCG_LOAD_UNROLL 4
 #define RCG_OLA_UNROLL 2
+// ... except at 512 threads per frame (W = 32768: one frame per SM, 16 warps), where the loops are latency-bound like
+// those of the CTA pair (rcg_frame_pair.h) and the factors matter
+#ifndef RCG_LOAD_UNROLL_512
+#define RCG_LOAD_UNROLL_512 4
+#endif
+#ifndef RCG_OLA_UNROLL_512
+#define RCG_OLA_UNROLL_512 2
+#endif
 #define RCG_PRAGMA(x) _Pragma(#x)
 #define RCG_UNROLL(n) RCG_PRAGMA(unroll n)
 
@@ -436,7 +444,7 @@ RCG_HD void phase_load(cf* S, int t, const StretchParams& prm, int channel, long
             load_finish<LOG2H, R, true>(S, c, m, x);
         }
     } else if (c.aligned) {
-RCG_UNROLL(RCG_LOAD_UNROLL)
+RCG_UNROLL((LOG2H >= 14 ? RCG_LOAD_UNROLL_512 : RCG_LOAD_UNROLL))
         for (int m = t; m < M; m += C::NT) {
             cf x[R];
             load_fetch<LOG2H, R, true>(c, prm, m, x);
@@ -904,7 +912,7 @@ RCG_HD void phase_ola_impl(cf* S, int t, const StretchParams& prm, int channel, 
     constexpr bool IO_PK = (RCG_PK_IO != 0);
     float* out = prm.out + (long long)channel * prm.out_stride;
     const TwSrc tw = tw_src(prm);
-RCG_UNROLL(RCG_OLA_UNROLL)
+RCG_UNROLL((LOG2H >= 14 ? RCG_OLA_UNROLL_512 : RCG_OLA_UNROLL))
     for (int m = t; m < M; m += C::NT) {
         cf* p = S + phys(m);
         cf x[R];
@@ -1038,7 +1046,7 @@ RCG_HD void phase_ola_hr(cf* S, int t, const StretchParams& prm, int channel, lo
         return;
     }
     const TwSrc tw = tw_src(prm);
-RCG_UNROLL(RCG_OLA_UNROLL)
+RCG_UNROLL((LOG2H >= 14 ? RCG_OLA_UNROLL_512 : RCG_OLA_UNROLL))
     for (int m = t; m < M; m += C::NT) {
         cf* p = S + phys(expand_hr(m));
         cf x[R];
