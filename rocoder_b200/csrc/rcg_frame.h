@@ -890,10 +890,16 @@ RCG_HD void phase_spectral_in(cf* S, int t, const StretchParams& prm, int channe
     }
 }
 
-// value i (0..W) of the frame held as packed pairs
+// value i (0..W) of the frame held as packed pairs: component i & 1 of slot phys(i >> 1), i.e. float number
+// 2 ((i >> 1) + (i >> 5)) + (i & 1) = i + 2 (i >> 5) of the buffer -- one scalar load instead of a 64-bit load, a parity
+// test and a select (the lerp walk of a negative pitch multiple reads two of them per output sample)
 RCG_HD float frame_value(const cf* S, int i) {
-    cf v = S[phys(i >> 1)];
-    return (i & 1) ? v.y : v.x;
+    return reinterpret_cast<const float*>(S)[i + ((i >> 5) << 1)];
+}
+// the same value addressed in bytes from a pointer that already stands at float i0: value i0 + c with c a constant
+// of the unrolled loop costs a shift, one shift-add and a load with an immediate offset
+RCG_HD float frame_value_at(const char* at_i0, int i0, int c) {
+    return *reinterpret_cast<const float*>(at_i0 + 4 * c + (((i0 + c) >> 5) << 3));
 }
 
 // ---- inverse pass 0 fused with EMIT part 1: last DIT pass out of shared memory, then scale +
@@ -1093,17 +1099,18 @@ RCG_HD void phase_resample(const cf* S, int t, const StretchParams& prm, int cha
         const bool bypass = plain_stage || (prm.flags & kFlagBypass);  // staged as S[phys(i)].x
         const long long g0 = frame * (long long)Q;
         const long long o_begin = (g0 + pe - 1) / pe, o_end = (g0 + Q + pe - 1) / pe;
-        for (long long o = o_begin + t; o < o_end; o += C::NT) {
-            const int i = (int)(o * pe - g0);
-            out[o - prm.out_origin] = bypass ? S[phys(i)].x : frame_value_hr(S, i);
-        }
+        // 32-bit index walk from the block's first output (the 64-bit products are loop invariants)
+        const int cnt = (int)(o_end - o_begin);
+        float* dp = out + (o_begin - prm.out_origin);
+        int i = (int)(o_begin * pe - g0) + t * pe;
+        for (int k = t; k < cnt; k += C::NT, i += C::NT * pe) dp[k] = bypass ? S[phys(i)].x : frame_value_hr(S, i);
     } else if (p > 1) {
         const long long g0 = frame * (long long)C::H;
         const long long o_begin = (g0 + p - 1) / p, o_end = (g0 + C::H + p - 1) / p;
-        for (long long o = o_begin + t; o < o_end; o += C::NT) {
-            const int i = (int)(o * p - g0);
-            out[o - prm.out_origin] = frame_value(S, i);
-        }
+        const int cnt = (int)(o_end - o_begin);
+        float* dp = out + (o_begin - prm.out_origin);
+        int i = (int)(o_begin * p - g0) + t * p;
+        for (int k = t; k < cnt; k += C::NT, i += C::NT * p) dp[k] = frame_value(S, i);
     } else if (p < -1) {
         // resample_slower (resampler.rs:20-35): out[i*q + j] = z[i] + (z[i+1] - z[i]) * (j / q), i < S - 1.
         // Consecutive threads write consecutive outputs (whole sectors per warp store; a thread per input interval
@@ -1116,12 +1123,19 @@ RCG_HD void phase_resample(const cf* S, int t, const StretchParams& prm, int cha
         const int nt_q = (C::NT / q) * q;
         if (nt_q > 0) {
             if (t < nt_q) {
+                // a running store pointer and a trip count known before the loop: unrolled, the stores and the index
+                // updates use immediate offsets (the loop was 25 instructions per output sample, a fifth of all
+                // instructions executed on config 4, with a 64-bit address rebuilt for every store)
                 const int di = nt_q / q;
                 int i = t / q;
                 const float ratio = prm.lerp_ratio[t - i * q];
-                for (int tt = t; tt < n; tt += nt_q, i += di) {
-                    const float cur = frame_value(S, i), nxt = frame_value(S, i + 1);
-                    dst[tt] = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), ratio));
+                float* dp = dst + t;
+                const char* sp = reinterpret_cast<const char*>(S) + 4 * i;
+                const int trips = (n - t + nt_q - 1) / nt_q;
+RCG_UNROLL(4)
+                for (int k = 0; k < trips; k++, i += di, sp += 4 * di, dp += nt_q) {
+                    const float cur = frame_value_at(sp, i, 0), nxt = frame_value_at(sp, i, 1);
+                    *dp = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), ratio));
                 }
             }
         } else {   // more steps per interval than threads in the lane (tiny windows with a large |p|)

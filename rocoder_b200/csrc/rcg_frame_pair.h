@@ -266,9 +266,14 @@ RCG_HD void pair_phase_resample(const float* stage, int tg, int nthr, const Stre
             const int di = nt_q / q;
             int i = tg / q;
             const float ratio = prm.lerp_ratio[tg - i * q];
-            for (int tt = tg; tt < n; tt += nt_q, i += di) {
-                const float cur = stage[i], nxt = stage[i + 1];
-                dst[tt] = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), ratio));
+            // running pointers and a trip count known before the loop (see phase_resample)
+            const float* sp = stage + i;
+            float* dp = dst + tg;
+            const int trips = (n - tg + nt_q - 1) / nt_q;
+RCG_UNROLL(4)
+            for (int k = 0; k < trips; k++, sp += di, dp += nt_q) {
+                const float cur = sp[0], nxt = sp[1];
+                *dp = RCG_ADD(cur, RCG_MUL(RCG_SUB(nxt, cur), ratio));
             }
         }
     }
