@@ -42,9 +42,15 @@ RCG_HD void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
 // rand 0.8.5 gen_range(0.0..PI) on f32 (fft.rs:13: the constant named TWO_PI is PI):
 // ((u >> 9) * 2^-23) * PI + 0.0
 // The scaling by 2^-23 is exact, so one product with the constant 2^-23 * PI (itself exact) rounds to the same value.
+// On the device the way rand itself gets there: v = u >> 9 becomes the mantissa of x = 1 + v 2^-23 in [1, 2) -- ONE funnel
+// shift, (0x7F : u) >> 9 = 0x3F800000 | v -- and x PI - PI as one fused multiply-add is the exact product v 2^-23 PI
+// rounded once: the same value bit for bit (tests/test_oracle_crosscheck.py), two instructions instead of three
+// (shift, int-to-float, multiply) for each of the W phases of a frame.
 RCG_HD float phase_from_u32(uint32_t u) {
 #if defined(RCG_PHASE_TWO_PRODUCTS)
     return (float)(u >> 9) * 1.1920928955078125e-07f * 3.14159274101257324f;
+#elif defined(__CUDA_ARCH__)
+    return __fmaf_rn(__uint_as_float(__funnelshift_r(u, 0x7Fu, 9)), 3.14159274101257324f, -3.14159274101257324f);
 #else
     return (float)(u >> 9) * (1.1920928955078125e-07f * 3.14159274101257324f);
 #endif

@@ -162,3 +162,20 @@ def test_random_phase_statistics():
     x = rng.standard_normal((1, 60000)).astype(np.float32) * 0.1
     out = ol.process_all(x, 2.0, 1, W, seed=7)
     assert abs(out.mean()) < 1e-3
+
+
+def test_device_phase_formula_is_the_oracles_for_every_mantissa():
+    """rcg_philox.h, device branch of phase_from_u32: x = 1 + v 2^-23 (v = u >> 9 as the mantissa of a float in [1, 2)),
+    phase = fma(x, PI, -PI).  x PI - PI is exactly v 2^-23 PI (48 significant bits: exact in float64), so the single
+    rounding of the fused multiply-add gives the value the oracle's product ((u >> 9) * 2^-23) * PI gives -- checked
+    here for all 2^23 mantissas against the oracle's own function on a sample and against its formula on all."""
+    L = ol.oracle()
+    v = np.arange(1 << 23, dtype=np.uint32)
+    pi32 = np.float64(np.float32(np.pi))
+    x = (v | np.uint32(0x3F800000)).view(np.float32).astype(np.float64)          # [1, 2)
+    fused = (x * pi32 - pi32).astype(np.float32)                                   # exact in float64, rounded once
+    product = (v.astype(np.float32) * np.float32(2.0 ** -23 * float(np.float32(np.pi)))).astype(np.float32)
+    assert np.array_equal(fused, product)
+    for vi in (0, 1, 2, 12345, (1 << 22) + 1, (1 << 23) - 1):
+        assert fused[vi] == np.float32(L.ro_phase_from_u32(int(vi) << 9))
+        assert fused[vi] == np.float32(L.ro_phase_from_u32((int(vi) << 9) | 0x1FF))
