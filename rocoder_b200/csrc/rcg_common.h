@@ -209,7 +209,26 @@ RCG_HD constexpr int tmem_spectral_offset(int log2h) { return tmem_total_cols(lo
 RCG_HD constexpr int tmem_spectral_cols(int log2h) {
     return spectral_in_tmem(log2h) ? 4 * ((1 << log2h) / 2 / threads_per_frame(log2h)) : 0;
 }
-RCG_HD constexpr int tmem_image_cols(int log2h) { return tmem_total_cols(log2h) + tmem_spectral_cols(log2h); }
+// W = 16384, full-rate launches (pitch 1, odd and negative multiples: BASELINE configs 3, 4, 5): the columns of the
+// half-rate plan's twiddles are free, and the row takes the thread's analysis / synthesis window and crossfade envelope
+// instead.  Load and overlap-add deal iteration i of their loops the same packed index m = t + NT i, and both touch
+// window[2m], [2m+1], [H+2m], [H+2m+1] (4 columns per iteration, 16 iterations), the overlap-add env[2m], [2m+1] too:
+// 64 + 32 columns.  Window: the half-rate plan's 80 columns from `tmem_window_offset` on; envelope: what is left of
+// them (iterations 0..7) and the 16 columns behind the spectral entries (8..15).  -DRCG_WIN_TMEM=0: tables stay global.
+#ifndef RCG_WIN_TMEM
+#define RCG_WIN_TMEM 1
+#endif
+RCG_HD constexpr bool window_in_tmem(int log2h) { return RCG_WIN_TMEM != 0 && log2h == 13 && tw_in_tmem(log2h, true) && spectral_in_tmem(log2h); }
+RCG_HD constexpr int tmem_window_offset(int log2h) { return tmem_col_offset(log2h, 0, true); }
+RCG_HD constexpr int tmem_window_iters(int log2h) { return (1 << make_plan(log2h).mlog2[0]) / threads_per_frame(log2h); }
+RCG_HD constexpr int tmem_env_col(int log2h, int iter) {
+    const int half = tmem_window_iters(log2h) / 2;
+    return iter < half ? tmem_window_offset(log2h) + 4 * tmem_window_iters(log2h) + 2 * iter
+                       : tmem_total_cols(log2h) + tmem_spectral_cols(log2h) + 2 * (iter - half);
+}
+RCG_HD constexpr int tmem_image_cols(int log2h) {
+    return tmem_total_cols(log2h) + tmem_spectral_cols(log2h) + (window_in_tmem(log2h) ? tmem_window_iters(log2h) : 0);
+}
 // the warps of a frame lane that share a row (equal mod 4) take one column group each
 RCG_HD constexpr int tmem_groups(int log2h) { return threads_per_frame(log2h) > 128 ? threads_per_frame(log2h) / 128 : 1; }
 RCG_HD constexpr int tmem_group_cols(int log2h) { return tmem_alloc_cols(log2h) / tmem_groups(log2h); }

@@ -435,7 +435,7 @@ extern "C" int rcg_create(const rcg_config* cfg_in, rcg_engine** out) {
         TRY_E(cudaMemcpy(e->d_lerp_ratio, ratio.data(), ratio.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     if (!e->bluestein && tw_in_tmem(plan_log2h)) {
-        std::vector<float> img = host_tmem_image(plan_log2h);
+        std::vector<float> img = host_tmem_image(plan_log2h, false, window.data(), env.data());
         TRY_E(cudaMalloc(&e->d_tw_image, img.size() * sizeof(float)));
         TRY_E(cudaMemcpy(e->d_tw_image, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
         if (spectral_in_tmem(plan_log2h)) {
@@ -570,6 +570,14 @@ extern "C" int rcg_set_window(rcg_engine* e, const float* window, size_t len) {
     std::vector<float> w(window, window + len), we = host_decimate2(w);
     CUDA_TRY(cudaMemcpy(e->d_window, w.data(), len * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(e->d_window_even, we.data(), we.size() * sizeof(float), cudaMemcpyHostToDevice));
+    const int plan_log2h = e->log2w - 1;
+    if (e->d_tw_image && !e->pair && !e->bluestein && !e->big && window_in_tmem(plan_log2h)) {
+        // the full-rate launches read the window from the Tensor Memory image (rcg_common.h: window_in_tmem)
+        std::vector<float> env(len / 2);
+        host_crossfade_compensation(env.data(), env.size());
+        const std::vector<float> img = host_tmem_image(plan_log2h, false, w.data(), env.data());
+        CUDA_TRY(cudaMemcpy(e->d_tw_image, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     return RCG_OK;
 }
 
@@ -1535,8 +1543,16 @@ static bool compile_fused_source(const std::string& user_src, int log2h, int mod
         std::lock_guard<std::mutex> g(load_mutex);
         if (!g_nvrtc.load()) { log = "libnvrtc could not be loaded"; return false; }
     }
-    const std::string src = user_src + "\n#define RCG_JIT_LOG2H " + std::to_string(log2h) + "\n#define RCG_JIT_MODE " +
-                            std::to_string(mode) + "\n#include \"rcg_jit_entry.h\"\n";
+    // the kernel NVRTC builds reads the same Tensor Memory image and tables as the library's own kernels: it must see
+    // the build-time switches the library was compiled with (they decide what the image holds)
+#define RCG_JIT_STR2(x) #x
+#define RCG_JIT_STR(x) RCG_JIT_STR2(x)
+    static const char kBuildSwitches[] =
+        "\n#define RCG_TW_TMEM " RCG_JIT_STR(RCG_TW_TMEM) "\n#define RCG_TW_TMEM_512 " RCG_JIT_STR(RCG_TW_TMEM_512)
+        "\n#define RCG_TW_TMEM_SMALL " RCG_JIT_STR(RCG_TW_TMEM_SMALL) "\n#define RCG_WIN_TMEM " RCG_JIT_STR(RCG_WIN_TMEM)
+        "\n#define RCG_TMEM_CHUNK " RCG_JIT_STR(RCG_TMEM_CHUNK) "\n#define RCG_PAIR_SPLIT_LOAD " RCG_JIT_STR(RCG_PAIR_SPLIT_LOAD) "\n";
+    const std::string src = user_src + kBuildSwitches + "#define RCG_JIT_LOG2H " + std::to_string(log2h) +
+                            "\n#define RCG_JIT_MODE " + std::to_string(mode) + "\n#include \"rcg_jit_entry.h\"\n";
     const int n_headers = (int)(sizeof(kJitHeaderNames) / sizeof(kJitHeaderNames[0]));
     nvrtcProgram_t prog = nullptr;
     if (g_nvrtc.create(&prog, src.c_str(), "fused_frequency_kernel.cu", n_headers, kJitHeaderSources, kJitHeaderNames) != 0) {

@@ -50,6 +50,7 @@ enum : uint32_t {
     kFlagDeferFirst = 2u,  // do not emit block frame_begin; write its raw first half to head_out
     kFlagSpectrumIn = 4u,  // plugin path: magnitudes come from prm.spectrum (plugin output), not the FFT
     kFlagHalfRate = 8u,    // even pitch multiple > 0: only even output samples survive the decimation
+    kFlagWinTmem = 16u,    // in-kernel only (with_mode_constants): window / envelope come from the Tensor Memory row
                            // (resampler.rs:15-18), so the synthesis side runs at half size
 };
 
@@ -252,11 +253,17 @@ RCG_HD void tw_fetch(const TwSrc& s, int m, int col, float (&v)[N]) {
 // N = 4 or 8 columns of the thread's row starting at absolute column `col`; host execution: row `row` of the image
 template <int LOG2H, int N>
 RCG_HD void row_fetch(const TwSrc& s, int row, int col, uint32_t (&r)[N]) {
-    static_assert(N == 4 || N == 8, "tcgen05.ld shapes used here");
+    static_assert(N == 4 || N == 8 || N == 16, "tcgen05.ld shapes used here");
 #if defined(__CUDA_ARCH__)
     (void)row;
     const uint32_t a = s.tmem + (uint32_t)col;
-    if constexpr (N == 8) {
+    if constexpr (N == 16) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+                     "tcgen05.wait::ld.sync.aligned;"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(a));
+    } else if constexpr (N == 8) {
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
                      "tcgen05.wait::ld.sync.aligned;"
                      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -442,6 +449,25 @@ RCG_HD void phase_load(cf* S, int t, const StretchParams& prm, int channel, long
             cf x[R];
             load_fetch<LOG2H, R, false>(c, prm, m, x);
             load_finish<LOG2H, R, true>(S, c, m, x);
+        }
+    } else if (window_in_tmem(LOG2H) && (prm.flags & kFlagWinTmem) && c.aligned) {
+        // the window from the thread's Tensor Memory row: 16 columns = the values of four iterations per load
+        if constexpr (window_in_tmem(LOG2H)) {
+            static_assert(R == 2 && tmem_window_iters(LOG2H) % 4 == 0, "4 window columns per iteration");
+            for (int g = 0; g < tmem_window_iters(LOG2H) / 4; g++) {
+                uint32_t wv[16];
+                row_fetch<LOG2H, 16>(c.tw, t, tmem_window_offset(LOG2H) + 16 * g, wv);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int m = t + C::NT * (4 * g + u);
+                    cf x[R];
+#pragma unroll
+                    for (int a = 0; a < R; a++)
+                        x[a] = ex_mul(ld_stream2(c.in + c.base + 2 * (m + a * M)),
+                                      make_cf(bits_to_float(wv[4 * u + 2 * a]), bits_to_float(wv[4 * u + 2 * a + 1])));
+                    load_finish<LOG2H, R>(S, c, m, x);
+                }
+            }
         }
     } else if (c.aligned) {
 RCG_UNROLL((LOG2H >= 14 ? RCG_LOAD_UNROLL_512 : RCG_LOAD_UNROLL))
@@ -918,8 +944,8 @@ RCG_HD void phase_ola_impl(cf* S, int t, const StretchParams& prm, int channel, 
     constexpr bool IO_PK = (RCG_PK_IO != 0);
     float* out = prm.out + (long long)channel * prm.out_stride;
     const TwSrc tw = tw_src(prm);
-RCG_UNROLL((LOG2H >= 14 ? RCG_OLA_UNROLL_512 : RCG_OLA_UNROLL))
-    for (int m = t; m < M; m += C::NT) {
+    // one iteration: packed index m; TM: window / envelope values of this iteration handed in (Tensor Memory row)
+    auto iteration = [&](int m, bool tm, const cf* wtm, cf etm) {
         cf* p = S + phys(m);
         cf x[R];
 #pragma unroll
@@ -933,7 +959,7 @@ RCG_UNROLL((LOG2H >= 14 ? RCG_OLA_UNROLL_512 : RCG_OLA_UNROLL))
 #pragma unroll
         for (int a = 0; a < RH; a++) {
             const int n = m + a * M;              // packed index inside the first half window
-            const cf wa = ld_stream2(prm.window + 2 * n), wb = ld_stream2(prm.window + C::H + 2 * n);
+            const cf wa = tm ? wtm[0] : ld_stream2(prm.window + 2 * n), wb = tm ? wtm[1] : ld_stream2(prm.window + C::H + 2 * n);
             cf y, tl;
             if constexpr (bypass) {
                 y = ex_mul(x[a], wa); tl = ex_mul(x[a + RH], wb);
@@ -943,7 +969,7 @@ RCG_UNROLL((LOG2H >= 14 ? RCG_OLA_UNROLL_512 : RCG_OLA_UNROLL))
             }
             const cf old = ld_pair(tail + 2 * n);
             st_cf(tail + 2 * n, tl);
-            const cf e = ld_stream2(prm.env + 2 * n);   // unconditional: keeps the loop body free of branches around loads
+            const cf e = tm ? etm : ld_stream2(prm.env + 2 * n);   // unconditional: keeps the loop body free of branches around loads
             if (write_head) st_cf(prm.head_out + (long long)channel * C::H + 2 * n, y);
             if (emit) {
                 const cf z = mul_chain<IO_PK>(mul_chain<IO_PK>(ex_add(y, old), e), pk_bcast(prm.amp));
@@ -954,7 +980,27 @@ RCG_UNROLL((LOG2H >= 14 ? RCG_OLA_UNROLL_512 : RCG_OLA_UNROLL))
                 }
             }
         }
+    };
+    if constexpr (window_in_tmem(LOG2H) && !bypass) {
+        if (prm.flags & kFlagWinTmem) {
+            // window (8 columns) and envelope (4 columns) of two iterations per pair of Tensor Memory loads
+            static_assert(R == 2 && tmem_window_iters(LOG2H) % 2 == 0, "4 window + 2 envelope columns per iteration");
+            for (int g = 0; g < tmem_window_iters(LOG2H) / 2; g++) {
+                uint32_t wv[8], ev[4];
+                row_fetch<LOG2H, 8>(tw, t, tmem_window_offset(LOG2H) + 8 * g, wv);
+                row_fetch<LOG2H, 4>(tw, t, tmem_env_col(LOG2H, 2 * g), ev);
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const cf w2[2] = {make_cf(bits_to_float(wv[4 * u]), bits_to_float(wv[4 * u + 1])),
+                                      make_cf(bits_to_float(wv[4 * u + 2]), bits_to_float(wv[4 * u + 3]))};
+                    iteration(t + C::NT * (2 * g + u), true, w2, make_cf(bits_to_float(ev[2 * u]), bits_to_float(ev[2 * u + 1])));
+                }
+            }
+            return;
+        }
     }
+RCG_UNROLL((LOG2H >= 14 ? RCG_OLA_UNROLL_512 : RCG_OLA_UNROLL))
+    for (int m = t; m < M; m += C::NT) iteration(m, false, nullptr, make_cf(0.0f, 0.0f));
 }
 template <int LOG2H>
 RCG_HD void phase_ola(cf* S, int t, const StretchParams& prm, int channel, long long frame,

@@ -134,10 +134,11 @@ template <int MODE>
 __device__ __forceinline__ StretchParams with_mode_constants(const StretchParams& in) {
     StretchParams p = in;
     if constexpr (MODE == 1) { p.pitch = 2; p.flags = (in.flags & kFlagDeferFirst) | kFlagHalfRate; }
-    if constexpr (MODE == 2) { p.pitch = 1; p.flags = in.flags & kFlagDeferFirst; }
-    if constexpr (MODE == 3) { p.flags = in.flags & kFlagDeferFirst; }
-    if constexpr (MODE == 4) { p.pitch = -2; p.flags = in.flags & kFlagDeferFirst; }
-    if constexpr (MODE == 5) { p.pitch = -3; p.flags = in.flags & kFlagDeferFirst; }
+    // the full-rate modes read window and envelope from the Tensor Memory row where the image holds them (window_in_tmem)
+    if constexpr (MODE == 2) { p.pitch = 1; p.flags = (in.flags & kFlagDeferFirst) | kFlagWinTmem; }
+    if constexpr (MODE == 3) { p.flags = (in.flags & kFlagDeferFirst) | kFlagWinTmem; }
+    if constexpr (MODE == 4) { p.pitch = -2; p.flags = (in.flags & kFlagDeferFirst) | kFlagWinTmem; }
+    if constexpr (MODE == 5) { p.pitch = -3; p.flags = (in.flags & kFlagDeferFirst) | kFlagWinTmem; }
     return p;
 }
 

@@ -228,7 +228,9 @@ inline std::vector<uint4> host_quad_table(int log2h) {
 // ---- pass twiddles as Tensor Memory rows (tw_in_tmem, rcg_common.h): image[column][thread] ------------------------
 // half_rate: which spectral-step table entries follow the twiddles (spectral_in_tmem): the quads of the half-rate path
 // or the pairs of the full-rate one
-inline std::vector<float> host_tmem_image(int log2h, bool half_rate = false) {
+// window / env (full-rate image only, window_in_tmem): the engine's analysis / synthesis window [W] and envelope [H]
+inline std::vector<float> host_tmem_image(int log2h, bool half_rate = false, const float* window = nullptr,
+                                          const float* env = nullptr) {
     const int NT = threads_per_frame(log2h), ncol = tmem_image_cols(log2h);
     std::vector<float> img((size_t)ncol * NT, 0.0f);
     const double two_pi = 6.283185307179586476925286766559;
@@ -250,6 +252,21 @@ inline std::vector<float> host_tmem_image(int log2h, bool half_rate = false) {
                     }
                 }
         }
+    }
+    if (window_in_tmem(log2h) && !half_rate && window && env) {
+        // over the half-rate plan's columns (a full-rate launch never reads them): iteration i of the load / overlap-add
+        // loops of thread t works on packed index m = t + NT i
+        const int H = 1 << log2h;
+        for (int t = 0; t < NT; t++)
+            for (int i = 0; i < tmem_window_iters(log2h); i++) {
+                const int m = t + NT * i, wc = tmem_window_offset(log2h) + 4 * i, ec = tmem_env_col(log2h, i);
+                img[(size_t)(wc + 0) * NT + t] = window[2 * m];
+                img[(size_t)(wc + 1) * NT + t] = window[2 * m + 1];
+                img[(size_t)(wc + 2) * NT + t] = window[H + 2 * m];
+                img[(size_t)(wc + 3) * NT + t] = window[H + 2 * m + 1];
+                img[(size_t)(ec + 0) * NT + t] = env[2 * m];
+                img[(size_t)(ec + 1) * NT + t] = env[2 * m + 1];
+            }
     }
     if (spectral_in_tmem(log2h)) {
         auto put = [&](int col, int t, uint32_t bits) { memcpy(&img[(size_t)col * NT + t], &bits, sizeof(float)); };

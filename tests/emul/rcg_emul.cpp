@@ -82,7 +82,9 @@ static int emul_run(StretchParams prm) {
     std::vector<uint4> qtab = host_quad_table(LOG2H);
     prm.pair_tab = ptab.data(); prm.quad_tab = qtab.data();
     if (use_half_rate(prm.pitch, prm.flags) && !g_disable_half_rate) prm.flags |= kFlagHalfRate;
-    if (C::TW_TMEM) { twi = host_tmem_image(LOG2H, (prm.flags & kFlagHalfRate) != 0); prm.tw_image = twi.data(); }
+    if (C::TW_TMEM) { twi = host_tmem_image(LOG2H, (prm.flags & kFlagHalfRate) != 0, window.data(), env.data()); prm.tw_image = twi.data(); }
+    // what with_mode_constants does on the device for the full-rate modes: window / envelope from the image
+    if (window_in_tmem(LOG2H) && stretch_mode_of(prm.pitch, prm.flags) >= 2) prm.flags |= kFlagWinTmem;
     std::vector<cf> S(C::SMEM_CF);
     std::vector<float> tail(H);
     HostExec ex{C::NT};

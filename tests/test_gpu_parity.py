@@ -311,3 +311,31 @@ def test_custom_window_vector():
     while not st.is_done():
         wins.append(st.next_window())
     assert np.array_equal(np.concatenate(wins), got)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pitch", [1, -3, 2])
+def test_custom_window_at_w16384_reaches_the_tensor_memory_image(pitch):
+    """W = 16384: the full-rate launches read window and envelope from the Tensor Memory image (rcg_common.h:
+    window_in_tmem), so rcg_set_window has to rebuild that image -- an asymmetric window tells a stale one apart.
+    pitch 2 (half-rate path, global tables) runs beside it."""
+    n, f, W = 120000, 2.0, 16384
+    x = _input(n, channels=2, seed=9)
+    win = (0.25 + 0.75 * np.linspace(0.0, 1.0, W, dtype=np.float64) ** 2).astype(np.float32)   # not symmetric
+    got_default = None
+    with rb.Engine(2, 48000, W, f, 1.0, pitch, seed=5) as e:
+        got_default = e.process_all(x)
+    with rb.Engine(2, 48000, W, f, 1.0, pitch, seed=5) as e:
+        e.set_window(win)
+        got = e.process_all(x)
+    assert not np.array_equal(got, got_default)
+    for c in range(2):
+        s = ol.OracleStretcher(f, pitch, W, window=win, precision=64)
+        s.set_philox(5, c)
+        s.send(x[c]); s.close()
+        ref = []
+        while not s.is_done():
+            ref.append(s.next_window())
+        ref = np.concatenate(ref)
+        assert got[c].shape == ref.shape
+        assert np.abs(got[c] - ref).max() <= 1e-4 * max(1.0, float(np.abs(ref).max())) and ol.snr_db(ref, got[c]) > 100.0
